@@ -1,0 +1,191 @@
+/*
+ * sgn_raster.h -- C ABI of libsgn_raster.so, the B200-native (sm_100a) Gaussian rasterizer hot path
+ * that replaces the gsplat 0.1.x calls made by street-gaussians-ns.
+ *
+ * Every entry point below names the reference interface it stands in for (paths relative to
+ * /root/reference/street_gaussians_ns/).  gsplat itself is an un-vendored pip dependency of the
+ * reference; its semantics are restated in SURVEY.md Appendix A.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers owned by the caller (e.g. torch allocations), fp32 /
+ *     int32, row-major contiguous, 16-byte aligned;  `stream` is a cudaStream_t passed as void*.
+ *   - structs (sgn_camera, sgn_segment, ...) are plain host structs passed by pointer; segment
+ *     tables are staged to a caller-provided device buffer with sgn_upload().
+ *   - every function returns 0 on success, a negative sgn_status otherwise; the message is
+ *     available from sgn_last_error() (thread local).  No exceptions cross the ABI, no global
+ *     state, no allocation inside the library: scratch sizes are queried, buffers are passed in.
+ *   - there is NO CPU fallback: a missing device or a failed launch is an error.
+ */
+#ifndef SGN_RASTER_H_
+#define SGN_RASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGN_ABI_VERSION 1
+#define SGN_MAX_FOURIER 8
+#define SGN_RECORD_FLOATS 12 /* per-Gaussian projected record, see below */
+
+typedef enum sgn_status {
+    SGN_OK = 0,
+    SGN_ERR_INVALID = -1,   /* bad argument (shape, alignment, block width ...) */
+    SGN_ERR_CUDA = -2,      /* a CUDA runtime call or launch failed */
+    SGN_ERR_WORKSPACE = -3, /* scratch buffer too small */
+    SGN_ERR_OVERFLOW = -4   /* intersection count exceeds the provided capacity */
+} sgn_status;
+
+/* Per-Gaussian projected record (12 floats, 48 B, 16-byte aligned):
+ *   [0] x  [1] y            pixel centre            == gsplat project_gaussians `xys`
+ *   [2] a  [3] b  [4] c     conic (inverse cov2d)   == `conics`
+ *   [5] opacity             sigmoid(logit)          (sgn_splatfacto.py:946-949)
+ *   [6] r  [7] g  [8] b     clamp(SH+0.5, min 0)    (sgn_splatfacto.py:939-940)
+ *   [9] depth               view-space z            == `depths`
+ *   [10] aux (int bits)     bits 0-2: colour clamp pass mask, bit 3: object class, bit 4: visible
+ *   [11] unused
+ * xys / conics / depths handed back to Python are strided views of this array. */
+
+/* One visible sub-model of the scene graph for one frame (sgn_splatfacto_scene_graph.py:332-360).
+ * Rows [row0, row0+count) of the concatenated index space; concatenation order is the reference's:
+ * background first, then actors in annotation order. */
+typedef struct sgn_segment {
+    int32_t row0;
+    int32_t count;
+    int32_t F;        /* fourier_features_dim of features_dc (1..8)            (:239-247) */
+    int32_t cls;      /* 0 background, 1 object                                 (:364-366) */
+    int32_t has_pose; /* apply R,t,q  (object2world_gs, :404-417)                          */
+    int32_t pad0;
+    float R[9];       /* object->world rotation, row-major (Box.rot cast to fp32, :411)    */
+    float t[3];       /* Box.center cast to fp32 (:410)                                    */
+    float q[4];       /* quaternion_from_matrix(rot), wxyz (:413)                          */
+    float idft[SGN_MAX_FOURIER]; /* IDFT(t, F) basis (:420-433); [1,0,..] when F == 1      */
+    const float* means;         /* [count,3]          gauss_params (sgn_splatfacto.py:291-300) */
+    const float* scales;        /* [count,3] log                                            */
+    const float* quats;         /* [count,4] wxyz, un-normalised                            */
+    const float* features_dc;   /* [count,F,3]                                              */
+    const float* features_rest; /* [count,(sh_degree+1)^2-1,3]                              */
+    const float* opacities;     /* [count,1] logit                                          */
+} sgn_segment;
+
+/* Gradient destinations, one per segment, same shapes as the parameters (dense: rows the
+ * rasterizer never touched receive zeros, as autograd of the reference produces). */
+typedef struct sgn_segment_grads {
+    float* means;
+    float* scales;
+    float* quats;
+    float* features_dc;
+    float* features_rest;
+    float* opacities;
+} sgn_segment_grads;
+
+/* Camera + render settings (sgn_splatfacto.py:822-841, 860-873, 934-938). */
+typedef struct sgn_camera {
+    float viewmat[12]; /* world->camera 3x4 row-major (viewmat[:3,:], :831-836) */
+    float fx, fy, cx, cy;
+    int32_t width, height;
+    float cam_pos[3];  /* camera_to_worlds[:3,3] for SH view directions (:934) */
+    float limx, limy;  /* 1.3*tan(fov/2), float32 as gsplat computes it */
+    float clip_thresh; /* 0.01 */
+    int32_t block_width;      /* config.block_width; binning semantics (tile AABB) */
+    int32_t sh_degree;        /* coefficients stored */
+    int32_t sh_degree_to_use; /* min(step//interval, sh_degree) train, sh_degree eval (:936-938) */
+} sgn_camera;
+
+/* Blend settings. */
+typedef struct sgn_blend_opts {
+    float alpha_clamp_fwd; /* 0.999  gsplat rasterize_forward  */
+    float alpha_clamp_bwd; /* 0.99   gsplat rasterize_backward */
+    int32_t class_streams; /* also produce objects-only / background-only accumulation
+                              (get_submodel_output, sgn_splatfacto_scene_graph.py:364-366) */
+    int32_t has_sky;       /* rgb = rgb*alpha + sky*(1-alpha) (sgn_splatfacto.py:971-972) */
+    int32_t eval_clamp;    /* not training: rgb.clamp(0,1) (:974-975) */
+} sgn_blend_opts;
+
+const char* sgn_last_error(void);
+int sgn_abi_version(void);
+size_t sgn_sizeof_segment(void);
+size_t sgn_sizeof_segment_grads(void);
+size_t sgn_sizeof_camera(void);
+
+/* Async H2D copy of a small host table (segment / grads table) into caller-provided device memory. */
+int sgn_upload(const void* host, size_t bytes, void* dev, void* stream);
+
+/* ---- fused compose + project + SH + sigmoid -------------------------------------------------
+ * Replaces, in ONE launch over all segments: get_fourier_features + object2world_gs + the six
+ * torch.cat (sgn_splatfacto_scene_graph.py:332-360), exp(scales) / cat(dc,rest) / quat normalise
+ * (sgn_splatfacto.py:857-858,864), gsplat project_gaussians (:860-873), view directions +
+ * spherical_harmonics + clamp (:934-940) and sigmoid(opacities) (:946-949).
+ * Outputs: records[N,12] (layout above), radii[N] i32, num_tiles_hit[N] i32, tile_bbox[N] (4 x u16:
+ * xmin,ymin,xmax,ymax in tiles). */
+int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, const sgn_camera* cam,
+                    float* records, int32_t* radii, int32_t* num_tiles_hit, uint16_t* tile_bbox,
+                    void* stream);
+
+/* Backward of the above.  v_records[N,12] holds the per-Gaussian cotangents in record layout
+ * ([0:2] v_xy, [2:5] v_conic, [5] v_opacity, [6:9] v_rgb, [9] v_depth), as accumulated by
+ * sgn_blend_bwd.  Writes dense parameter gradients for every segment.
+ * Replaces gsplat project_gaussians backward + compute_sh_backward + autograd of the glue. */
+int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N,
+                    const sgn_camera* cam, const float* records, const int32_t* radii,
+                    const float* v_records, void* stream);
+
+/* ---- binning: cumulative intersects, key emit, radix sort, tile bin edges ---------------------
+ * Replaces the inside of gsplat rasterize_gaussians: compute_cumulative_intersects,
+ * map_gaussian_to_intersects, torch.sort, get_tile_bin_edges. */
+/* step 1: inclusive scan of num_tiles_hit -> cum[N]; total also written to *total_dev (int64). */
+size_t sgn_bin_scan_scratch_bytes(int N);
+int sgn_bin_scan(int N, const int32_t* num_tiles_hit, int32_t* cum, int64_t* total_dev,
+                 void* scratch, size_t scratch_bytes, void* stream);
+/* step 2: emit + sort + bin edges for M = total intersections (caller read total back, or passes
+ * an upper bound capacity together with total_dev: entries beyond the true total are ignored). */
+size_t sgn_bin_sort_scratch_bytes(int64_t M);
+int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, const int32_t* radii,
+                 const uint16_t* tile_bbox, const int32_t* cum, int32_t* sorted_ids /*[M]*/,
+                 int32_t* tile_bins /*[tiles,2]*/, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- alpha blending ------------------------------------------------------------------------------
+ * Forward: gsplat rasterize_forward for rgb AND the depth pass in one traversal
+ * (sgn_splatfacto.py:954-996), optionally the two accumulation-only re-renders
+ * (sgn_splatfacto_scene_graph.py:364-366), with the reference's post-ops fused in the epilogue
+ * (:968-975, :995).  Saves raw[H,W,4] (premultiplied rgb + depth), final_T / final_idx per stream. */
+typedef struct sgn_blend_fwd_out {
+    float* rgb;            /* [H,W,3] final */
+    float* accumulation;   /* [H,W]   1 - T */
+    float* depth;          /* [H,W]   where(alpha>1e-3, d/alpha, 10) */
+    float* object_acc;     /* [H,W] or NULL */
+    float* background_acc; /* [H,W] or NULL */
+    float* raw;            /* [H,W,4] saved for backward */
+    float* final_T;        /* [H,W,S] S = 1 or 3 streams (main, object, background) */
+    int32_t* final_idx;    /* [H,W,S] */
+} sgn_blend_fwd_out;
+
+int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
+                  const int32_t* sorted_ids, const int32_t* tile_bins, const float* sky /*[H,W,3] or NULL*/,
+                  const sgn_blend_fwd_out* out, void* stream);
+
+typedef struct sgn_blend_bwd_in {
+    const float* v_rgb;            /* [H,W,3] or NULL */
+    const float* v_accumulation;   /* [H,W]   or NULL */
+    const float* v_depth;          /* [H,W]   or NULL */
+    const float* v_object_acc;     /* [H,W]   or NULL */
+    const float* v_background_acc; /* [H,W]   or NULL */
+    const float* raw;
+    const float* final_T;
+    const int32_t* final_idx;
+    const float* sky;              /* [H,W,3] or NULL */
+    float* v_sky;                  /* [H,W,3] or NULL: gradient to the sky colour */
+} sgn_blend_bwd_in;
+
+/* Backward: gsplat rasterize_backward for all streams in one traversal.  v_records[N,12] must be
+ * zero on entry; it is accumulated into (record layout, see sgn_project_bwd). */
+int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
+                  const int32_t* sorted_ids, const int32_t* tile_bins, const sgn_blend_bwd_in* in,
+                  float* v_records, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGN_RASTER_H_ */

@@ -320,7 +320,10 @@ def post_ops(img4: torch.Tensor, alpha: torch.Tensor, sky: Optional[torch.Tensor
         rgb = rgb * a + sky * (1 - a)
     if not training:
         rgb = rgb.clamp(0.0, 1.0)
-    depth = torch.where(a > 1e-3, img4[..., 3:4] / a, torch.full_like(a, 10.0))
+    # same values as torch.where(alpha > 1e-3, depth_im / alpha, 10); the guarded denominator only keeps
+    # autograd from producing 0/0 in the unselected branch
+    safe = torch.where(a > 1e-3, a, torch.ones_like(a))
+    depth = torch.where(a > 1e-3, img4[..., 3:4] / safe, torch.full_like(a, 10.0))
     return rgb, a, depth
 
 

@@ -1,0 +1,123 @@
+"""ctypes binding of libsgn_raster.so (include/sgn_raster.h).
+
+The product path has NO CPU fallback: if the shared library is missing or a call fails this module
+raises.  The library is built in-tree by build.py (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsgn_raster.so")
+MAX_FOURIER = 8
+RECORD_FLOATS = 12
+
+
+class SgnError(RuntimeError):
+    pass
+
+
+class Segment(C.Structure):
+    _fields_ = [
+        ("row0", C.c_int32), ("count", C.c_int32), ("F", C.c_int32), ("cls", C.c_int32),
+        ("has_pose", C.c_int32), ("pad0", C.c_int32),
+        ("R", C.c_float * 9), ("t", C.c_float * 3), ("q", C.c_float * 4), ("idft", C.c_float * MAX_FOURIER),
+        ("means", C.c_void_p), ("scales", C.c_void_p), ("quats", C.c_void_p),
+        ("features_dc", C.c_void_p), ("features_rest", C.c_void_p), ("opacities", C.c_void_p),
+    ]
+
+
+class SegmentGrads(C.Structure):
+    _fields_ = [
+        ("means", C.c_void_p), ("scales", C.c_void_p), ("quats", C.c_void_p),
+        ("features_dc", C.c_void_p), ("features_rest", C.c_void_p), ("opacities", C.c_void_p),
+    ]
+
+
+class CameraStruct(C.Structure):
+    _fields_ = [
+        ("viewmat", C.c_float * 12),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("cam_pos", C.c_float * 3),
+        ("limx", C.c_float), ("limy", C.c_float),
+        ("clip_thresh", C.c_float),
+        ("block_width", C.c_int32),
+        ("sh_degree", C.c_int32), ("sh_degree_to_use", C.c_int32),
+    ]
+
+
+class BlendOpts(C.Structure):
+    _fields_ = [
+        ("alpha_clamp_fwd", C.c_float), ("alpha_clamp_bwd", C.c_float),
+        ("class_streams", C.c_int32), ("has_sky", C.c_int32), ("eval_clamp", C.c_int32),
+    ]
+
+
+class BlendFwdOut(C.Structure):
+    _fields_ = [
+        ("rgb", C.c_void_p), ("accumulation", C.c_void_p), ("depth", C.c_void_p),
+        ("object_acc", C.c_void_p), ("background_acc", C.c_void_p),
+        ("raw", C.c_void_p), ("final_T", C.c_void_p), ("final_idx", C.c_void_p),
+    ]
+
+
+class BlendBwdIn(C.Structure):
+    _fields_ = [
+        ("v_rgb", C.c_void_p), ("v_accumulation", C.c_void_p), ("v_depth", C.c_void_p),
+        ("v_object_acc", C.c_void_p), ("v_background_acc", C.c_void_p),
+        ("raw", C.c_void_p), ("final_T", C.c_void_p), ("final_idx", C.c_void_p),
+        ("sky", C.c_void_p), ("v_sky", C.c_void_p),
+    ]
+
+
+_lib = None
+
+EXPORTS = [
+    "sgn_last_error", "sgn_abi_version", "sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera",
+    "sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
+    "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_blend_fwd", "sgn_blend_bwd",
+]
+
+
+def load():
+    """Load libsgn_raster.so; raise loudly if it is not there (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SgnError(
+            f"{LIB_PATH} is missing. Build it with `python street-gaussians-ns_b200/build.py` "
+            "(or __graft_entry__.build()). There is no CPU fallback for the rasterizer.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    L.sgn_last_error.restype = C.c_char_p
+    L.sgn_abi_version.restype = C.c_int
+    for f in ("sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera"):
+        getattr(L, f).restype = sz
+    L.sgn_upload.argtypes = [vp, sz, vp, vp]
+    L.sgn_project_fwd.argtypes = [vp, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp]
+    L.sgn_project_bwd.argtypes = [vp, vp, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp]
+    L.sgn_bin_scan_scratch_bytes.argtypes = [i32]
+    L.sgn_bin_scan_scratch_bytes.restype = sz
+    L.sgn_bin_scan.argtypes = [i32, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_sort_scratch_bytes.argtypes = [i64]
+    L.sgn_bin_sort_scratch_bytes.restype = sz
+    L.sgn_bin_sort.argtypes = [i32, i64, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_blend_fwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, vp, C.POINTER(BlendFwdOut), vp]
+    L.sgn_blend_bwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, C.POINTER(BlendBwdIn), vp, vp]
+    for f in ("sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan", "sgn_bin_sort", "sgn_blend_fwd",
+              "sgn_blend_bwd"):
+        getattr(L, f).restype = C.c_int
+    assert L.sgn_sizeof_segment() == C.sizeof(Segment), "sgn_segment layout mismatch between header and ctypes"
+    assert L.sgn_sizeof_segment_grads() == C.sizeof(SegmentGrads)
+    assert L.sgn_sizeof_camera() == C.sizeof(CameraStruct), "sgn_camera layout mismatch"
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().sgn_last_error().decode("utf-8", "replace")
+        raise SgnError(f"{what} failed (status {rc}): {msg}")

@@ -1,0 +1,129 @@
+// Tile binning: cumulative intersects, (tile|depth) key emit, radix sort, per-tile bin edges.
+// Semantics: gsplat 0.1.x rasterize_gaussians internals; sort order ==
+// stable sort of (tile_id << 32 | float_bits(depth)) with emission order as the tie break.
+#include <cub/cub.cuh>
+
+#include "sgn_common.cuh"
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void write_total_kernel(const int32_t* __restrict__ cum, int N, int64_t* __restrict__ total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *total = (N > 0) ? (int64_t)cum[N - 1] : 0;
+}
+
+extern "C" size_t sgn_bin_scan_scratch_bytes(int N) {
+    size_t temp = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, temp, (const int32_t*)nullptr, (int32_t*)nullptr, N > 0 ? N : 1);
+    return align_up(temp, 256) + 256;
+}
+
+extern "C" int sgn_bin_scan(int N, const int32_t* num_tiles_hit, int32_t* cum, int64_t* total_dev, void* scratch,
+                            size_t scratch_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SGN_REQUIRE(num_tiles_hit && cum && total_dev && scratch, "sgn_bin_scan: null pointer");
+    if (scratch_bytes < sgn_bin_scan_scratch_bytes(N)) {
+        sgn_set_error("sgn_bin_scan: scratch too small (%zu < %zu)", scratch_bytes, sgn_bin_scan_scratch_bytes(N));
+        return SGN_ERR_WORKSPACE;
+    }
+    if (N > 0) {
+        size_t temp = scratch_bytes;
+        SGN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(scratch, temp, num_tiles_hit, cum, N, stream));
+    }
+    write_total_kernel<<<1, 32, 0, stream>>>(cum, N, total_dev);
+    SGN_CHECK_LAUNCH("write_total_kernel");
+    return SGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// key emit: one thread per Gaussian (map_gaussian_to_intersects)
+__global__ void __launch_bounds__(256)
+emit_keys_kernel(int N, int tiles_x, const float4* __restrict__ records, const int32_t* __restrict__ radii,
+                 const ushort4* __restrict__ tile_bbox, const int32_t* __restrict__ cum,
+                 uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    if (radii[g] <= 0) return;
+    const ushort4 bb = tile_bbox[g];
+    const uint32_t dbits = (uint32_t)__float_as_int(records[3 * (size_t)g + 2].y);
+    int64_t cur = (g == 0) ? 0 : (int64_t)cum[g - 1];
+    for (int ty = bb.y; ty < bb.w; ++ty) {
+        for (int tx = bb.x; tx < bb.z; ++tx) {
+            const uint64_t tile = (uint64_t)(ty * tiles_x + tx);
+            keys[cur] = (tile << 32) | (uint64_t)dbits;
+            vals[cur] = g;
+            ++cur;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bin_edges_kernel(int64_t M, const uint64_t* __restrict__ keys_sorted, int32_t* __restrict__ tile_bins) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int32_t cur = (int32_t)(keys_sorted[i] >> 32);
+    if (i == 0) tile_bins[2 * cur] = 0;
+    else {
+        const int32_t prev = (int32_t)(keys_sorted[i - 1] >> 32);
+        if (prev != cur) {
+            tile_bins[2 * prev + 1] = (int32_t)i;
+            tile_bins[2 * cur] = (int32_t)i;
+        }
+    }
+    if (i == M - 1) tile_bins[2 * cur + 1] = (int32_t)M;
+}
+
+struct SortLayout {
+    size_t keys_in, keys_out, vals_in, temp, temp_bytes, total;
+};
+
+static SortLayout sort_layout(int64_t M) {
+    SortLayout L;
+    const size_t m = (size_t)(M > 0 ? M : 1);
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int64_t)m, 0, 64);
+    L.keys_in = 0;
+    L.keys_out = align_up(L.keys_in + m * 8, 256);
+    L.vals_in = align_up(L.keys_out + m * 8, 256);
+    L.temp = align_up(L.vals_in + m * 4, 256);
+    L.temp_bytes = temp;
+    L.total = align_up(L.temp + temp, 256);
+    return L;
+}
+
+extern "C" size_t sgn_bin_sort_scratch_bytes(int64_t M) { return sort_layout(M).total; }
+
+extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, const int32_t* radii,
+                            const uint16_t* tile_bbox, const int32_t* cum, int32_t* sorted_ids, int32_t* tile_bins,
+                            void* scratch, size_t scratch_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SGN_REQUIRE(cam && records && radii && tile_bbox && cum && tile_bins && scratch, "sgn_bin_sort: null pointer");
+    SGN_REQUIRE(M >= 0 && M < ((int64_t)1 << 31), "sgn_bin_sort: M=%lld out of the int32 range gsplat's cum_tiles_hit supports", (long long)M);
+    const int bw = cam->block_width;
+    const int tiles_x = (cam->width + bw - 1) / bw, tiles_y = (cam->height + bw - 1) / bw;
+    const int tiles = tiles_x * tiles_y;
+    SGN_CHECK_CUDA(cudaMemsetAsync(tile_bins, 0, sizeof(int32_t) * 2 * (size_t)tiles, stream));
+    if (M == 0 || N == 0) return SGN_OK;
+    SGN_REQUIRE(sorted_ids, "sgn_bin_sort: sorted_ids is null");
+    const SortLayout L = sort_layout(M);
+    if (scratch_bytes < L.total) {
+        sgn_set_error("sgn_bin_sort: scratch too small (%zu < %zu)", scratch_bytes, L.total);
+        return SGN_ERR_WORKSPACE;
+    }
+    char* base = (char*)scratch;
+    uint64_t* keys_in = (uint64_t*)(base + L.keys_in);
+    uint64_t* keys_out = (uint64_t*)(base + L.keys_out);
+    int32_t* vals_in = (int32_t*)(base + L.vals_in);
+    emit_keys_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, tiles_x, reinterpret_cast<const float4*>(records), radii,
+                                                          reinterpret_cast<const ushort4*>(tile_bbox), cum, keys_in, vals_in);
+    SGN_CHECK_LAUNCH("emit_keys_kernel");
+    int tile_bits = 1;
+    while ((1 << tile_bits) < tiles) ++tile_bits;
+    size_t temp = L.temp_bytes;
+    SGN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(base + L.temp, temp, keys_in, keys_out, vals_in, sorted_ids, M, 0,
+                                                   32 + tile_bits, stream));
+    bin_edges_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, keys_out, tile_bins);
+    SGN_CHECK_LAUNCH("bin_edges_kernel");
+    return SGN_OK;
+}

@@ -1,0 +1,344 @@
+// Fused scene-graph compose + EWA projection + SH colour + sigmoid, forward and backward.
+// One thread per Gaussian over the concatenated row space; HBM-bound.
+// Compiled with --fmad=false (see sgn_exact.cuh).
+#include <stdarg.h>
+#include <string.h>
+
+#include "sgn_exact.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing + tiny ABI helpers
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void sgn_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* sgn_last_error(void) { return g_err; }
+extern "C" int sgn_abi_version(void) { return SGN_ABI_VERSION; }
+extern "C" size_t sgn_sizeof_segment(void) { return sizeof(sgn_segment); }
+extern "C" size_t sgn_sizeof_segment_grads(void) { return sizeof(sgn_segment_grads); }
+extern "C" size_t sgn_sizeof_camera(void) { return sizeof(sgn_camera); }
+
+extern "C" int sgn_upload(const void* host, size_t bytes, void* dev, void* stream) {
+    SGN_REQUIRE(host && dev, "sgn_upload: null pointer");
+    SGN_CHECK_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return SGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// segment lookup: rows of a block may straddle sub-models; the row0 table lives in shared memory
+// ------------------------------------------------------------------------------------------------
+#define SGN_MAX_SEGMENTS 1024
+#define PROJ_THREADS 256
+
+__device__ __forceinline__ int find_segment(const int* s_row0, int nseg, int g) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_row0[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(PROJ_THREADS)
+project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, int N, const sgn_camera cam,
+                   float4* __restrict__ records, int32_t* __restrict__ radii, int32_t* __restrict__ num_tiles_hit,
+                   ushort4* __restrict__ tile_bbox) {
+    extern __shared__ int s_row0[];
+    for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_row0[i] = segs[i].row0;
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const int si = find_segment(s_row0, nseg, g);
+    const sgn_segment& sg = segs[si];
+    const int i = g - sg.row0;
+
+    float m[3], ls[3], q[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { m[k] = __ldg(sg.means + 3 * (size_t)i + k); ls[k] = __ldg(sg.scales + 3 * (size_t)i + k); }
+    {
+        const float4 qq = __ldg(reinterpret_cast<const float4*>(sg.quats) + i);
+        q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
+    }
+    SgnProj st;
+    const bool vis = sgn_project_exact(sg, cam, m, ls, q, st);
+
+    // colour: Fourier DC (scene graph :239-247), SH (sgn_splatfacto.py:933-940)
+    const int K = (cam.sh_degree + 1) * (cam.sh_degree + 1);
+    float c0[3] = {0.f, 0.f, 0.f};
+    for (int f = 0; f < sg.F; ++f) {
+        const float w = sg.idft[f];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) c0[ch] += __ldg(sg.features_dc + ((size_t)i * sg.F + f) * 3 + ch) * w;
+    }
+    float rgb[3];
+    int aux = 0;
+    if (cam.sh_degree > 0) {
+        float d[3] = {st.mw[0] - cam.cam_pos[0], st.mw[1] - cam.cam_pos[1], st.mw[2] - cam.cam_pos[2]};
+        const float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        d[0] /= n; d[1] /= n; d[2] /= n;
+        float Y[16];
+        sgn_sh_basis(cam.sh_degree_to_use, d[0], d[1], d[2], Y);
+        const int Kuse = min((cam.sh_degree_to_use + 1) * (cam.sh_degree_to_use + 1), K);
+        float acc[3] = {Y[0] * c0[0], Y[0] * c0[1], Y[0] * c0[2]};
+        const float* rest = sg.features_rest + (size_t)i * (K - 1) * 3;
+        for (int k = 1; k < Kuse; ++k) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) acc[ch] += Y[k] * __ldg(rest + (k - 1) * 3 + ch);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float pre = acc[ch] + 0.5f;
+            if (pre >= 0.f) aux |= (1 << ch);
+            rgb[ch] = pre > 0.f ? pre : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) { rgb[ch] = 1.f / (1.f + expf(-c0[ch])); aux |= (1 << ch); }
+    }
+    const float opac = 1.f / (1.f + expf(-__ldg(sg.opacities + i)));
+    if (sg.cls == 1) aux |= SGN_AUX_OBJECT;
+    if (vis) aux |= SGN_AUX_VISIBLE;
+
+    float4* rec = records + 3 * (size_t)g;
+    rec[0] = make_float4(st.xy[0], st.xy[1], st.conic[0], st.conic[1]);
+    rec[1] = make_float4(st.conic[2], opac, rgb[0], rgb[1]);
+    rec[2] = make_float4(rgb[2], vis ? st.pv[2] : 0.f, __int_as_float(aux), 0.f);
+    radii[g] = st.radius;
+    num_tiles_hit[g] = vis ? (st.tmax[0] - st.tmin[0]) * (st.tmax[1] - st.tmin[1]) : 0;
+    tile_bbox[g] = make_ushort4((unsigned short)st.tmin[0], (unsigned short)st.tmin[1],
+                                (unsigned short)st.tmax[0], (unsigned short)st.tmax[1]);
+}
+
+extern "C" int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, const sgn_camera* cam,
+                               float* records, int32_t* radii, int32_t* num_tiles_hit, uint16_t* tile_bbox,
+                               void* stream) {
+    SGN_REQUIRE(segs_dev && cam && records && radii && num_tiles_hit && tile_bbox, "sgn_project_fwd: null pointer");
+    SGN_REQUIRE(nseg >= 1 && nseg <= SGN_MAX_SEGMENTS, "sgn_project_fwd: nseg=%d out of range [1,%d]", nseg, SGN_MAX_SEGMENTS);
+    SGN_REQUIRE(N >= 0, "sgn_project_fwd: N < 0");
+    SGN_REQUIRE(cam->block_width >= 2 && cam->block_width <= 16, "block_width must be between 2 and 16 (got %d)", cam->block_width);
+    SGN_REQUIRE(cam->sh_degree >= 0 && cam->sh_degree <= 3 && cam->sh_degree_to_use >= 0 && cam->sh_degree_to_use <= cam->sh_degree,
+                "sh_degree must be in [0,3] and sh_degree_to_use <= sh_degree");
+    SGN_REQUIRE((cam->width + cam->block_width - 1) / cam->block_width < 65536 && (cam->height + cam->block_width - 1) / cam->block_width < 65536,
+                "image too large for 16-bit tile coordinates");
+    SGN_REQUIRE(sgn_aligned16(records), "records must be 16-byte aligned");
+    if (N == 0) return SGN_OK;
+    const int blocks = (N + PROJ_THREADS - 1) / PROJ_THREADS;
+    project_fwd_kernel<<<blocks, PROJ_THREADS, nseg * sizeof(int), (cudaStream_t)stream>>>(
+        segs_dev, nseg, N, *cam, reinterpret_cast<float4*>(records), radii, num_tiles_hit,
+        reinterpret_cast<ushort4*>(tile_bbox));
+    SGN_CHECK_LAUNCH("project_fwd_kernel");
+    return SGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PROJ_THREADS)
+project_bwd_kernel(const sgn_segment* __restrict__ segs, const sgn_segment_grads* __restrict__ grads, int nseg, int N,
+                   const sgn_camera cam, const float4* __restrict__ records, const int32_t* __restrict__ radii,
+                   const float4* __restrict__ v_records) {
+    extern __shared__ int s_row0[];
+    for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_row0[i] = segs[i].row0;
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const int si = find_segment(s_row0, nseg, g);
+    const sgn_segment& sg = segs[si];
+    const sgn_segment_grads& gr = grads[si];
+    const int i = g - sg.row0;
+    const int K = (cam.sh_degree + 1) * (cam.sh_degree + 1);
+
+    const float4 v0 = v_records[3 * (size_t)g], v1 = v_records[3 * (size_t)g + 1], v2 = v_records[3 * (size_t)g + 2];
+    const float v_xy[2] = {v0.x, v0.y};
+    const float v_conic[3] = {v0.z, v0.w, v1.x};
+    const float v_opac = v1.y;
+    const float v_rgb[3] = {v1.z, v1.w, v2.x};
+    const float v_depth = v2.y;
+    const float4 r1 = records[3 * (size_t)g + 1], r2 = records[3 * (size_t)g + 2];
+    const int aux = __float_as_int(r2.z);
+
+    // opacity: sigmoid backward
+    {
+        const float o = r1.y;
+        gr.opacities[i] = v_opac * o * (1.f - o);
+    }
+    float m[3], ls[3], q[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { m[k] = __ldg(sg.means + 3 * (size_t)i + k); ls[k] = __ldg(sg.scales + 3 * (size_t)i + k); }
+    {
+        const float4 qq = __ldg(reinterpret_cast<const float4*>(sg.quats) + i);
+        q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
+    }
+    SgnProj st;
+    const bool vis = sgn_project_exact(sg, cam, m, ls, q, st);
+
+    // colour backward (compute_sh_backward + clamp mask + Fourier DC)
+    {
+        float vc[3];
+        float* grest = gr.features_rest + (size_t)i * (K - 1) * 3;
+        if (cam.sh_degree > 0) {
+            float d[3] = {st.mw[0] - cam.cam_pos[0], st.mw[1] - cam.cam_pos[1], st.mw[2] - cam.cam_pos[2]};
+            const float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            d[0] /= n; d[1] /= n; d[2] /= n;
+            float Y[16];
+            sgn_sh_basis(cam.sh_degree_to_use, d[0], d[1], d[2], Y);
+            const int Kuse = (cam.sh_degree_to_use + 1) * (cam.sh_degree_to_use + 1);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) vc[ch] = (aux & (1 << ch)) ? v_rgb[ch] : 0.f;
+            for (int k = 1; k < K; ++k) {
+                const float y = (k < Kuse) ? Y[k] : 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) grest[(k - 1) * 3 + ch] = y * vc[ch];
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) vc[ch] *= Y[0];
+        } else {
+            const float rgb[3] = {r1.z, r1.w, r2.x};
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) vc[ch] = v_rgb[ch] * rgb[ch] * (1.f - rgb[ch]);
+            for (int k = 1; k < K; ++k)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) grest[(k - 1) * 3 + ch] = 0.f;
+        }
+        float* gdc = gr.features_dc + (size_t)i * sg.F * 3;
+        for (int f = 0; f < sg.F; ++f) {
+            const float w = sg.idft[f];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) gdc[f * 3 + ch] = w * vc[ch];
+        }
+    }
+
+    float gm[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vis && radii[g] > 0) {
+        const float* W = cam.viewmat;
+        const float fx = cam.fx, fy = cam.fy;
+        float vpv[3];
+        {
+            const float rw = 1.f / (st.pv[2] + 1e-6f);
+            const float vx = fx * v_xy[0], vy = fy * v_xy[1];
+            vpv[0] = vx * rw;
+            vpv[1] = vy * rw;
+            vpv[2] = -(vx * st.pv[0] + vy * st.pv[1]) * rw * rw + v_depth;
+        }
+        float vA, vB, vC;
+        {
+            const float X0 = st.conic[0], X1 = st.conic[1], X2 = st.conic[2];
+            const float G0 = v_conic[0], G1 = 0.5f * v_conic[1], G2 = v_conic[2];
+            const float a00 = X0 * G0 + X1 * G1, a01 = X0 * G1 + X1 * G2;
+            const float a10 = X1 * G0 + X2 * G1, a11 = X1 * G1 + X2 * G2;
+            const float s00 = -(a00 * X0 + a01 * X1);
+            const float s01 = -(a00 * X1 + a01 * X2);
+            const float s10 = -(a10 * X0 + a11 * X1);
+            const float s11 = -(a10 * X1 + a11 * X2);
+            vA = s00; vB = s01 + s10; vC = s11;
+        }
+        const float g00 = vA, g01 = 0.5f * vB, g11 = vC;
+        const float* T = st.T;
+        const float Sf[9] = {st.S[0], st.S[1], st.S[2], st.S[1], st.S[3], st.S[4], st.S[2], st.S[4], st.S[5]};
+        float GT[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            GT[c] = g00 * T[c] + g01 * T[3 + c];
+            GT[3 + c] = g01 * T[c] + g11 * T[3 + c];
+        }
+        float vS[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) vS[3 * r + c] = T[r] * GT[c] + T[3 + r] * GT[3 + c];
+        float vT[6];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                vT[3 * r + c] = 2.f * (GT[3 * r] * Sf[c] + GT[3 * r + 1] * Sf[3 + c] + GT[3 * r + 2] * Sf[6 + c]);
+        const float vJ00 = vT[0] * W[0] + vT[1] * W[1] + vT[2] * W[2];
+        const float vJ02 = vT[0] * W[8] + vT[1] * W[9] + vT[2] * W[10];
+        const float vJ11 = vT[3] * W[4] + vT[4] * W[5] + vT[5] * W[6];
+        const float vJ12 = vT[3] * W[8] + vT[4] * W[9] + vT[5] * W[10];
+        {
+            const float rz = 1.f / st.pv[2], rz2 = rz * rz, rz3 = rz2 * rz;
+            const float vtx = -fx * rz2 * vJ02;
+            const float vty = -fy * rz2 * vJ12;
+            const float vtz = -fx * rz2 * vJ00 - fy * rz2 * vJ11 + 2.f * fx * st.tx * rz3 * vJ02 + 2.f * fy * st.ty * rz3 * vJ12;
+            if (st.clampx == 0) vpv[0] += vtx; else vpv[2] += (st.clampx > 0 ? cam.limx : -cam.limx) * vtx;
+            if (st.clampy == 0) vpv[1] += vty; else vpv[2] += (st.clampy > 0 ? cam.limy : -cam.limy) * vty;
+            vpv[2] += vtz;
+        }
+        float vmw[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vmw[c] = W[c] * vpv[0] + W[4 + c] * vpv[1] + W[8 + c] * vpv[2];
+        if (sg.has_pose) {
+            const float* R = sg.R;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gm[c] = R[c] * vmw[0] + R[3 + c] * vmw[1] + R[6 + c] * vmw[2];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gm[c] = vmw[c];
+        }
+        float M[9], vM[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) M[3 * r + c] = st.Rg[3 * r + c] * st.s[c];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                vM[3 * r + c] = 2.f * (vS[3 * r] * M[c] + vS[3 * r + 1] * M[3 + c] + vS[3 * r + 2] * M[6 + c]);
+        float vR[9];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float vs = st.Rg[c] * vM[c] + st.Rg[3 + c] * vM[3 + c] + st.Rg[6 + c] * vM[6 + c];
+            gs[c] = vs * st.s[c];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) vR[3 * r + c] = vM[3 * r + c] * st.s[c];
+        }
+        float vqn[4];
+        {
+            const float w = st.qn[0], x = st.qn[1], y = st.qn[2], z = st.qn[3];
+            vqn[0] = 2.f * (x * (vR[7] - vR[5]) + y * (vR[2] - vR[6]) + z * (vR[3] - vR[1]));
+            vqn[1] = 2.f * (-2.f * x * (vR[4] + vR[8]) + y * (vR[1] + vR[3]) + z * (vR[2] + vR[6]) + w * (vR[7] - vR[5]));
+            vqn[2] = 2.f * (x * (vR[1] + vR[3]) - 2.f * y * (vR[0] + vR[8]) + z * (vR[5] + vR[7]) + w * (vR[2] - vR[6]));
+            vqn[3] = 2.f * (x * (vR[2] + vR[6]) + y * (vR[5] + vR[7]) - 2.f * z * (vR[0] + vR[4]) + w * (vR[3] - vR[1]));
+        }
+        float vqr[4];
+        {
+            const float dot = vqn[0] * st.qn[0] + vqn[1] * st.qn[1] + vqn[2] * st.qn[2] + vqn[3] * st.qn[3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) vqr[k] = (vqn[k] - st.qn[k] * dot) / st.qnorm;
+        }
+        if (sg.has_pose) {
+            const float aw = sg.q[0], ax = sg.q[1], ay = sg.q[2], az = sg.q[3];
+            gq[0] = aw * vqr[0] + ax * vqr[1] + ay * vqr[2] + az * vqr[3];
+            gq[1] = -ax * vqr[0] + aw * vqr[1] + az * vqr[2] - ay * vqr[3];
+            gq[2] = -ay * vqr[0] - az * vqr[1] + aw * vqr[2] + ax * vqr[3];
+            gq[3] = -az * vqr[0] + ay * vqr[1] - ax * vqr[2] + aw * vqr[3];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gq[k] = vqr[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { gr.means[3 * (size_t)i + k] = gm[k]; gr.scales[3 * (size_t)i + k] = gs[k]; }
+    reinterpret_cast<float4*>(gr.quats)[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
+}
+
+extern "C" int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N,
+                               const sgn_camera* cam, const float* records, const int32_t* radii,
+                               const float* v_records, void* stream) {
+    SGN_REQUIRE(segs_dev && grads_dev && cam && records && radii && v_records, "sgn_project_bwd: null pointer");
+    SGN_REQUIRE(nseg >= 1 && nseg <= SGN_MAX_SEGMENTS, "sgn_project_bwd: nseg=%d out of range", nseg);
+    SGN_REQUIRE(sgn_aligned16(records) && sgn_aligned16(v_records), "records / v_records must be 16-byte aligned");
+    if (N == 0) return SGN_OK;
+    const int blocks = (N + PROJ_THREADS - 1) / PROJ_THREADS;
+    project_bwd_kernel<<<blocks, PROJ_THREADS, nseg * sizeof(int), (cudaStream_t)stream>>>(
+        segs_dev, grads_dev, nseg, N, *cam, reinterpret_cast<const float4*>(records), radii,
+        reinterpret_cast<const float4*>(v_records));
+    SGN_CHECK_LAUNCH("project_bwd_kernel");
+    return SGN_OK;
+}

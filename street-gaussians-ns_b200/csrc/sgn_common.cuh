@@ -1,0 +1,45 @@
+// Shared host/device helpers for libsgn_raster.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sgn_raster.h"
+
+// ---- error plumbing (thread-local message, negative status; nothing throws across the ABI) ----
+void sgn_set_error(const char* fmt, ...);
+
+#define SGN_CHECK_CUDA(expr)                                                                     \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            sgn_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return SGN_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+#define SGN_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            sgn_set_error(__VA_ARGS__);        \
+            return SGN_ERR_INVALID;            \
+        }                                      \
+    } while (0)
+
+#define SGN_CHECK_LAUNCH(name)                                                                   \
+    do {                                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess) {                                                                 \
+            sgn_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));              \
+            return SGN_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+static inline bool sgn_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// aux word of the projected record
+#define SGN_AUX_CLAMP_MASK 0x7
+#define SGN_AUX_OBJECT 0x8
+#define SGN_AUX_VISIBLE 0x10
+
+#define SGN_TILE 16  // the fused blend kernels are specialised for block_width 16

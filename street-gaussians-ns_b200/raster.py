@@ -1,0 +1,288 @@
+"""Host side of the fused rasterizer: stages the segment table, calls the C-ABI kernels of
+libsgn_raster.so on the current torch CUDA stream, and wires them into autograd.
+
+``render_frame`` is what ``SplatfactoSceneGraphModel.get_outputs`` reduces to
+(street_gaussians_ns/sgn_splatfacto_scene_graph.py:305-374 + street_gaussians_ns/sgn_splatfacto.py:793-1001):
+one compose+project launch, one binning pass, ONE blend traversal for rgb / accumulation / depth /
+object_acc / background_acc (the reference runs four sorts + four traversals).
+
+PyTorch is plumbing here (allocation, streams, autograd bookkeeping); all arithmetic is in the
+CUDA library.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .scene import PARAM_NAMES, Camera, Frame
+
+
+@dataclass
+class RenderSettings:
+    sh_degree: int = 3
+    sh_degree_to_use: Optional[int] = None  # None -> sh_degree
+    block_width: int = 16
+    clip_thresh: float = 0.01
+    alpha_clamp_fwd: float = 0.999  # gsplat rasterize_forward
+    alpha_clamp_bwd: float = 0.99   # gsplat rasterize_backward
+    class_streams: bool = True      # object_acc / background_acc (scene graph :364-366)
+    training: bool = True           # eval adds rgb.clamp(0,1) (sgn_splatfacto.py:974-975)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def camera_struct(cam: Camera, s: RenderSettings) -> _lib.CameraStruct:
+    cs = _lib.CameraStruct()
+    vm = cam.viewmat().reshape(-1)
+    for i in range(12):
+        cs.viewmat[i] = float(vm[i])
+    cs.fx, cs.fy, cs.cx, cs.cy = cam.fx, cam.fy, cam.cx, cam.cy
+    cs.width, cs.height = cam.width, cam.height
+    cp = cam.cam_pos()
+    for i in range(3):
+        cs.cam_pos[i] = float(cp[i])
+    cs.limx, cs.limy = cam.fov_limits()
+    cs.clip_thresh = s.clip_thresh
+    cs.block_width = s.block_width
+    cs.sh_degree = s.sh_degree
+    cs.sh_degree_to_use = s.sh_degree if s.sh_degree_to_use is None else s.sh_degree_to_use
+    return cs
+
+
+def _check_param(t: torch.Tensor, name: str, device) -> None:
+    if not (t.is_cuda and t.device == device):
+        raise _lib.SgnError(f"{name} must live on {device} (got {t.device}); the rasterizer has no CPU path")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise _lib.SgnError(f"{name} must be contiguous float32")
+    if t.data_ptr() % 16 != 0:
+        raise _lib.SgnError(f"{name} must be 16-byte aligned")
+
+
+class SegmentTable:
+    """Host array of sgn_segment + its device copy."""
+
+    def __init__(self, frame: Frame, params: List[List[torch.Tensor]], device):
+        n = len(frame.segments)
+        self.host = (_lib.Segment * n)()
+        row = 0
+        for i, (seg, ps) in enumerate(zip(frame.segments, params)):
+            sg = self.host[i]
+            means, scales, quats, dc, rest, opac = ps
+            for t, nm in zip(ps, PARAM_NAMES):
+                _check_param(t, f"segment {i} {nm}", device)
+            sg.row0, sg.count, sg.F, sg.cls, sg.has_pose = row, means.shape[0], dc.shape[1], seg.cls, int(seg.has_pose)
+            R, t, q = seg.pose_f32()
+            sg.R[:] = R.tolist()
+            sg.t[:] = t.tolist()
+            sg.q[:] = q.tolist()
+            sg.idft[:] = seg.idft_f32().tolist()
+            sg.means, sg.scales, sg.quats = means.data_ptr(), scales.data_ptr(), quats.data_ptr()
+            sg.features_dc, sg.features_rest, sg.opacities = dc.data_ptr(), rest.data_ptr(), opac.data_ptr()
+            row += means.shape[0]
+        self.N = row
+        self.nseg = n
+        raw = np.frombuffer(bytes(self.host), dtype=np.uint8)
+        self.dev = torch.from_numpy(raw.copy()).to(device)
+
+
+def _grads_table(grads: List[List[torch.Tensor]], device) -> torch.Tensor:
+    arr = (_lib.SegmentGrads * len(grads))()
+    for i, gs in enumerate(grads):
+        (arr[i].means, arr[i].scales, arr[i].quats, arr[i].features_dc, arr[i].features_rest,
+         arr[i].opacities) = [g.data_ptr() for g in gs]
+    raw = np.frombuffer(bytes(arr), dtype=np.uint8)
+    return torch.from_numpy(raw.copy()).to(device)
+
+
+# --------------------------------------------------------------------------------------------------
+# stage wrappers (also used directly by tests and bench.py)
+# --------------------------------------------------------------------------------------------------
+def project_fwd(table: SegmentTable, cs: _lib.CameraStruct, device):
+    L = _lib.load()
+    N = table.N
+    records = torch.empty(N, _lib.RECORD_FLOATS, device=device, dtype=torch.float32)
+    radii = torch.empty(N, device=device, dtype=torch.int32)
+    tiles_hit = torch.empty(N, device=device, dtype=torch.int32)
+    bbox = torch.empty(N, 4, device=device, dtype=torch.int16)
+    _lib.check(L.sgn_project_fwd(_ptr(table.dev), table.nseg, N, C.byref(cs), _ptr(records), _ptr(radii),
+                                 _ptr(tiles_hit), _ptr(bbox), _stream()), "sgn_project_fwd")
+    return records, radii, tiles_hit, bbox
+
+
+def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit, bbox):
+    """Returns (M, sorted_ids[M], tile_bins[tiles,2]).  One host sync to read M (as gsplat does)."""
+    L = _lib.load()
+    device = records.device
+    N = records.shape[0]
+    cum = torch.empty(max(N, 1), device=device, dtype=torch.int32)
+    total = torch.empty(1, device=device, dtype=torch.int64)
+    sb = L.sgn_bin_scan_scratch_bytes(N)
+    scratch = torch.empty(sb, device=device, dtype=torch.uint8)
+    _lib.check(L.sgn_bin_scan(N, _ptr(tiles_hit), _ptr(cum), _ptr(total), _ptr(scratch), sb, _stream()), "sgn_bin_scan")
+    M = int(total.item())
+    bw = cs.block_width
+    tiles = ((cs.width + bw - 1) // bw) * ((cs.height + bw - 1) // bw)
+    tile_bins = torch.empty(tiles, 2, device=device, dtype=torch.int32)
+    sorted_ids = torch.empty(max(M, 1), device=device, dtype=torch.int32)
+    sb2 = L.sgn_bin_sort_scratch_bytes(M)
+    scratch2 = torch.empty(sb2, device=device, dtype=torch.uint8)
+    _lib.check(L.sgn_bin_sort(N, M, C.byref(cs), _ptr(records), _ptr(radii), _ptr(bbox), _ptr(cum), _ptr(sorted_ids),
+                              _ptr(tile_bins), _ptr(scratch2), sb2, _stream()), "sgn_bin_sort")
+    return M, sorted_ids, tile_bins
+
+
+def blend_opts(s: RenderSettings, has_sky: bool) -> _lib.BlendOpts:
+    bo = _lib.BlendOpts()
+    bo.alpha_clamp_fwd, bo.alpha_clamp_bwd = s.alpha_clamp_fwd, s.alpha_clamp_bwd
+    bo.class_streams, bo.has_sky, bo.eval_clamp = int(s.class_streams), int(has_sky), int(not s.training)
+    return bo
+
+
+def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor]):
+    L = _lib.load()
+    device = records.device
+    H, W = cs.height, cs.width
+    S = 3 if bo.class_streams else 1
+    out = dict(
+        rgb=torch.empty(H, W, 3, device=device), accumulation=torch.empty(H, W, 1, device=device),
+        depth=torch.empty(H, W, 1, device=device), raw=torch.empty(H, W, 4, device=device),
+        final_T=torch.empty(H, W, S, device=device), final_idx=torch.empty(H, W, S, device=device, dtype=torch.int32))
+    if bo.class_streams:
+        out["object_acc"] = torch.empty(H, W, 1, device=device)
+        out["background_acc"] = torch.empty(H, W, 1, device=device)
+    fo = _lib.BlendFwdOut()
+    fo.rgb, fo.accumulation, fo.depth = out["rgb"].data_ptr(), out["accumulation"].data_ptr(), out["depth"].data_ptr()
+    fo.object_acc = out["object_acc"].data_ptr() if bo.class_streams else None
+    fo.background_acc = out["background_acc"].data_ptr() if bo.class_streams else None
+    fo.raw, fo.final_T, fo.final_idx = out["raw"].data_ptr(), out["final_T"].data_ptr(), out["final_idx"].data_ptr()
+    _lib.check(L.sgn_blend_fwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins), _ptr(sky),
+                               C.byref(fo), _stream()), "sgn_blend_fwd")
+    return out
+
+
+def blend_bwd(cs, bo, records, sorted_ids, tile_bins, saved: Dict[str, torch.Tensor], sky, v: Dict[str, Optional[torch.Tensor]],
+              want_v_sky: bool):
+    """Returns (v_records[N,12], v_sky or None)."""
+    L = _lib.load()
+    device = records.device
+    v_records = torch.zeros_like(records)
+    bi = _lib.BlendBwdIn()
+
+    def c(t):
+        return None if t is None else t.contiguous()
+
+    keep = {k: c(t) for k, t in v.items()}
+    bi.v_rgb = keep["rgb"].data_ptr() if keep.get("rgb") is not None else None
+    bi.v_accumulation = keep["accumulation"].data_ptr() if keep.get("accumulation") is not None else None
+    bi.v_depth = keep["depth"].data_ptr() if keep.get("depth") is not None else None
+    bi.v_object_acc = keep["object_acc"].data_ptr() if keep.get("object_acc") is not None else None
+    bi.v_background_acc = keep["background_acc"].data_ptr() if keep.get("background_acc") is not None else None
+    bi.raw, bi.final_T, bi.final_idx = saved["raw"].data_ptr(), saved["final_T"].data_ptr(), saved["final_idx"].data_ptr()
+    bi.sky = sky.data_ptr() if sky is not None else None
+    v_sky = torch.zeros(cs.height, cs.width, 3, device=device) if (want_v_sky and sky is not None) else None
+    bi.v_sky = v_sky.data_ptr() if v_sky is not None else None
+    _lib.check(L.sgn_blend_bwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins), C.byref(bi),
+                               _ptr(v_records), _stream()), "sgn_blend_bwd")
+    return v_records, v_sky
+
+
+def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, records, radii, v_records):
+    """Dense parameter gradients, one flat arena (a single allocation, 16-byte aligned slices)."""
+    L = _lib.load()
+    device = records.device
+    sizes = [[(t.numel() + 3) // 4 * 4 for t in ps] for ps in params]
+    arena = torch.empty(sum(sum(s) for s in sizes), device=device, dtype=torch.float32)
+    grads, off = [], 0
+    for ps, ss in zip(params, sizes):
+        gs = []
+        for t, n in zip(ps, ss):
+            gs.append(arena[off: off + t.numel()].view(t.shape))
+            off += n
+        grads.append(gs)
+    gt = _grads_table(grads, device)
+    _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, C.byref(cs), _ptr(records), _ptr(radii),
+                                 _ptr(v_records), _stream()), "sgn_project_bwd")
+    return grads, arena
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd
+# --------------------------------------------------------------------------------------------------
+class _Holder:
+    """Per-call state the model surface reads back (side-effect attributes)."""
+
+    def __init__(self):
+        self.xys = self.depths = self.radii = self.conics = self.num_tiles_hit = None
+        self.records = None
+        self.v_records = None
+        self.grad_arena = None
+        self.M = 0
+
+
+class _SceneGraphRasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, frame: Frame, settings: RenderSettings, holder: _Holder, sky: Optional[torch.Tensor], *flat):
+        nseg = len(frame.segments)
+        assert len(flat) == 6 * nseg
+        params = [list(flat[6 * i: 6 * i + 6]) for i in range(nseg)]
+        device = flat[0].device
+        for seg, ps in zip(frame.segments, params):
+            K = (settings.sh_degree + 1) ** 2
+            if ps[4].shape[1] != K - 1:
+                raise _lib.SgnError(f"features_rest has {ps[4].shape[1]} coefficients, sh_degree={settings.sh_degree} needs {K - 1}")
+        cs = camera_struct(frame.camera, settings)
+        if sky is not None:
+            sky = sky.contiguous()
+            assert sky.shape == (cs.height, cs.width, 3)
+        bo = blend_opts(settings, sky is not None)
+        table = SegmentTable(frame, params, device)
+        records, radii, tiles_hit, bbox = project_fwd(table, cs, device)
+        M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, tiles_hit, bbox)
+        out = blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky)
+        holder.records, holder.radii, holder.num_tiles_hit, holder.M = records, radii, tiles_hit, M
+        holder.xys, holder.conics, holder.depths = records[:, 0:2], records[:, 2:5], records[:, 9]
+        ctx.frame, ctx.settings, ctx.holder = frame, settings, holder
+        ctx.cs, ctx.bo, ctx.table, ctx.params = cs, bo, table, params
+        ctx.saved = dict(raw=out["raw"], final_T=out["final_T"], final_idx=out["final_idx"])
+        ctx.records, ctx.radii, ctx.sorted_ids, ctx.tile_bins, ctx.sky = records, radii, sorted_ids, tile_bins, sky
+        ctx.sky_needs_grad = sky is not None and sky.requires_grad
+        outs = [out["rgb"], out["accumulation"], out["depth"]]
+        if settings.class_streams:
+            outs += [out["object_acc"], out["background_acc"]]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *v):
+        names = ["rgb", "accumulation", "depth", "object_acc", "background_acc"][: len(v)]
+        vd = {k: t for k, t in zip(names, v)}
+        v_records, v_sky = blend_bwd(ctx.cs, ctx.bo, ctx.records, ctx.sorted_ids, ctx.tile_bins, ctx.saved, ctx.sky, vd,
+                                     ctx.sky_needs_grad)
+        grads, arena = project_bwd(ctx.table, ctx.params, ctx.cs, ctx.records, ctx.radii, v_records)
+        h = ctx.holder
+        h.v_records, h.grad_arena = v_records, arena
+        flat = [g for gs in grads for g in gs]
+        return (None, None, None, v_sky, *flat)
+
+
+def render_frame(frame: Frame, settings: Optional[RenderSettings] = None, sky: Optional[torch.Tensor] = None):
+    """Render one camera.  Returns (outputs dict, holder).  Segment parameters must be CUDA tensors."""
+    settings = settings or RenderSettings()
+    holder = _Holder()
+    flat = [t for seg in frame.segments for t in seg.params.tensors()]
+    outs = _SceneGraphRasterize.apply(frame, settings, holder, sky, *flat)
+    names = ["rgb", "accumulation", "depth", "object_acc", "background_acc"][: len(outs)]
+    out = {k: t for k, t in zip(names, outs)}
+    if sky is not None:
+        out["sky"] = sky
+    return out, holder
