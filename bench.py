@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- rendered frames/s (forward+backward) of the rasterizer hot path on BASELINE.json's
+headline configuration (config 3: 1 M background + 32 actors x 10 k Gaussians, 1920x1280, deg-3 SH,
+Fourier-5 actor colour, rgb/accumulation/depth/object_acc/background_acc).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the path's CPU implementation
+                                                           # (oracle/ C port, all host threads), rank 0 only
+
+One "step" = one frame: compose+project+SH -> bin/sort -> blend forward -> blend backward ->
+project/SH/compose backward, with fixed seeded cotangents on rgb, accumulation and object_acc.
+N > 1: one process per GPU (torchrun), every rank renders its own camera (camera-sharded data
+parallelism) and the per-Gaussian gradient arena is all-reduced (NCCL) inside the step.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rendered frames/sec (fwd+bwd) at 1920x1280, 1M+32x10k Gaussians"
+UNIT = "frames/s"
+
+
+def workload_config(cfg: int):
+    return {
+        1: "cfg1: 50k background Gaussians, 640x480",
+        2: "cfg2: 1M background Gaussians, 1920x1280",
+        3: "cfg3: 1M background + 32 actors x 10k Gaussians (Fourier-5 DC), deg-3 SH, 1920x1280, "
+           "outputs rgb/accumulation/depth/object_acc/background_acc",
+    }[cfg]
+
+
+def make_frames(cfg: int, n_ranks: int, rank: int):
+    """Rank r renders the scene from a camera advanced 0.5*r m along -z (camera sharding)."""
+    import numpy as np
+    import street_gaussians_ns_b200.synthetic as syn
+    fr = syn.config_frame(cfg)
+    if rank > 0:
+        c2w = np.concatenate([np.eye(3), np.array([[0.0], [0.0], [-0.5 * rank]])], axis=1)
+        fr.camera = syn.make_camera(fr.camera.width, fr.camera.height, c2w=c2w, time=fr.camera.time)
+    return fr
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, reasons, smax = [], set(), None
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax = float(p[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's C port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_frame_fn(cfg: int):
+    """Returns (fn, info): fn() runs ONE full frame (forward + backward) of the workload on the CPU."""
+    import numpy as np
+    import street_gaussians_ns_b200.synthetic as syn
+    from oracle import oracle_c  # the one place bench.py may execute oracle/: as the timed CPU baseline
+    fr = syn.config_frame(cfg)
+    orc = oracle_c.Oracle(fr)
+    H, W = fr.camera.height, fr.camera.width
+    w, v = syn.cotangents(H, W)
+    v_img = np.concatenate([w.numpy(), np.zeros((H, W, 1), np.float32)], axis=2)
+    v_alpha = v.numpy()
+    v_obj = (0.1 * v).numpy()
+
+    def fn():
+        fw = orc.forward(class_renders=True)
+        orc.backward(fw, v_img, v_alpha, v_obj, None)
+        return fw.M
+
+    return fn, dict(cores=oracle_c.num_threads(), N=orc.N)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fn, info = cpu_frame_fn(args.cfg)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        M = fn()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = 1.0 / dt
+    line = {
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": workload_config(args.cfg), "M_intersections": int(M), "N_gaussians": info["N"]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": "port",
+                         "sample": f"{args.steps} full frames (forward+backward) of the same workload, OpenMP C port of "
+                                   "the gsplat-0.1.x path (oracle/sgn_oracle.c); the reference itself needs gsplat's "
+                                   "CUDA kernels and cannot run on host cores"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(N, A, M, P, n_vis, S):
+    """Per-launch ALGORITHMIC bytes of every kernel (DESIGN.md 'Kernels and rooflines')."""
+    return {
+        # read 236 B/Gaussian of parameters (+48 B per actor Gaussian for the 4 extra Fourier terms),
+        # write the 48 B record + radii/tiles/bbox (16 B)
+        "project_fwd": 236 * N + 48 * A + 64 * N,
+        # scan r+w 8 B/Gaussian; emit 12 B/intersection; one ideal sort pass r+w 24 B; bin edges read 8 B; ids out 4 B
+        "bin_sort": 8 * N + (12 + 24 + 8 + 4) * M,
+        # ids 4 B + gathered record 48 B per intersection; per pixel: rgb 12 + acc 4 + depth 4 + raw 16 + (T,idx) 8*S (+ class acc 8)
+        "blend_fwd": 52 * M + (36 + 8 * S + (8 if S == 3 else 0)) * P,
+        # ids + record per intersection; per pixel cotangents 12+4 (+4 object) + raw 16 + (T,idx) 8*S; 40 B of gradient per touched Gaussian
+        "blend_bwd": 52 * M + (32 + 8 * S + (4 if S == 3 else 0)) * P + 40 * n_vis,
+        # read v_record 48 + record 48 + params 44 (geometry) per Gaussian, write 236 B (+48 per actor Gaussian) of dense gradients
+        "project_bwd": (48 + 48 + 44) * N + 236 * N + 48 * A,
+    }
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import street_gaussians_ns_b200.synthetic as syn
+    from street_gaussians_ns_b200 import _lib, raster
+    from street_gaussians_ns_b200.model import ActorPose, SceneGraphConfig, SceneGraphRasterModel
+    from street_gaussians_ns_b200.scene import CLS_OBJECT, Frame, Segment
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.load()
+
+    fr = make_frames(args.cfg, world, rank)
+    frc = Frame(fr.camera, [Segment(s.params.to(dev).requires_grad_(True), s.cls, s.rot, s.center, s.idft, s.name)
+                            for s in fr.segments])
+    settings = raster.RenderSettings()
+    H, W = fr.camera.height, fr.camera.width
+    w, v = syn.cotangents(H, W)
+    w, v = w.to(dev), v.to(dev)
+    vo = 0.1 * v
+    leaves = [t for s in frc.segments for t in s.params.tensors()]
+
+    def step():
+        out, holder = raster.render_frame(frc, settings)
+        torch.autograd.backward([out["rgb"], out["accumulation"], out["object_acc"]],
+                                [w, v[..., None], vo[..., None]])
+        if world > 1:  # camera-sharded DP: sum the flat per-Gaussian gradient arena
+            dist.all_reduce(holder.grad_arena)
+        for t in leaves:
+            t.grad = None
+        return holder
+
+    def barrier_sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier_sync()
+
+    # ---- timed region 1: device-resident inputs, CUDA events, max over ranks --------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    raster.TIMER = raster.StageTimer()
+    launches0 = L.sgn_launch_count()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync()
+    e0.record()
+    for _ in range(args.steps):
+        holder = step()
+    e1.record()
+    barrier_sync()
+    ms = e0.elapsed_time(e1)
+    launches = L.sgn_launch_count() - launches0
+    stage_ms = raster.TIMER.mean_ms()
+    raster.TIMER = None
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = world / (ms_per_step * 1e-3)
+
+    # ---- timed region 2: end to end through the model API with host inputs ------------------------
+    # per step: camera + segment table built on the host, the ground-truth image copied H2D from pinned
+    # memory, get_outputs(), L1 loss, backward, and the loss read back D2H.
+    bg = frc.segments[0].params
+    actors = {s.name.replace("object_", ""): s.params for s in frc.segments[1:]}
+    poses = [ActorPose(s.name.replace("object_", ""), s.rot, s.center, 21, list(range(85))) for s in frc.segments[1:]]
+    model = SceneGraphRasterModel(bg, actors, SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0),
+                                  poses_at=lambda t: poses).to(dev)
+    model.train()
+    model.step = 30000
+    g = torch.Generator().manual_seed(5)
+    gt_host = (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).pin_memory()
+    mparams = [p for p in model.parameters()]
+
+    def e2e_step():
+        gt = gt_host.to(dev, non_blocking=True).float() / 255.0
+        out = model.get_outputs(fr.camera)
+        losses = model.get_loss_dict(out, {"image": gt})
+        loss = sum(losses.values())
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(model._holder.grad_arena)
+        val = float(loss.item())
+        for p in mparams:
+            p.grad = None
+        return val
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier_sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier_sync()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t2 = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world / (float(t2.item()) / args.steps * 1e-3)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        N = sum(s.params.num_points for s in frc.segments)
+        A = sum(s.params.num_points for s in frc.segments if s.cls == CLS_OBJECT)
+        M = holder.M
+        n_vis = int((holder.radii > 0).sum().item())
+        P = H * W
+        S = 3 if settings.class_streams else 1
+        alg = algorithmic_bytes(N, A, M, P, n_vis, S)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        per_kernel = {}
+        for k, b in alg.items():
+            key = k if k != "bin_sort" else None
+            t = stage_ms.get(k) if key else (stage_ms.get("bin_scan", 0.0) + stage_ms.get("bin_sort", 0.0))
+            if t:
+                per_kernel[k] = {"ms": round(t, 4), "alg_bytes": int(b), "GBps": round(b / t / 1e6, 1),
+                                 "frac": round(b / t / 1e6 / peak, 4)}
+        dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"]) if per_kernel else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        except Exception:
+            pass
+        roofline = None
+        if dom:
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                        "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                        "note": "alpha-blend kernels are FP32/MUFU issue-bound, not HBM-bound (SURVEY.md 8d); "
+                                "all per-kernel fractions are in roofline_all",
+                        "pair_evals_per_s": None}
+        total_alg = sum(alg.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_config(args.cfg), "N_gaussians": N, "N_actor_gaussians": A,
+                       "M_intersections": M, "N_visible": n_vis, "parallelism": f"camera-sharded dp{world}",
+                       "l2": "inputs larger than L2 (330 MB of parameters + 0.4 GB of intersection lists per step vs 126 MB)",
+                       "collective": "all-reduce(SUM) of the flat gradient arena inside the step" if world > 1 else "none"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(gt_host.numel() + len(frc.segments) * 168 + 96),
+                    "d2h_bytes_per_step": 4 + 8,
+                    "what": "SceneGraphRasterModel.get_outputs(camera) + L1 loss + backward through the model API; "
+                            "host camera/poses, pinned uint8 ground-truth image H2D, loss D2H each step; "
+                            "Gaussian parameters are model state and stay resident (as in the reference)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "roofline_all": per_kernel,
+            "whole_step": {"alg_bytes": int(total_alg), "GBps": round(total_alg / ms_per_step / 1e6, 1),
+                           "frac": round(total_alg / ms_per_step / 1e6 / peak, 4)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            fn, info = cpu_frame_fn(args.cfg)
+            fn()
+            t0 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                fn()
+            dt = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": info["cores"], "kind": "port",
+                                    "sample": f"{reps} full frames (fwd+bwd) of the same workload after 1 warm-up, OpenMP C port"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

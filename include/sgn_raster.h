@@ -106,6 +106,8 @@ typedef struct sgn_blend_opts {
 
 const char* sgn_last_error(void);
 int sgn_abi_version(void);
+/* number of kernel launches this library has issued in this process (a CUB device-wide call counts as 1) */
+long long sgn_launch_count(void);
 size_t sgn_sizeof_segment(void);
 size_t sgn_sizeof_segment_grads(void);
 size_t sgn_sizeof_camera(void);

@@ -75,7 +75,7 @@ class BlendBwdIn(C.Structure):
 _lib = None
 
 EXPORTS = [
-    "sgn_last_error", "sgn_abi_version", "sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera",
+    "sgn_last_error", "sgn_abi_version", "sgn_launch_count", "sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera",
     "sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
     "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_blend_fwd", "sgn_blend_bwd",
 ]
@@ -94,6 +94,7 @@ def load():
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
     L.sgn_last_error.restype = C.c_char_p
     L.sgn_abi_version.restype = C.c_int
+    L.sgn_launch_count.restype = C.c_longlong
     for f in ("sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera"):
         getattr(L, f).restype = sz
     L.sgn_upload.argtypes = [vp, sz, vp, vp]

@@ -29,6 +29,7 @@ extern "C" int sgn_bin_scan(int N, const int32_t* num_tiles_hit, int32_t* cum, i
     if (N > 0) {
         size_t temp = scratch_bytes;
         SGN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(scratch, temp, num_tiles_hit, cum, N, stream));
+        sgn_count_launch(1);
     }
     write_total_kernel<<<1, 32, 0, stream>>>(cum, N, total_dev);
     SGN_CHECK_LAUNCH("write_total_kernel");
@@ -123,6 +124,7 @@ extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float
     size_t temp = L.temp_bytes;
     SGN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(base + L.temp, temp, keys_in, keys_out, vals_in, sorted_ids, M, 0,
                                                    32 + tile_bits, stream));
+    sgn_count_launch(1);
     bin_edges_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, keys_out, tile_bins);
     SGN_CHECK_LAUNCH("bin_edges_kernel");
     return SGN_OK;

@@ -16,6 +16,10 @@ void sgn_set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void sgn_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long sgn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* sgn_last_error(void) { return g_err; }
 extern "C" int sgn_abi_version(void) { return SGN_ABI_VERSION; }
 extern "C" size_t sgn_sizeof_segment(void) { return sizeof(sgn_segment); }

@@ -26,8 +26,13 @@ void sgn_set_error(const char* fmt, ...);
         }                                      \
     } while (0)
 
+// every kernel launch this library makes is counted (bench.py reports it as gpu_launches); a CUB
+// device-wide call counts as one
+void sgn_count_launch(int n);
+
 #define SGN_CHECK_LAUNCH(name)                                                                   \
     do {                                                                                         \
+        sgn_count_launch(1);                                                                     \
         cudaError_t _e = cudaGetLastError();                                                     \
         if (_e != cudaSuccess) {                                                                 \
             sgn_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));              \

@@ -1,0 +1,248 @@
+"""Level-2 drop-in surface: the nerfstudio ``Model`` methods of the reference's scene-graph model
+that sit on the hot path, re-hosted on the fused rasterizer.
+
+Mirrors ``SplatfactoSceneGraphModel`` (street_gaussians_ns/sgn_splatfacto_scene_graph.py:41-401) and the
+parts of ``SplatfactoModel`` it inherits (street_gaussians_ns/sgn_splatfacto.py:793-1001, :1042-1094):
+
+  * ``all_models`` ModuleDict: "background", "object_<id>" ... each holding the six ``gauss_params``
+    (names/shapes unchanged, so reference checkpoints load: ``all_models.<name>.gauss_params.<p>``);
+  * ``get_outputs(camera)`` -> {"rgb","accumulation","depth","sky","object_acc","background_acc"
+    (+ "background_rgb","object_rgb" in eval)} with the reference's early-outs;
+  * side-effect attributes ``xys`` (with ``.grad`` = pixel-space mean gradient after backward),
+    ``depths, radii, conics, num_tiles_hit, last_size`` on the model and split per sub-model
+    (``SplatfactoModel.after_train`` reads ``self.xys.grad`` and ``self.radii``, :513-541);
+  * ``get_loss_dict`` (L1 + SSIM + sky accumulation + object-accumulation entropy).
+
+nerfstudio is not a dependency here: ``camera`` is any object with the fields of
+``street_gaussians_ns_b200.scene.Camera`` (SURVEY.md 8b lists what the path reads from ``Cameras``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import raster
+from .scene import CLS_BACKGROUND, CLS_OBJECT, Camera, Frame, GaussianSet, Segment, fourier_time, idft_basis
+
+
+@dataclass
+class ActorPose:
+    """What the path needs from a reference ``Box`` (data/utils/dynamic_annotation.py): trackId,
+    center, rot, frame; plus the actor's frame list for the Fourier time (scene graph :239-245)."""
+
+    track_id: str
+    rot: np.ndarray
+    center: np.ndarray
+    frame: int
+    frame_list: Sequence[int]
+
+
+@dataclass
+class SceneGraphConfig:
+    sh_degree: int = 3
+    sh_degree_interval: int = 1000
+    block_width: int = 16
+    fourier_features_dim: int = 5
+    fourier_features_scale: float = 1.0
+    use_sky_sphere: bool = True
+    ssim_lambda: float = 0.2
+    sky_acc_loss_mult: float = 1.0
+    object_acc_entropy_loss_mult: float = 0.001
+    stop_split_at: int = 25000
+    alpha_clamp_fwd: float = 0.999
+    alpha_clamp_bwd: float = 0.99
+    render_background_acc: bool = True
+
+
+class GaussianSubModel(torch.nn.Module):
+    """One entry of ``all_models``: the ``gauss_params`` ParameterDict (sgn_splatfacto.py:291-300)."""
+
+    def __init__(self, params: GaussianSet):
+        super().__init__()
+        self.gauss_params = torch.nn.ParameterDict(
+            {k: torch.nn.Parameter(getattr(params, k).detach().clone()) for k in
+             ("means", "scales", "quats", "features_dc", "features_rest", "opacities")})
+        self.xys = self.depths = self.radii = self.conics = self.num_tiles_hit = None
+        self.last_size = None
+
+    @property
+    def num_points(self) -> int:
+        return int(self.gauss_params["means"].shape[0])
+
+    def as_set(self) -> GaussianSet:
+        g = self.gauss_params
+        return GaussianSet(g["means"], g["scales"], g["quats"], g["features_dc"], g["features_rest"], g["opacities"])
+
+
+class SceneGraphRasterModel(torch.nn.Module):
+    def __init__(self, background: GaussianSet, actors: Dict[str, GaussianSet], config: Optional[SceneGraphConfig] = None,
+                 poses_at: Optional[Callable[[float], List[ActorPose]]] = None,
+                 sky: Optional[Callable[[Camera, bool], torch.Tensor]] = None):
+        super().__init__()
+        self.config = config or SceneGraphConfig()
+        self.all_models = torch.nn.ModuleDict()
+        self.all_models["background"] = GaussianSubModel(background)
+        for obj_id, ps in actors.items():
+            self.all_models[self.get_object_model_name(obj_id)] = GaussianSubModel(ps)
+        self.poses_at = poses_at or (lambda t: [])
+        self.env_map = sky  # stays on nvdiffrast in the reference (EnvLight, sgn_splatfacto.py:109-150)
+        self.step = 0
+        self.visible_model_names: List[str] = ["background"]
+        self.xys = self.depths = self.radii = self.conics = self.num_tiles_hit = None
+        self.last_size = None
+        self._holder = None
+
+    @staticmethod
+    def get_object_model_name(object_id) -> str:
+        return f"object_{object_id}"
+
+    @property
+    def device(self):
+        return self.all_models["background"].gauss_params["means"].device
+
+    # ------------------------------------------------------------------------------------------
+    def _frame(self, camera: Camera) -> Frame:
+        segs = [Segment(self.all_models["background"].as_set(), CLS_BACKGROUND, name="background")]
+        self.visible_model_names = ["background"]
+        for pose in self.poses_at(camera.time):
+            name = self.get_object_model_name(pose.track_id)
+            assert name not in self.visible_model_names
+            sub = self.all_models[name]
+            if sub.num_points == 0:  # "prevent empty object" (scene graph :337-338)
+                continue
+            ps = sub.as_set()
+            basis = None
+            if ps.fourier_dim > 1:
+                t = fourier_time(pose.frame, pose.frame_list, self.config.fourier_features_scale)
+                basis = idft_basis(t, ps.fourier_dim)
+            segs.append(Segment(ps, CLS_OBJECT, rot=pose.rot, center=pose.center, idft=basis, name=name))
+            self.visible_model_names.append(name)
+        return Frame(camera, segs)
+
+    def _settings(self, class_streams: bool) -> raster.RenderSettings:
+        c = self.config
+        n = min(self.step // c.sh_degree_interval, c.sh_degree) if self.training else c.sh_degree
+        return raster.RenderSettings(sh_degree=c.sh_degree, sh_degree_to_use=n, block_width=c.block_width,
+                                     alpha_clamp_fwd=c.alpha_clamp_fwd, alpha_clamp_bwd=c.alpha_clamp_bwd,
+                                     class_streams=class_streams, training=self.training)
+
+    def get_outputs(self, camera: Camera) -> Dict[str, torch.Tensor]:
+        """``SplatfactoSceneGraphModel.get_outputs`` (scene graph :305-374)."""
+        assert camera.time is not None
+        frame = self._frame(camera)
+        H, W = camera.height, camera.width
+        self.last_size = (H, W)
+        sky = self.env_map(camera, self.training) if (self.config.use_sky_sphere and self.env_map is not None) else None
+        out, holder = raster.render_frame(frame, self._settings(class_streams=True), sky=sky)
+        self._holder = holder
+        self._publish_side_effects(frame, holder)
+        if holder.M == 0:
+            # reference early-out when nothing is visible (sgn_splatfacto.py:878-886): background colour
+            # (zeros), zero accumulation and ZERO depth
+            dev = self.device
+            res = {"rgb": torch.zeros(H, W, 3, device=dev), "accumulation": torch.zeros(H, W, 1, device=dev),
+                   "depth": torch.zeros(H, W, 1, device=dev)}
+            if sky is not None:
+                res["sky"] = sky
+            res["object_acc"] = torch.zeros(H, W, 1, device=dev)
+            res["background_acc"] = torch.zeros(H, W, 1, device=dev)
+            return res
+        if not self.training:
+            # eval-only extra renders (scene graph :367-372): per-class rgb
+            with torch.no_grad():
+                out["background_rgb"] = self._class_rgb(frame, CLS_BACKGROUND, sky)
+                out["object_rgb"] = self._class_rgb(frame, CLS_OBJECT, None)
+        return out
+
+    def _class_rgb(self, frame: Frame, cls: int, sky):
+        segs = [s for s in frame.segments if s.cls == cls]
+        H, W = frame.camera.height, frame.camera.width
+        if not segs:
+            return torch.zeros(H, W, 1, device=self.device) if sky is None else sky
+        sub, _ = raster.render_frame(Frame(frame.camera, segs), self._settings(class_streams=False), sky=sky)
+        return sub["rgb"]
+
+    def _publish_side_effects(self, frame: Frame, holder) -> None:
+        self.xys, self.depths, self.radii = holder.xys, holder.depths, holder.radii
+        self.conics, self.num_tiles_hit = holder.conics, holder.num_tiles_hit
+        for name, sub in self.all_models.items():
+            if name not in self.visible_model_names:
+                sub.xys = None
+        row = 0
+        self._slices = []
+        for seg in frame.segments:
+            sub = self.all_models[seg.name]
+            n = sub.num_points
+            sl = slice(row, row + n)
+            sub.xys, sub.depths, sub.radii = holder.xys[sl], holder.depths[sl], holder.radii[sl]
+            sub.conics, sub.num_tiles_hit, sub.last_size = holder.conics[sl], holder.num_tiles_hit[sl], self.last_size
+            self._slices.append((sub, sl))
+            row += n
+        holder.post_backward = self._split_xys_grad(self._slices)
+
+    @staticmethod
+    def _split_xys_grad(slices):
+        """After ``loss.backward()``: ``sub.xys.grad`` for every visible sub-model, as the reference's
+        ``set_split_tensor_variable(..., retain_grad=True)`` provides (scene graph :153-179)."""
+        def hook(h):
+            v_xy = h.v_records[:, 0:2]
+            for sub, sl in slices:
+                sub.xys.grad = v_xy[sl]
+        return hook
+
+    # ------------------------------------------------------------------------------------------
+    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:
+        """sgn_splatfacto.py:1042-1094 + scene graph :376-391."""
+        c = self.config
+        gt_img = batch["image"]
+        rgb = outputs["rgb"]
+        if "mask" in batch:
+            gt_img = gt_img * batch["mask"]
+            rgb = rgb * batch["mask"]
+        losses = {}
+        Ll1 = torch.abs(gt_img - rgb).mean()
+        losses["Ll1"] = (1 - c.ssim_lambda) * Ll1
+        if c.ssim_lambda > 0:
+            simloss = 1 - ssim(gt_img.permute(2, 0, 1)[None, ...], rgb.permute(2, 0, 1)[None, ...])
+            losses["simloss"] = c.ssim_lambda * simloss
+        if "semantic" in batch and c.sky_acc_loss_mult > 0:
+            sky_mask = (batch["semantic"] == 2)  # SemanticType.SKY (data/utils/data_utils.py:26-29)
+            losses["sky_accumulation"] = c.sky_acc_loss_mult * (sky_mask * outputs["accumulation"]).mean()
+        if c.object_acc_entropy_loss_mult > 0.0 and self.step > c.stop_split_at:
+            oa = torch.clamp(outputs["object_acc"], min=1e-5, max=1 - 1e-5)
+            losses["object_acc_entropy_loss"] = c.object_acc_entropy_loss_mult * -(
+                oa * torch.log(oa) + (1.0 - oa) * torch.log(1.0 - oa)).mean()
+        return losses
+
+
+def _gauss_window(size: int, sigma: float, device, dtype):
+    x = torch.arange(size, device=device, dtype=dtype) - size // 2
+    g = torch.exp(-(x ** 2) / (2 * sigma ** 2))
+    return (g / g.sum())
+
+
+def ssim(x: torch.Tensor, y: torch.Tensor, data_range: float = 1.0, size: int = 11, sigma: float = 1.5) -> torch.Tensor:
+    """pytorch_msssim.SSIM(data_range=1.0, size_average=True, channel=3) as the reference configures it
+    (sgn_splatfacto.py:393): separable 11-tap Gaussian, valid padding, mean over the map."""
+    C = x.shape[1]
+    w = _gauss_window(size, sigma, x.device, x.dtype)
+    wh = w.view(1, 1, size, 1).repeat(C, 1, 1, 1)
+    ww = w.view(1, 1, 1, size).repeat(C, 1, 1, 1)
+
+    def filt(t):
+        return F.conv2d(F.conv2d(t, wh, groups=C), ww, groups=C)
+
+    K1, K2 = 0.01, 0.03
+    C1, C2 = (K1 * data_range) ** 2, (K2 * data_range) ** 2
+    mu1, mu2 = filt(x), filt(y)
+    mu1_sq, mu2_sq, mu12 = mu1 * mu1, mu2 * mu2, mu1 * mu2
+    s1 = filt(x * x) - mu1_sq
+    s2 = filt(y * y) - mu2_sq
+    s12 = filt(x * y) - mu12
+    cs_map = (2 * s12 + C2) / (s1 + s2 + C2)
+    ssim_map = ((2 * mu12 + C1) / (mu1_sq + mu2_sq + C1)) * cs_map
+    return ssim_map.flatten(2).mean(-1).mean()

@@ -34,6 +34,42 @@ class RenderSettings:
     training: bool = True           # eval adds rgb.clamp(0,1) (sgn_splatfacto.py:974-975)
 
 
+class StageTimer:
+    """Optional CUDA-event timing of each C-ABI stage on the launching stream (bench.py / tools)."""
+
+    def __init__(self):
+        self.events: Dict[str, list] = {}
+
+    def record(self, name: str):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        self.events.setdefault(name, []).append(ev)
+
+    def mean_ms(self) -> Dict[str, float]:
+        out = {}
+        for name in {k[:-6] for k in self.events if k.endswith(":start")}:
+            st, en = self.events[name + ":start"], self.events[name + ":end"]
+            out[name] = sum(a.elapsed_time(b) for a, b in zip(st, en)) / max(len(st), 1)
+        return out
+
+
+TIMER: Optional[StageTimer] = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMER is not None:
+            TIMER.record(self.name + ":start")
+
+    def __exit__(self, *a):
+        if TIMER is not None:
+            TIMER.record(self.name + ":end")
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -115,8 +151,9 @@ def project_fwd(table: SegmentTable, cs: _lib.CameraStruct, device):
     radii = torch.empty(N, device=device, dtype=torch.int32)
     tiles_hit = torch.empty(N, device=device, dtype=torch.int32)
     bbox = torch.empty(N, 4, device=device, dtype=torch.int16)
-    _lib.check(L.sgn_project_fwd(_ptr(table.dev), table.nseg, N, C.byref(cs), _ptr(records), _ptr(radii),
-                                 _ptr(tiles_hit), _ptr(bbox), _stream()), "sgn_project_fwd")
+    with _timed("project_fwd"):
+        _lib.check(L.sgn_project_fwd(_ptr(table.dev), table.nseg, N, C.byref(cs), _ptr(records), _ptr(radii),
+                                     _ptr(tiles_hit), _ptr(bbox), _stream()), "sgn_project_fwd")
     return records, radii, tiles_hit, bbox
 
 
@@ -129,7 +166,8 @@ def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit, bbox):
     total = torch.empty(1, device=device, dtype=torch.int64)
     sb = L.sgn_bin_scan_scratch_bytes(N)
     scratch = torch.empty(sb, device=device, dtype=torch.uint8)
-    _lib.check(L.sgn_bin_scan(N, _ptr(tiles_hit), _ptr(cum), _ptr(total), _ptr(scratch), sb, _stream()), "sgn_bin_scan")
+    with _timed("bin_scan"):
+        _lib.check(L.sgn_bin_scan(N, _ptr(tiles_hit), _ptr(cum), _ptr(total), _ptr(scratch), sb, _stream()), "sgn_bin_scan")
     M = int(total.item())
     bw = cs.block_width
     tiles = ((cs.width + bw - 1) // bw) * ((cs.height + bw - 1) // bw)
@@ -137,8 +175,9 @@ def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit, bbox):
     sorted_ids = torch.empty(max(M, 1), device=device, dtype=torch.int32)
     sb2 = L.sgn_bin_sort_scratch_bytes(M)
     scratch2 = torch.empty(sb2, device=device, dtype=torch.uint8)
-    _lib.check(L.sgn_bin_sort(N, M, C.byref(cs), _ptr(records), _ptr(radii), _ptr(bbox), _ptr(cum), _ptr(sorted_ids),
-                              _ptr(tile_bins), _ptr(scratch2), sb2, _stream()), "sgn_bin_sort")
+    with _timed("bin_sort"):
+        _lib.check(L.sgn_bin_sort(N, M, C.byref(cs), _ptr(records), _ptr(radii), _ptr(bbox), _ptr(cum), _ptr(sorted_ids),
+                                  _ptr(tile_bins), _ptr(scratch2), sb2, _stream()), "sgn_bin_sort")
     return M, sorted_ids, tile_bins
 
 
@@ -166,8 +205,9 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
     fo.object_acc = out["object_acc"].data_ptr() if bo.class_streams else None
     fo.background_acc = out["background_acc"].data_ptr() if bo.class_streams else None
     fo.raw, fo.final_T, fo.final_idx = out["raw"].data_ptr(), out["final_T"].data_ptr(), out["final_idx"].data_ptr()
-    _lib.check(L.sgn_blend_fwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins), _ptr(sky),
-                               C.byref(fo), _stream()), "sgn_blend_fwd")
+    with _timed("blend_fwd"):
+        _lib.check(L.sgn_blend_fwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins), _ptr(sky),
+                                   C.byref(fo), _stream()), "sgn_blend_fwd")
     return out
 
 
@@ -192,8 +232,9 @@ def blend_bwd(cs, bo, records, sorted_ids, tile_bins, saved: Dict[str, torch.Ten
     bi.sky = sky.data_ptr() if sky is not None else None
     v_sky = torch.zeros(cs.height, cs.width, 3, device=device) if (want_v_sky and sky is not None) else None
     bi.v_sky = v_sky.data_ptr() if v_sky is not None else None
-    _lib.check(L.sgn_blend_bwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins), C.byref(bi),
-                               _ptr(v_records), _stream()), "sgn_blend_bwd")
+    with _timed("blend_bwd"):
+        _lib.check(L.sgn_blend_bwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins), C.byref(bi),
+                                   _ptr(v_records), _stream()), "sgn_blend_bwd")
     return v_records, v_sky
 
 
@@ -211,8 +252,9 @@ def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, recor
             off += n
         grads.append(gs)
     gt = _grads_table(grads, device)
-    _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, C.byref(cs), _ptr(records), _ptr(radii),
-                                 _ptr(v_records), _stream()), "sgn_project_bwd")
+    with _timed("project_bwd"):
+        _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, C.byref(cs), _ptr(records), _ptr(radii),
+                                     _ptr(v_records), _stream()), "sgn_project_bwd")
     return grads, arena
 
 
@@ -228,6 +270,7 @@ class _Holder:
         self.v_records = None
         self.grad_arena = None
         self.M = 0
+        self.post_backward = None
 
 
 class _SceneGraphRasterize(torch.autograd.Function):
@@ -271,6 +314,11 @@ class _SceneGraphRasterize(torch.autograd.Function):
         grads, arena = project_bwd(ctx.table, ctx.params, ctx.cs, ctx.records, ctx.radii, v_records)
         h = ctx.holder
         h.v_records, h.grad_arena = v_records, arena
+        # the reference reads ``self.xys.grad`` after backward (densification statistics,
+        # sgn_splatfacto.py:520-524): xys is a view of the record array, its gradient a view of v_records
+        h.xys.grad = v_records[:, 0:2]
+        if h.post_backward is not None:
+            h.post_backward(h)
         flat = [g for gs in grads for g in gs]
         return (None, None, None, v_sky, *flat)
 
