@@ -147,6 +147,13 @@ size_t sgn_bin_sort_scratch_bytes(int64_t M);
 int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, const int32_t* radii,
                  const uint16_t* tile_bbox, const int32_t* cum, int32_t* sorted_ids /*[M]*/,
                  int32_t* tile_bins /*[tiles,2]*/, void* scratch, size_t scratch_bytes, void* stream);
+/* sorted_ids payload: bits 0-30 = Gaussian row (concatenated index space), bit 31 = object class.
+ * step 3 (only for the class renders): per-tile OBJECT sub-lists, a stable compaction of sorted_ids
+ * (what the reference's objects-only re-render sorts and traverses, sgn_splatfacto_scene_graph.py:
+ * 255-303,364-365).  obj_ids has capacity M; obj_bins is [tiles,2]. */
+size_t sgn_bin_class_scratch_bytes(int tiles);
+int sgn_bin_class_lists(const sgn_camera* cam, const int32_t* sorted_ids, const int32_t* tile_bins,
+                        int32_t* obj_ids, int32_t* obj_bins, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- alpha blending ------------------------------------------------------------------------------
  * Forward: gsplat rasterize_forward for rgb AND the depth pass in one traversal
@@ -160,13 +167,14 @@ typedef struct sgn_blend_fwd_out {
     float* object_acc;     /* [H,W] or NULL */
     float* background_acc; /* [H,W] or NULL */
     float* raw;            /* [H,W,4] saved for backward */
-    float* final_T;        /* [H,W,S] S = 1 or 3 streams (main, object, background) */
-    int32_t* final_idx;    /* [H,W,S] */
+    float* final_T;        /* [3,H,W] planar: slot 0 main, 1 object, 2 background */
+    int32_t* final_idx;    /* [3,H,W] */
 } sgn_blend_fwd_out;
 
 int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
-                  const int32_t* sorted_ids, const int32_t* tile_bins, const float* sky /*[H,W,3] or NULL*/,
-                  const sgn_blend_fwd_out* out, void* stream);
+                  const int32_t* sorted_ids, const int32_t* tile_bins,
+                  const int32_t* obj_ids /*or NULL*/, const int32_t* obj_bins /*or NULL*/,
+                  const float* sky /*[H,W,3] or NULL*/, const sgn_blend_fwd_out* out, void* stream);
 
 typedef struct sgn_blend_bwd_in {
     const float* v_rgb;            /* [H,W,3] or NULL */
@@ -184,8 +192,9 @@ typedef struct sgn_blend_bwd_in {
 /* Backward: gsplat rasterize_backward for all streams in one traversal.  v_records[N,12] must be
  * zero on entry; it is accumulated into (record layout, see sgn_project_bwd). */
 int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
-                  const int32_t* sorted_ids, const int32_t* tile_bins, const sgn_blend_bwd_in* in,
-                  float* v_records, void* stream);
+                  const int32_t* sorted_ids, const int32_t* tile_bins,
+                  const int32_t* obj_ids /*or NULL*/, const int32_t* obj_bins /*or NULL*/,
+                  const sgn_blend_bwd_in* in, float* v_records, void* stream);
 
 #ifdef __cplusplus
 }

@@ -77,7 +77,8 @@ _lib = None
 EXPORTS = [
     "sgn_last_error", "sgn_abi_version", "sgn_launch_count", "sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera",
     "sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
-    "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_blend_fwd", "sgn_blend_bwd",
+    "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_bin_class_scratch_bytes", "sgn_bin_class_lists",
+    "sgn_blend_fwd", "sgn_blend_bwd",
 ]
 
 
@@ -106,10 +107,15 @@ def load():
     L.sgn_bin_sort_scratch_bytes.argtypes = [i64]
     L.sgn_bin_sort_scratch_bytes.restype = sz
     L.sgn_bin_sort.argtypes = [i32, i64, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, sz, vp]
-    L.sgn_blend_fwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, vp, C.POINTER(BlendFwdOut), vp]
-    L.sgn_blend_bwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, C.POINTER(BlendBwdIn), vp, vp]
-    for f in ("sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan", "sgn_bin_sort", "sgn_blend_fwd",
-              "sgn_blend_bwd"):
+    L.sgn_bin_class_scratch_bytes.argtypes = [i32]
+    L.sgn_bin_class_scratch_bytes.restype = sz
+    L.sgn_bin_class_lists.argtypes = [C.POINTER(CameraStruct), vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_blend_fwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, vp, vp, vp,
+                                C.POINTER(BlendFwdOut), vp]
+    L.sgn_blend_bwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, vp, vp,
+                                C.POINTER(BlendBwdIn), vp, vp]
+    for f in ("sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan", "sgn_bin_sort", "sgn_bin_class_lists",
+              "sgn_blend_fwd", "sgn_blend_bwd"):
         getattr(L, f).restype = C.c_int
     assert L.sgn_sizeof_segment() == C.sizeof(Segment), "sgn_segment layout mismatch between header and ctypes"
     assert L.sgn_sizeof_segment_grads() == C.sizeof(SegmentGrads)

@@ -46,13 +46,16 @@ emit_keys_kernel(int N, int tiles_x, const float4* __restrict__ records, const i
     if (g >= N) return;
     if (radii[g] <= 0) return;
     const ushort4 bb = tile_bbox[g];
-    const uint32_t dbits = (uint32_t)__float_as_int(records[3 * (size_t)g + 2].y);
+    const float4 r2 = records[3 * (size_t)g + 2];
+    const uint32_t dbits = (uint32_t)__float_as_int(r2.y);
+    // payload: Gaussian row in the low 31 bits, object-class flag in bit 31 (no gather needed later)
+    const int32_t payload = g | ((__float_as_int(r2.z) & SGN_AUX_OBJECT) ? (int32_t)0x80000000 : 0);
     int64_t cur = (g == 0) ? 0 : (int64_t)cum[g - 1];
     for (int ty = bb.y; ty < bb.w; ++ty) {
         for (int tx = bb.x; tx < bb.z; ++tx) {
             const uint64_t tile = (uint64_t)(ty * tiles_x + tx);
             keys[cur] = (tile << 32) | (uint64_t)dbits;
-            vals[cur] = g;
+            vals[cur] = payload;
             ++cur;
         }
     }
@@ -127,5 +130,76 @@ extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float
     sgn_count_launch(1);
     bin_edges_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, keys_out, tile_bins);
     SGN_CHECK_LAUNCH("bin_edges_kernel");
+    return SGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-tile object sub-lists: stable compaction of the entries whose payload carries the object bit.
+// The objects-only accumulation of the reference (get_submodel_output, scene graph :364-365) sees
+// exactly these entries in exactly this order.
+__global__ void __launch_bounds__(256)
+class_count_kernel(const int2* __restrict__ tile_bins, const int32_t* __restrict__ sorted_ids, int32_t* __restrict__ counts) {
+    const int tile = blockIdx.x;
+    const int2 range = tile_bins[tile];
+    int c = 0;
+    for (int k = range.x + threadIdx.x; k < range.y; k += blockDim.x) c += (sorted_ids[k] < 0) ? 1 : 0;
+    typedef cub::BlockReduce<int, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const int total = BR(tmp).Sum(c);
+    if (threadIdx.x == 0) counts[tile] = total;
+}
+
+__global__ void __launch_bounds__(256)
+class_compact_kernel(const int2* __restrict__ tile_bins, const int32_t* __restrict__ sorted_ids,
+                     const int32_t* __restrict__ offsets /* exclusive scan of counts */, const int32_t* __restrict__ counts,
+                     int32_t* __restrict__ obj_ids, int2* __restrict__ obj_bins) {
+    const int tile = blockIdx.x;
+    const int2 range = tile_bins[tile];
+    const int base = offsets[tile];
+    if (threadIdx.x == 0) obj_bins[tile] = make_int2(base, base + counts[tile]);
+    typedef cub::BlockScan<int, 256> BS;
+    __shared__ typename BS::TempStorage tmp;
+    int running = 0;
+    for (int k0 = range.x; k0 < range.y; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        const int id = (k < range.y) ? sorted_ids[k] : 0;
+        const int flag = (id < 0) ? 1 : 0;
+        int pos, total;
+        BS(tmp).ExclusiveSum(flag, pos, total);
+        if (flag) obj_ids[base + running + pos] = id;
+        running += total;
+        __syncthreads();
+    }
+}
+
+extern "C" size_t sgn_bin_class_scratch_bytes(int tiles) {
+    size_t temp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp, (const int32_t*)nullptr, (int32_t*)nullptr, tiles > 0 ? tiles : 1);
+    return align_up(temp, 256) + 2 * align_up(sizeof(int32_t) * (size_t)(tiles > 0 ? tiles : 1), 256);
+}
+
+extern "C" int sgn_bin_class_lists(const sgn_camera* cam, const int32_t* sorted_ids, const int32_t* tile_bins,
+                                   int32_t* obj_ids, int32_t* obj_bins, void* scratch, size_t scratch_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SGN_REQUIRE(cam && tile_bins && obj_ids && obj_bins && scratch, "sgn_bin_class_lists: null pointer");
+    const int bw = cam->block_width;
+    const int tiles = ((cam->width + bw - 1) / bw) * ((cam->height + bw - 1) / bw);
+    if (scratch_bytes < sgn_bin_class_scratch_bytes(tiles)) {
+        sgn_set_error("sgn_bin_class_lists: scratch too small");
+        return SGN_ERR_WORKSPACE;
+    }
+    char* base = (char*)scratch;
+    const size_t arr = align_up(sizeof(int32_t) * (size_t)tiles, 256);
+    int32_t* counts = (int32_t*)base;
+    int32_t* offsets = (int32_t*)(base + arr);
+    void* temp = base + 2 * arr;
+    size_t temp_bytes = scratch_bytes - 2 * arr;
+    class_count_kernel<<<tiles, 256, 0, stream>>>(reinterpret_cast<const int2*>(tile_bins), sorted_ids, counts);
+    SGN_CHECK_LAUNCH("class_count_kernel");
+    SGN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, offsets, tiles, stream));
+    sgn_count_launch(1);
+    class_compact_kernel<<<tiles, 256, 0, stream>>>(reinterpret_cast<const int2*>(tile_bins), sorted_ids, offsets, counts,
+                                                    obj_ids, reinterpret_cast<int2*>(obj_bins));
+    SGN_CHECK_LAUNCH("class_compact_kernel");
     return SGN_OK;
 }

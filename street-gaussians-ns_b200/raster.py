@@ -181,6 +181,24 @@ def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit, bbox):
     return M, sorted_ids, tile_bins
 
 
+ID_MASK = 0x7FFFFFFF  # sorted payload: bits 0-30 Gaussian row, bit 31 object class
+
+
+def class_lists(cs: _lib.CameraStruct, M: int, sorted_ids, tile_bins):
+    """Per-tile object sub-lists (stable compaction of the sorted list).  Returns (obj_ids, obj_bins)."""
+    L = _lib.load()
+    device = sorted_ids.device
+    tiles = tile_bins.shape[0]
+    obj_ids = torch.empty(max(M, 1), device=device, dtype=torch.int32)
+    obj_bins = torch.empty(tiles, 2, device=device, dtype=torch.int32)
+    sb = L.sgn_bin_class_scratch_bytes(tiles)
+    scratch = torch.empty(sb, device=device, dtype=torch.uint8)
+    with _timed("class_lists"):
+        _lib.check(L.sgn_bin_class_lists(C.byref(cs), _ptr(sorted_ids), _ptr(tile_bins), _ptr(obj_ids), _ptr(obj_bins),
+                                         _ptr(scratch), sb, _stream()), "sgn_bin_class_lists")
+    return obj_ids, obj_bins
+
+
 def blend_opts(s: RenderSettings, has_sky: bool) -> _lib.BlendOpts:
     bo = _lib.BlendOpts()
     bo.alpha_clamp_fwd, bo.alpha_clamp_bwd = s.alpha_clamp_fwd, s.alpha_clamp_bwd
@@ -188,7 +206,7 @@ def blend_opts(s: RenderSettings, has_sky: bool) -> _lib.BlendOpts:
     return bo
 
 
-def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor]):
+def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor], obj_ids=None, obj_bins=None):
     L = _lib.load()
     device = records.device
     H, W = cs.height, cs.width
@@ -196,7 +214,7 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
     out = dict(
         rgb=torch.empty(H, W, 3, device=device), accumulation=torch.empty(H, W, 1, device=device),
         depth=torch.empty(H, W, 1, device=device), raw=torch.empty(H, W, 4, device=device),
-        final_T=torch.empty(H, W, S, device=device), final_idx=torch.empty(H, W, S, device=device, dtype=torch.int32))
+        final_T=torch.empty(S, H, W, device=device), final_idx=torch.empty(S, H, W, device=device, dtype=torch.int32))
     if bo.class_streams:
         out["object_acc"] = torch.empty(H, W, 1, device=device)
         out["background_acc"] = torch.empty(H, W, 1, device=device)
@@ -206,13 +224,13 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
     fo.background_acc = out["background_acc"].data_ptr() if bo.class_streams else None
     fo.raw, fo.final_T, fo.final_idx = out["raw"].data_ptr(), out["final_T"].data_ptr(), out["final_idx"].data_ptr()
     with _timed("blend_fwd"):
-        _lib.check(L.sgn_blend_fwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins), _ptr(sky),
-                                   C.byref(fo), _stream()), "sgn_blend_fwd")
+        _lib.check(L.sgn_blend_fwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins),
+                                   _ptr(obj_ids), _ptr(obj_bins), _ptr(sky), C.byref(fo), _stream()), "sgn_blend_fwd")
     return out
 
 
 def blend_bwd(cs, bo, records, sorted_ids, tile_bins, saved: Dict[str, torch.Tensor], sky, v: Dict[str, Optional[torch.Tensor]],
-              want_v_sky: bool):
+              want_v_sky: bool, obj_ids=None, obj_bins=None):
     """Returns (v_records[N,12], v_sky or None)."""
     L = _lib.load()
     device = records.device
@@ -233,8 +251,8 @@ def blend_bwd(cs, bo, records, sorted_ids, tile_bins, saved: Dict[str, torch.Ten
     v_sky = torch.zeros(cs.height, cs.width, 3, device=device) if (want_v_sky and sky is not None) else None
     bi.v_sky = v_sky.data_ptr() if v_sky is not None else None
     with _timed("blend_bwd"):
-        _lib.check(L.sgn_blend_bwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins), C.byref(bi),
-                                   _ptr(v_records), _stream()), "sgn_blend_bwd")
+        _lib.check(L.sgn_blend_bwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins),
+                                   _ptr(obj_ids), _ptr(obj_bins), C.byref(bi), _ptr(v_records), _stream()), "sgn_blend_bwd")
     return v_records, v_sky
 
 
@@ -292,13 +310,17 @@ class _SceneGraphRasterize(torch.autograd.Function):
         table = SegmentTable(frame, params, device)
         records, radii, tiles_hit, bbox = project_fwd(table, cs, device)
         M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, tiles_hit, bbox)
-        out = blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky)
+        obj_ids = obj_bins = None
+        if settings.class_streams:
+            obj_ids, obj_bins = class_lists(cs, M, sorted_ids, tile_bins)
+        out = blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky, obj_ids, obj_bins)
         holder.records, holder.radii, holder.num_tiles_hit, holder.M = records, radii, tiles_hit, M
         holder.xys, holder.conics, holder.depths = records[:, 0:2], records[:, 2:5], records[:, 9]
         ctx.frame, ctx.settings, ctx.holder = frame, settings, holder
         ctx.cs, ctx.bo, ctx.table, ctx.params = cs, bo, table, params
         ctx.saved = dict(raw=out["raw"], final_T=out["final_T"], final_idx=out["final_idx"])
         ctx.records, ctx.radii, ctx.sorted_ids, ctx.tile_bins, ctx.sky = records, radii, sorted_ids, tile_bins, sky
+        ctx.obj_ids, ctx.obj_bins = obj_ids, obj_bins
         ctx.sky_needs_grad = sky is not None and sky.requires_grad
         outs = [out["rgb"], out["accumulation"], out["depth"]]
         if settings.class_streams:
@@ -310,7 +332,7 @@ class _SceneGraphRasterize(torch.autograd.Function):
         names = ["rgb", "accumulation", "depth", "object_acc", "background_acc"][: len(v)]
         vd = {k: t for k, t in zip(names, v)}
         v_records, v_sky = blend_bwd(ctx.cs, ctx.bo, ctx.records, ctx.sorted_ids, ctx.tile_bins, ctx.saved, ctx.sky, vd,
-                                     ctx.sky_needs_grad)
+                                     ctx.sky_needs_grad, ctx.obj_ids, ctx.obj_bins)
         grads, arena = project_bwd(ctx.table, ctx.params, ctx.cs, ctx.records, ctx.radii, v_records)
         h = ctx.holder
         h.v_records, h.grad_arena = v_records, arena

@@ -90,7 +90,9 @@ def test_binning_bit_exact(scene):
     assert M == fw.M
     np.testing.assert_array_equal(tile_bins.cpu().numpy()[fw.tile_bins[:, 1] > fw.tile_bins[:, 0]],
                                   fw.tile_bins[fw.tile_bins[:, 1] > fw.tile_bins[:, 0]])
-    np.testing.assert_array_equal(sorted_ids.cpu().numpy()[:M], fw.sorted_ids)
+    ids = sorted_ids.cpu().numpy()[:M]
+    np.testing.assert_array_equal(ids & 0x7FFFFFFF, fw.sorted_ids)
+    np.testing.assert_array_equal((ids < 0).astype(np.int32), fw.cls[fw.sorted_ids])  # bit 31 = object class
 
 
 def _render(frc, training=True, sky=None, **kw):
@@ -230,7 +232,7 @@ def test_full_size_properties_cfg3():
     nonempty = tb[:, 1] > tb[:, 0]
     assert tb[nonempty][0, 0] == 0 and tb[nonempty][-1, 1] == M
     assert np.all(tb[nonempty][1:, 0] == tb[nonempty][:-1, 1])  # bins tile the list
-    depth = records[:, 9][sorted_ids[:M].long()].cpu().numpy()
+    depth = records[:, 9][(sorted_ids[:M] & 0x7FFFFFFF).long()].cpu().numpy()
     seg_start = np.zeros(M, bool)
     seg_start[tb[nonempty][:, 0]] = True
     assert np.all((np.diff(depth) >= 0) | seg_start[1:])  # depth-sorted inside every tile

@@ -38,8 +38,11 @@ def main():
         table = raster.SegmentTable(frc, params, dev); ev[1].record()
         records, radii, tiles_hit, bbox = raster.project_fwd(table, cs, dev); ev[2].record()
         M, sorted_ids, tile_bins = raster.bin_and_sort(cs, records, radii, tiles_hit, bbox); ev[3].record()
-        out = raster.blend_fwd(cs, bo, records, sorted_ids, tile_bins, None); ev[4].record()
-        v_records, _ = raster.blend_bwd(cs, bo, records, sorted_ids, tile_bins, out, None, vd, False); ev[5].record()
+        oi = ob = None
+        if s.class_streams:
+            oi, ob = raster.class_lists(cs, M, sorted_ids, tile_bins)
+        out = raster.blend_fwd(cs, bo, records, sorted_ids, tile_bins, None, oi, ob); ev[4].record()
+        v_records, _ = raster.blend_bwd(cs, bo, records, sorted_ids, tile_bins, out, None, vd, False, oi, ob); ev[5].record()
         grads, arena = raster.project_bwd(table, params, cs, records, radii, v_records); ev[6].record()
         torch.cuda.synchronize()
         if it >= 3:
