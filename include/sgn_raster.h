@@ -137,9 +137,13 @@ int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_
 /* ---- binning: cumulative intersects, key emit, radix sort, tile bin edges ---------------------
  * Replaces the inside of gsplat rasterize_gaussians: compute_cumulative_intersects,
  * map_gaussian_to_intersects, torch.sort, get_tile_bin_edges. */
-/* step 1: inclusive scan of num_tiles_hit -> cum[N]; total also written to *total_dev (int64). */
+/* step 1: per-Gaussian count of the AABB tiles it can actually reach (exact, conservative
+ * ellipse-vs-tile test: a tile where no pixel centre can have alpha >= 1/255 is a no-op for every
+ * stream and is dropped; gsplat's num_tiles_hit is NOT changed), inclusive scan -> cum[N];
+ * the total M is also written to *total_dev (int64). */
 size_t sgn_bin_scan_scratch_bytes(int N);
-int sgn_bin_scan(int N, const int32_t* num_tiles_hit, int32_t* cum, int64_t* total_dev,
+int sgn_bin_scan(int N, const sgn_camera* cam, const float* records, const int32_t* radii,
+                 const uint16_t* tile_bbox, int32_t* cum, int64_t* total_dev,
                  void* scratch, size_t scratch_bytes, void* stream);
 /* step 2: emit + sort + bin edges for M = total intersections (caller read total back, or passes
  * an upper bound capacity together with total_dev: entries beyond the true total are ignored). */

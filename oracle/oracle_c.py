@@ -203,6 +203,17 @@ class Oracle:
         assert got == M, f"bin_sort returned {got}, expected {M}"
         return M, sorted_ids[:M] if M else sorted_ids[:0], tile_bins
 
+    def entry_any_valid(self, fw) -> np.ndarray:
+        """uint8[M]: can any pixel centre of the entry's tile accept it (alpha >= 1/255)?"""
+        cam = self.frame.camera
+        out = np.zeros(max(fw.M, 1), np.uint8)
+        ids = fw.sorted_ids if fw.sorted_ids.size else np.zeros(1, np.int32)
+        rc = self.L.sgn_oracle_entry_any_valid(
+            C.c_int(cam.width), C.c_int(cam.height), C.c_int(self.bw), _p(ids), _p(fw.tile_bins), _p(fw.xys),
+            _p(fw.conics), _p(fw.opac), _p(out))
+        assert rc == 0
+        return out[: fw.M]
+
     def blend(self, pr, sorted_ids, tile_bins, colors: np.ndarray, cls_filter: int = -1,
               background: Optional[np.ndarray] = None):
         cam = self.frame.camera

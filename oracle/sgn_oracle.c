@@ -753,3 +753,37 @@ void sgn_oracle_set_threads(int n) {
     (void)n;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* For every entry of the (gsplat AABB) per-tile lists: can ANY pixel centre of that tile accept */
+/* it (sigma >= 0 and alpha >= 1/255)?  Used to check that the product's exact tile culling only */
+/* drops entries that are no-ops for every pixel.                                               */
+/* ------------------------------------------------------------------------------------------ */
+int sgn_oracle_entry_any_valid(int width, int height, int block_width, const int32_t* sorted_ids,
+                               const int32_t* tile_bins, const float* xys, const float* conics,
+                               const float* opac, uint8_t* any_valid) {
+    const int tiles_x = (width + block_width - 1) / block_width;
+    const int tiles_y = (height + block_width - 1) / block_width;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int t = 0; t < tiles_x * tiles_y; ++t) {
+        const int ty = t / tiles_x, tx = t % tiles_x;
+        for (int k = tile_bins[2 * t]; k < tile_bins[2 * t + 1]; ++k) {
+            const int g = sorted_ids[k];
+            const float ca = conics[3 * g], cb = conics[3 * g + 1], cc = conics[3 * g + 2];
+            int any = 0;
+            for (int ly = 0; ly < block_width && !any; ++ly) {
+                const int i = ty * block_width + ly;
+                if (i >= height) break;
+                for (int lx = 0; lx < block_width; ++lx) {
+                    const int j = tx * block_width + lx;
+                    if (j >= width) break;
+                    const float dx = xys[2 * g] - ((float)j + 0.5f), dy = xys[2 * g + 1] - ((float)i + 0.5f);
+                    const float sigma = 0.5f * (ca * dx * dx + cc * dy * dy) + cb * dx * dy;
+                    if (sigma >= 0.f && opac[g] * expf(-sigma) >= 1.f / 255.f) { any = 1; break; }
+                }
+            }
+            any_valid[k] = (uint8_t)any;
+        }
+    }
+    return 0;
+}

@@ -103,7 +103,7 @@ def load():
     L.sgn_project_bwd.argtypes = [vp, vp, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp]
     L.sgn_bin_scan_scratch_bytes.argtypes = [i32]
     L.sgn_bin_scan_scratch_bytes.restype = sz
-    L.sgn_bin_scan.argtypes = [i32, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_scan.argtypes = [i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, sz, vp]
     L.sgn_bin_sort_scratch_bytes.argtypes = [i64]
     L.sgn_bin_sort_scratch_bytes.restype = sz
     L.sgn_bin_sort.argtypes = [i32, i64, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, sz, vp]

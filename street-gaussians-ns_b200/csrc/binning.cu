@@ -8,6 +8,73 @@
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------------
+// Exact (conservative) tile culling.
+//
+// gsplat lists a Gaussian in every tile of the AABB of its 3-sigma radius, but a pixel only ever
+// uses it when alpha = min(clamp, o*exp(-sigma)) >= 1/255, i.e. sigma <= tau = ln(255*o)
+// (SURVEY.md Appendix A.6).  A tile whose pixel centres ALL have sigma > tau is a no-op for every
+// stream, forward and backward, so it is dropped from the lists here (about half of the entries on
+// the synthetic street scenes).  num_tiles_hit -- the value gsplat reports -- is untouched.
+// The test minimises the (convex) quadratic form over the rectangle of the tile's pixel centres; a
+// margin covers float rounding in both this test and the blend kernels' own evaluation, so no pair
+// the blend would accept is ever dropped.  tests/ check "dropped => no valid pixel" against the oracle.
+struct TouchCtx {
+    float gx, gy, a, b, c, tau;
+    bool always;  // degenerate conic: keep every AABB tile
+};
+
+__device__ __forceinline__ TouchCtx make_touch_ctx(const float4 r0, const float4 r1) {
+    TouchCtx t;
+    t.gx = r0.x; t.gy = r0.y; t.a = r0.z; t.b = r0.w; t.c = r1.x;
+    const float o = r1.y;
+    t.tau = __logf(255.f * o);
+    t.always = !(t.a > 0.f && t.c > 0.f && __fsub_rn(__fmul_rn(t.a, t.c), __fmul_rn(t.b, t.b)) > 0.f) || !(t.tau == t.tau);
+    return t;
+}
+
+__device__ __forceinline__ float touch_q(const TouchCtx& t, float dx, float dy, float& mag) {
+    // explicit, un-contractable operations: count_tiles_kernel and emit_keys_kernel must take
+    // bit-identical decisions
+    const float qa = __fmul_rn(__fmul_rn(0.5f * t.a, dx), dx), qc = __fmul_rn(__fmul_rn(0.5f * t.c, dy), dy);
+    const float qb = __fmul_rn(__fmul_rn(t.b, dx), dy);
+    const float s = __fadd_rn(qa, qc);
+    mag = __fadd_rn(s, fabsf(qb));
+    return __fadd_rn(s, qb);
+}
+
+// does the Gaussian reach any pixel centre of tile (tx,ty)?  (pixel centres: 16*tx+0.5 ... +15.5, clipped to the image)
+__device__ __forceinline__ bool tile_touched(const TouchCtx& t, int tx, int ty, int width, int height, int bw) {
+    if (t.always) return true;
+    if (t.tau < 0.f) return false;  // opacity < 1/255: alpha can never reach 1/255
+    const float x0 = __fsub_rn((float)(tx * bw) + 0.5f, t.gx), x1 = __fsub_rn(fminf((float)(tx * bw + bw), (float)width) - 0.5f, t.gx);
+    const float y0 = __fsub_rn((float)(ty * bw) + 0.5f, t.gy), y1 = __fsub_rn(fminf((float)(ty * bw + bw), (float)height) - 0.5f, t.gy);
+    if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;  // centre inside the rectangle
+    const float nbc = __fdiv_rn(-t.b, t.c), nba = __fdiv_rn(-t.b, t.a);
+    float best = 3.4e38f, best_mag = 0.f, mag, q;
+    // edges x = x0, x = x1: minimise over dy
+    q = touch_q(t, x0, fminf(fmaxf(__fmul_rn(nbc, x0), y0), y1), mag); if (q < best) { best = q; best_mag = mag; }
+    q = touch_q(t, x1, fminf(fmaxf(__fmul_rn(nbc, x1), y0), y1), mag); if (q < best) { best = q; best_mag = mag; }
+    // edges y = y0, y = y1: minimise over dx
+    q = touch_q(t, fminf(fmaxf(__fmul_rn(nba, y0), x0), x1), y0, mag); if (q < best) { best = q; best_mag = mag; }
+    q = touch_q(t, fminf(fmaxf(__fmul_rn(nba, y1), x0), x1), y1, mag); if (q < best) { best = q; best_mag = mag; }
+    return best <= __fadd_rn(__fadd_rn(t.tau, 1e-3f), __fmul_rn(8e-6f, best_mag));
+}
+
+__global__ void __launch_bounds__(256)
+count_tiles_kernel(int N, int width, int height, int bw, const float4* __restrict__ records, const int32_t* __restrict__ radii,
+                   const ushort4* __restrict__ tile_bbox, int32_t* __restrict__ tiles_touched) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    int n = 0;
+    if (radii[g] > 0) {
+        const ushort4 bb = tile_bbox[g];
+        const TouchCtx t = make_touch_ctx(records[3 * (size_t)g], records[3 * (size_t)g + 1]);
+        for (int ty = bb.y; ty < bb.w; ++ty)
+            for (int tx = bb.x; tx < bb.z; ++tx) n += tile_touched(t, tx, ty, width, height, bw) ? 1 : 0;
+    }
+    tiles_touched[g] = n;
+}
+
 __global__ void write_total_kernel(const int32_t* __restrict__ cum, int N, int64_t* __restrict__ total) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *total = (N > 0) ? (int64_t)cum[N - 1] : 0;
 }
@@ -15,20 +82,27 @@ __global__ void write_total_kernel(const int32_t* __restrict__ cum, int N, int64
 extern "C" size_t sgn_bin_scan_scratch_bytes(int N) {
     size_t temp = 0;
     cub::DeviceScan::InclusiveSum(nullptr, temp, (const int32_t*)nullptr, (int32_t*)nullptr, N > 0 ? N : 1);
-    return align_up(temp, 256) + 256;
+    return align_up(temp, 256) + 256 + align_up(sizeof(int32_t) * (size_t)(N > 0 ? N : 1), 256);
 }
 
-extern "C" int sgn_bin_scan(int N, const int32_t* num_tiles_hit, int32_t* cum, int64_t* total_dev, void* scratch,
+extern "C" int sgn_bin_scan(int N, const sgn_camera* cam, const float* records, const int32_t* radii,
+                            const uint16_t* tile_bbox, int32_t* cum, int64_t* total_dev, void* scratch,
                             size_t scratch_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    SGN_REQUIRE(num_tiles_hit && cum && total_dev && scratch, "sgn_bin_scan: null pointer");
+    SGN_REQUIRE(cam && records && radii && tile_bbox && cum && total_dev && scratch, "sgn_bin_scan: null pointer");
     if (scratch_bytes < sgn_bin_scan_scratch_bytes(N)) {
         sgn_set_error("sgn_bin_scan: scratch too small (%zu < %zu)", scratch_bytes, sgn_bin_scan_scratch_bytes(N));
         return SGN_ERR_WORKSPACE;
     }
     if (N > 0) {
-        size_t temp = scratch_bytes;
-        SGN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(scratch, temp, num_tiles_hit, cum, N, stream));
+        const size_t cnt_bytes = align_up(sizeof(int32_t) * (size_t)N, 256);
+        int32_t* touched = (int32_t*)scratch;
+        count_tiles_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, cam->width, cam->height, cam->block_width,
+                                                                reinterpret_cast<const float4*>(records), radii,
+                                                                reinterpret_cast<const ushort4*>(tile_bbox), touched);
+        SGN_CHECK_LAUNCH("count_tiles_kernel");
+        size_t temp = scratch_bytes - cnt_bytes;
+        SGN_CHECK_CUDA(cub::DeviceScan::InclusiveSum((char*)scratch + cnt_bytes, temp, touched, cum, N, stream));
         sgn_count_launch(1);
     }
     write_total_kernel<<<1, 32, 0, stream>>>(cum, N, total_dev);
@@ -37,22 +111,26 @@ extern "C" int sgn_bin_scan(int N, const int32_t* num_tiles_hit, int32_t* cum, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// key emit: one thread per Gaussian (map_gaussian_to_intersects)
+// key emit: one thread per Gaussian (map_gaussian_to_intersects), only tiles that pass tile_touched
 __global__ void __launch_bounds__(256)
-emit_keys_kernel(int N, int tiles_x, const float4* __restrict__ records, const int32_t* __restrict__ radii,
-                 const ushort4* __restrict__ tile_bbox, const int32_t* __restrict__ cum,
+emit_keys_kernel(int N, int tiles_x, int width, int height, int bw, const float4* __restrict__ records,
+                 const int32_t* __restrict__ radii, const ushort4* __restrict__ tile_bbox, const int32_t* __restrict__ cum,
                  uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
     if (radii[g] <= 0) return;
     const ushort4 bb = tile_bbox[g];
-    const float4 r2 = records[3 * (size_t)g + 2];
+    const float4 r0 = records[3 * (size_t)g], r1 = records[3 * (size_t)g + 1], r2 = records[3 * (size_t)g + 2];
+    const TouchCtx t = make_touch_ctx(r0, r1);
     const uint32_t dbits = (uint32_t)__float_as_int(r2.y);
     // payload: Gaussian row in the low 31 bits, object-class flag in bit 31 (no gather needed later)
     const int32_t payload = g | ((__float_as_int(r2.z) & SGN_AUX_OBJECT) ? (int32_t)0x80000000 : 0);
     int64_t cur = (g == 0) ? 0 : (int64_t)cum[g - 1];
+    const int64_t end = (int64_t)cum[g];
     for (int ty = bb.y; ty < bb.w; ++ty) {
         for (int tx = bb.x; tx < bb.z; ++tx) {
+            if (!tile_touched(t, tx, ty, width, height, bw)) continue;
+            if (cur >= end) return;  // cannot happen (same test as count_tiles_kernel); never overrun the slot range
             const uint64_t tile = (uint64_t)(ty * tiles_x + tx);
             keys[cur] = (tile << 32) | (uint64_t)dbits;
             vals[cur] = payload;
@@ -119,7 +197,8 @@ extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float
     uint64_t* keys_in = (uint64_t*)(base + L.keys_in);
     uint64_t* keys_out = (uint64_t*)(base + L.keys_out);
     int32_t* vals_in = (int32_t*)(base + L.vals_in);
-    emit_keys_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, tiles_x, reinterpret_cast<const float4*>(records), radii,
+    emit_keys_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, tiles_x, cam->width, cam->height, bw,
+                                                          reinterpret_cast<const float4*>(records), radii,
                                                           reinterpret_cast<const ushort4*>(tile_bbox), cum, keys_in, vals_in);
     SGN_CHECK_LAUNCH("emit_keys_kernel");
     int tile_bits = 1;

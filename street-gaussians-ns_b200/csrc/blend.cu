@@ -9,18 +9,27 @@
 // what the reference's subset re-render sees.  The reference's post-ops (:968-975, :995) run in
 // the epilogue.
 //
+// Execution shape (B200): the loops are FP32/MUFU issue-bound, not HBM-bound (profiles/), so the
+// design minimises instructions per (pixel, Gaussian) pair:
+//   * ONE WARP PER TILE, 8 pixels per lane (lane = column, 8 rows two apart): dx and the dx-terms of
+//     the quadratic form are computed once per lane and shared by its 8 pixels; the per-Gaussian
+//     gradient reduction (10 values x 5 shuffle levels) is paid once per 256 pixels instead of once
+//     per 32;  the geometric gradients are accumulated per lane as three moments (S0, Sy, Syy);
+//   * exp(-sigma) is one MUFU.EX2: the conic is pre-scaled by log2(e) when an entry is staged;
+//   * entries are staged through a double-buffered shared-memory ring by the warp itself, the next
+//     batch's gathers are in flight while the current batch is blended (no block-wide barriers);
+//   * tiles are pre-culled exactly at binning time (binning.cu), so most staged entries are useful.
+//
 // Sorted payloads carry the Gaussian row in bits 0-30 and the object-class flag in bit 31.
-#include <cooperative_groups.h>
-#include <cooperative_groups/reduce.h>
-
 #include "sgn_common.cuh"
 
-namespace cg = cooperative_groups;
-
-#define BLEND_THREADS 256
 #define ALPHA_MIN (1.f / 255.f)
 #define T_STOP 1e-4f
 #define ID_MASK 0x7fffffff
+#define PPL 8  // pixels per lane
+#define FULL 0xffffffffu
+#define LOG2E 1.4426950408889634f
+#define LN2 0.6931471805599453f
 
 // saved per-pixel state is planar: slot 0 main, 1 object, 2 background
 #define SLOT_MAIN 0
@@ -47,148 +56,193 @@ struct BlendFwdParams {
     int32_t* final_idx;  // [3][H*W]
 };
 
-// sigma with a fixed operation sequence so the forward and backward kernels take identical
-// skip decisions on identical inputs.
-__device__ __forceinline__ float sgn_sigma(float ca, float cb, float cc, float dx, float dy) {
-    const float t0 = __fmul_rn(ca, __fmul_rn(dx, dx));
-    const float t1 = __fmaf_rn(cc, __fmul_rn(dy, dy), t0);
-    return __fmaf_rn(cb, __fmul_rn(dx, dy), __fmul_rn(0.5f, t1));
+// One staged entry: A = (gx, gy, 0.5*a*log2e, b*log2e)  B = (0.5*c*log2e, opacity, r, g)  C = (b, depth, id bits, -)
+struct Staged {
+    float4 A, B, C;
+};
+
+__device__ __forceinline__ Staged gather_entry(const float4* __restrict__ records, int id) {
+    const float4* rec = records + 3 * (size_t)(id & ID_MASK);
+    const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+    Staged s;
+    s.A = make_float4(r0.x, r0.y, 0.5f * LOG2E * r0.z, LOG2E * r0.w);
+    s.B = make_float4(0.5f * LOG2E * r1.x, r1.y, r1.z, r1.w);
+    s.C = make_float4(r2.x, r2.y, __int_as_float(id), 0.f);
+    return s;
+}
+
+// sigma*log2(e) for the pixel at (dx, dy) from the staged conic; identical in forward and backward
+__device__ __forceinline__ float sgn_sigma2(float hax2, float bdx, float hc, float dy) {
+    return __fmaf_rn(dy, __fmaf_rn(hc, dy, bdx), hax2);
+}
+
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 template <bool BG>
-__global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(const BlendFwdParams p) {
-    __shared__ float4 sA[BLEND_THREADS];  // x y ca cb
-    __shared__ float4 sB[BLEND_THREADS];  // cc opac r g
-    __shared__ float2 sC[BLEND_THREADS];  // b depth
-    __shared__ int sId[BLEND_THREADS];
+__global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
+    __shared__ float4 sA[2][32];
+    __shared__ float4 sB[2][32];
+    __shared__ float4 sC[2][32];
     const int tile = blockIdx.x;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    const int tr = threadIdx.x;
-    const int j = tx * SGN_TILE + (tr & 15), i = ty * SGN_TILE + (tr >> 4);
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-    const bool inside = (i < p.height) && (j < p.width);
+    const int lane = threadIdx.x;
+    const int j = tx * SGN_TILE + (lane & 15);
+    const int i0 = ty * SGN_TILE + (lane >> 4);
+    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
     const int2 range = p.tile_bins[tile];
-    const int num_batches = (range.y - range.x + BLEND_THREADS - 1) / BLEND_THREADS;
 
-    float T = 1.f, Tb = 1.f;
-    int idx = 0, idxb = 0;
-    bool done = !inside, doneb = !inside || !BG;
-    float4 pix = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    for (int b = 0; b < num_batches; ++b) {
-        if (__syncthreads_count(done && doneb) >= BLEND_THREADS) break;
-        const int batch_start = range.x + BLEND_THREADS * b;
-        const int k = batch_start + tr;
-        if (k < range.y) {
-            const int id = p.sorted_ids[k];
-            const float4* rec = p.records + 3 * (size_t)(id & ID_MASK);
-            sA[tr] = __ldg(rec);
-            sB[tr] = __ldg(rec + 1);
-            const float4 c = __ldg(rec + 2);
-            sC[tr] = make_float2(c.x, c.y);
-            sId[tr] = id;
-        }
-        __syncthreads();
-        const int batch_size = min(BLEND_THREADS, range.y - batch_start);
-        for (int t = 0; t < batch_size && !(done && doneb); ++t) {
-            const float4 A = sA[t];
-            const float4 B = sB[t];
-            const float dx = A.x - px, dy = A.y - py;
-            const float sigma = sgn_sigma(A.z, A.w, B.x, dx, dy);
-            const float alpha = fminf(p.clamp_fwd, B.y * __expf(-sigma));
-            if (sigma < 0.f || alpha < ALPHA_MIN) continue;
-            const float om = 1.f - alpha;
-            if (!done) {
-                const float nT = T * om;
-                if (nT <= T_STOP) done = true;
-                else {
-                    const float2 Cc = sC[t];
-                    const float vis = alpha * T;
-                    pix.x += B.z * vis; pix.y += B.w * vis; pix.z += Cc.x * vis; pix.w += Cc.y * vis;
-                    T = nT;
-                    idx = batch_start + t;
-                }
-            }
-            if (BG) {
-                if (!doneb && sId[t] >= 0) {
-                    const float nT = Tb * om;
-                    if (nT <= T_STOP) doneb = true; else { Tb = nT; idxb = batch_start + t; }
-                }
-            }
-        }
+    float T[PPL], Tb[PPL], pr[PPL], pg[PPL], pb[PPL], pd[PPL];
+    int idx[PPL], idxb[PPL];
+    unsigned done = 0, doneb = BG ? 0u : 0xffu;
+#pragma unroll
+    for (int s = 0; s < PPL; ++s) {
+        T[s] = 1.f; Tb[s] = 1.f; pr[s] = pg[s] = pb[s] = pd[s] = 0.f;
+        idx[s] = -1; idxb[s] = -1;
+        const bool inside = (j < p.width) && (i0 + 2 * s < p.height);
+        if (!inside) { done |= 1u << s; doneb |= 1u << s; }
     }
-    if (!inside) return;
+
+    Staged nxt;
+    if (range.x + lane < range.y) nxt = gather_entry(p.records, p.sorted_ids[range.x + lane]);
+    int buf = 0;
+    bool finished = false;
+    for (int base = range.x; base < range.y && !finished; base += 32) {
+        sA[buf][lane] = nxt.A; sB[buf][lane] = nxt.B; sC[buf][lane] = nxt.C;
+        __syncwarp();
+        if (base + 32 + lane < range.y) nxt = gather_entry(p.records, p.sorted_ids[base + 32 + lane]);
+        const int n = min(32, range.y - base);
+        for (int t = 0; t < n; ++t) {
+            if (__all_sync(FULL, (done & doneb) == 0xffu)) { finished = true; break; }
+            const float4 A = sA[buf][t];
+            const float4 B = sB[buf][t];
+            const float4 Cc = sC[buf][t];
+            const bool isobj = __float_as_int(Cc.z) < 0;
+            const float dx = A.x - px;
+            const float bdx = A.w * dx, hax2 = A.z * dx * dx;
+            const float dy0 = A.y - py0;
+            const int k = base + t;
+#pragma unroll
+            for (int s = 0; s < PPL; ++s) {
+                const float dy = dy0 - (float)(2 * s);
+                const float sg = sgn_sigma2(hax2, bdx, B.x, dy);
+                const float alpha = fminf(p.clamp_fwd, B.y * fast_ex2(-sg));
+                if (sg < 0.f || alpha < ALPHA_MIN) continue;
+                const float om = 1.f - alpha;
+                if (!(done & (1u << s))) {
+                    const float nT = T[s] * om;
+                    if (nT <= T_STOP) done |= 1u << s;
+                    else {
+                        const float w = alpha * T[s];
+                        pr[s] += B.z * w; pg[s] += B.w * w; pb[s] += Cc.x * w; pd[s] += Cc.y * w;
+                        T[s] = nT;
+                        idx[s] = k;
+                    }
+                }
+                if (BG) {
+                    if (!isobj && !(doneb & (1u << s))) {
+                        const float nT = Tb[s] * om;
+                        if (nT <= T_STOP) doneb |= 1u << s; else { Tb[s] = nT; idxb[s] = k; }
+                    }
+                }
+            }
+        }
+        buf ^= 1;
+    }
     const size_t P = (size_t)p.width * p.height;
-    const size_t pid = (size_t)i * p.width + j;
-    const float alpha = 1.f - T;
-    p.raw[pid] = pix;
-    // post-ops (sgn_splatfacto.py:968-975): clamp(max=1), sky blend (premultiplied rgb times alpha again), eval clamp
-    float r = fminf(pix.x, 1.f), g = fminf(pix.y, 1.f), bl = fminf(pix.z, 1.f);
-    if (p.has_sky) {
-        const float* s = p.sky + 3 * pid;
-        r = r * alpha + s[0] * (1.f - alpha);
-        g = g * alpha + s[1] * (1.f - alpha);
-        bl = bl * alpha + s[2] * (1.f - alpha);
-    }
-    if (p.eval_clamp) {
-        r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f); bl = fminf(fmaxf(bl, 0.f), 1.f);
-    }
-    p.rgb[3 * pid] = r; p.rgb[3 * pid + 1] = g; p.rgb[3 * pid + 2] = bl;
-    p.acc[pid] = alpha;
-    p.depth[pid] = alpha > 1e-3f ? pix.w / alpha : 10.f;  // sgn_splatfacto.py:995
-    p.final_T[SLOT_MAIN * P + pid] = T;
-    p.final_idx[SLOT_MAIN * P + pid] = idx;
-    if (BG) {
-        p.final_T[SLOT_BG * P + pid] = Tb;
-        p.final_idx[SLOT_BG * P + pid] = idxb;
-        p.bg_acc[pid] = 1.f - Tb;
+#pragma unroll
+    for (int s = 0; s < PPL; ++s) {
+        const int i = i0 + 2 * s;
+        if (j >= p.width || i >= p.height) continue;
+        const size_t pid = (size_t)i * p.width + j;
+        const float alpha = 1.f - T[s];
+        p.raw[pid] = make_float4(pr[s], pg[s], pb[s], pd[s]);
+        // post-ops (sgn_splatfacto.py:968-975): clamp(max=1), sky blend (premultiplied rgb times alpha again), eval clamp
+        float r = fminf(pr[s], 1.f), g = fminf(pg[s], 1.f), bl = fminf(pb[s], 1.f);
+        if (p.has_sky) {
+            const float* sk = p.sky + 3 * pid;
+            r = r * alpha + sk[0] * (1.f - alpha);
+            g = g * alpha + sk[1] * (1.f - alpha);
+            bl = bl * alpha + sk[2] * (1.f - alpha);
+        }
+        if (p.eval_clamp) {
+            r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f); bl = fminf(fmaxf(bl, 0.f), 1.f);
+        }
+        p.rgb[3 * pid] = r; p.rgb[3 * pid + 1] = g; p.rgb[3 * pid + 2] = bl;
+        p.acc[pid] = alpha;
+        p.depth[pid] = alpha > 1e-3f ? pd[s] / alpha : 10.f;  // sgn_splatfacto.py:995
+        p.final_T[SLOT_MAIN * P + pid] = T[s];
+        p.final_idx[SLOT_MAIN * P + pid] = idx[s];
+        if (BG) {
+            p.final_T[SLOT_BG * P + pid] = Tb[s];
+            p.final_idx[SLOT_BG * P + pid] = idxb[s];
+            p.bg_acc[pid] = 1.f - Tb[s];
+        }
     }
 }
 
 // accumulation-only pass over per-tile sub-lists (objects-only render)
-__global__ void __launch_bounds__(BLEND_THREADS) acc_fwd_kernel(const BlendFwdParams p) {
-    __shared__ float4 sA[BLEND_THREADS];
-    __shared__ float2 sB[BLEND_THREADS];  // cc opac
+__global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p) {
+    __shared__ float4 sA[2][32];
+    __shared__ float2 sB[2][32];
     const int tile = blockIdx.x;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    const int tr = threadIdx.x;
-    const int j = tx * SGN_TILE + (tr & 15), i = ty * SGN_TILE + (tr >> 4);
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-    const bool inside = (i < p.height) && (j < p.width);
+    const int lane = threadIdx.x;
+    const int j = tx * SGN_TILE + (lane & 15);
+    const int i0 = ty * SGN_TILE + (lane >> 4);
+    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
     const int2 range = p.obj_bins[tile];
-    const int num_batches = (range.y - range.x + BLEND_THREADS - 1) / BLEND_THREADS;
-    float T = 1.f;
-    int idx = 0;
-    bool done = !inside;
-    for (int b = 0; b < num_batches; ++b) {
-        if (__syncthreads_count(done) >= BLEND_THREADS) break;
-        const int batch_start = range.x + BLEND_THREADS * b;
-        const int k = batch_start + tr;
-        if (k < range.y) {
-            const float4* rec = p.records + 3 * (size_t)(p.obj_ids[k] & ID_MASK);
-            sA[tr] = __ldg(rec);
-            const float4 B = __ldg(rec + 1);
-            sB[tr] = make_float2(B.x, B.y);
-        }
-        __syncthreads();
-        const int batch_size = min(BLEND_THREADS, range.y - batch_start);
-        for (int t = 0; t < batch_size && !done; ++t) {
-            const float4 A = sA[t];
-            const float2 B = sB[t];
-            const float dx = A.x - px, dy = A.y - py;
-            const float sigma = sgn_sigma(A.z, A.w, B.x, dx, dy);
-            const float alpha = fminf(p.clamp_fwd, B.y * __expf(-sigma));
-            if (sigma < 0.f || alpha < ALPHA_MIN) continue;
-            const float nT = T * (1.f - alpha);
-            if (nT <= T_STOP) done = true; else { T = nT; idx = batch_start + t; }
-        }
+    float T[PPL];
+    int idx[PPL];
+    unsigned done = 0;
+#pragma unroll
+    for (int s = 0; s < PPL; ++s) {
+        T[s] = 1.f; idx[s] = -1;
+        if (!((j < p.width) && (i0 + 2 * s < p.height))) done |= 1u << s;
     }
-    if (!inside) return;
+    Staged nxt;
+    if (range.x + lane < range.y) nxt = gather_entry(p.records, p.obj_ids[range.x + lane]);
+    int buf = 0;
+    bool finished = false;
+    for (int base = range.x; base < range.y && !finished; base += 32) {
+        sA[buf][lane] = nxt.A; sB[buf][lane] = make_float2(nxt.B.x, nxt.B.y);
+        __syncwarp();
+        if (base + 32 + lane < range.y) nxt = gather_entry(p.records, p.obj_ids[base + 32 + lane]);
+        const int n = min(32, range.y - base);
+        for (int t = 0; t < n; ++t) {
+            if (__all_sync(FULL, done == 0xffu)) { finished = true; break; }
+            const float4 A = sA[buf][t];
+            const float2 B = sB[buf][t];
+            const float dx = A.x - px;
+            const float bdx = A.w * dx, hax2 = A.z * dx * dx;
+            const float dy0 = A.y - py0;
+#pragma unroll
+            for (int s = 0; s < PPL; ++s) {
+                const float dy = dy0 - (float)(2 * s);
+                const float sg = sgn_sigma2(hax2, bdx, B.x, dy);
+                const float alpha = fminf(p.clamp_fwd, B.y * fast_ex2(-sg));
+                if (sg < 0.f || alpha < ALPHA_MIN) continue;
+                if (!(done & (1u << s))) {
+                    const float nT = T[s] * (1.f - alpha);
+                    if (nT <= T_STOP) done |= 1u << s; else { T[s] = nT; idx[s] = base + t; }
+                }
+            }
+        }
+        buf ^= 1;
+    }
     const size_t P = (size_t)p.width * p.height;
-    const size_t pid = (size_t)i * p.width + j;
-    p.final_T[SLOT_OBJ * P + pid] = T;
-    p.final_idx[SLOT_OBJ * P + pid] = idx;
-    p.obj_acc[pid] = 1.f - T;
+#pragma unroll
+    for (int s = 0; s < PPL; ++s) {
+        const int i = i0 + 2 * s;
+        if (j >= p.width || i >= p.height) continue;
+        const size_t pid = (size_t)i * p.width + j;
+        p.final_T[SLOT_OBJ * P + pid] = T[s];
+        p.final_idx[SLOT_OBJ * P + pid] = idx[s];
+        p.obj_acc[pid] = 1.f - T[s];
+    }
 }
 
 static int check_cam(const sgn_camera* cam) {
@@ -227,12 +281,12 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.final_T = out->final_T; p.final_idx = out->final_idx;
     const int tiles = p.tiles_x * tiles_y;
     if (opts->class_streams) {
-        blend_fwd_kernel<true><<<tiles, BLEND_THREADS, 0, (cudaStream_t)stream>>>(p);
+        blend_fwd_kernel<true><<<tiles, 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("blend_fwd_kernel<bg>");
-        acc_fwd_kernel<<<tiles, BLEND_THREADS, 0, (cudaStream_t)stream>>>(p);
+        acc_fwd_kernel<<<tiles, 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("acc_fwd_kernel");
     } else {
-        blend_fwd_kernel<false><<<tiles, BLEND_THREADS, 0, (cudaStream_t)stream>>>(p);
+        blend_fwd_kernel<false><<<tiles, 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("blend_fwd_kernel");
     }
     return SGN_OK;
@@ -263,51 +317,56 @@ struct BlendBwdParams {
     float* v_records;
 };
 
-__device__ __forceinline__ int block_max(int v, int* s_max, cg::thread_block_tile<32>& warp, int tr) {
-    const int w = cg::reduce(warp, v, cg::greater<int>());
-    if (warp.thread_rank() == 0) s_max[tr >> 5] = w;
-    __syncthreads();
-    int m = s_max[0];
+__device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
-    for (int k = 1; k < BLEND_THREADS / 32; ++k) m = max(m, s_max[k]);
-    return m;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    return v;
 }
 
-template <bool BG>
-__global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(const BlendBwdParams p) {
-    __shared__ float4 sA[BLEND_THREADS];
-    __shared__ float4 sB[BLEND_THREADS];
-    __shared__ float2 sC[BLEND_THREADS];
-    __shared__ int sId[BLEND_THREADS];
-    __shared__ int s_max[BLEND_THREADS / 32];
-    auto block = cg::this_thread_block();
-    cg::thread_block_tile<32> warp = cg::tiled_partition<32>(block);
+// BG: background stream has a cotangent.  DEPTHG: the depth output has a cotangent.
+template <bool BG, bool DEPTHG>
+__global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
+    __shared__ float4 sA[2][32];
+    __shared__ float4 sB[2][32];
+    __shared__ float4 sC[2][32];
     const int tile = blockIdx.x;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    const int tr = threadIdx.x;
-    const int j = tx * SGN_TILE + (tr & 15), i = ty * SGN_TILE + (tr >> 4);
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-    const bool inside = (i < p.height) && (j < p.width);
+    const int lane = threadIdx.x;
+    const int j = tx * SGN_TILE + (lane & 15);
+    const int i0 = ty * SGN_TILE + (lane >> 4);
+    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
     const int2 range = p.tile_bins[tile];
     const size_t P = (size_t)p.width * p.height;
 
     // ---- per-pixel prologue: cotangents of the RAW blend outputs from those of the final outputs
-    float4 vo = make_float4(0.f, 0.f, 0.f, 0.f);  // d/d raw rgb, d/d raw depth
-    float voa = 0.f, vbg = 0.f;
-    float Tf = 1.f, Tfb = 1.f;
-    int idx = -1, idxb = -1;
-    if (inside) {
+    float T[PPL], tfv[PPL], tfbv[PPL];
+    float vr[PPL], vg[PPL], vb[PPL], vd[PPL];
+    float br[PPL], bgc[PPL], bb[PPL], bd[PPL];
+    int idx[PPL], idxb[PPL];
+    int kmax = -1;
+#pragma unroll
+    for (int s = 0; s < PPL; ++s) {
+        T[s] = 1.f; tfv[s] = 0.f; tfbv[s] = 0.f; vr[s] = vg[s] = vb[s] = vd[s] = 0.f;
+        br[s] = bgc[s] = bb[s] = bd[s] = 0.f;
+        idx[s] = -1; idxb[s] = -1;
+        const int i = i0 + 2 * s;
+        if (j >= p.width || i >= p.height) continue;
         const size_t pid = (size_t)i * p.width + j;
-        Tf = p.final_T[SLOT_MAIN * P + pid];
-        idx = p.final_idx[SLOT_MAIN * P + pid];
-        if (BG && p.v_bg) {
-            Tfb = p.final_T[SLOT_BG * P + pid];
-            idxb = p.final_idx[SLOT_BG * P + pid];
-            vbg = p.v_bg[pid];
+        const float Tf = p.final_T[SLOT_MAIN * P + pid];
+        idx[s] = p.final_idx[SLOT_MAIN * P + pid];
+        T[s] = Tf;
+        if (BG) {
+            tfbv[s] = p.final_T[SLOT_BG * P + pid] * p.v_bg[pid];
+            idxb[s] = p.final_idx[SLOT_BG * P + pid];
         }
         const float alpha = 1.f - Tf;
         const float4 raw = p.raw[pid];
-        if (p.v_acc) voa = p.v_acc[pid];
+        float voa = p.v_acc ? p.v_acc[pid] : 0.f;
         if (p.v_rgb) {
             float v[3] = {p.v_rgb[3 * pid], p.v_rgb[3 * pid + 1], p.v_rgb[3 * pid + 2]};
             const float rr[3] = {raw.x, raw.y, raw.z};
@@ -316,205 +375,193 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(const BlendBwd
             for (int c = 0; c < 3; ++c) {
                 const float cl = fminf(rr[c], 1.f);
                 float fin = cl;
-                float s = 0.f;
-                if (p.has_sky) { s = p.sky[3 * pid + c]; fin = cl * alpha + s * (1.f - alpha); }
+                float sk = 0.f;
+                if (p.has_sky) { sk = p.sky[3 * pid + c]; fin = cl * alpha + sk * (1.f - alpha); }
                 if (p.eval_clamp && (fin < 0.f || fin > 1.f)) v[c] = 0.f;
                 if (p.has_sky) {
-                    voa += v[c] * (cl - s);
+                    voa += v[c] * (cl - sk);
                     if (p.v_sky) p.v_sky[3 * pid + c] = v[c] * (1.f - alpha);
                     vraw[c] = (rr[c] <= 1.f) ? v[c] * alpha : 0.f;
                 } else {
                     vraw[c] = (rr[c] <= 1.f) ? v[c] : 0.f;
                 }
             }
-            vo.x = vraw[0]; vo.y = vraw[1]; vo.z = vraw[2];
+            vr[s] = vraw[0]; vg[s] = vraw[1]; vb[s] = vraw[2];
         }
-        if (p.v_depth && alpha > 1e-3f) {
-            const float vd = p.v_depth[pid];
-            vo.w = vd / alpha;
-            voa += -vd * raw.w / (alpha * alpha);
+        if (DEPTHG) {
+            if (alpha > 1e-3f) {
+                const float vdep = p.v_depth[pid];
+                vd[s] = vdep / alpha;
+                voa += -vdep * raw.w / (alpha * alpha);
+            }
         }
+        tfv[s] = Tf * voa;
+        kmax = max(kmax, BG ? max(idx[s], idxb[s]) : idx[s]);
     }
     if (range.y <= range.x) return;  // empty tile (after the prologue: v_sky is written for every pixel)
-    // a pair at sorted position k matters to this pixel iff k <= kmax
-    const int kmax = BG ? max(idx, idxb) : idx;
-    const int warp_kmax = cg::reduce(warp, kmax, cg::greater<int>());
-    const int block_kmax = block_max(kmax, s_max, warp, tr);
-    const int range_end = min(range.y, block_kmax + 1);
-    if (range_end <= range.x) return;
-    const int num_batches = (range_end - range.x + BLEND_THREADS - 1) / BLEND_THREADS;
+    const int wkmax = warp_max(kmax);
+    const int hi0 = min(range.y, wkmax + 1);  // entries at positions >= hi0 matter to no pixel of this tile
+    if (hi0 <= range.x) return;
 
-    float T = Tf;
-    float4 buffer = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    for (int b = 0; b < num_batches; ++b) {
-        __syncthreads();
-        const int batch_end = range_end - 1 - BLEND_THREADS * b;
-        const int batch_size = min(BLEND_THREADS, batch_end + 1 - range.x);
-        const int kk = batch_end - tr;
-        if (kk >= range.x) {
-            const int id = p.sorted_ids[kk];
-            sId[tr] = id;
-            const float4* rec = p.records + 3 * (size_t)(id & ID_MASK);
-            sA[tr] = __ldg(rec);
-            sB[tr] = __ldg(rec + 1);
-            const float4 c = __ldg(rec + 2);
-            sC[tr] = make_float2(c.x, c.y);
-        }
-        __syncthreads();
-        for (int t = max(0, batch_end - warp_kmax); t < batch_size; ++t) {
-            const int k = batch_end - t;
-            const float4 A = sA[t];
-            const float4 B = sB[t];
-            bool valid = inside && (k <= kmax);
-            float alpha = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
-            if (valid) {
-                dx = A.x - px; dy = A.y - py;
-                const float sigma = sgn_sigma(A.z, A.w, B.x, dx, dy);
-                vis = __expf(-sigma);
-                alpha = fminf(p.clamp_bwd, B.y * vis);
-                if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
-            }
-            if (!warp.any(valid)) continue;
-            float l_xy0 = 0.f, l_xy1 = 0.f, l_c0 = 0.f, l_c1 = 0.f, l_c2 = 0.f, l_o = 0.f;
-            float l_r = 0.f, l_g = 0.f, l_b = 0.f, l_d = 0.f;
-            if (valid) {
-                const float ra = 1.f / (1.f - alpha);
+    Staged nxt;
+    if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, p.sorted_ids[hi0 - 1 - lane]);
+    int buf = 0;
+    for (int hi = hi0; hi > range.x; hi -= 32) {
+        sA[buf][lane] = nxt.A; sB[buf][lane] = nxt.B; sC[buf][lane] = nxt.C;
+        __syncwarp();
+        if (hi - 33 - lane >= range.x) nxt = gather_entry(p.records, p.sorted_ids[hi - 33 - lane]);
+        const int n = min(32, hi - range.x);
+        for (int t = 0; t < n; ++t) {
+            const int k = hi - 1 - t;
+            const float4 A = sA[buf][t];
+            const float4 B = sB[buf][t];
+            const float4 Cc = sC[buf][t];
+            const bool isobj = __float_as_int(Cc.z) < 0;
+            const float dx = A.x - px;
+            const float bdx = A.w * dx, hax2 = A.z * dx * dx;
+            const float dy0 = A.y - py0;
+            const float o = B.y;
+            float S0 = 0.f, Sy = 0.f, Syy = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
+            bool any = false;
+#pragma unroll
+            for (int s = 0; s < PPL; ++s) {
+                const bool in_main = k <= idx[s];
+                const bool in_bg = BG && !isobj && (k <= idxb[s]);
+                if (!(in_main || in_bg)) continue;
+                const float dy = dy0 - (float)(2 * s);
+                const float sg = sgn_sigma2(hax2, bdx, B.x, dy);
+                const float vis = fast_ex2(-sg);
+                const float alpha = fminf(p.clamp_bwd, o * vis);
+                if (sg < 0.f || alpha < ALPHA_MIN) continue;
+                any = true;
+                const float ra = __frcp_rn(1.f - alpha);
                 float v_alpha = 0.f;
-                if (k <= idx) {
-                    const float2 Cc = sC[t];
-                    T *= ra;
-                    const float fac = alpha * T;
-                    l_r = fac * vo.x; l_g = fac * vo.y; l_b = fac * vo.z; l_d = fac * vo.w;
-                    v_alpha += (B.z * T - buffer.x * ra) * vo.x;
-                    v_alpha += (B.w * T - buffer.y * ra) * vo.y;
-                    v_alpha += (Cc.x * T - buffer.z * ra) * vo.z;
-                    v_alpha += (Cc.y * T - buffer.w * ra) * vo.w;
-                    v_alpha += Tf * ra * voa;
-                    buffer.x += B.z * fac; buffer.y += B.w * fac; buffer.z += Cc.x * fac; buffer.w += Cc.y * fac;
+                if (in_main) {
+                    T[s] *= ra;
+                    const float Tk = T[s];
+                    const float fac = alpha * Tk;
+                    cr += fac * vr[s]; cg += fac * vg[s]; cb += fac * vb[s];
+                    v_alpha = (B.z * Tk - br[s] * ra) * vr[s] + (B.w * Tk - bgc[s] * ra) * vg[s] + (Cc.x * Tk - bb[s] * ra) * vb[s];
+                    br[s] += B.z * fac; bgc[s] += B.w * fac; bb[s] += Cc.x * fac;
+                    if (DEPTHG) {
+                        cd += fac * vd[s];
+                        v_alpha += (Cc.y * Tk - bd[s] * ra) * vd[s];
+                        bd[s] += Cc.y * fac;
+                    }
+                    v_alpha += tfv[s] * ra;
                 }
                 if (BG) {
-                    if (sId[t] >= 0 && k <= idxb) v_alpha += Tfb * ra * vbg;
+                    if (in_bg) v_alpha += tfbv[s] * ra;
                 }
-                const float v_sigma = -B.y * vis * v_alpha;
-                l_xy0 = v_sigma * (A.z * dx + A.w * dy);
-                l_xy1 = v_sigma * (A.w * dx + B.x * dy);
-                l_c0 = 0.5f * v_sigma * dx * dx;
-                l_c1 = v_sigma * dx * dy;
-                l_c2 = 0.5f * v_sigma * dy * dy;
-                l_o = vis * v_alpha;
+                const float vs = -o * vis * v_alpha;
+                S0 += vs; Sy += vs * dy; Syy += vs * dy * dy;
             }
-            l_xy0 = cg::reduce(warp, l_xy0, cg::plus<float>());
-            l_xy1 = cg::reduce(warp, l_xy1, cg::plus<float>());
-            l_c0 = cg::reduce(warp, l_c0, cg::plus<float>());
-            l_c1 = cg::reduce(warp, l_c1, cg::plus<float>());
-            l_c2 = cg::reduce(warp, l_c2, cg::plus<float>());
-            l_o = cg::reduce(warp, l_o, cg::plus<float>());
-            l_r = cg::reduce(warp, l_r, cg::plus<float>());
-            l_g = cg::reduce(warp, l_g, cg::plus<float>());
-            l_b = cg::reduce(warp, l_b, cg::plus<float>());
-            l_d = cg::reduce(warp, l_d, cg::plus<float>());
-            if (warp.thread_rank() == 0) {
-                float* dst = p.v_records + (size_t)(sId[t] & ID_MASK) * SGN_RECORD_FLOATS;
-                atomicAdd(dst + 0, l_xy0); atomicAdd(dst + 1, l_xy1);
-                atomicAdd(dst + 2, l_c0); atomicAdd(dst + 3, l_c1); atomicAdd(dst + 4, l_c2);
-                atomicAdd(dst + 5, l_o);
-                atomicAdd(dst + 6, l_r); atomicAdd(dst + 7, l_g); atomicAdd(dst + 8, l_b);
-                atomicAdd(dst + 9, l_d);
-            }
+            if (!__any_sync(FULL, any)) continue;
+            // true conic from the staged (log2e-scaled) one
+            const float ca = A.z * (2.f * LN2), cbb = A.w * LN2, cc = B.x * (2.f * LN2);
+            float l0 = ca * dx * S0 + cbb * Sy;     // v_xy.x
+            float l1 = cbb * dx * S0 + cc * Sy;     // v_xy.y
+            float l2 = 0.5f * dx * dx * S0;         // v_conic.x
+            float l3 = dx * Sy;                     // v_conic.y
+            float l4 = 0.5f * Syy;                  // v_conic.z
+            float l5 = -S0 / o;                     // v_opacity = sum vis * v_alpha
+            l0 = warp_sum(l0); l1 = warp_sum(l1); l2 = warp_sum(l2); l3 = warp_sum(l3); l4 = warp_sum(l4); l5 = warp_sum(l5);
+            cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+            if (DEPTHG) cd = warp_sum(cd);
+            // lanes 0..9 each own one component of the record-layout gradient
+            float mine = l0;
+            mine = lane == 1 ? l1 : mine; mine = lane == 2 ? l2 : mine; mine = lane == 3 ? l3 : mine;
+            mine = lane == 4 ? l4 : mine; mine = lane == 5 ? l5 : mine; mine = lane == 6 ? cr : mine;
+            mine = lane == 7 ? cg : mine; mine = lane == 8 ? cb : mine; mine = lane == 9 ? cd : mine;
+            if (lane < (DEPTHG ? 10 : 9))
+                atomicAdd(p.v_records + (size_t)(__float_as_int(Cc.z) & ID_MASK) * SGN_RECORD_FLOATS + lane, mine);
         }
+        buf ^= 1;
     }
 }
 
 // backward of the accumulation-only pass: out = 1 - T_final  =>  v_alpha_k = T_final * ra_k * v_out
-__global__ void __launch_bounds__(BLEND_THREADS) acc_bwd_kernel(const BlendBwdParams p) {
-    __shared__ float4 sA[BLEND_THREADS];
-    __shared__ float2 sB[BLEND_THREADS];
-    __shared__ int sId[BLEND_THREADS];
-    __shared__ int s_max[BLEND_THREADS / 32];
-    auto block = cg::this_thread_block();
-    cg::thread_block_tile<32> warp = cg::tiled_partition<32>(block);
+__global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p) {
+    __shared__ float4 sA[2][32];
+    __shared__ float4 sB[2][32];
     const int tile = blockIdx.x;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    const int tr = threadIdx.x;
-    const int j = tx * SGN_TILE + (tr & 15), i = ty * SGN_TILE + (tr >> 4);
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-    const bool inside = (i < p.height) && (j < p.width);
+    const int lane = threadIdx.x;
+    const int j = tx * SGN_TILE + (lane & 15);
+    const int i0 = ty * SGN_TILE + (lane >> 4);
+    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
     const int2 range = p.obj_bins[tile];
     if (range.y <= range.x) return;
     const size_t P = (size_t)p.width * p.height;
-    float Tf = 1.f, vout = 0.f;
-    int idx = -1;
-    if (inside) {
+    float tfv[PPL];
+    int idx[PPL];
+    int kmax = -1;
+#pragma unroll
+    for (int s = 0; s < PPL; ++s) {
+        tfv[s] = 0.f; idx[s] = -1;
+        const int i = i0 + 2 * s;
+        if (j >= p.width || i >= p.height) continue;
         const size_t pid = (size_t)i * p.width + j;
-        Tf = p.final_T[SLOT_OBJ * P + pid];
-        idx = p.final_idx[SLOT_OBJ * P + pid];
-        vout = p.v_obj[pid];
+        tfv[s] = p.final_T[SLOT_OBJ * P + pid] * p.v_obj[pid];
+        idx[s] = p.final_idx[SLOT_OBJ * P + pid];
+        kmax = max(kmax, idx[s]);
     }
-    const int warp_kmax = cg::reduce(warp, idx, cg::greater<int>());
-    const int block_kmax = block_max(idx, s_max, warp, tr);
-    const int range_end = min(range.y, block_kmax + 1);
-    if (range_end <= range.x) return;
-    const int num_batches = (range_end - range.x + BLEND_THREADS - 1) / BLEND_THREADS;
-    for (int b = 0; b < num_batches; ++b) {
-        __syncthreads();
-        const int batch_end = range_end - 1 - BLEND_THREADS * b;
-        const int batch_size = min(BLEND_THREADS, batch_end + 1 - range.x);
-        const int kk = batch_end - tr;
-        if (kk >= range.x) {
-            const int id = p.obj_ids[kk];
-            sId[tr] = id;
-            const float4* rec = p.records + 3 * (size_t)(id & ID_MASK);
-            sA[tr] = __ldg(rec);
-            const float4 B = __ldg(rec + 1);
-            sB[tr] = make_float2(B.x, B.y);
+    const int wkmax = warp_max(kmax);
+    const int hi0 = min(range.y, wkmax + 1);
+    if (hi0 <= range.x) return;
+    Staged nxt;
+    if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, p.obj_ids[hi0 - 1 - lane]);
+    int buf = 0;
+    for (int hi = hi0; hi > range.x; hi -= 32) {
+        sA[buf][lane] = nxt.A; sB[buf][lane] = make_float4(nxt.B.x, nxt.B.y, nxt.C.z, 0.f);
+        __syncwarp();
+        if (hi - 33 - lane >= range.x) nxt = gather_entry(p.records, p.obj_ids[hi - 33 - lane]);
+        const int n = min(32, hi - range.x);
+        for (int t = 0; t < n; ++t) {
+            const int k = hi - 1 - t;
+            const float4 A = sA[buf][t];
+            const float4 B = sB[buf][t];
+            const float dx = A.x - px;
+            const float bdx = A.w * dx, hax2 = A.z * dx * dx;
+            const float dy0 = A.y - py0;
+            const float o = B.y;
+            float S0 = 0.f, Sy = 0.f, Syy = 0.f;
+            bool any = false;
+#pragma unroll
+            for (int s = 0; s < PPL; ++s) {
+                if (k > idx[s]) continue;
+                const float dy = dy0 - (float)(2 * s);
+                const float sg = sgn_sigma2(hax2, bdx, B.x, dy);
+                const float vis = fast_ex2(-sg);
+                const float alpha = fminf(p.clamp_bwd, o * vis);
+                if (sg < 0.f || alpha < ALPHA_MIN) continue;
+                any = true;
+                const float ra = __frcp_rn(1.f - alpha);
+                const float vs = -o * vis * (tfv[s] * ra);
+                S0 += vs; Sy += vs * dy; Syy += vs * dy * dy;
+            }
+            if (!__any_sync(FULL, any)) continue;
+            const float ca = A.z * (2.f * LN2), cbb = A.w * LN2, cc = B.x * (2.f * LN2);
+            float l0 = ca * dx * S0 + cbb * Sy;
+            float l1 = cbb * dx * S0 + cc * Sy;
+            float l2 = 0.5f * dx * dx * S0;
+            float l3 = dx * Sy;
+            float l4 = 0.5f * Syy;
+            float l5 = -S0 / o;
+            l0 = warp_sum(l0); l1 = warp_sum(l1); l2 = warp_sum(l2); l3 = warp_sum(l3); l4 = warp_sum(l4); l5 = warp_sum(l5);
+            float mine = l0;
+            mine = lane == 1 ? l1 : mine; mine = lane == 2 ? l2 : mine; mine = lane == 3 ? l3 : mine;
+            mine = lane == 4 ? l4 : mine; mine = lane == 5 ? l5 : mine;
+            if (lane < 6) atomicAdd(p.v_records + (size_t)(__float_as_int(B.z) & ID_MASK) * SGN_RECORD_FLOATS + lane, mine);
         }
-        __syncthreads();
-        for (int t = max(0, batch_end - warp_kmax); t < batch_size; ++t) {
-            const int k = batch_end - t;
-            const float4 A = sA[t];
-            const float2 B = sB[t];
-            bool valid = inside && (k <= idx);
-            float alpha = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
-            if (valid) {
-                dx = A.x - px; dy = A.y - py;
-                const float sigma = sgn_sigma(A.z, A.w, B.x, dx, dy);
-                vis = __expf(-sigma);
-                alpha = fminf(p.clamp_bwd, B.y * vis);
-                if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
-            }
-            if (!warp.any(valid)) continue;
-            float l_xy0 = 0.f, l_xy1 = 0.f, l_c0 = 0.f, l_c1 = 0.f, l_c2 = 0.f, l_o = 0.f;
-            if (valid) {
-                const float ra = 1.f / (1.f - alpha);
-                const float v_alpha = Tf * ra * vout;
-                const float v_sigma = -B.y * vis * v_alpha;
-                l_xy0 = v_sigma * (A.z * dx + A.w * dy);
-                l_xy1 = v_sigma * (A.w * dx + B.x * dy);
-                l_c0 = 0.5f * v_sigma * dx * dx;
-                l_c1 = v_sigma * dx * dy;
-                l_c2 = 0.5f * v_sigma * dy * dy;
-                l_o = vis * v_alpha;
-            }
-            l_xy0 = cg::reduce(warp, l_xy0, cg::plus<float>());
-            l_xy1 = cg::reduce(warp, l_xy1, cg::plus<float>());
-            l_c0 = cg::reduce(warp, l_c0, cg::plus<float>());
-            l_c1 = cg::reduce(warp, l_c1, cg::plus<float>());
-            l_c2 = cg::reduce(warp, l_c2, cg::plus<float>());
-            l_o = cg::reduce(warp, l_o, cg::plus<float>());
-            if (warp.thread_rank() == 0) {
-                float* dst = p.v_records + (size_t)(sId[t] & ID_MASK) * SGN_RECORD_FLOATS;
-                atomicAdd(dst + 0, l_xy0); atomicAdd(dst + 1, l_xy1);
-                atomicAdd(dst + 2, l_c0); atomicAdd(dst + 3, l_c1); atomicAdd(dst + 4, l_c2);
-                atomicAdd(dst + 5, l_o);
-            }
-        }
+        buf ^= 1;
     }
 }
 
 extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
                              const int32_t* sorted_ids, const int32_t* tile_bins, const int32_t* obj_ids,
-                             const int32_t* obj_bins, const sgn_blend_bwd_in* in, float* v_records, void* stream) {
+                             const int32_t* obj_bins, const sgn_blend_bwd_in* in, float* v_records, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
     if (int rc = check_cam(cam)) return rc;
     SGN_REQUIRE(opts && records && tile_bins && in && v_records, "sgn_blend_bwd: null pointer");
     SGN_REQUIRE(in->raw && in->final_T && in->final_idx, "sgn_blend_bwd: saved forward state missing");
@@ -541,15 +588,15 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.sky = in->sky; p.v_sky = in->v_sky;
     p.v_records = v_records;
     const int tiles = p.tiles_x * tiles_y;
-    if (opts->class_streams && in->v_background_acc) {
-        blend_bwd_kernel<true><<<tiles, BLEND_THREADS, 0, (cudaStream_t)stream>>>(p);
-        SGN_CHECK_LAUNCH("blend_bwd_kernel<bg>");
-    } else {
-        blend_bwd_kernel<false><<<tiles, BLEND_THREADS, 0, (cudaStream_t)stream>>>(p);
-        SGN_CHECK_LAUNCH("blend_bwd_kernel");
-    }
+    const bool bg = opts->class_streams && in->v_background_acc;
+    const bool dg = in->v_depth != nullptr;
+    if (bg && dg) blend_bwd_kernel<true, true><<<tiles, 32, 0, stream>>>(p);
+    else if (bg) blend_bwd_kernel<true, false><<<tiles, 32, 0, stream>>>(p);
+    else if (dg) blend_bwd_kernel<false, true><<<tiles, 32, 0, stream>>>(p);
+    else blend_bwd_kernel<false, false><<<tiles, 32, 0, stream>>>(p);
+    SGN_CHECK_LAUNCH("blend_bwd_kernel");
     if (in->v_object_acc) {
-        acc_bwd_kernel<<<tiles, BLEND_THREADS, 0, (cudaStream_t)stream>>>(p);
+        acc_bwd_kernel<<<tiles, 32, 0, stream>>>(p);
         SGN_CHECK_LAUNCH("acc_bwd_kernel");
     }
     return SGN_OK;

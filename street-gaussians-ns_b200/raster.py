@@ -167,7 +167,8 @@ def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit, bbox):
     sb = L.sgn_bin_scan_scratch_bytes(N)
     scratch = torch.empty(sb, device=device, dtype=torch.uint8)
     with _timed("bin_scan"):
-        _lib.check(L.sgn_bin_scan(N, _ptr(tiles_hit), _ptr(cum), _ptr(total), _ptr(scratch), sb, _stream()), "sgn_bin_scan")
+        _lib.check(L.sgn_bin_scan(N, C.byref(cs), _ptr(records), _ptr(radii), _ptr(bbox), _ptr(cum), _ptr(total),
+                                  _ptr(scratch), sb, _stream()), "sgn_bin_scan")
     M = int(total.item())
     bw = cs.block_width
     tiles = ((cs.width + bw - 1) // bw) * ((cs.height + bw - 1) // bw)
