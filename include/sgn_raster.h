@@ -173,6 +173,7 @@ typedef struct sgn_blend_fwd_out {
     float* raw;            /* [H,W,4] saved for backward */
     float* final_T;        /* [3,H,W] planar: slot 0 main, 1 object, 2 background */
     int32_t* final_idx;    /* [3,H,W] */
+    int32_t* tile_depth;   /* [2,tiles] entries traversed per tile (main pass, object pass); sizes the backward */
 } sgn_blend_fwd_out;
 
 int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
@@ -189,6 +190,7 @@ typedef struct sgn_blend_bwd_in {
     const float* raw;
     const float* final_T;
     const int32_t* final_idx;
+    const int32_t* tile_depth;     /* [2,tiles] from the forward */
     const float* sky;              /* [H,W,3] or NULL */
     float* v_sky;                  /* [H,W,3] or NULL: gradient to the sky colour */
 } sgn_blend_bwd_in;

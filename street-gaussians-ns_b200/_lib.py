@@ -59,7 +59,7 @@ class BlendFwdOut(C.Structure):
     _fields_ = [
         ("rgb", C.c_void_p), ("accumulation", C.c_void_p), ("depth", C.c_void_p),
         ("object_acc", C.c_void_p), ("background_acc", C.c_void_p),
-        ("raw", C.c_void_p), ("final_T", C.c_void_p), ("final_idx", C.c_void_p),
+        ("raw", C.c_void_p), ("final_T", C.c_void_p), ("final_idx", C.c_void_p), ("tile_depth", C.c_void_p),
     ]
 
 
@@ -67,7 +67,7 @@ class BlendBwdIn(C.Structure):
     _fields_ = [
         ("v_rgb", C.c_void_p), ("v_accumulation", C.c_void_p), ("v_depth", C.c_void_p),
         ("v_object_acc", C.c_void_p), ("v_background_acc", C.c_void_p),
-        ("raw", C.c_void_p), ("final_T", C.c_void_p), ("final_idx", C.c_void_p),
+        ("raw", C.c_void_p), ("final_T", C.c_void_p), ("final_idx", C.c_void_p), ("tile_depth", C.c_void_p),
         ("sky", C.c_void_p), ("v_sky", C.c_void_p),
     ]
 

@@ -20,7 +20,8 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // the blend would accept is ever dropped.  tests/ check "dropped => no valid pixel" against the oracle.
 struct TouchCtx {
     float gx, gy, a, b, c, tau;
-    bool always;  // degenerate conic: keep every AABB tile
+    float nbc, nba;  // -b/c, -b/a: minimiser slopes along the rectangle edges
+    int always;      // degenerate conic: keep every AABB tile
 };
 
 __device__ __forceinline__ TouchCtx make_touch_ctx(const float4 r0, const float4 r1) {
@@ -28,7 +29,9 @@ __device__ __forceinline__ TouchCtx make_touch_ctx(const float4 r0, const float4
     t.gx = r0.x; t.gy = r0.y; t.a = r0.z; t.b = r0.w; t.c = r1.x;
     const float o = r1.y;
     t.tau = __logf(255.f * o);
-    t.always = !(t.a > 0.f && t.c > 0.f && __fsub_rn(__fmul_rn(t.a, t.c), __fmul_rn(t.b, t.b)) > 0.f) || !(t.tau == t.tau);
+    t.always = (!(t.a > 0.f && t.c > 0.f && __fsub_rn(__fmul_rn(t.a, t.c), __fmul_rn(t.b, t.b)) > 0.f) || !(t.tau == t.tau)) ? 1 : 0;
+    t.nbc = t.always ? 0.f : __fdiv_rn(-t.b, t.c);
+    t.nba = t.always ? 0.f : __fdiv_rn(-t.b, t.a);
     return t;
 }
 
@@ -49,7 +52,7 @@ __device__ __forceinline__ bool tile_touched(const TouchCtx& t, int tx, int ty, 
     const float x0 = __fsub_rn((float)(tx * bw) + 0.5f, t.gx), x1 = __fsub_rn(fminf((float)(tx * bw + bw), (float)width) - 0.5f, t.gx);
     const float y0 = __fsub_rn((float)(ty * bw) + 0.5f, t.gy), y1 = __fsub_rn(fminf((float)(ty * bw + bw), (float)height) - 0.5f, t.gy);
     if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;  // centre inside the rectangle
-    const float nbc = __fdiv_rn(-t.b, t.c), nba = __fdiv_rn(-t.b, t.a);
+    const float nbc = t.nbc, nba = t.nba;
     float best = 3.4e38f, best_mag = 0.f, mag, q;
     // edges x = x0, x = x1: minimise over dy
     q = touch_q(t, x0, fminf(fmaxf(__fmul_rn(nbc, x0), y0), y1), mag); if (q < best) { best = q; best_mag = mag; }
@@ -60,19 +63,54 @@ __device__ __forceinline__ bool tile_touched(const TouchCtx& t, int tx, int ty, 
     return best <= __fadd_rn(__fadd_rn(t.tau, 1e-3f), __fmul_rn(8e-6f, best_mag));
 }
 
+// Gaussians whose AABB spans more than COOP_AREA tiles are handled by the whole warp (32 tiles per
+// step) after the per-thread pass, so one huge splat does not serialise its warp.
+#define COOP_AREA 32
+
+__device__ __forceinline__ TouchCtx shfl_ctx(const TouchCtx& t, int src) {
+    TouchCtx r;
+    r.gx = __shfl_sync(0xffffffffu, t.gx, src); r.gy = __shfl_sync(0xffffffffu, t.gy, src);
+    r.a = __shfl_sync(0xffffffffu, t.a, src); r.b = __shfl_sync(0xffffffffu, t.b, src);
+    r.c = __shfl_sync(0xffffffffu, t.c, src); r.tau = __shfl_sync(0xffffffffu, t.tau, src);
+    r.nbc = __shfl_sync(0xffffffffu, t.nbc, src); r.nba = __shfl_sync(0xffffffffu, t.nba, src);
+    r.always = __shfl_sync(0xffffffffu, t.always, src);
+    return r;
+}
+
 __global__ void __launch_bounds__(256)
 count_tiles_kernel(int N, int width, int height, int bw, const float4* __restrict__ records, const int32_t* __restrict__ radii,
                    const ushort4* __restrict__ tile_bbox, int32_t* __restrict__ tiles_touched) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= N) return;
+    const int lane = threadIdx.x & 31;
+    const bool vis = (g < N) && radii[g] > 0;
+    ushort4 bb = make_ushort4(0, 0, 0, 0);
+    TouchCtx t = {};
+    if (vis) {
+        bb = tile_bbox[g];
+        t = make_touch_ctx(records[3 * (size_t)g], records[3 * (size_t)g + 1]);
+    }
+    const int bwid = bb.z - bb.x, area = bwid * (bb.w - bb.y);
     int n = 0;
-    if (radii[g] > 0) {
-        const ushort4 bb = tile_bbox[g];
-        const TouchCtx t = make_touch_ctx(records[3 * (size_t)g], records[3 * (size_t)g + 1]);
+    if (vis && area <= COOP_AREA) {
         for (int ty = bb.y; ty < bb.w; ++ty)
             for (int tx = bb.x; tx < bb.z; ++tx) n += tile_touched(t, tx, ty, width, height, bw) ? 1 : 0;
     }
-    tiles_touched[g] = n;
+    unsigned big = __ballot_sync(0xffffffffu, vis && area > COOP_AREA);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const TouchCtx c = shfl_ctx(t, src);
+        const int x0 = __shfl_sync(0xffffffffu, (int)bb.x, src), y0 = __shfl_sync(0xffffffffu, (int)bb.y, src);
+        const int w = __shfl_sync(0xffffffffu, bwid, src), ar = __shfl_sync(0xffffffffu, area, src);
+        int cnt = 0;
+        for (int base = 0; base < ar; base += 32) {
+            const int ti = base + lane;
+            const bool ok = (ti < ar) && tile_touched(c, x0 + ti % w, y0 + ti / w, width, height, bw);
+            cnt += __popc(__ballot_sync(0xffffffffu, ok));
+        }
+        if (lane == src) n = cnt;
+    }
+    if (g < N) tiles_touched[g] = n;
 }
 
 __global__ void write_total_kernel(const int32_t* __restrict__ cum, int N, int64_t* __restrict__ total) {
@@ -117,24 +155,57 @@ emit_keys_kernel(int N, int tiles_x, int width, int height, int bw, const float4
                  const int32_t* __restrict__ radii, const ushort4* __restrict__ tile_bbox, const int32_t* __restrict__ cum,
                  uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= N) return;
-    if (radii[g] <= 0) return;
-    const ushort4 bb = tile_bbox[g];
-    const float4 r0 = records[3 * (size_t)g], r1 = records[3 * (size_t)g + 1], r2 = records[3 * (size_t)g + 2];
-    const TouchCtx t = make_touch_ctx(r0, r1);
-    const uint32_t dbits = (uint32_t)__float_as_int(r2.y);
-    // payload: Gaussian row in the low 31 bits, object-class flag in bit 31 (no gather needed later)
-    const int32_t payload = g | ((__float_as_int(r2.z) & SGN_AUX_OBJECT) ? (int32_t)0x80000000 : 0);
-    int64_t cur = (g == 0) ? 0 : (int64_t)cum[g - 1];
-    const int64_t end = (int64_t)cum[g];
-    for (int ty = bb.y; ty < bb.w; ++ty) {
-        for (int tx = bb.x; tx < bb.z; ++tx) {
-            if (!tile_touched(t, tx, ty, width, height, bw)) continue;
-            if (cur >= end) return;  // cannot happen (same test as count_tiles_kernel); never overrun the slot range
-            const uint64_t tile = (uint64_t)(ty * tiles_x + tx);
-            keys[cur] = (tile << 32) | (uint64_t)dbits;
-            vals[cur] = payload;
-            ++cur;
+    const int lane = threadIdx.x & 31;
+    const bool vis = (g < N) && radii[g] > 0;
+    ushort4 bb = make_ushort4(0, 0, 0, 0);
+    TouchCtx t = {};
+    uint32_t dbits = 0;
+    int32_t payload = 0;
+    int cur = 0, end = 0;
+    if (vis) {
+        bb = tile_bbox[g];
+        const float4 r0 = records[3 * (size_t)g], r1 = records[3 * (size_t)g + 1], r2 = records[3 * (size_t)g + 2];
+        t = make_touch_ctx(r0, r1);
+        dbits = (uint32_t)__float_as_int(r2.y);
+        // payload: Gaussian row in the low 31 bits, object-class flag in bit 31 (no gather needed later)
+        payload = g | ((__float_as_int(r2.z) & SGN_AUX_OBJECT) ? (int32_t)0x80000000 : 0);
+        cur = (g == 0) ? 0 : cum[g - 1];
+        end = cum[g];
+    }
+    const int bwid = bb.z - bb.x, area = bwid * (bb.w - bb.y);
+    if (vis && area <= COOP_AREA) {
+        for (int ty = bb.y; ty < bb.w; ++ty) {
+            for (int tx = bb.x; tx < bb.z; ++tx) {
+                if (!tile_touched(t, tx, ty, width, height, bw)) continue;
+                if (cur >= end) break;  // cannot happen (same test as count_tiles_kernel); never overrun the slot range
+                keys[cur] = ((uint64_t)(ty * tiles_x + tx) << 32) | (uint64_t)dbits;
+                vals[cur] = payload;
+                ++cur;
+            }
+        }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, vis && area > COOP_AREA);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const TouchCtx c = shfl_ctx(t, src);
+        const int x0 = __shfl_sync(0xffffffffu, (int)bb.x, src), y0 = __shfl_sync(0xffffffffu, (int)bb.y, src);
+        const int w = __shfl_sync(0xffffffffu, bwid, src), ar = __shfl_sync(0xffffffffu, area, src);
+        const uint32_t db = __shfl_sync(0xffffffffu, dbits, src);
+        const int32_t pl = __shfl_sync(0xffffffffu, payload, src);
+        int pos = __shfl_sync(0xffffffffu, cur, src);
+        const int lim = __shfl_sync(0xffffffffu, end, src);
+        for (int base = 0; base < ar; base += 32) {
+            const int ti = base + lane;
+            const int tx = x0 + ti % w, ty = y0 + ti / w;
+            const bool ok = (ti < ar) && tile_touched(c, tx, ty, width, height, bw);
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            const int my = pos + __popc(m & ((1u << lane) - 1u));
+            if (ok && my < lim) {
+                keys[my] = ((uint64_t)(ty * tiles_x + tx) << 32) | (uint64_t)db;
+                vals[my] = pl;
+            }
+            pos += __popc(m);
         }
     }
 }

@@ -11,10 +11,13 @@
 //
 // Execution shape (B200): the loops are FP32/MUFU issue-bound, not HBM-bound (profiles/), so the
 // design minimises instructions per (pixel, Gaussian) pair:
-//   * ONE WARP PER TILE, 8 pixels per lane (lane = column, 8 rows two apart): dx and the dx-terms of
-//     the quadratic form are computed once per lane and shared by its 8 pixels; the per-Gaussian
-//     gradient reduction (10 values x 5 shuffle levels) is paid once per 256 pixels instead of once
-//     per 32;  the geometric gradients are accumulated per lane as three moments (S0, Sy, Syy);
+//   * a warp owns a 16-column strip of a tile and each lane PPL pixels of one column (rows two apart):
+//     dx and the dx-terms of the quadratic form are computed once per lane and shared by its pixels;
+//     the per-Gaussian gradient reduction (10 values x 5 shuffle levels) is paid once per 32*PPL
+//     pixels; the geometric gradients are accumulated per lane as three moments (S0, Sy, Syy);
+//   * PPL = 8 (one warp per tile) is the throughput shape; tiles with long lists are split into
+//     2/4/8 independent strips (PPL 4/2/1) so that no single warp's serial traversal becomes the
+//     kernel's tail (per-tile lists reach thousands of entries behind dense actors);
 //   * exp(-sigma) is one MUFU.EX2: the conic is pre-scaled by log2(e) when an entry is staged;
 //   * entries are staged through a double-buffered shared-memory ring by the warp itself, the next
 //     batch's gathers are in flight while the current batch is blended (no block-wide barriers);
@@ -26,7 +29,6 @@
 #define ALPHA_MIN (1.f / 255.f)
 #define T_STOP 1e-4f
 #define ID_MASK 0x7fffffff
-#define PPL 8  // pixels per lane
 #define FULL 0xffffffffu
 #define LOG2E 1.4426950408889634f
 #define LN2 0.6931471805599453f
@@ -37,7 +39,9 @@
 #define SLOT_BG 2
 
 struct BlendFwdParams {
-    int width, height, tiles_x;
+    int width, height, tiles_x, tiles;
+    int32_t* tile_depth;  // [tiles] entries traversed per tile (main/bg pass), atomicMax'ed by the forward
+    int32_t* obj_depth;   // [tiles] same for the object pass
     float clamp_fwd;
     int has_sky, eval_clamp;
     const float4* records;
@@ -55,6 +59,17 @@ struct BlendFwdParams {
     float* final_T;      // [3][H*W]
     int32_t* final_idx;  // [3][H*W]
 };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
 
 // One staged entry: A = (gx, gy, 0.5*a*log2e, b*log2e)  B = (0.5*c*log2e, opacity, r, g)  C = (b, depth, id bits, -)
 struct Staged {
@@ -82,22 +97,22 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return y;
 }
 
-template <bool BG>
-__global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
-    __shared__ float4 sA[2][32];
-    __shared__ float4 sB[2][32];
-    __shared__ float4 sC[2][32];
-    const int tile = blockIdx.x;
+// number of strips (warps) a tile is split into, from the length of the list it has to traverse
+__device__ __forceinline__ int strips_for(int len) { return len <= 384 ? 1 : (len <= 768 ? 2 : (len <= 1536 ? 4 : 8)); }
+
+template <int PPL, bool BG>
+__device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int tile, int strip, const int2 range,
+                                                float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int lane = threadIdx.x;
     const int j = tx * SGN_TILE + (lane & 15);
-    const int i0 = ty * SGN_TILE + (lane >> 4);
+    const int i0 = ty * SGN_TILE + strip * (2 * PPL) + (lane >> 4);
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
-    const int2 range = p.tile_bins[tile];
+    constexpr unsigned ALL = (1u << PPL) - 1u;
 
     float T[PPL], Tb[PPL], pr[PPL], pg[PPL], pb[PPL], pd[PPL];
     int idx[PPL], idxb[PPL];
-    unsigned done = 0, doneb = BG ? 0u : 0xffu;
+    unsigned done = 0, doneb = BG ? 0u : ALL;
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
         T[s] = 1.f; Tb[s] = 1.f; pr[s] = pg[s] = pb[s] = pd[s] = 0.f;
@@ -116,7 +131,7 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
         if (base + 32 + lane < range.y) nxt = gather_entry(p.records, p.sorted_ids[base + 32 + lane]);
         const int n = min(32, range.y - base);
         for (int t = 0; t < n; ++t) {
-            if (__all_sync(FULL, (done & doneb) == 0xffu)) { finished = true; break; }
+            if (__all_sync(FULL, (done & doneb) == ALL)) { finished = true; break; }
             const float4 A = sA[buf][t];
             const float4 B = sB[buf][t];
             const float4 Cc = sC[buf][t];
@@ -153,6 +168,13 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
         buf ^= 1;
     }
     const size_t P = (size_t)p.width * p.height;
+    {   // how deep this tile was traversed: the backward sizes its strips from it
+        int kdeep = -1;
+#pragma unroll
+        for (int s = 0; s < PPL; ++s) kdeep = max(kdeep, BG ? max(idx[s], idxb[s]) : idx[s]);
+        kdeep = warp_max(kdeep);
+        if (lane == 0 && kdeep >= 0) atomicMax(p.tile_depth + tile, kdeep + 1 - range.x);
+    }
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
         const int i = i0 + 2 * s;
@@ -184,17 +206,35 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     }
 }
 
-// accumulation-only pass over per-tile sub-lists (objects-only render)
-__global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p) {
+// grid = tiles x 8 one-warp CTAs: block b -> strip b / tiles of tile b % tiles; strips beyond the
+// tile's split exit at once (registers are per CTA, so they cost nothing once gone)
+template <bool BG>
+__global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     __shared__ float4 sA[2][32];
-    __shared__ float2 sB[2][32];
-    const int tile = blockIdx.x;
+    __shared__ float4 sB[2][32];
+    __shared__ float4 sC[2][32];
+    const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
+    const int2 range = p.tile_bins[tile];
+    const int W = strips_for(range.y - range.x);
+    if (strip >= W) return;
+    switch (W) {
+        case 1: blend_fwd_strip<8, BG>(p, tile, strip, range, sA, sB, sC); break;
+        case 2: blend_fwd_strip<4, BG>(p, tile, strip, range, sA, sB, sC); break;
+        case 4: blend_fwd_strip<2, BG>(p, tile, strip, range, sA, sB, sC); break;
+        default: blend_fwd_strip<1, BG>(p, tile, strip, range, sA, sB, sC); break;
+    }
+}
+
+// accumulation-only pass over per-tile sub-lists (objects-only render)
+template <int PPL>
+__device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int tile, int strip, const int2 range,
+                                              float4 (*sA)[32], float2 (*sB)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int lane = threadIdx.x;
     const int j = tx * SGN_TILE + (lane & 15);
-    const int i0 = ty * SGN_TILE + (lane >> 4);
+    const int i0 = ty * SGN_TILE + strip * (2 * PPL) + (lane >> 4);
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
-    const int2 range = p.obj_bins[tile];
+    constexpr unsigned ALL = (1u << PPL) - 1u;
     float T[PPL];
     int idx[PPL];
     unsigned done = 0;
@@ -213,7 +253,7 @@ __global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p) {
         if (base + 32 + lane < range.y) nxt = gather_entry(p.records, p.obj_ids[base + 32 + lane]);
         const int n = min(32, range.y - base);
         for (int t = 0; t < n; ++t) {
-            if (__all_sync(FULL, done == 0xffu)) { finished = true; break; }
+            if (__all_sync(FULL, done == ALL)) { finished = true; break; }
             const float4 A = sA[buf][t];
             const float2 B = sB[buf][t];
             const float dx = A.x - px;
@@ -234,6 +274,13 @@ __global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p) {
         buf ^= 1;
     }
     const size_t P = (size_t)p.width * p.height;
+    {
+        int kdeep = -1;
+#pragma unroll
+        for (int s = 0; s < PPL; ++s) kdeep = max(kdeep, idx[s]);
+        kdeep = warp_max(kdeep);
+        if (lane == 0 && kdeep >= 0) atomicMax(p.obj_depth + tile, kdeep + 1 - range.x);
+    }
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
         const int i = i0 + 2 * s;
@@ -242,6 +289,21 @@ __global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p) {
         p.final_T[SLOT_OBJ * P + pid] = T[s];
         p.final_idx[SLOT_OBJ * P + pid] = idx[s];
         p.obj_acc[pid] = 1.f - T[s];
+    }
+}
+
+__global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p) {
+    __shared__ float4 sA[2][32];
+    __shared__ float2 sB[2][32];
+    const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
+    const int2 range = p.obj_bins[tile];
+    const int W = strips_for(range.y - range.x);
+    if (strip >= W) return;
+    switch (W) {
+        case 1: acc_fwd_strip<8>(p, tile, strip, range, sA, sB); break;
+        case 2: acc_fwd_strip<4>(p, tile, strip, range, sA, sB); break;
+        case 4: acc_fwd_strip<2>(p, tile, strip, range, sA, sB); break;
+        default: acc_fwd_strip<1>(p, tile, strip, range, sA, sB); break;
     }
 }
 
@@ -280,13 +342,18 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.raw = reinterpret_cast<float4*>(out->raw);
     p.final_T = out->final_T; p.final_idx = out->final_idx;
     const int tiles = p.tiles_x * tiles_y;
+    p.tiles = tiles;
+    SGN_REQUIRE(out->tile_depth, "sgn_blend_fwd: tile_depth is null");
+    p.tile_depth = out->tile_depth;
+    p.obj_depth = out->tile_depth + tiles;
+    SGN_CHECK_CUDA(cudaMemsetAsync(out->tile_depth, 0, sizeof(int32_t) * 2 * (size_t)tiles, (cudaStream_t)stream));
     if (opts->class_streams) {
-        blend_fwd_kernel<true><<<tiles, 32, 0, (cudaStream_t)stream>>>(p);
+        blend_fwd_kernel<true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("blend_fwd_kernel<bg>");
-        acc_fwd_kernel<<<tiles, 32, 0, (cudaStream_t)stream>>>(p);
+        acc_fwd_kernel<<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("acc_fwd_kernel");
     } else {
-        blend_fwd_kernel<false><<<tiles, 32, 0, (cudaStream_t)stream>>>(p);
+        blend_fwd_kernel<false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("blend_fwd_kernel");
     }
     return SGN_OK;
@@ -296,7 +363,9 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
 // backward
 // ------------------------------------------------------------------------------------------------
 struct BlendBwdParams {
-    int width, height, tiles_x;
+    int width, height, tiles_x, tiles;
+    const int32_t* tile_depth;
+    const int32_t* obj_depth;
     float clamp_bwd;
     int has_sky, eval_clamp;
     const float4* records;
@@ -317,30 +386,15 @@ struct BlendBwdParams {
     float* v_records;
 };
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ int warp_max(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-
 // BG: background stream has a cotangent.  DEPTHG: the depth output has a cotangent.
-template <bool BG, bool DEPTHG>
-__global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
-    __shared__ float4 sA[2][32];
-    __shared__ float4 sB[2][32];
-    __shared__ float4 sC[2][32];
-    const int tile = blockIdx.x;
+template <int PPL, bool BG, bool DEPTHG>
+__device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int tile, int strip, const int2 range,
+                                                float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int lane = threadIdx.x;
     const int j = tx * SGN_TILE + (lane & 15);
-    const int i0 = ty * SGN_TILE + (lane >> 4);
+    const int i0 = ty * SGN_TILE + strip * (2 * PPL) + (lane >> 4);
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
-    const int2 range = p.tile_bins[tile];
     const size_t P = (size_t)p.width * p.height;
 
     // ---- per-pixel prologue: cotangents of the RAW blend outputs from those of the final outputs
@@ -480,17 +534,34 @@ __global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
     }
 }
 
-// backward of the accumulation-only pass: out = 1 - T_final  =>  v_alpha_k = T_final * ra_k * v_out
-__global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p) {
+// the prologue (v_sky, cotangent chain) must run for every pixel, so strips are always launched for the
+// whole tile: W strips of 16/W rows
+template <bool BG, bool DEPTHG>
+__global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
-    const int tile = blockIdx.x;
+    __shared__ float4 sC[2][32];
+    const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
+    const int2 range = p.tile_bins[tile];
+    const int W = strips_for(p.tile_depth[tile]);
+    if (strip >= W) return;
+    switch (W) {
+        case 1: blend_bwd_strip<8, BG, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
+        case 2: blend_bwd_strip<4, BG, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
+        case 4: blend_bwd_strip<2, BG, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
+        default: blend_bwd_strip<1, BG, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
+    }
+}
+
+// backward of the accumulation-only pass: out = 1 - T_final  =>  v_alpha_k = T_final * ra_k * v_out
+template <int PPL>
+__device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int tile, int strip, const int2 range,
+                                              float4 (*sA)[32], float4 (*sB)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int lane = threadIdx.x;
     const int j = tx * SGN_TILE + (lane & 15);
-    const int i0 = ty * SGN_TILE + (lane >> 4);
+    const int i0 = ty * SGN_TILE + strip * (2 * PPL) + (lane >> 4);
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
-    const int2 range = p.obj_bins[tile];
     if (range.y <= range.x) return;
     const size_t P = (size_t)p.width * p.height;
     float tfv[PPL];
@@ -558,6 +629,21 @@ __global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p) {
     }
 }
 
+__global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p) {
+    __shared__ float4 sA[2][32];
+    __shared__ float4 sB[2][32];
+    const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
+    const int2 range = p.obj_bins[tile];
+    const int W = strips_for(p.obj_depth[tile]);
+    if (strip >= W) return;
+    switch (W) {
+        case 1: acc_bwd_strip<8>(p, tile, strip, range, sA, sB); break;
+        case 2: acc_bwd_strip<4>(p, tile, strip, range, sA, sB); break;
+        case 4: acc_bwd_strip<2>(p, tile, strip, range, sA, sB); break;
+        default: acc_bwd_strip<1>(p, tile, strip, range, sA, sB); break;
+    }
+}
+
 extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
                              const int32_t* sorted_ids, const int32_t* tile_bins, const int32_t* obj_ids,
                              const int32_t* obj_bins, const sgn_blend_bwd_in* in, float* v_records, void* stream_) {
@@ -588,15 +674,19 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.sky = in->sky; p.v_sky = in->v_sky;
     p.v_records = v_records;
     const int tiles = p.tiles_x * tiles_y;
+    p.tiles = tiles;
+    SGN_REQUIRE(in->tile_depth, "sgn_blend_bwd: tile_depth (saved by the forward) is null");
+    p.tile_depth = in->tile_depth;
+    p.obj_depth = in->tile_depth + tiles;
     const bool bg = opts->class_streams && in->v_background_acc;
     const bool dg = in->v_depth != nullptr;
-    if (bg && dg) blend_bwd_kernel<true, true><<<tiles, 32, 0, stream>>>(p);
-    else if (bg) blend_bwd_kernel<true, false><<<tiles, 32, 0, stream>>>(p);
-    else if (dg) blend_bwd_kernel<false, true><<<tiles, 32, 0, stream>>>(p);
-    else blend_bwd_kernel<false, false><<<tiles, 32, 0, stream>>>(p);
+    if (bg && dg) blend_bwd_kernel<true, true><<<tiles * 8, 32, 0, stream>>>(p);
+    else if (bg) blend_bwd_kernel<true, false><<<tiles * 8, 32, 0, stream>>>(p);
+    else if (dg) blend_bwd_kernel<false, true><<<tiles * 8, 32, 0, stream>>>(p);
+    else blend_bwd_kernel<false, false><<<tiles * 8, 32, 0, stream>>>(p);
     SGN_CHECK_LAUNCH("blend_bwd_kernel");
     if (in->v_object_acc) {
-        acc_bwd_kernel<<<tiles, 32, 0, stream>>>(p);
+        acc_bwd_kernel<<<tiles * 8, 32, 0, stream>>>(p);
         SGN_CHECK_LAUNCH("acc_bwd_kernel");
     }
     return SGN_OK;

@@ -215,7 +215,8 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
     out = dict(
         rgb=torch.empty(H, W, 3, device=device), accumulation=torch.empty(H, W, 1, device=device),
         depth=torch.empty(H, W, 1, device=device), raw=torch.empty(H, W, 4, device=device),
-        final_T=torch.empty(S, H, W, device=device), final_idx=torch.empty(S, H, W, device=device, dtype=torch.int32))
+        final_T=torch.empty(S, H, W, device=device), final_idx=torch.empty(S, H, W, device=device, dtype=torch.int32),
+        tile_depth=torch.empty(2, tile_bins.shape[0], device=device, dtype=torch.int32))
     if bo.class_streams:
         out["object_acc"] = torch.empty(H, W, 1, device=device)
         out["background_acc"] = torch.empty(H, W, 1, device=device)
@@ -224,6 +225,7 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
     fo.object_acc = out["object_acc"].data_ptr() if bo.class_streams else None
     fo.background_acc = out["background_acc"].data_ptr() if bo.class_streams else None
     fo.raw, fo.final_T, fo.final_idx = out["raw"].data_ptr(), out["final_T"].data_ptr(), out["final_idx"].data_ptr()
+    fo.tile_depth = out["tile_depth"].data_ptr()
     with _timed("blend_fwd"):
         _lib.check(L.sgn_blend_fwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins),
                                    _ptr(obj_ids), _ptr(obj_bins), _ptr(sky), C.byref(fo), _stream()), "sgn_blend_fwd")
@@ -248,6 +250,7 @@ def blend_bwd(cs, bo, records, sorted_ids, tile_bins, saved: Dict[str, torch.Ten
     bi.v_object_acc = keep["object_acc"].data_ptr() if keep.get("object_acc") is not None else None
     bi.v_background_acc = keep["background_acc"].data_ptr() if keep.get("background_acc") is not None else None
     bi.raw, bi.final_T, bi.final_idx = saved["raw"].data_ptr(), saved["final_T"].data_ptr(), saved["final_idx"].data_ptr()
+    bi.tile_depth = saved["tile_depth"].data_ptr()
     bi.sky = sky.data_ptr() if sky is not None else None
     v_sky = torch.zeros(cs.height, cs.width, 3, device=device) if (want_v_sky and sky is not None) else None
     bi.v_sky = v_sky.data_ptr() if v_sky is not None else None
@@ -319,7 +322,7 @@ class _SceneGraphRasterize(torch.autograd.Function):
         holder.xys, holder.conics, holder.depths = records[:, 0:2], records[:, 2:5], records[:, 9]
         ctx.frame, ctx.settings, ctx.holder = frame, settings, holder
         ctx.cs, ctx.bo, ctx.table, ctx.params = cs, bo, table, params
-        ctx.saved = dict(raw=out["raw"], final_T=out["final_T"], final_idx=out["final_idx"])
+        ctx.saved = dict(raw=out["raw"], final_T=out["final_T"], final_idx=out["final_idx"], tile_depth=out["tile_depth"])
         ctx.records, ctx.radii, ctx.sorted_ids, ctx.tile_bins, ctx.sky = records, radii, sorted_ids, tile_bins, sky
         ctx.obj_ids, ctx.obj_bins = obj_ids, obj_bins
         ctx.sky_needs_grad = sky is not None and sky.requires_grad

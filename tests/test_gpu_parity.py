@@ -247,7 +247,7 @@ def test_full_size_properties_cfg3():
     table = raster.SegmentTable(frc, [seg.params.tensors() for seg in frc.segments], dev)
     records, radii, tiles_hit, bbox = raster.project_fwd(table, cs, dev)
     M, sorted_ids, tile_bins = raster.bin_and_sort(cs, records, radii, tiles_hit, bbox)
-    assert M == int(tiles_hit.sum().item()) and M > 1_000_000
+    assert 1_000_000 < M <= int(tiles_hit.sum().item())  # exact tile culling only removes no-op entries
     tb = tile_bins.cpu().numpy()
     nonempty = tb[:, 1] > tb[:, 0]
     assert tb[nonempty][0, 0] == 0 and tb[nonempty][-1, 1] == M

@@ -3,6 +3,7 @@ import argparse
 import json
 import os
 import sys
+import time
 
 import torch
 
@@ -17,41 +18,41 @@ def main():
     ap.add_argument("--cfg", type=int, default=3)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-class", action="store_true")
+    ap.add_argument("--bg-grad", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     fr = syn.config_frame(a.cfg)
-    frc = Frame(fr.camera, [Segment(s.params.to(dev), s.cls, s.rot, s.center, s.idft) for s in fr.segments])
+    frc = Frame(fr.camera, [Segment(s.params.to(dev).requires_grad_(True), s.cls, s.rot, s.center, s.idft, s.name)
+                            for s in fr.segments])
     s = raster.RenderSettings(class_streams=not a.no_class)
-    cs = raster.camera_struct(frc.camera, s)
-    bo = raster.blend_opts(s, False)
-    params = [seg.params.tensors() for seg in frc.segments]
-    H, W = cs.height, cs.width
+    H, W = fr.camera.height, fr.camera.width
     w, v = syn.cotangents(H, W)
-    vd = dict(rgb=w.to(dev), accumulation=v.to(dev), depth=None,
-              object_acc=(0.1 * v).to(dev) if s.class_streams else None, background_acc=None)
-    names = ["table", "project_fwd", "bin_sort", "blend_fwd", "blend_bwd", "project_bwd"]
-    acc = {n: 0.0 for n in names}
-    M = 0
-    for it in range(a.iters + 3):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-        ev[0].record()
-        table = raster.SegmentTable(frc, params, dev); ev[1].record()
-        records, radii, tiles_hit, bbox = raster.project_fwd(table, cs, dev); ev[2].record()
-        M, sorted_ids, tile_bins = raster.bin_and_sort(cs, records, radii, tiles_hit, bbox); ev[3].record()
-        oi = ob = None
+    w, v = w.to(dev), v.to(dev)[..., None]
+
+    def step():
+        out, holder = raster.render_frame(frc, s)
+        outs, gr = [out["rgb"], out["accumulation"]], [w, v]
         if s.class_streams:
-            oi, ob = raster.class_lists(cs, M, sorted_ids, tile_bins)
-        out = raster.blend_fwd(cs, bo, records, sorted_ids, tile_bins, None, oi, ob); ev[4].record()
-        v_records, _ = raster.blend_bwd(cs, bo, records, sorted_ids, tile_bins, out, None, vd, False, oi, ob); ev[5].record()
-        grads, arena = raster.project_bwd(table, params, cs, records, radii, v_records); ev[6].record()
-        torch.cuda.synchronize()
-        if it >= 3:
-            for i, n in enumerate(names):
-                acc[n] += ev[i].elapsed_time(ev[i + 1])
-    res = {n: round(acc[n] / a.iters, 4) for n in names}
-    res["total_ms"] = round(sum(res.values()), 4)
-    res.update(N=table.N, M=M, n_visible=int((radii > 0).sum().item()), cfg=a.cfg, class_streams=s.class_streams,
-               mean_alpha=float(out["accumulation"].mean().item()))
+            outs.append(out["object_acc"]); gr.append(0.1 * v)
+            if a.bg_grad:
+                outs.append(out["background_acc"]); gr.append(0.1 * v)
+        torch.autograd.backward(outs, gr)
+        return out, holder
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    raster.TIMER = raster.StageTimer()
+    t0 = time.perf_counter()
+    for _ in range(a.iters):
+        out, holder = step()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / a.iters * 1e3
+    res = {k: round(val, 4) for k, val in sorted(raster.TIMER.mean_ms().items())}
+    res["gpu_sum_ms"] = round(sum(res.values()), 4)
+    res["wall_ms_per_step"] = round(wall, 3)
+    res.update(N=holder.records.shape[0], M=holder.M, n_visible=int((holder.radii > 0).sum().item()), cfg=a.cfg,
+               class_streams=s.class_streams)
     print(json.dumps(res))
 
 
