@@ -71,7 +71,10 @@ __device__ __forceinline__ int warp_max(int v) {
     return v;
 }
 
-// One staged entry: A = (gx, gy, 0.5*a*log2e, b*log2e)  B = (0.5*c*log2e, opacity, r, g)  C = (b, depth, id bits, -)
+// One staged entry: A = (gx, gy, 0.5*a*log2e, b*log2e)  B = (0.5*c*log2e, log2(opacity), r, g)
+//                   C = (b, depth, id bits, opacity)
+// With s2 = sigma*log2e - log2(o):  o*exp(-sigma) = 2^(-s2);  sigma >= 0 <=> s2 >= -log2(o);
+// alpha >= 1/255 <=> s2 <= log2(255).  Both tests only need s2, so validity is known before the MUFU result.
 struct Staged {
     float4 A, B, C;
 };
@@ -81,14 +84,22 @@ __device__ __forceinline__ Staged gather_entry(const float4* __restrict__ record
     const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
     Staged s;
     s.A = make_float4(r0.x, r0.y, 0.5f * LOG2E * r0.z, LOG2E * r0.w);
-    s.B = make_float4(0.5f * LOG2E * r1.x, r1.y, r1.z, r1.w);
-    s.C = make_float4(r2.x, r2.y, __int_as_float(id), 0.f);
+    s.B = make_float4(0.5f * LOG2E * r1.x, __log2f(r1.y), r1.z, r1.w);
+    s.C = make_float4(r2.x, r2.y, __int_as_float(id), r1.y);
     return s;
 }
 
 // sigma*log2(e) for the pixel at (dx, dy) from the staged conic; identical in forward and backward
 __device__ __forceinline__ float sgn_sigma2(float hax2, float bdx, float hc, float dy) {
     return __fmaf_rn(dy, __fmaf_rn(hc, dy, bdx), hax2);
+}
+
+#define LOG2_255 7.994353436858858f
+
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ float fast_ex2(float x) {
@@ -137,31 +148,36 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
             const float4 Cc = sC[buf][t];
             const bool isobj = __float_as_int(Cc.z) < 0;
             const float dx = A.x - px;
-            const float bdx = A.w * dx, hax2 = A.z * dx * dx;
+            const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
+            const float nlo = -B.y;
             const int k = base + t;
+            // straight-line, predicated: the PPL pixel chains are independent and interleave (ILP)
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
                 const float dy = dy0 - (float)(2 * s);
-                const float sg = sgn_sigma2(hax2, bdx, B.x, dy);
-                const float alpha = fminf(p.clamp_fwd, B.y * fast_ex2(-sg));
-                if (sg < 0.f || alpha < ALPHA_MIN) continue;
+                const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
+                const bool valid = (s2 >= nlo) && (s2 <= LOG2_255);
+                const float alpha = fminf(p.clamp_fwd, fast_ex2(-s2));
                 const float om = 1.f - alpha;
-                if (!(done & (1u << s))) {
-                    const float nT = T[s] * om;
-                    if (nT <= T_STOP) done |= 1u << s;
-                    else {
-                        const float w = alpha * T[s];
-                        pr[s] += B.z * w; pg[s] += B.w * w; pb[s] += Cc.x * w; pd[s] += Cc.y * w;
-                        T[s] = nT;
-                        idx[s] = k;
-                    }
-                }
+                const bool act = valid && !((done >> s) & 1u);
+                const float nT = T[s] * om;
+                const bool stop = act && (nT <= T_STOP);
+                const bool upd = act && !stop;
+                const float w = upd ? alpha * T[s] : 0.f;
+                pr[s] = __fmaf_rn(B.z, w, pr[s]); pg[s] = __fmaf_rn(B.w, w, pg[s]);
+                pb[s] = __fmaf_rn(Cc.x, w, pb[s]); pd[s] = __fmaf_rn(Cc.y, w, pd[s]);
+                T[s] = upd ? nT : T[s];
+                idx[s] = upd ? k : idx[s];
+                done |= stop ? (1u << s) : 0u;
                 if (BG) {
-                    if (!isobj && !(doneb & (1u << s))) {
-                        const float nT = Tb[s] * om;
-                        if (nT <= T_STOP) doneb |= 1u << s; else { Tb[s] = nT; idxb[s] = k; }
-                    }
+                    const bool actb = valid && !isobj && !((doneb >> s) & 1u);
+                    const float nTb = Tb[s] * om;
+                    const bool stopb = actb && (nTb <= T_STOP);
+                    const bool updb = actb && !stopb;
+                    Tb[s] = updb ? nTb : Tb[s];
+                    idxb[s] = updb ? k : idxb[s];
+                    doneb |= stopb ? (1u << s) : 0u;
                 }
             }
         }
@@ -257,18 +273,23 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int tile,
             const float4 A = sA[buf][t];
             const float2 B = sB[buf][t];
             const float dx = A.x - px;
-            const float bdx = A.w * dx, hax2 = A.z * dx * dx;
+            const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
+            const float nlo = -B.y;
+            const int k = base + t;
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
                 const float dy = dy0 - (float)(2 * s);
-                const float sg = sgn_sigma2(hax2, bdx, B.x, dy);
-                const float alpha = fminf(p.clamp_fwd, B.y * fast_ex2(-sg));
-                if (sg < 0.f || alpha < ALPHA_MIN) continue;
-                if (!(done & (1u << s))) {
-                    const float nT = T[s] * (1.f - alpha);
-                    if (nT <= T_STOP) done |= 1u << s; else { T[s] = nT; idx[s] = base + t; }
-                }
+                const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
+                const bool valid = (s2 >= nlo) && (s2 <= LOG2_255);
+                const float alpha = fminf(p.clamp_fwd, fast_ex2(-s2));
+                const bool act = valid && !((done >> s) & 1u);
+                const float nT = T[s] * (1.f - alpha);
+                const bool stop = act && (nT <= T_STOP);
+                const bool upd = act && !stop;
+                T[s] = upd ? nT : T[s];
+                idx[s] = upd ? k : idx[s];
+                done |= stop ? (1u << s) : 0u;
             }
         }
         buf ^= 1;
@@ -472,43 +493,44 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             const float4 Cc = sC[buf][t];
             const bool isobj = __float_as_int(Cc.z) < 0;
             const float dx = A.x - px;
-            const float bdx = A.w * dx, hax2 = A.z * dx * dx;
+            const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
-            const float o = B.y;
+            const float nlo = -B.y;
+            const float o = Cc.w;
             float S0 = 0.f, Sy = 0.f, Syy = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
             bool any = false;
+            // straight-line, predicated (see the forward)
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
                 const bool in_main = k <= idx[s];
                 const bool in_bg = BG && !isobj && (k <= idxb[s]);
-                if (!(in_main || in_bg)) continue;
                 const float dy = dy0 - (float)(2 * s);
-                const float sg = sgn_sigma2(hax2, bdx, B.x, dy);
-                const float vis = fast_ex2(-sg);
-                const float alpha = fminf(p.clamp_bwd, o * vis);
-                if (sg < 0.f || alpha < ALPHA_MIN) continue;
-                any = true;
-                const float ra = __frcp_rn(1.f - alpha);
-                float v_alpha = 0.f;
-                if (in_main) {
-                    T[s] *= ra;
-                    const float Tk = T[s];
-                    const float fac = alpha * Tk;
-                    cr += fac * vr[s]; cg += fac * vg[s]; cb += fac * vb[s];
-                    v_alpha = (B.z * Tk - br[s] * ra) * vr[s] + (B.w * Tk - bgc[s] * ra) * vg[s] + (Cc.x * Tk - bb[s] * ra) * vb[s];
-                    br[s] += B.z * fac; bgc[s] += B.w * fac; bb[s] += Cc.x * fac;
-                    if (DEPTHG) {
-                        cd += fac * vd[s];
-                        v_alpha += (Cc.y * Tk - bd[s] * ra) * vd[s];
-                        bd[s] += Cc.y * fac;
-                    }
-                    v_alpha += tfv[s] * ra;
+                const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
+                const bool valid = (s2 >= nlo) && (s2 <= LOG2_255) && (in_main || in_bg);
+                const float raw = fast_ex2(-s2);            // o * exp(-sigma)
+                const float alpha = fminf(p.clamp_bwd, raw);
+                const float ra = fast_rcp(1.f - alpha);
+                const bool vm = valid && in_main;
+                any = any || valid;
+                const float Tk = vm ? T[s] * ra : T[s];
+                T[s] = Tk;
+                const float fac = vm ? alpha * Tk : 0.f;
+                cr = __fmaf_rn(fac, vr[s], cr); cg = __fmaf_rn(fac, vg[s], cg); cb = __fmaf_rn(fac, vb[s], cb);
+                float v_alpha = (B.z * Tk - br[s] * ra) * vr[s] + (B.w * Tk - bgc[s] * ra) * vg[s] + (Cc.x * Tk - bb[s] * ra) * vb[s];
+                br[s] = __fmaf_rn(B.z, fac, br[s]); bgc[s] = __fmaf_rn(B.w, fac, bgc[s]); bb[s] = __fmaf_rn(Cc.x, fac, bb[s]);
+                if (DEPTHG) {
+                    cd = __fmaf_rn(fac, vd[s], cd);
+                    v_alpha += (Cc.y * Tk - bd[s] * ra) * vd[s];
+                    bd[s] = __fmaf_rn(Cc.y, fac, bd[s]);
                 }
-                if (BG) {
-                    if (in_bg) v_alpha += tfbv[s] * ra;
-                }
-                const float vs = -o * vis * v_alpha;
-                S0 += vs; Sy += vs * dy; Syy += vs * dy * dy;
+                v_alpha = __fmaf_rn(tfv[s], ra, v_alpha);
+                v_alpha = vm ? v_alpha : 0.f;
+                if (BG) v_alpha = (valid && in_bg) ? __fmaf_rn(tfbv[s], ra, v_alpha) : v_alpha;
+                const float vs = valid ? -raw * v_alpha : 0.f;   // d/d sigma = -o*vis*v_alpha
+                S0 += vs;
+                const float vsy = vs * dy;
+                Sy += vsy;
+                Syy = __fmaf_rn(vsy, dy, Syy);
             }
             if (!__any_sync(FULL, any)) continue;
             // true conic from the staged (log2e-scaled) one
@@ -584,7 +606,7 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int tile,
     if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, p.obj_ids[hi0 - 1 - lane]);
     int buf = 0;
     for (int hi = hi0; hi > range.x; hi -= 32) {
-        sA[buf][lane] = nxt.A; sB[buf][lane] = make_float4(nxt.B.x, nxt.B.y, nxt.C.z, 0.f);
+        sA[buf][lane] = nxt.A; sB[buf][lane] = make_float4(nxt.B.x, nxt.B.y, nxt.C.z, nxt.C.w);
         __syncwarp();
         if (hi - 33 - lane >= range.x) nxt = gather_entry(p.records, p.obj_ids[hi - 33 - lane]);
         const int n = min(32, hi - range.x);
@@ -593,23 +615,26 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int tile,
             const float4 A = sA[buf][t];
             const float4 B = sB[buf][t];
             const float dx = A.x - px;
-            const float bdx = A.w * dx, hax2 = A.z * dx * dx;
+            const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
-            const float o = B.y;
+            const float nlo = -B.y;
+            const float o = B.w;
             float S0 = 0.f, Sy = 0.f, Syy = 0.f;
             bool any = false;
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
-                if (k > idx[s]) continue;
                 const float dy = dy0 - (float)(2 * s);
-                const float sg = sgn_sigma2(hax2, bdx, B.x, dy);
-                const float vis = fast_ex2(-sg);
-                const float alpha = fminf(p.clamp_bwd, o * vis);
-                if (sg < 0.f || alpha < ALPHA_MIN) continue;
-                any = true;
-                const float ra = __frcp_rn(1.f - alpha);
-                const float vs = -o * vis * (tfv[s] * ra);
-                S0 += vs; Sy += vs * dy; Syy += vs * dy * dy;
+                const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
+                const bool valid = (s2 >= nlo) && (s2 <= LOG2_255) && (k <= idx[s]);
+                const float raw = fast_ex2(-s2);
+                const float alpha = fminf(p.clamp_bwd, raw);
+                const float ra = fast_rcp(1.f - alpha);
+                any = any || valid;
+                const float vs = valid ? -raw * (tfv[s] * ra) : 0.f;
+                S0 += vs;
+                const float vsy = vs * dy;
+                Sy += vsy;
+                Syy = __fmaf_rn(vsy, dy, Syy);
             }
             if (!__any_sync(FULL, any)) continue;
             const float ca = A.z * (2.f * LN2), cbb = A.w * LN2, cc = B.x * (2.f * LN2);

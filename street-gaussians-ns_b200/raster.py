@@ -298,6 +298,9 @@ class _Holder:
 class _SceneGraphRasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, frame: Frame, settings: RenderSettings, holder: _Holder, sky: Optional[torch.Tensor], *flat):
+        # unused outputs must reach backward as None, not as zero tensors: the kernels specialise on
+        # which cotangents exist (depth / background_acc have none in training)
+        ctx.set_materialize_grads(False)
         nseg = len(frame.segments)
         assert len(flat) == 6 * nseg
         params = [list(flat[6 * i: 6 * i + 6]) for i in range(nseg)]
