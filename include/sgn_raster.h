@@ -152,12 +152,13 @@ int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, 
                  const uint16_t* tile_bbox, const int32_t* cum, int32_t* sorted_ids /*[M]*/,
                  int32_t* tile_bins /*[tiles,2]*/, void* scratch, size_t scratch_bytes, void* stream);
 /* sorted_ids payload: bits 0-30 = Gaussian row (concatenated index space), bit 31 = object class.
- * step 3 (only for the class renders): per-tile OBJECT sub-lists, a stable compaction of sorted_ids
- * (what the reference's objects-only re-render sorts and traverses, sgn_splatfacto_scene_graph.py:
- * 255-303,364-365).  obj_ids has capacity M; obj_bins is [tiles,2]. */
+ * step 3 (only for the class renders): per-tile class sub-lists, a stable partition of every tile's
+ * list into background entries (class 0) and object entries (class 1) -- what the reference's
+ * objects-only / background-only re-renders sort and traverse (sgn_splatfacto_scene_graph.py:
+ * 255-303,364-366).  cls_ids is [2,M] (class c at cls_ids + c*M), cls_bins is [2,tiles,2]. */
 size_t sgn_bin_class_scratch_bytes(int tiles);
-int sgn_bin_class_lists(const sgn_camera* cam, const int32_t* sorted_ids, const int32_t* tile_bins,
-                        int32_t* obj_ids, int32_t* obj_bins, void* scratch, size_t scratch_bytes, void* stream);
+int sgn_bin_class_lists(const sgn_camera* cam, int64_t M, const int32_t* sorted_ids, const int32_t* tile_bins,
+                        int32_t* cls_ids, int32_t* cls_bins, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- alpha blending ------------------------------------------------------------------------------
  * Forward: gsplat rasterize_forward for rgb AND the depth pass in one traversal
@@ -173,12 +174,12 @@ typedef struct sgn_blend_fwd_out {
     float* raw;            /* [H,W,4] saved for backward */
     float* final_T;        /* [3,H,W] planar: slot 0 main, 1 object, 2 background */
     int32_t* final_idx;    /* [3,H,W] */
-    int32_t* tile_depth;   /* [2,tiles] entries traversed per tile (main pass, object pass); sizes the backward */
+    int32_t* tile_depth;   /* [3,tiles] entries traversed per tile (main, object, background pass); sizes the backward */
 } sgn_blend_fwd_out;
 
 int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
-                  const int32_t* sorted_ids, const int32_t* tile_bins,
-                  const int32_t* obj_ids /*or NULL*/, const int32_t* obj_bins /*or NULL*/,
+                  const int32_t* sorted_ids, const int32_t* tile_bins, int64_t M,
+                  const int32_t* cls_ids /*[2,M] or NULL*/, const int32_t* cls_bins /*[2,tiles,2] or NULL*/,
                   const float* sky /*[H,W,3] or NULL*/, const sgn_blend_fwd_out* out, void* stream);
 
 typedef struct sgn_blend_bwd_in {
@@ -190,7 +191,7 @@ typedef struct sgn_blend_bwd_in {
     const float* raw;
     const float* final_T;
     const int32_t* final_idx;
-    const int32_t* tile_depth;     /* [2,tiles] from the forward */
+    const int32_t* tile_depth;     /* [3,tiles] from the forward */
     const float* sky;              /* [H,W,3] or NULL */
     float* v_sky;                  /* [H,W,3] or NULL: gradient to the sky colour */
 } sgn_blend_bwd_in;
@@ -198,8 +199,8 @@ typedef struct sgn_blend_bwd_in {
 /* Backward: gsplat rasterize_backward for all streams in one traversal.  v_records[N,12] must be
  * zero on entry; it is accumulated into (record layout, see sgn_project_bwd). */
 int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
-                  const int32_t* sorted_ids, const int32_t* tile_bins,
-                  const int32_t* obj_ids /*or NULL*/, const int32_t* obj_bins /*or NULL*/,
+                  const int32_t* sorted_ids, const int32_t* tile_bins, int64_t M,
+                  const int32_t* cls_ids /*[2,M] or NULL*/, const int32_t* cls_bins /*[2,tiles,2] or NULL*/,
                   const sgn_blend_bwd_in* in, float* v_records, void* stream);
 
 #ifdef __cplusplus

@@ -109,10 +109,10 @@ def load():
     L.sgn_bin_sort.argtypes = [i32, i64, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.sgn_bin_class_scratch_bytes.argtypes = [i32]
     L.sgn_bin_class_scratch_bytes.restype = sz
-    L.sgn_bin_class_lists.argtypes = [C.POINTER(CameraStruct), vp, vp, vp, vp, vp, sz, vp]
-    L.sgn_blend_fwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, vp, vp, vp,
+    L.sgn_bin_class_lists.argtypes = [C.POINTER(CameraStruct), i64, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_blend_fwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, i64, vp, vp, vp,
                                 C.POINTER(BlendFwdOut), vp]
-    L.sgn_blend_bwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, vp, vp,
+    L.sgn_blend_bwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, i64, vp, vp,
                                 C.POINTER(BlendBwdIn), vp, vp]
     for f in ("sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan", "sgn_bin_sort", "sgn_bin_class_lists",
               "sgn_blend_fwd", "sgn_blend_bwd"):

@@ -284,11 +284,13 @@ extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-tile object sub-lists: stable compaction of the entries whose payload carries the object bit.
-// The objects-only accumulation of the reference (get_submodel_output, scene graph :364-365) sees
-// exactly these entries in exactly this order.
+// per-tile class sub-lists: stable partition of every tile's list into its object entries and its
+// background entries.  The objects-only / background-only accumulation renders of the reference
+// (get_submodel_output, scene graph :255-303,364-366) see exactly these entries in exactly this order.
+// Layout: class c (0 = background, 1 = object) owns cls_ids[c*M ...) and cls_bins[c][tiles][2].
 __global__ void __launch_bounds__(256)
-class_count_kernel(const int2* __restrict__ tile_bins, const int32_t* __restrict__ sorted_ids, int32_t* __restrict__ counts) {
+class_count_kernel(int tiles, const int2* __restrict__ tile_bins, const int32_t* __restrict__ sorted_ids,
+                   int32_t* __restrict__ counts /*[2][tiles]*/) {
     const int tile = blockIdx.x;
     const int2 range = tile_bins[tile];
     int c = 0;
@@ -296,42 +298,57 @@ class_count_kernel(const int2* __restrict__ tile_bins, const int32_t* __restrict
     typedef cub::BlockReduce<int, 256> BR;
     __shared__ typename BR::TempStorage tmp;
     const int total = BR(tmp).Sum(c);
-    if (threadIdx.x == 0) counts[tile] = total;
+    if (threadIdx.x == 0) {
+        counts[tiles + tile] = total;
+        counts[tile] = (range.y - range.x) - total;
+    }
 }
 
 __global__ void __launch_bounds__(256)
-class_compact_kernel(const int2* __restrict__ tile_bins, const int32_t* __restrict__ sorted_ids,
-                     const int32_t* __restrict__ offsets /* exclusive scan of counts */, const int32_t* __restrict__ counts,
-                     int32_t* __restrict__ obj_ids, int2* __restrict__ obj_bins) {
+class_compact_kernel(int tiles, int64_t M, const int2* __restrict__ tile_bins, const int32_t* __restrict__ sorted_ids,
+                     const int32_t* __restrict__ offsets /* exclusive scan over [2][tiles] */,
+                     const int32_t* __restrict__ counts, int32_t* __restrict__ cls_ids, int2* __restrict__ cls_bins) {
     const int tile = blockIdx.x;
     const int2 range = tile_bins[tile];
-    const int base = offsets[tile];
-    if (threadIdx.x == 0) obj_bins[tile] = make_int2(base, base + counts[tile]);
+    // offsets run over the concatenation [background tiles..., object tiles...]; class 1's base within its own
+    // array is offsets - (total background) = offsets - offsets[tiles]
+    const int base0 = offsets[tile];
+    const int base1 = offsets[tiles + tile] - offsets[tiles];
+    if (threadIdx.x == 0) {
+        cls_bins[tile] = make_int2(base0, base0 + counts[tile]);
+        cls_bins[tiles + tile] = make_int2(base1, base1 + counts[tiles + tile]);
+    }
     typedef cub::BlockScan<int, 256> BS;
     __shared__ typename BS::TempStorage tmp;
-    int running = 0;
+    int run0 = 0, run1 = 0;
     for (int k0 = range.x; k0 < range.y; k0 += blockDim.x) {
         const int k = k0 + threadIdx.x;
-        const int id = (k < range.y) ? sorted_ids[k] : 0;
-        const int flag = (id < 0) ? 1 : 0;
+        const bool in = k < range.y;
+        const int id = in ? sorted_ids[k] : 0;
+        const int flag = (in && id < 0) ? 1 : 0;
         int pos, total;
         BS(tmp).ExclusiveSum(flag, pos, total);
-        if (flag) obj_ids[base + running + pos] = id;
-        running += total;
+        if (in) {
+            if (flag) cls_ids[M + base1 + run1 + pos] = id;
+            else cls_ids[base0 + run0 + (threadIdx.x - pos)] = id;
+        }
+        run1 += total;
+        run0 += min((int)blockDim.x, range.y - k0) - total;
         __syncthreads();
     }
 }
 
 extern "C" size_t sgn_bin_class_scratch_bytes(int tiles) {
     size_t temp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, temp, (const int32_t*)nullptr, (int32_t*)nullptr, tiles > 0 ? tiles : 1);
-    return align_up(temp, 256) + 2 * align_up(sizeof(int32_t) * (size_t)(tiles > 0 ? tiles : 1), 256);
+    const int n = 2 * (tiles > 0 ? tiles : 1);
+    cub::DeviceScan::ExclusiveSum(nullptr, temp, (const int32_t*)nullptr, (int32_t*)nullptr, n);
+    return align_up(temp, 256) + 2 * align_up(sizeof(int32_t) * (size_t)n, 256);
 }
 
-extern "C" int sgn_bin_class_lists(const sgn_camera* cam, const int32_t* sorted_ids, const int32_t* tile_bins,
-                                   int32_t* obj_ids, int32_t* obj_bins, void* scratch, size_t scratch_bytes, void* stream_) {
+extern "C" int sgn_bin_class_lists(const sgn_camera* cam, int64_t M, const int32_t* sorted_ids, const int32_t* tile_bins,
+                                   int32_t* cls_ids, int32_t* cls_bins, void* scratch, size_t scratch_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    SGN_REQUIRE(cam && tile_bins && obj_ids && obj_bins && scratch, "sgn_bin_class_lists: null pointer");
+    SGN_REQUIRE(cam && tile_bins && cls_ids && cls_bins && scratch, "sgn_bin_class_lists: null pointer");
     const int bw = cam->block_width;
     const int tiles = ((cam->width + bw - 1) / bw) * ((cam->height + bw - 1) / bw);
     if (scratch_bytes < sgn_bin_class_scratch_bytes(tiles)) {
@@ -339,17 +356,17 @@ extern "C" int sgn_bin_class_lists(const sgn_camera* cam, const int32_t* sorted_
         return SGN_ERR_WORKSPACE;
     }
     char* base = (char*)scratch;
-    const size_t arr = align_up(sizeof(int32_t) * (size_t)tiles, 256);
+    const size_t arr = align_up(sizeof(int32_t) * 2 * (size_t)tiles, 256);
     int32_t* counts = (int32_t*)base;
     int32_t* offsets = (int32_t*)(base + arr);
     void* temp = base + 2 * arr;
     size_t temp_bytes = scratch_bytes - 2 * arr;
-    class_count_kernel<<<tiles, 256, 0, stream>>>(reinterpret_cast<const int2*>(tile_bins), sorted_ids, counts);
+    class_count_kernel<<<tiles, 256, 0, stream>>>(tiles, reinterpret_cast<const int2*>(tile_bins), sorted_ids, counts);
     SGN_CHECK_LAUNCH("class_count_kernel");
-    SGN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, offsets, tiles, stream));
+    SGN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, offsets, 2 * tiles, stream));
     sgn_count_launch(1);
-    class_compact_kernel<<<tiles, 256, 0, stream>>>(reinterpret_cast<const int2*>(tile_bins), sorted_ids, offsets, counts,
-                                                    obj_ids, reinterpret_cast<int2*>(obj_bins));
+    class_compact_kernel<<<tiles, 256, 0, stream>>>(tiles, M, reinterpret_cast<const int2*>(tile_bins), sorted_ids, offsets, counts,
+                                                    cls_ids, reinterpret_cast<int2*>(cls_bins));
     SGN_CHECK_LAUNCH("class_compact_kernel");
     return SGN_OK;
 }

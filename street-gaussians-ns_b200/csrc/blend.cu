@@ -1,12 +1,11 @@
 // Front-to-back alpha compositing, forward and backward, for 16x16 tiles.
 //
-// One traversal of each tile's depth-sorted list produces what the reference obtains from three
-// gsplat rasterize_gaussians calls (street_gaussians_ns/sgn_splatfacto.py:954-996 rgb+alpha and the
-// depth pass; street_gaussians_ns/sgn_splatfacto_scene_graph.py:366 background-only accumulation): the
-// per-pair alpha is evaluated once and fed to two transmittance streams (main / background), each
-// with gsplat's own skip and termination rules.  The objects-only
-// accumulation (:364-365) runs over the compacted per-tile object sub-lists (binning.cu), which is
-// what the reference's subset re-render sees.  The reference's post-ops (:968-975, :995) run in
+// One traversal of each tile's depth-sorted list produces what the reference obtains from two gsplat
+// rasterize_gaussians calls (street_gaussians_ns/sgn_splatfacto.py:954-996: rgb+alpha and the depth
+// pass), with gsplat's skip and termination rules.  The objects-only and
+// background-only accumulations (street_gaussians_ns/sgn_splatfacto_scene_graph.py:364-366) are
+// accumulation-only traversals of the compacted per-tile class sub-lists (binning.cu), which is
+// what the reference's subset re-renders see.  The reference's post-ops (:968-975, :995) run in
 // the epilogue.
 //
 // Execution shape (B200): the loops are FP32/MUFU issue-bound, not HBM-bound (profiles/), so the
@@ -40,15 +39,14 @@
 
 struct BlendFwdParams {
     int width, height, tiles_x, tiles;
-    int32_t* tile_depth;  // [tiles] entries traversed per tile (main/bg pass), atomicMax'ed by the forward
-    int32_t* obj_depth;   // [tiles] same for the object pass
+    int32_t* tile_depth;  // [3][tiles] entries traversed per tile by the main / object / background pass (atomicMax)
     float clamp_fwd;
     int has_sky, eval_clamp;
     const float4* records;
     const int32_t* sorted_ids;
     const int2* tile_bins;
-    const int32_t* obj_ids;
-    const int2* obj_bins;
+    const int32_t* cls_ids[2];  // class sub-lists: [0] background, [1] object
+    const int2* cls_bins[2];
     const float* sky;
     float* rgb;
     float* acc;
@@ -111,7 +109,7 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // number of strips (warps) a tile is split into, from the length of the list it has to traverse
 __device__ __forceinline__ int strips_for(int len) { return len <= 384 ? 1 : (len <= 768 ? 2 : (len <= 1536 ? 4 : 8)); }
 
-template <int PPL, bool BG>
+template <int PPL>
 __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int tile, int strip, const int2 range,
                                                 float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -121,15 +119,15 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
     constexpr unsigned ALL = (1u << PPL) - 1u;
 
-    float T[PPL], Tb[PPL], pr[PPL], pg[PPL], pb[PPL], pd[PPL];
-    int idx[PPL], idxb[PPL];
-    unsigned done = 0, doneb = BG ? 0u : ALL;
+    float T[PPL], pr[PPL], pg[PPL], pb[PPL], pd[PPL];
+    int idx[PPL];
+    unsigned done = 0;
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
-        T[s] = 1.f; Tb[s] = 1.f; pr[s] = pg[s] = pb[s] = pd[s] = 0.f;
-        idx[s] = -1; idxb[s] = -1;
+        T[s] = 1.f; pr[s] = pg[s] = pb[s] = pd[s] = 0.f;
+        idx[s] = -1;
         const bool inside = (j < p.width) && (i0 + 2 * s < p.height);
-        if (!inside) { done |= 1u << s; doneb |= 1u << s; }
+        if (!inside) done |= 1u << s;
     }
 
     Staged nxt;
@@ -142,11 +140,10 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
         if (base + 32 + lane < range.y) nxt = gather_entry(p.records, p.sorted_ids[base + 32 + lane]);
         const int n = min(32, range.y - base);
         for (int t = 0; t < n; ++t) {
-            if (__all_sync(FULL, (done & doneb) == ALL)) { finished = true; break; }
+            if (__all_sync(FULL, done == ALL)) { finished = true; break; }
             const float4 A = sA[buf][t];
             const float4 B = sB[buf][t];
             const float4 Cc = sC[buf][t];
-            const bool isobj = __float_as_int(Cc.z) < 0;
             const float dx = A.x - px;
             const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
@@ -170,15 +167,6 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
                 T[s] = upd ? nT : T[s];
                 idx[s] = upd ? k : idx[s];
                 done |= stop ? (1u << s) : 0u;
-                if (BG) {
-                    const bool actb = valid && !isobj && !((doneb >> s) & 1u);
-                    const float nTb = Tb[s] * om;
-                    const bool stopb = actb && (nTb <= T_STOP);
-                    const bool updb = actb && !stopb;
-                    Tb[s] = updb ? nTb : Tb[s];
-                    idxb[s] = updb ? k : idxb[s];
-                    doneb |= stopb ? (1u << s) : 0u;
-                }
             }
         }
         buf ^= 1;
@@ -187,7 +175,7 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
     {   // how deep this tile was traversed: the backward sizes its strips from it
         int kdeep = -1;
 #pragma unroll
-        for (int s = 0; s < PPL; ++s) kdeep = max(kdeep, BG ? max(idx[s], idxb[s]) : idx[s]);
+        for (int s = 0; s < PPL; ++s) kdeep = max(kdeep, idx[s]);
         kdeep = warp_max(kdeep);
         if (lane == 0 && kdeep >= 0) atomicMax(p.tile_depth + tile, kdeep + 1 - range.x);
     }
@@ -214,17 +202,11 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
         p.depth[pid] = alpha > 1e-3f ? pd[s] / alpha : 10.f;  // sgn_splatfacto.py:995
         p.final_T[SLOT_MAIN * P + pid] = T[s];
         p.final_idx[SLOT_MAIN * P + pid] = idx[s];
-        if (BG) {
-            p.final_T[SLOT_BG * P + pid] = Tb[s];
-            p.final_idx[SLOT_BG * P + pid] = idxb[s];
-            p.bg_acc[pid] = 1.f - Tb[s];
-        }
     }
 }
 
 // grid = tiles x 8 one-warp CTAs: block b -> strip b / tiles of tile b % tiles; strips beyond the
 // tile's split exit at once (registers are per CTA, so they cost nothing once gone)
-template <bool BG>
 __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
@@ -234,17 +216,20 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     const int W = strips_for(range.y - range.x);
     if (strip >= W) return;
     switch (W) {
-        case 1: blend_fwd_strip<8, BG>(p, tile, strip, range, sA, sB, sC); break;
-        case 2: blend_fwd_strip<4, BG>(p, tile, strip, range, sA, sB, sC); break;
-        case 4: blend_fwd_strip<2, BG>(p, tile, strip, range, sA, sB, sC); break;
-        default: blend_fwd_strip<1, BG>(p, tile, strip, range, sA, sB, sC); break;
+        case 1: blend_fwd_strip<8>(p, tile, strip, range, sA, sB, sC); break;
+        case 2: blend_fwd_strip<4>(p, tile, strip, range, sA, sB, sC); break;
+        case 4: blend_fwd_strip<2>(p, tile, strip, range, sA, sB, sC); break;
+        default: blend_fwd_strip<1>(p, tile, strip, range, sA, sB, sC); break;
     }
 }
 
-// accumulation-only pass over per-tile sub-lists (objects-only render)
+// accumulation-only pass over one class's per-tile sub-lists (objects-only / background-only render)
 template <int PPL>
-__device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int tile, int strip, const int2 range,
+__device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, int tile, int strip, const int2 range,
                                               float4 (*sA)[32], float2 (*sB)[32]) {
+    const int32_t* __restrict__ ids = p.cls_ids[cls];
+    const int slot = cls ? SLOT_OBJ : SLOT_BG;
+    float* __restrict__ out_acc = cls ? p.obj_acc : p.bg_acc;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int lane = threadIdx.x;
     const int j = tx * SGN_TILE + (lane & 15);
@@ -260,13 +245,13 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int tile,
         if (!((j < p.width) && (i0 + 2 * s < p.height))) done |= 1u << s;
     }
     Staged nxt;
-    if (range.x + lane < range.y) nxt = gather_entry(p.records, p.obj_ids[range.x + lane]);
+    if (range.x + lane < range.y) nxt = gather_entry(p.records, ids[range.x + lane]);
     int buf = 0;
     bool finished = false;
     for (int base = range.x; base < range.y && !finished; base += 32) {
         sA[buf][lane] = nxt.A; sB[buf][lane] = make_float2(nxt.B.x, nxt.B.y);
         __syncwarp();
-        if (base + 32 + lane < range.y) nxt = gather_entry(p.records, p.obj_ids[base + 32 + lane]);
+        if (base + 32 + lane < range.y) nxt = gather_entry(p.records, ids[base + 32 + lane]);
         const int n = min(32, range.y - base);
         for (int t = 0; t < n; ++t) {
             if (__all_sync(FULL, done == ALL)) { finished = true; break; }
@@ -300,31 +285,33 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int tile,
 #pragma unroll
         for (int s = 0; s < PPL; ++s) kdeep = max(kdeep, idx[s]);
         kdeep = warp_max(kdeep);
-        if (lane == 0 && kdeep >= 0) atomicMax(p.obj_depth + tile, kdeep + 1 - range.x);
+        if (lane == 0 && kdeep >= 0) atomicMax(p.tile_depth + (size_t)slot * p.tiles + tile, kdeep + 1 - range.x);
     }
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
         const int i = i0 + 2 * s;
         if (j >= p.width || i >= p.height) continue;
         const size_t pid = (size_t)i * p.width + j;
-        p.final_T[SLOT_OBJ * P + pid] = T[s];
-        p.final_idx[SLOT_OBJ * P + pid] = idx[s];
-        p.obj_acc[pid] = 1.f - T[s];
+        p.final_T[slot * P + pid] = T[s];
+        p.final_idx[slot * P + pid] = idx[s];
+        out_acc[pid] = 1.f - T[s];
     }
 }
 
+// blockIdx.y selects the class: 0 background, 1 object
 __global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float2 sB[2][32];
+    const int cls = blockIdx.y;
     const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
-    const int2 range = p.obj_bins[tile];
+    const int2 range = p.cls_bins[cls][tile];
     const int W = strips_for(range.y - range.x);
     if (strip >= W) return;
     switch (W) {
-        case 1: acc_fwd_strip<8>(p, tile, strip, range, sA, sB); break;
-        case 2: acc_fwd_strip<4>(p, tile, strip, range, sA, sB); break;
-        case 4: acc_fwd_strip<2>(p, tile, strip, range, sA, sB); break;
-        default: acc_fwd_strip<1>(p, tile, strip, range, sA, sB); break;
+        case 1: acc_fwd_strip<8>(p, cls, tile, strip, range, sA, sB); break;
+        case 2: acc_fwd_strip<4>(p, cls, tile, strip, range, sA, sB); break;
+        case 4: acc_fwd_strip<2>(p, cls, tile, strip, range, sA, sB); break;
+        default: acc_fwd_strip<1>(p, cls, tile, strip, range, sA, sB); break;
     }
 }
 
@@ -336,14 +323,14 @@ static int check_cam(const sgn_camera* cam) {
 }
 
 extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
-                             const int32_t* sorted_ids, const int32_t* tile_bins, const int32_t* obj_ids,
-                             const int32_t* obj_bins, const float* sky, const sgn_blend_fwd_out* out, void* stream) {
+                             const int32_t* sorted_ids, const int32_t* tile_bins, int64_t M, const int32_t* cls_ids,
+                             const int32_t* cls_bins, const float* sky, const sgn_blend_fwd_out* out, void* stream) {
     if (int rc = check_cam(cam)) return rc;
     SGN_REQUIRE(opts && records && tile_bins && out, "sgn_blend_fwd: null pointer");
     SGN_REQUIRE(out->rgb && out->accumulation && out->depth && out->raw && out->final_T && out->final_idx,
                 "sgn_blend_fwd: null output");
-    SGN_REQUIRE(!opts->class_streams || (out->object_acc && out->background_acc && obj_ids && obj_bins),
-                "class_streams needs object_acc/background_acc outputs and the object sub-lists");
+    SGN_REQUIRE(!opts->class_streams || (out->object_acc && out->background_acc && cls_ids && cls_bins),
+                "class_streams needs object_acc/background_acc outputs and the class sub-lists");
     SGN_REQUIRE(!opts->has_sky || sky, "has_sky set but sky is null");
     SGN_REQUIRE(sgn_aligned16(records) && sgn_aligned16(out->raw), "records / raw must be 16-byte aligned");
     BlendFwdParams p;
@@ -355,27 +342,24 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.records = reinterpret_cast<const float4*>(records);
     p.sorted_ids = sorted_ids;
     p.tile_bins = reinterpret_cast<const int2*>(tile_bins);
-    p.obj_ids = obj_ids;
-    p.obj_bins = reinterpret_cast<const int2*>(obj_bins);
+    const int tiles = p.tiles_x * tiles_y;
+    p.tiles = tiles;
+    p.cls_ids[0] = cls_ids; p.cls_ids[1] = cls_ids ? cls_ids + M : nullptr;
+    p.cls_bins[0] = reinterpret_cast<const int2*>(cls_bins);
+    p.cls_bins[1] = cls_bins ? reinterpret_cast<const int2*>(cls_bins) + tiles : nullptr;
     p.sky = sky;
     p.rgb = out->rgb; p.acc = out->accumulation; p.depth = out->depth;
     p.obj_acc = out->object_acc; p.bg_acc = out->background_acc;
     p.raw = reinterpret_cast<float4*>(out->raw);
     p.final_T = out->final_T; p.final_idx = out->final_idx;
-    const int tiles = p.tiles_x * tiles_y;
-    p.tiles = tiles;
     SGN_REQUIRE(out->tile_depth, "sgn_blend_fwd: tile_depth is null");
     p.tile_depth = out->tile_depth;
-    p.obj_depth = out->tile_depth + tiles;
-    SGN_CHECK_CUDA(cudaMemsetAsync(out->tile_depth, 0, sizeof(int32_t) * 2 * (size_t)tiles, (cudaStream_t)stream));
+    SGN_CHECK_CUDA(cudaMemsetAsync(out->tile_depth, 0, sizeof(int32_t) * 3 * (size_t)tiles, (cudaStream_t)stream));
+    blend_fwd_kernel<<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+    SGN_CHECK_LAUNCH("blend_fwd_kernel");
     if (opts->class_streams) {
-        blend_fwd_kernel<true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
-        SGN_CHECK_LAUNCH("blend_fwd_kernel<bg>");
-        acc_fwd_kernel<<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        acc_fwd_kernel<<<dim3(tiles * 8, 2), 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("acc_fwd_kernel");
-    } else {
-        blend_fwd_kernel<false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
-        SGN_CHECK_LAUNCH("blend_fwd_kernel");
     }
     return SGN_OK;
 }
@@ -385,15 +369,14 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
 // ------------------------------------------------------------------------------------------------
 struct BlendBwdParams {
     int width, height, tiles_x, tiles;
-    const int32_t* tile_depth;
-    const int32_t* obj_depth;
+    const int32_t* tile_depth;  // [3][tiles]
     float clamp_bwd;
     int has_sky, eval_clamp;
     const float4* records;
     const int32_t* sorted_ids;
     const int2* tile_bins;
-    const int32_t* obj_ids;
-    const int2* obj_bins;
+    const int32_t* cls_ids[2];
+    const int2* cls_bins[2];
     const float* v_rgb;
     const float* v_acc;
     const float* v_depth;
@@ -407,8 +390,8 @@ struct BlendBwdParams {
     float* v_records;
 };
 
-// BG: background stream has a cotangent.  DEPTHG: the depth output has a cotangent.
-template <int PPL, bool BG, bool DEPTHG>
+// DEPTHG: the depth output has a cotangent.
+template <int PPL, bool DEPTHG>
 __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int tile, int strip, const int2 range,
                                                 float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -419,26 +402,22 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
     const size_t P = (size_t)p.width * p.height;
 
     // ---- per-pixel prologue: cotangents of the RAW blend outputs from those of the final outputs
-    float T[PPL], tfv[PPL], tfbv[PPL];
+    float T[PPL], tfv[PPL];
     float vr[PPL], vg[PPL], vb[PPL], vd[PPL];
     float br[PPL], bgc[PPL], bb[PPL], bd[PPL];
-    int idx[PPL], idxb[PPL];
+    int idx[PPL];
     int kmax = -1;
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
-        T[s] = 1.f; tfv[s] = 0.f; tfbv[s] = 0.f; vr[s] = vg[s] = vb[s] = vd[s] = 0.f;
+        T[s] = 1.f; tfv[s] = 0.f; vr[s] = vg[s] = vb[s] = vd[s] = 0.f;
         br[s] = bgc[s] = bb[s] = bd[s] = 0.f;
-        idx[s] = -1; idxb[s] = -1;
+        idx[s] = -1;
         const int i = i0 + 2 * s;
         if (j >= p.width || i >= p.height) continue;
         const size_t pid = (size_t)i * p.width + j;
         const float Tf = p.final_T[SLOT_MAIN * P + pid];
         idx[s] = p.final_idx[SLOT_MAIN * P + pid];
         T[s] = Tf;
-        if (BG) {
-            tfbv[s] = p.final_T[SLOT_BG * P + pid] * p.v_bg[pid];
-            idxb[s] = p.final_idx[SLOT_BG * P + pid];
-        }
         const float alpha = 1.f - Tf;
         const float4 raw = p.raw[pid];
         float voa = p.v_acc ? p.v_acc[pid] : 0.f;
@@ -471,7 +450,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             }
         }
         tfv[s] = Tf * voa;
-        kmax = max(kmax, BG ? max(idx[s], idxb[s]) : idx[s]);
+        kmax = max(kmax, idx[s]);
     }
     if (range.y <= range.x) return;  // empty tile (after the prologue: v_sky is written for every pixel)
     const int wkmax = warp_max(kmax);
@@ -491,7 +470,6 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             const float4 A = sA[buf][t];
             const float4 B = sB[buf][t];
             const float4 Cc = sC[buf][t];
-            const bool isobj = __float_as_int(Cc.z) < 0;
             const float dx = A.x - px;
             const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
@@ -502,15 +480,13 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             // straight-line, predicated (see the forward)
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
-                const bool in_main = k <= idx[s];
-                const bool in_bg = BG && !isobj && (k <= idxb[s]);
                 const float dy = dy0 - (float)(2 * s);
                 const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
-                const bool valid = (s2 >= nlo) && (s2 <= LOG2_255) && (in_main || in_bg);
+                const bool valid = (s2 >= nlo) && (s2 <= LOG2_255) && (k <= idx[s]);
                 const float raw = fast_ex2(-s2);            // o * exp(-sigma)
                 const float alpha = fminf(p.clamp_bwd, raw);
                 const float ra = fast_rcp(1.f - alpha);
-                const bool vm = valid && in_main;
+                const bool vm = valid;
                 any = any || valid;
                 const float Tk = vm ? T[s] * ra : T[s];
                 T[s] = Tk;
@@ -524,8 +500,6 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
                     bd[s] = __fmaf_rn(Cc.y, fac, bd[s]);
                 }
                 v_alpha = __fmaf_rn(tfv[s], ra, v_alpha);
-                v_alpha = vm ? v_alpha : 0.f;
-                if (BG) v_alpha = (valid && in_bg) ? __fmaf_rn(tfbv[s], ra, v_alpha) : v_alpha;
                 const float vs = valid ? -raw * v_alpha : 0.f;   // d/d sigma = -o*vis*v_alpha
                 S0 += vs;
                 const float vsy = vs * dy;
@@ -558,7 +532,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
 
 // the prologue (v_sky, cotangent chain) must run for every pixel, so strips are always launched for the
 // whole tile: W strips of 16/W rows
-template <bool BG, bool DEPTHG>
+template <bool DEPTHG>
 __global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
@@ -568,17 +542,20 @@ __global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
     const int W = strips_for(p.tile_depth[tile]);
     if (strip >= W) return;
     switch (W) {
-        case 1: blend_bwd_strip<8, BG, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
-        case 2: blend_bwd_strip<4, BG, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
-        case 4: blend_bwd_strip<2, BG, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
-        default: blend_bwd_strip<1, BG, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
+        case 1: blend_bwd_strip<8, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
+        case 2: blend_bwd_strip<4, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
+        case 4: blend_bwd_strip<2, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
+        default: blend_bwd_strip<1, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
     }
 }
 
 // backward of the accumulation-only pass: out = 1 - T_final  =>  v_alpha_k = T_final * ra_k * v_out
 template <int PPL>
-__device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int tile, int strip, const int2 range,
+__device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, int tile, int strip, const int2 range,
                                               float4 (*sA)[32], float4 (*sB)[32]) {
+    const int32_t* __restrict__ ids = p.cls_ids[cls];
+    const int slot = cls ? SLOT_OBJ : SLOT_BG;
+    const float* __restrict__ v_out = cls ? p.v_obj : p.v_bg;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int lane = threadIdx.x;
     const int j = tx * SGN_TILE + (lane & 15);
@@ -595,20 +572,20 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int tile,
         const int i = i0 + 2 * s;
         if (j >= p.width || i >= p.height) continue;
         const size_t pid = (size_t)i * p.width + j;
-        tfv[s] = p.final_T[SLOT_OBJ * P + pid] * p.v_obj[pid];
-        idx[s] = p.final_idx[SLOT_OBJ * P + pid];
+        tfv[s] = p.final_T[slot * P + pid] * v_out[pid];
+        idx[s] = p.final_idx[slot * P + pid];
         kmax = max(kmax, idx[s]);
     }
     const int wkmax = warp_max(kmax);
     const int hi0 = min(range.y, wkmax + 1);
     if (hi0 <= range.x) return;
     Staged nxt;
-    if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, p.obj_ids[hi0 - 1 - lane]);
+    if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, ids[hi0 - 1 - lane]);
     int buf = 0;
     for (int hi = hi0; hi > range.x; hi -= 32) {
         sA[buf][lane] = nxt.A; sB[buf][lane] = make_float4(nxt.B.x, nxt.B.y, nxt.C.z, nxt.C.w);
         __syncwarp();
-        if (hi - 33 - lane >= range.x) nxt = gather_entry(p.records, p.obj_ids[hi - 33 - lane]);
+        if (hi - 33 - lane >= range.x) nxt = gather_entry(p.records, ids[hi - 33 - lane]);
         const int n = min(32, hi - range.x);
         for (int t = 0; t < n; ++t) {
             const int k = hi - 1 - t;
@@ -654,24 +631,24 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int tile,
     }
 }
 
-__global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p) {
+__global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p, const int cls) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
     const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
-    const int2 range = p.obj_bins[tile];
-    const int W = strips_for(p.obj_depth[tile]);
+    const int2 range = p.cls_bins[cls][tile];
+    const int W = strips_for(p.tile_depth[(size_t)(cls ? SLOT_OBJ : SLOT_BG) * p.tiles + tile]);
     if (strip >= W) return;
     switch (W) {
-        case 1: acc_bwd_strip<8>(p, tile, strip, range, sA, sB); break;
-        case 2: acc_bwd_strip<4>(p, tile, strip, range, sA, sB); break;
-        case 4: acc_bwd_strip<2>(p, tile, strip, range, sA, sB); break;
-        default: acc_bwd_strip<1>(p, tile, strip, range, sA, sB); break;
+        case 1: acc_bwd_strip<8>(p, cls, tile, strip, range, sA, sB); break;
+        case 2: acc_bwd_strip<4>(p, cls, tile, strip, range, sA, sB); break;
+        case 4: acc_bwd_strip<2>(p, cls, tile, strip, range, sA, sB); break;
+        default: acc_bwd_strip<1>(p, cls, tile, strip, range, sA, sB); break;
     }
 }
 
 extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
-                             const int32_t* sorted_ids, const int32_t* tile_bins, const int32_t* obj_ids,
-                             const int32_t* obj_bins, const sgn_blend_bwd_in* in, float* v_records, void* stream_) {
+                             const int32_t* sorted_ids, const int32_t* tile_bins, int64_t M, const int32_t* cls_ids,
+                             const int32_t* cls_bins, const sgn_blend_bwd_in* in, float* v_records, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (int rc = check_cam(cam)) return rc;
     SGN_REQUIRE(opts && records && tile_bins && in && v_records, "sgn_blend_bwd: null pointer");
@@ -679,7 +656,7 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     SGN_REQUIRE(!opts->has_sky || in->sky, "has_sky set but sky is null");
     SGN_REQUIRE(!(in->v_object_acc || in->v_background_acc) || opts->class_streams,
                 "cotangents for object_acc/background_acc need class_streams");
-    SGN_REQUIRE(!in->v_object_acc || (obj_ids && obj_bins), "v_object_acc needs the object sub-lists");
+    SGN_REQUIRE(!(in->v_object_acc || in->v_background_acc) || (cls_ids && cls_bins), "class cotangents need the class sub-lists");
     SGN_REQUIRE(sgn_aligned16(records) && sgn_aligned16(in->raw), "records / raw must be 16-byte aligned");
     BlendBwdParams p;
     p.width = cam->width; p.height = cam->height;
@@ -690,29 +667,29 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.records = reinterpret_cast<const float4*>(records);
     p.sorted_ids = sorted_ids;
     p.tile_bins = reinterpret_cast<const int2*>(tile_bins);
-    p.obj_ids = obj_ids;
-    p.obj_bins = reinterpret_cast<const int2*>(obj_bins);
+    const int tiles = p.tiles_x * tiles_y;
+    p.tiles = tiles;
+    p.cls_ids[0] = cls_ids; p.cls_ids[1] = cls_ids ? cls_ids + M : nullptr;
+    p.cls_bins[0] = reinterpret_cast<const int2*>(cls_bins);
+    p.cls_bins[1] = cls_bins ? reinterpret_cast<const int2*>(cls_bins) + tiles : nullptr;
     p.v_rgb = in->v_rgb; p.v_acc = in->v_accumulation; p.v_depth = in->v_depth;
     p.v_obj = in->v_object_acc; p.v_bg = in->v_background_acc;
     p.raw = reinterpret_cast<const float4*>(in->raw);
     p.final_T = in->final_T; p.final_idx = in->final_idx;
     p.sky = in->sky; p.v_sky = in->v_sky;
     p.v_records = v_records;
-    const int tiles = p.tiles_x * tiles_y;
-    p.tiles = tiles;
     SGN_REQUIRE(in->tile_depth, "sgn_blend_bwd: tile_depth (saved by the forward) is null");
     p.tile_depth = in->tile_depth;
-    p.obj_depth = in->tile_depth + tiles;
-    const bool bg = opts->class_streams && in->v_background_acc;
-    const bool dg = in->v_depth != nullptr;
-    if (bg && dg) blend_bwd_kernel<true, true><<<tiles * 8, 32, 0, stream>>>(p);
-    else if (bg) blend_bwd_kernel<true, false><<<tiles * 8, 32, 0, stream>>>(p);
-    else if (dg) blend_bwd_kernel<false, true><<<tiles * 8, 32, 0, stream>>>(p);
-    else blend_bwd_kernel<false, false><<<tiles * 8, 32, 0, stream>>>(p);
+    if (in->v_depth) blend_bwd_kernel<true><<<tiles * 8, 32, 0, stream>>>(p);
+    else blend_bwd_kernel<false><<<tiles * 8, 32, 0, stream>>>(p);
     SGN_CHECK_LAUNCH("blend_bwd_kernel");
     if (in->v_object_acc) {
-        acc_bwd_kernel<<<tiles * 8, 32, 0, stream>>>(p);
-        SGN_CHECK_LAUNCH("acc_bwd_kernel");
+        acc_bwd_kernel<<<tiles * 8, 32, 0, stream>>>(p, 1);
+        SGN_CHECK_LAUNCH("acc_bwd_kernel<object>");
+    }
+    if (in->v_background_acc) {
+        acc_bwd_kernel<<<tiles * 8, 32, 0, stream>>>(p, 0);
+        SGN_CHECK_LAUNCH("acc_bwd_kernel<background>");
     }
     return SGN_OK;
 }

@@ -186,16 +186,17 @@ ID_MASK = 0x7FFFFFFF  # sorted payload: bits 0-30 Gaussian row, bit 31 object cl
 
 
 def class_lists(cs: _lib.CameraStruct, M: int, sorted_ids, tile_bins):
-    """Per-tile object sub-lists (stable compaction of the sorted list).  Returns (obj_ids, obj_bins)."""
+    """Per-tile class sub-lists (stable partition of the sorted list into background / object entries).
+    Returns (cls_ids[2,M], cls_bins[2,tiles,2])."""
     L = _lib.load()
     device = sorted_ids.device
     tiles = tile_bins.shape[0]
-    obj_ids = torch.empty(max(M, 1), device=device, dtype=torch.int32)
-    obj_bins = torch.empty(tiles, 2, device=device, dtype=torch.int32)
+    obj_ids = torch.empty(2, max(M, 1), device=device, dtype=torch.int32)
+    obj_bins = torch.empty(2, tiles, 2, device=device, dtype=torch.int32)
     sb = L.sgn_bin_class_scratch_bytes(tiles)
     scratch = torch.empty(sb, device=device, dtype=torch.uint8)
     with _timed("class_lists"):
-        _lib.check(L.sgn_bin_class_lists(C.byref(cs), _ptr(sorted_ids), _ptr(tile_bins), _ptr(obj_ids), _ptr(obj_bins),
+        _lib.check(L.sgn_bin_class_lists(C.byref(cs), max(M, 1), _ptr(sorted_ids), _ptr(tile_bins), _ptr(obj_ids), _ptr(obj_bins),
                                          _ptr(scratch), sb, _stream()), "sgn_bin_class_lists")
     return obj_ids, obj_bins
 
@@ -216,7 +217,7 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
         rgb=torch.empty(H, W, 3, device=device), accumulation=torch.empty(H, W, 1, device=device),
         depth=torch.empty(H, W, 1, device=device), raw=torch.empty(H, W, 4, device=device),
         final_T=torch.empty(S, H, W, device=device), final_idx=torch.empty(S, H, W, device=device, dtype=torch.int32),
-        tile_depth=torch.empty(2, tile_bins.shape[0], device=device, dtype=torch.int32))
+        tile_depth=torch.empty(3, tile_bins.shape[0], device=device, dtype=torch.int32))
     if bo.class_streams:
         out["object_acc"] = torch.empty(H, W, 1, device=device)
         out["background_acc"] = torch.empty(H, W, 1, device=device)
@@ -228,7 +229,8 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
     fo.tile_depth = out["tile_depth"].data_ptr()
     with _timed("blend_fwd"):
         _lib.check(L.sgn_blend_fwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins),
-                                   _ptr(obj_ids), _ptr(obj_bins), _ptr(sky), C.byref(fo), _stream()), "sgn_blend_fwd")
+                                   max(sorted_ids.shape[0], 1), _ptr(obj_ids), _ptr(obj_bins), _ptr(sky), C.byref(fo), _stream()),
+                   "sgn_blend_fwd")
     return out
 
 
@@ -256,7 +258,8 @@ def blend_bwd(cs, bo, records, sorted_ids, tile_bins, saved: Dict[str, torch.Ten
     bi.v_sky = v_sky.data_ptr() if v_sky is not None else None
     with _timed("blend_bwd"):
         _lib.check(L.sgn_blend_bwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins),
-                                   _ptr(obj_ids), _ptr(obj_bins), C.byref(bi), _ptr(v_records), _stream()), "sgn_blend_bwd")
+                                   max(sorted_ids.shape[0], 1), _ptr(obj_ids), _ptr(obj_bins), C.byref(bi), _ptr(v_records), _stream()),
+                   "sgn_blend_bwd")
     return v_records, v_sky
 
 
