@@ -36,6 +36,10 @@
 #define SLOT_MAIN 0
 #define SLOT_OBJ 1
 #define SLOT_BG 2
+// background slot of final_idx: a pixel whose main stream met no valid object entry has a background
+// accumulation bit-identical to its main accumulation (same alphas, same order, same products)
+#define BG_SAME_AS_MAIN (-2)  // written by the main forward: T/idx/background_acc already final
+#define BG_TODO (-3)          // an object entry took part: the background pass must traverse this pixel
 
 struct BlendFwdParams {
     int width, height, tiles_x, tiles;
@@ -109,7 +113,7 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // number of strips (warps) a tile is split into, from the length of the list it has to traverse
 __device__ __forceinline__ int strips_for(int len) { return len <= 384 ? 1 : (len <= 768 ? 2 : (len <= 1536 ? 4 : 8)); }
 
-template <int PPL>
+template <int PPL, bool CLS>
 __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int tile, int strip, const int2 range,
                                                 float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -121,7 +125,7 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
 
     float T[PPL], pr[PPL], pg[PPL], pb[PPL], pd[PPL];
     int idx[PPL];
-    unsigned done = 0;
+    unsigned done = 0, objhit = 0;
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
         T[s] = 1.f; pr[s] = pg[s] = pb[s] = pd[s] = 0.f;
@@ -144,6 +148,7 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
             const float4 A = sA[buf][t];
             const float4 B = sB[buf][t];
             const float4 Cc = sC[buf][t];
+            const bool isobj = CLS && (__float_as_int(Cc.z) < 0);
             const float dx = A.x - px;
             const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
@@ -167,6 +172,7 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
                 T[s] = upd ? nT : T[s];
                 idx[s] = upd ? k : idx[s];
                 done |= stop ? (1u << s) : 0u;
+                if (CLS) objhit |= (act && isobj) ? (1u << s) : 0u;
             }
         }
         buf ^= 1;
@@ -202,11 +208,17 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
         p.depth[pid] = alpha > 1e-3f ? pd[s] / alpha : 10.f;  // sgn_splatfacto.py:995
         p.final_T[SLOT_MAIN * P + pid] = T[s];
         p.final_idx[SLOT_MAIN * P + pid] = idx[s];
+        if (CLS) {
+            const bool hit = (objhit >> s) & 1u;
+            p.final_idx[SLOT_BG * P + pid] = hit ? BG_TODO : BG_SAME_AS_MAIN;
+            if (!hit) { p.final_T[SLOT_BG * P + pid] = T[s]; p.bg_acc[pid] = alpha; }
+        }
     }
 }
 
 // grid = tiles x 8 one-warp CTAs: block b -> strip b / tiles of tile b % tiles; strips beyond the
 // tile's split exit at once (registers are per CTA, so they cost nothing once gone)
+template <bool CLS>
 __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
@@ -216,10 +228,10 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     const int W = strips_for(range.y - range.x);
     if (strip >= W) return;
     switch (W) {
-        case 1: blend_fwd_strip<8>(p, tile, strip, range, sA, sB, sC); break;
-        case 2: blend_fwd_strip<4>(p, tile, strip, range, sA, sB, sC); break;
-        case 4: blend_fwd_strip<2>(p, tile, strip, range, sA, sB, sC); break;
-        default: blend_fwd_strip<1>(p, tile, strip, range, sA, sB, sC); break;
+        case 1: blend_fwd_strip<8, CLS>(p, tile, strip, range, sA, sB, sC); break;
+        case 2: blend_fwd_strip<4, CLS>(p, tile, strip, range, sA, sB, sC); break;
+        case 4: blend_fwd_strip<2, CLS>(p, tile, strip, range, sA, sB, sC); break;
+        default: blend_fwd_strip<1, CLS>(p, tile, strip, range, sA, sB, sC); break;
     }
 }
 
@@ -238,12 +250,18 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
     constexpr unsigned ALL = (1u << PPL) - 1u;
     float T[PPL];
     int idx[PPL];
-    unsigned done = 0;
+    unsigned done = 0, skip = 0;
+    const size_t P = (size_t)p.width * p.height;
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
         T[s] = 1.f; idx[s] = -1;
-        if (!((j < p.width) && (i0 + 2 * s < p.height))) done |= 1u << s;
+        const int i = i0 + 2 * s;
+        if (!((j < p.width) && (i < p.height))) { done |= 1u << s; skip |= 1u << s; }
+        else if (cls == 0 && p.final_idx[SLOT_BG * P + (size_t)i * p.width + j] != BG_TODO) {
+            done |= 1u << s; skip |= 1u << s;  // the main forward already wrote this pixel's background result
+        }
     }
+    if (__all_sync(FULL, skip == ALL)) return;
     Staged nxt;
     if (range.x + lane < range.y) nxt = gather_entry(p.records, ids[range.x + lane]);
     int buf = 0;
@@ -279,7 +297,6 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
         }
         buf ^= 1;
     }
-    const size_t P = (size_t)p.width * p.height;
     {
         int kdeep = -1;
 #pragma unroll
@@ -290,7 +307,7 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
         const int i = i0 + 2 * s;
-        if (j >= p.width || i >= p.height) continue;
+        if ((skip >> s) & 1u) continue;
         const size_t pid = (size_t)i * p.width + j;
         p.final_T[slot * P + pid] = T[s];
         p.final_idx[slot * P + pid] = idx[s];
@@ -355,7 +372,8 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     SGN_REQUIRE(out->tile_depth, "sgn_blend_fwd: tile_depth is null");
     p.tile_depth = out->tile_depth;
     SGN_CHECK_CUDA(cudaMemsetAsync(out->tile_depth, 0, sizeof(int32_t) * 3 * (size_t)tiles, (cudaStream_t)stream));
-    blend_fwd_kernel<<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+    if (opts->class_streams) blend_fwd_kernel<true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+    else blend_fwd_kernel<false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
     SGN_CHECK_LAUNCH("blend_fwd_kernel");
     if (opts->class_streams) {
         acc_fwd_kernel<<<dim3(tiles * 8, 2), 32, 0, (cudaStream_t)stream>>>(p);
@@ -421,6 +439,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
         const float alpha = 1.f - Tf;
         const float4 raw = p.raw[pid];
         float voa = p.v_acc ? p.v_acc[pid] : 0.f;
+        if (p.v_bg && p.final_idx[SLOT_BG * P + pid] == BG_SAME_AS_MAIN) voa += p.v_bg[pid];  // background_acc == accumulation here
         if (p.v_rgb) {
             float v[3] = {p.v_rgb[3 * pid], p.v_rgb[3 * pid + 1], p.v_rgb[3 * pid + 2]};
             const float rr[3] = {raw.x, raw.y, raw.z};

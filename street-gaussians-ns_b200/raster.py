@@ -105,40 +105,67 @@ def _check_param(t: torch.Tensor, name: str, device) -> None:
         raise _lib.SgnError(f"{name} must be 16-byte aligned")
 
 
+SEG_DTYPE = np.dtype([
+    ("row0", "<i4"), ("count", "<i4"), ("F", "<i4"), ("cls", "<i4"), ("has_pose", "<i4"), ("pad0", "<i4"),
+    ("R", "<f4", (9,)), ("t", "<f4", (3,)), ("q", "<f4", (4,)), ("idft", "<f4", (8,)),
+    ("means", "<u8"), ("scales", "<u8"), ("quats", "<u8"), ("features_dc", "<u8"), ("features_rest", "<u8"),
+    ("opacities", "<u8")])
+assert SEG_DTYPE.itemsize == C.sizeof(_lib.Segment), "numpy mirror of sgn_segment is out of sync"
+
+_STATIC_CACHE: Dict[tuple, dict] = {}
+
+
 class SegmentTable:
-    """Host array of sgn_segment + its device copy."""
+    """Host array of sgn_segment (numpy mirror of the C struct) + its device copy.
+
+    The per-model part (pointers, row offsets, shapes; validated once) is cached on the parameter
+    storage addresses; per frame only the poses and the IDFT bases are rewritten."""
 
     def __init__(self, frame: Frame, params: List[List[torch.Tensor]], device):
         n = len(frame.segments)
-        self.host = (_lib.Segment * n)()
-        row = 0
-        for i, (seg, ps) in enumerate(zip(frame.segments, params)):
-            sg = self.host[i]
-            means, scales, quats, dc, rest, opac = ps
-            for t, nm in zip(ps, PARAM_NAMES):
-                _check_param(t, f"segment {i} {nm}", device)
-            sg.row0, sg.count, sg.F, sg.cls, sg.has_pose = row, means.shape[0], dc.shape[1], seg.cls, int(seg.has_pose)
+        ptrs = tuple(t.data_ptr() for ps in params for t in ps)
+        key = (ptrs, tuple(ps[0].shape[0] for ps in params), tuple(ps[3].shape[1] for ps in params),
+               tuple(ps[4].shape[1] for ps in params), str(device))
+        st = _STATIC_CACHE.get(key)
+        if st is None:
+            for i, ps in enumerate(params):
+                for t, nm in zip(ps, PARAM_NAMES):
+                    _check_param(t, f"segment {i} {nm}", device)
+            host = np.zeros(n, SEG_DTYPE)
+            counts = np.array([ps[0].shape[0] for ps in params], np.int64)
+            host["count"] = counts
+            host["row0"] = np.concatenate([[0], np.cumsum(counts)[:-1]])
+            host["F"] = [ps[3].shape[1] for ps in params]
+            P = np.array(ptrs, np.uint64).reshape(n, 6)
+            for c, nm in enumerate(PARAM_NAMES):
+                host[nm] = P[:, c]
+            sizes = [[(t.numel() + 3) // 4 * 4 for t in ps] for ps in params]
+            st = dict(host=host, N=int(counts.sum()), sizes=sizes, shapes=[[tuple(t.shape) for t in ps] for ps in params])
+            if len(_STATIC_CACHE) > 64:
+                _STATIC_CACHE.clear()
+            _STATIC_CACHE[key] = st
+        host = st["host"].copy()
+        host["cls"] = [s.cls for s in frame.segments]
+        host["has_pose"] = [int(s.has_pose) for s in frame.segments]
+        for i, seg in enumerate(frame.segments):
             R, t, q = seg.pose_f32()
-            sg.R[:] = R.tolist()
-            sg.t[:] = t.tolist()
-            sg.q[:] = q.tolist()
-            sg.idft[:] = seg.idft_f32().tolist()
-            sg.means, sg.scales, sg.quats = means.data_ptr(), scales.data_ptr(), quats.data_ptr()
-            sg.features_dc, sg.features_rest, sg.opacities = dc.data_ptr(), rest.data_ptr(), opac.data_ptr()
-            row += means.shape[0]
-        self.N = row
+            host["R"][i], host["t"][i], host["q"][i] = R, t, q
+            host["idft"][i] = seg.idft_f32()
+        self.host = host
+        self.N = st["N"]
         self.nseg = n
-        raw = np.frombuffer(bytes(self.host), dtype=np.uint8)
-        self.dev = torch.from_numpy(raw.copy()).to(device)
+        self.static = st
+        self.dev = torch.from_numpy(host.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
 
 
-def _grads_table(grads: List[List[torch.Tensor]], device) -> torch.Tensor:
-    arr = (_lib.SegmentGrads * len(grads))()
-    for i, gs in enumerate(grads):
-        (arr[i].means, arr[i].scales, arr[i].quats, arr[i].features_dc, arr[i].features_rest,
-         arr[i].opacities) = [g.data_ptr() for g in gs]
-    raw = np.frombuffer(bytes(arr), dtype=np.uint8)
-    return torch.from_numpy(raw.copy()).to(device)
+def _grads_table(arena: torch.Tensor, static: dict, device) -> torch.Tensor:
+    """sgn_segment_grads rows: pointers into the flat gradient arena (offsets are static per model)."""
+    off = static.get("grad_offsets")
+    if off is None:
+        flat = np.array([x for ss in static["sizes"] for x in ss], np.uint64)
+        off = static["grad_offsets"] = (np.concatenate([[0], np.cumsum(flat)[:-1]]) * 4).astype(np.uint64)
+    tab = (np.uint64(arena.data_ptr()) + off).view(np.uint8)
+    return torch.from_numpy(tab).to(device, non_blocking=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -267,20 +294,21 @@ def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, recor
     """Dense parameter gradients, one flat arena (a single allocation, 16-byte aligned slices)."""
     L = _lib.load()
     device = records.device
-    sizes = [[(t.numel() + 3) // 4 * 4 for t in ps] for ps in params]
-    arena = torch.empty(sum(sum(s) for s in sizes), device=device, dtype=torch.float32)
-    grads, off = [], 0
-    for ps, ss in zip(params, sizes):
-        gs = []
-        for t, n in zip(ps, ss):
-            gs.append(arena[off: off + t.numel()].view(t.shape))
-            off += n
-        grads.append(gs)
-    gt = _grads_table(grads, device)
+    st = table.static
+    flat_sizes = st.get("flat_sizes")
+    if flat_sizes is None:
+        flat_sizes = st["flat_sizes"] = [x for ss in st["sizes"] for x in ss]
+        st["flat_shapes"] = [x for ss in st["shapes"] for x in ss]
+        st["flat_numel"] = [int(np.prod(x)) for x in st["flat_shapes"]]
+    arena = torch.empty(sum(flat_sizes), device=device, dtype=torch.float32)
+    chunks = arena.split_with_sizes(flat_sizes)
+    flat = [c[:n].view(shp) if n != c.shape[0] else c.view(shp)
+            for c, n, shp in zip(chunks, st["flat_numel"], st["flat_shapes"])]
+    gt = _grads_table(arena, st, device)
     with _timed("project_bwd"):
         _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, C.byref(cs), _ptr(records), _ptr(radii),
                                      _ptr(v_records), _stream()), "sgn_project_bwd")
-    return grads, arena
+    return flat, arena
 
 
 # --------------------------------------------------------------------------------------------------
@@ -343,7 +371,7 @@ class _SceneGraphRasterize(torch.autograd.Function):
         vd = {k: t for k, t in zip(names, v)}
         v_records, v_sky = blend_bwd(ctx.cs, ctx.bo, ctx.records, ctx.sorted_ids, ctx.tile_bins, ctx.saved, ctx.sky, vd,
                                      ctx.sky_needs_grad, ctx.obj_ids, ctx.obj_bins)
-        grads, arena = project_bwd(ctx.table, ctx.params, ctx.cs, ctx.records, ctx.radii, v_records)
+        flat, arena = project_bwd(ctx.table, ctx.params, ctx.cs, ctx.records, ctx.radii, v_records)
         h = ctx.holder
         h.v_records, h.grad_arena = v_records, arena
         # the reference reads ``self.xys.grad`` after backward (densification statistics,
@@ -351,7 +379,6 @@ class _SceneGraphRasterize(torch.autograd.Function):
         h.xys.grad = v_records[:, 0:2]
         if h.post_backward is not None:
             h.post_backward(h)
-        flat = [g for gs in grads for g in gs]
         return (None, None, None, v_sky, *flat)
 
 

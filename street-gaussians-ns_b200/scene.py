@@ -77,6 +77,21 @@ class GaussianSet:
 
 
 def idft_basis(time: float, dim: int) -> np.ndarray:
+    """Cached front of :func:`_idft_basis` (all actors of a frame share the same few time values)."""
+    key = (float(time), int(dim))
+    hit = _IDFT_CACHE.get(key)
+    if hit is None:
+        if len(_IDFT_CACHE) > 4096:
+            _IDFT_CACHE.clear()
+        hit = _IDFT_CACHE[key] = _idft_basis(*key)
+    return hit
+
+
+_IDFT_CACHE: dict = {}
+_POSE_CACHE: dict = {}
+
+
+def _idft_basis(time: float, dim: int) -> np.ndarray:
     """The reference's ``IDFT`` (street_gaussians_ns/sgn_splatfacto_scene_graph.py:420-433).
 
     basis[k] = cos(2*pi*t*k/dim) for even k, sin(2*pi*t*(k+1)/dim) for odd k, evaluated in float32
@@ -153,12 +168,14 @@ class Segment:
                 np.array([1, 0, 0, 0], dtype=np.float32),
             )
         R = np.asarray(self.rot, dtype=np.float64)
-        q = quaternion_from_matrix(R)
-        return (
-            R.astype(np.float32).reshape(-1),
-            np.asarray(self.center, dtype=np.float64).astype(np.float32),
-            q.astype(np.float32),
-        )
+        # box rotations are static per (frame, actor): cache the eigen-decomposition based quaternion
+        key = R.tobytes()
+        hit = _POSE_CACHE.get(key)
+        if hit is None:
+            if len(_POSE_CACHE) > 65536:
+                _POSE_CACHE.clear()
+            hit = _POSE_CACHE[key] = (R.astype(np.float32).reshape(-1), quaternion_from_matrix(R).astype(np.float32))
+        return (hit[0], np.asarray(self.center, dtype=np.float64).astype(np.float32), hit[1])
 
     def idft_f32(self) -> np.ndarray:
         F = self.params.fourier_dim
@@ -197,6 +214,15 @@ class Camera:
 
     def viewmat(self) -> np.ndarray:
         """World->camera 3x4, float32 (street_gaussians_ns/sgn_splatfacto.py:825-836)."""
+        key = self.c2w.tobytes()
+        cached = getattr(self, "_vm_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        vm = self._viewmat()
+        self._vm_cache = (key, vm)
+        return vm
+
+    def _viewmat(self) -> np.ndarray:
         c2w = torch.from_numpy(self.c2w)
         R = c2w[:3, :3]
         T = c2w[:3, 3:4]
