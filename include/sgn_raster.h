@@ -102,6 +102,9 @@ typedef struct sgn_blend_opts {
                               (get_submodel_output, sgn_splatfacto_scene_graph.py:364-366) */
     int32_t has_sky;       /* rgb = rgb*alpha + sky*(1-alpha) (sgn_splatfacto.py:971-972) */
     int32_t eval_clamp;    /* not training: rgb.clamp(0,1) (:974-975) */
+    /* tuning (0 = default): list length / traversal depth up to which one warp renders a whole tile;
+     * each doubling splits the tile into 2/4/8 row strips rendered by independent warps */
+    int32_t split_fwd_main, split_fwd_acc, split_bwd_main, split_bwd_acc;
 } sgn_blend_opts;
 
 const char* sgn_last_error(void);

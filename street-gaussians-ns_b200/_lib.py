@@ -52,6 +52,8 @@ class BlendOpts(C.Structure):
     _fields_ = [
         ("alpha_clamp_fwd", C.c_float), ("alpha_clamp_bwd", C.c_float),
         ("class_streams", C.c_int32), ("has_sky", C.c_int32), ("eval_clamp", C.c_int32),
+        ("split_fwd_main", C.c_int32), ("split_fwd_acc", C.c_int32), ("split_bwd_main", C.c_int32),
+        ("split_bwd_acc", C.c_int32),
     ]
 
 

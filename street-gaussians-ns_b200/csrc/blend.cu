@@ -43,6 +43,7 @@
 
 struct BlendFwdParams {
     int width, height, tiles_x, tiles;
+    int split_main, split_acc;  // list length up to which a tile is one strip (doubles per extra split)
     int32_t* tile_depth;  // [3][tiles] entries traversed per tile by the main / object / background pass (atomicMax)
     float clamp_fwd;
     int has_sky, eval_clamp;
@@ -111,7 +112,7 @@ __device__ __forceinline__ float fast_ex2(float x) {
 }
 
 // number of strips (warps) a tile is split into, from the length of the list it has to traverse
-__device__ __forceinline__ int strips_for(int len) { return len <= 384 ? 1 : (len <= 768 ? 2 : (len <= 1536 ? 4 : 8)); }
+__device__ __forceinline__ int strips_for(int len, int t1) { return len <= t1 ? 1 : (len <= 2 * t1 ? 2 : (len <= 4 * t1 ? 4 : 8)); }
 
 template <int PPL, bool CLS>
 __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int tile, int strip, const int2 range,
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     __shared__ float4 sC[2][32];
     const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
     const int2 range = p.tile_bins[tile];
-    const int W = strips_for(range.y - range.x);
+    const int W = strips_for(range.y - range.x, p.split_main);
     if (strip >= W) return;
     switch (W) {
         case 1: blend_fwd_strip<8, CLS>(p, tile, strip, range, sA, sB, sC); break;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p) {
     const int cls = blockIdx.y;
     const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
     const int2 range = p.cls_bins[cls][tile];
-    const int W = strips_for(range.y - range.x);
+    const int W = strips_for(range.y - range.x, p.split_acc);
     if (strip >= W) return;
     switch (W) {
         case 1: acc_fwd_strip<8>(p, cls, tile, strip, range, sA, sB); break;
@@ -355,6 +356,8 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.tiles_x = (cam->width + SGN_TILE - 1) / SGN_TILE;
     const int tiles_y = (cam->height + SGN_TILE - 1) / SGN_TILE;
     p.clamp_fwd = opts->alpha_clamp_fwd;
+    p.split_main = opts->split_fwd_main > 0 ? opts->split_fwd_main : 1024;
+    p.split_acc = opts->split_fwd_acc > 0 ? opts->split_fwd_acc : 512;
     p.has_sky = opts->has_sky; p.eval_clamp = opts->eval_clamp;
     p.records = reinterpret_cast<const float4*>(records);
     p.sorted_ids = sorted_ids;
@@ -387,6 +390,7 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
 // ------------------------------------------------------------------------------------------------
 struct BlendBwdParams {
     int width, height, tiles_x, tiles;
+    int split_main, split_acc;
     const int32_t* tile_depth;  // [3][tiles]
     float clamp_bwd;
     int has_sky, eval_clamp;
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
     __shared__ float4 sC[2][32];
     const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
     const int2 range = p.tile_bins[tile];
-    const int W = strips_for(p.tile_depth[tile]);
+    const int W = strips_for(p.tile_depth[tile], p.split_main);
     if (strip >= W) return;
     switch (W) {
         case 1: blend_bwd_strip<8, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
@@ -655,7 +659,7 @@ __global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p, con
     __shared__ float4 sB[2][32];
     const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
     const int2 range = p.cls_bins[cls][tile];
-    const int W = strips_for(p.tile_depth[(size_t)(cls ? SLOT_OBJ : SLOT_BG) * p.tiles + tile]);
+    const int W = strips_for(p.tile_depth[(size_t)(cls ? SLOT_OBJ : SLOT_BG) * p.tiles + tile], p.split_acc);
     if (strip >= W) return;
     switch (W) {
         case 1: acc_bwd_strip<8>(p, cls, tile, strip, range, sA, sB); break;
@@ -682,6 +686,8 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.tiles_x = (cam->width + SGN_TILE - 1) / SGN_TILE;
     const int tiles_y = (cam->height + SGN_TILE - 1) / SGN_TILE;
     p.clamp_bwd = opts->alpha_clamp_bwd;
+    p.split_main = opts->split_bwd_main > 0 ? opts->split_bwd_main : 384;
+    p.split_acc = opts->split_bwd_acc > 0 ? opts->split_bwd_acc : 384;
     p.has_sky = opts->has_sky; p.eval_clamp = opts->eval_clamp;
     p.records = reinterpret_cast<const float4*>(records);
     p.sorted_ids = sorted_ids;

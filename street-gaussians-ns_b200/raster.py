@@ -232,6 +232,11 @@ def blend_opts(s: RenderSettings, has_sky: bool) -> _lib.BlendOpts:
     bo = _lib.BlendOpts()
     bo.alpha_clamp_fwd, bo.alpha_clamp_bwd = s.alpha_clamp_fwd, s.alpha_clamp_bwd
     bo.class_streams, bo.has_sky, bo.eval_clamp = int(s.class_streams), int(has_sky), int(not s.training)
+    import os
+    bo.split_fwd_main = int(os.environ.get("SGN_SPLIT_FWD_MAIN", "0"))
+    bo.split_fwd_acc = int(os.environ.get("SGN_SPLIT_FWD_ACC", "0"))
+    bo.split_bwd_main = int(os.environ.get("SGN_SPLIT_BWD_MAIN", "0"))
+    bo.split_bwd_acc = int(os.environ.get("SGN_SPLIT_BWD_ACC", "0"))
     return bo
 
 
