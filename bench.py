@@ -178,7 +178,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import street_gaussians_ns_b200.synthetic as syn
-    from street_gaussians_ns_b200 import _lib, raster
+    from street_gaussians_ns_b200 import _lib, dp, raster
     from street_gaussians_ns_b200.model import ActorPose, SceneGraphConfig, SceneGraphRasterModel
     from street_gaussians_ns_b200.scene import CLS_OBJECT, Frame, Segment
 
@@ -207,8 +207,7 @@ def run_ours(args):
         out, holder = raster.render_frame(frc, settings)
         torch.autograd.backward([out["rgb"], out["accumulation"], out["object_acc"]],
                                 [w, v[..., None], vo[..., None]])
-        if world > 1:  # camera-sharded DP: sum the flat per-Gaussian gradient arena
-            dist.all_reduce(holder.grad_arena)
+        dp.allreduce_gradients(holder.grad_arena)  # camera-sharded DP: one SUM over the flat arena
         for t in leaves:
             t.grad = None
         return holder
@@ -265,8 +264,7 @@ def run_ours(args):
         losses = model.get_loss_dict(out, {"image": gt})
         loss = sum(losses.values())
         loss.backward()
-        if world > 1:
-            dist.all_reduce(model._holder.grad_arena)
+        dp.allreduce_gradients(model._holder.grad_arena)
         val = float(loss.item())
         for p in mparams:
             p.grad = None

@@ -105,6 +105,10 @@ typedef struct sgn_blend_opts {
     /* tuning (0 = default): list length / traversal depth up to which one warp renders a whole tile;
      * each doubling splits the tile into 2/4/8 row strips rendered by independent warps */
     int32_t split_fwd_main, split_fwd_acc, split_bwd_main, split_bwd_acc;
+    /* raw mode (gsplat rasterize_gaussians semantics, Level-1 shim): no post-ops; the four blended
+     * channels come back as out = sum(c*alpha*T) + T_final*background[c] in rgb[...,0:3] and depth */
+    int32_t raw_mode;
+    float background[4];
 } sgn_blend_opts;
 
 const char* sgn_last_error(void);
@@ -136,6 +140,21 @@ int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, const sgn_came
 int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N,
                     const sgn_camera* cam, const float* records, const int32_t* radii,
                     const float* v_records, void* stream);
+
+/* ---- Level-1: gsplat 0.1.x function API on plain tensors (sgn_splatfacto.py:11-14) -------------------
+ * gsplat.project_gaussians(means3d, scales, glob_scale, quats, viewmat, fx, fy, cx, cy, H, W, block_width,
+ * clip_thresh) -> xys[N,2], depths[N], radii[N] i32, conics[N,3], compensation[N], num_tiles_hit[N] i32,
+ * cov3d[N,6]   (call site sgn_splatfacto.py:860-873), and its backward (cotangent pointers may be NULL). */
+int sgn_l1_project_fwd(int N, const float* means, const float* scales, float glob_scale, const float* quats,
+                       const sgn_camera* cam, float* xys, float* depths, int32_t* radii, float* conics,
+                       float* compensation, int32_t* num_tiles_hit, float* cov3d, void* stream);
+int sgn_l1_project_bwd(int N, const float* means, const float* scales, float glob_scale, const float* quats,
+                       const sgn_camera* cam, const int32_t* radii, const float* v_xys, const float* v_depths,
+                       const float* v_conics, float* v_means, float* v_scales, float* v_quats, void* stream);
+/* gsplat.spherical_harmonics(degrees_to_use, viewdirs[N,3], coeffs[N,K,3]) (call site :939): forward when
+ * `colors` is non-NULL, backward (v_coeffs = Y_k * v_colors) when `v_coeffs` is non-NULL. */
+int sgn_l1_sh(int N, int K, int degree, const float* viewdirs, const float* coeffs, const float* v_colors,
+              float* colors, float* v_coeffs, void* stream);
 
 /* ---- binning: cumulative intersects, key emit, radix sort, tile bin edges ---------------------
  * Replaces the inside of gsplat rasterize_gaussians: compute_cumulative_intersects,

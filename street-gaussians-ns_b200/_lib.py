@@ -54,6 +54,7 @@ class BlendOpts(C.Structure):
         ("class_streams", C.c_int32), ("has_sky", C.c_int32), ("eval_clamp", C.c_int32),
         ("split_fwd_main", C.c_int32), ("split_fwd_acc", C.c_int32), ("split_bwd_main", C.c_int32),
         ("split_bwd_acc", C.c_int32),
+        ("raw_mode", C.c_int32), ("background", C.c_float * 4),
     ]
 
 
@@ -78,7 +79,7 @@ _lib = None
 
 EXPORTS = [
     "sgn_last_error", "sgn_abi_version", "sgn_launch_count", "sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera",
-    "sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
+    "sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_l1_project_fwd", "sgn_l1_project_bwd", "sgn_l1_sh", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
     "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_bin_class_scratch_bytes", "sgn_bin_class_lists",
     "sgn_blend_fwd", "sgn_blend_bwd",
 ]
@@ -103,6 +104,12 @@ def load():
     L.sgn_upload.argtypes = [vp, sz, vp, vp]
     L.sgn_project_fwd.argtypes = [vp, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp]
     L.sgn_project_bwd.argtypes = [vp, vp, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp]
+    fl = C.c_float
+    L.sgn_l1_project_fwd.argtypes = [i32, vp, vp, fl, vp, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sgn_l1_project_bwd.argtypes = [i32, vp, vp, fl, vp, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sgn_l1_sh.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    for f in ("sgn_l1_project_fwd", "sgn_l1_project_bwd", "sgn_l1_sh"):
+        getattr(L, f).restype = C.c_int
     L.sgn_bin_scan_scratch_bytes.argtypes = [i32]
     L.sgn_bin_scan_scratch_bytes.restype = sz
     L.sgn_bin_scan.argtypes = [i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, sz, vp]

@@ -46,7 +46,8 @@ struct BlendFwdParams {
     int split_main, split_acc;  // list length up to which a tile is one strip (doubles per extra split)
     int32_t* tile_depth;  // [3][tiles] entries traversed per tile by the main / object / background pass (atomicMax)
     float clamp_fwd;
-    int has_sky, eval_clamp;
+    int has_sky, eval_clamp, raw_mode;
+    float bg[4];
     const float4* records;
     const int32_t* sorted_ids;
     const int2* tile_bins;
@@ -193,6 +194,15 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
         const size_t pid = (size_t)i * p.width + j;
         const float alpha = 1.f - T[s];
         p.raw[pid] = make_float4(pr[s], pg[s], pb[s], pd[s]);
+        if (p.raw_mode) {  // gsplat rasterize_gaussians: out = blended + T_final * background
+            p.rgb[3 * pid] = pr[s] + T[s] * p.bg[0]; p.rgb[3 * pid + 1] = pg[s] + T[s] * p.bg[1];
+            p.rgb[3 * pid + 2] = pb[s] + T[s] * p.bg[2];
+            p.depth[pid] = pd[s] + T[s] * p.bg[3];
+            p.acc[pid] = alpha;
+            p.final_T[SLOT_MAIN * P + pid] = T[s];
+            p.final_idx[SLOT_MAIN * P + pid] = idx[s];
+            continue;
+        }
         // post-ops (sgn_splatfacto.py:968-975): clamp(max=1), sky blend (premultiplied rgb times alpha again), eval clamp
         float r = fminf(pr[s], 1.f), g = fminf(pg[s], 1.f), bl = fminf(pb[s], 1.f);
         if (p.has_sky) {
@@ -358,7 +368,8 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.clamp_fwd = opts->alpha_clamp_fwd;
     p.split_main = opts->split_fwd_main > 0 ? opts->split_fwd_main : 1024;
     p.split_acc = opts->split_fwd_acc > 0 ? opts->split_fwd_acc : 512;
-    p.has_sky = opts->has_sky; p.eval_clamp = opts->eval_clamp;
+    p.has_sky = opts->has_sky; p.eval_clamp = opts->eval_clamp; p.raw_mode = opts->raw_mode;
+    for (int c = 0; c < 4; ++c) p.bg[c] = opts->background[c];
     p.records = reinterpret_cast<const float4*>(records);
     p.sorted_ids = sorted_ids;
     p.tile_bins = reinterpret_cast<const int2*>(tile_bins);
@@ -393,7 +404,8 @@ struct BlendBwdParams {
     int split_main, split_acc;
     const int32_t* tile_depth;  // [3][tiles]
     float clamp_bwd;
-    int has_sky, eval_clamp;
+    int has_sky, eval_clamp, raw_mode;
+    float bg[4];
     const float4* records;
     const int32_t* sorted_ids;
     const int2* tile_bins;
@@ -444,7 +456,13 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
         const float4 raw = p.raw[pid];
         float voa = p.v_acc ? p.v_acc[pid] : 0.f;
         if (p.v_bg && p.final_idx[SLOT_BG * P + pid] == BG_SAME_AS_MAIN) voa += p.v_bg[pid];  // background_acc == accumulation here
-        if (p.v_rgb) {
+        if (p.raw_mode) {  // out_c = blended_c + (1 - alpha) * bg_c
+            if (p.v_rgb) {
+                vr[s] = p.v_rgb[3 * pid]; vg[s] = p.v_rgb[3 * pid + 1]; vb[s] = p.v_rgb[3 * pid + 2];
+                voa -= p.bg[0] * vr[s] + p.bg[1] * vg[s] + p.bg[2] * vb[s];
+            }
+            if (DEPTHG) { vd[s] = p.v_depth[pid]; voa -= p.bg[3] * vd[s]; }
+        } else if (p.v_rgb) {
             float v[3] = {p.v_rgb[3 * pid], p.v_rgb[3 * pid + 1], p.v_rgb[3 * pid + 2]};
             const float rr[3] = {raw.x, raw.y, raw.z};
             float vraw[3];
@@ -465,7 +483,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             }
             vr[s] = vraw[0]; vg[s] = vraw[1]; vb[s] = vraw[2];
         }
-        if (DEPTHG) {
+        if (DEPTHG && !p.raw_mode) {
             if (alpha > 1e-3f) {
                 const float vdep = p.v_depth[pid];
                 vd[s] = vdep / alpha;
@@ -688,7 +706,8 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.clamp_bwd = opts->alpha_clamp_bwd;
     p.split_main = opts->split_bwd_main > 0 ? opts->split_bwd_main : 384;
     p.split_acc = opts->split_bwd_acc > 0 ? opts->split_bwd_acc : 384;
-    p.has_sky = opts->has_sky; p.eval_clamp = opts->eval_clamp;
+    p.has_sky = opts->has_sky; p.eval_clamp = opts->eval_clamp; p.raw_mode = opts->raw_mode;
+    for (int c = 0; c < 4; ++c) p.bg[c] = opts->background[c];
     p.records = reinterpret_cast<const float4*>(records);
     p.sorted_ids = sorted_ids;
     p.tile_bins = reinterpret_cast<const int2*>(tile_bins);

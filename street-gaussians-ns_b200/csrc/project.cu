@@ -138,6 +138,95 @@ extern "C" int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, con
     return SGN_OK;
 }
 
+// geometry backward shared by the fused and the Level-1 kernels: cotangents of (xy, depth, conic) ->
+// (world mean, scale as used [st.s], composed quaternion qr)
+__device__ __forceinline__ void sgn_project_vjp(const sgn_camera& cam, const SgnProj& st, const float v_xy[2], float v_depth,
+                                                const float v_conic[3], float vmw[3], float vs[3], float vqr[4]) {
+    const float* W = cam.viewmat;
+    const float fx = cam.fx, fy = cam.fy;
+    float vpv[3];
+    {
+        const float rw = 1.f / (st.pv[2] + 1e-6f);
+        const float vx = fx * v_xy[0], vy = fy * v_xy[1];
+        vpv[0] = vx * rw;
+        vpv[1] = vy * rw;
+        vpv[2] = -(vx * st.pv[0] + vy * st.pv[1]) * rw * rw + v_depth;
+    }
+    float vA, vB, vC;
+    {
+        const float X0 = st.conic[0], X1 = st.conic[1], X2 = st.conic[2];
+        const float G0 = v_conic[0], G1 = 0.5f * v_conic[1], G2 = v_conic[2];
+        const float a00 = X0 * G0 + X1 * G1, a01 = X0 * G1 + X1 * G2;
+        const float a10 = X1 * G0 + X2 * G1, a11 = X1 * G1 + X2 * G2;
+        vA = -(a00 * X0 + a01 * X1);
+        vB = -(a00 * X1 + a01 * X2) - (a10 * X0 + a11 * X1);
+        vC = -(a10 * X1 + a11 * X2);
+    }
+    const float g00 = vA, g01 = 0.5f * vB, g11 = vC;
+    const float* T = st.T;
+    const float Sf[9] = {st.S[0], st.S[1], st.S[2], st.S[1], st.S[3], st.S[4], st.S[2], st.S[4], st.S[5]};
+    float GT[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        GT[c] = g00 * T[c] + g01 * T[3 + c];
+        GT[3 + c] = g01 * T[c] + g11 * T[3 + c];
+    }
+    float vS[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vS[3 * r + c] = T[r] * GT[c] + T[3 + r] * GT[3 + c];
+    float vT[6];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            vT[3 * r + c] = 2.f * (GT[3 * r] * Sf[c] + GT[3 * r + 1] * Sf[3 + c] + GT[3 * r + 2] * Sf[6 + c]);
+    const float vJ00 = vT[0] * W[0] + vT[1] * W[1] + vT[2] * W[2];
+    const float vJ02 = vT[0] * W[8] + vT[1] * W[9] + vT[2] * W[10];
+    const float vJ11 = vT[3] * W[4] + vT[4] * W[5] + vT[5] * W[6];
+    const float vJ12 = vT[3] * W[8] + vT[4] * W[9] + vT[5] * W[10];
+    {
+        const float rz = 1.f / st.pv[2], rz2 = rz * rz, rz3 = rz2 * rz;
+        const float vtx = -fx * rz2 * vJ02;
+        const float vty = -fy * rz2 * vJ12;
+        const float vtz = -fx * rz2 * vJ00 - fy * rz2 * vJ11 + 2.f * fx * st.tx * rz3 * vJ02 + 2.f * fy * st.ty * rz3 * vJ12;
+        if (st.clampx == 0) vpv[0] += vtx; else vpv[2] += (st.clampx > 0 ? cam.limx : -cam.limx) * vtx;
+        if (st.clampy == 0) vpv[1] += vty; else vpv[2] += (st.clampy > 0 ? cam.limy : -cam.limy) * vty;
+        vpv[2] += vtz;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) vmw[c] = W[c] * vpv[0] + W[4 + c] * vpv[1] + W[8 + c] * vpv[2];
+    float M[9], vM[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) M[3 * r + c] = st.Rg[3 * r + c] * st.s[c];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            vM[3 * r + c] = 2.f * (vS[3 * r] * M[c] + vS[3 * r + 1] * M[3 + c] + vS[3 * r + 2] * M[6 + c]);
+    float vR[9];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        vs[c] = st.Rg[c] * vM[c] + st.Rg[3 + c] * vM[3 + c] + st.Rg[6 + c] * vM[6 + c];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) vR[3 * r + c] = vM[3 * r + c] * st.s[c];
+    }
+    float vqn[4];
+    {
+        const float w = st.qn[0], x = st.qn[1], y = st.qn[2], z = st.qn[3];
+        vqn[0] = 2.f * (x * (vR[7] - vR[5]) + y * (vR[2] - vR[6]) + z * (vR[3] - vR[1]));
+        vqn[1] = 2.f * (-2.f * x * (vR[4] + vR[8]) + y * (vR[1] + vR[3]) + z * (vR[2] + vR[6]) + w * (vR[7] - vR[5]));
+        vqn[2] = 2.f * (x * (vR[1] + vR[3]) - 2.f * y * (vR[0] + vR[8]) + z * (vR[5] + vR[7]) + w * (vR[2] - vR[6]));
+        vqn[3] = 2.f * (x * (vR[2] + vR[6]) + y * (vR[5] + vR[7]) - 2.f * z * (vR[0] + vR[4]) + w * (vR[3] - vR[1]));
+    }
+    const float dot = vqn[0] * st.qn[0] + vqn[1] * st.qn[1] + vqn[2] * st.qn[2] + vqn[3] * st.qn[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) vqr[k] = (vqn[k] - st.qn[k] * dot) / st.qnorm;
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
@@ -218,111 +307,22 @@ project_bwd_kernel(const sgn_segment* __restrict__ segs, const sgn_segment_grads
 
     float gm[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
     if (vis && radii[g] > 0) {
-        const float* W = cam.viewmat;
-        const float fx = cam.fx, fy = cam.fy;
-        float vpv[3];
-        {
-            const float rw = 1.f / (st.pv[2] + 1e-6f);
-            const float vx = fx * v_xy[0], vy = fy * v_xy[1];
-            vpv[0] = vx * rw;
-            vpv[1] = vy * rw;
-            vpv[2] = -(vx * st.pv[0] + vy * st.pv[1]) * rw * rw + v_depth;
-        }
-        float vA, vB, vC;
-        {
-            const float X0 = st.conic[0], X1 = st.conic[1], X2 = st.conic[2];
-            const float G0 = v_conic[0], G1 = 0.5f * v_conic[1], G2 = v_conic[2];
-            const float a00 = X0 * G0 + X1 * G1, a01 = X0 * G1 + X1 * G2;
-            const float a10 = X1 * G0 + X2 * G1, a11 = X1 * G1 + X2 * G2;
-            const float s00 = -(a00 * X0 + a01 * X1);
-            const float s01 = -(a00 * X1 + a01 * X2);
-            const float s10 = -(a10 * X0 + a11 * X1);
-            const float s11 = -(a10 * X1 + a11 * X2);
-            vA = s00; vB = s01 + s10; vC = s11;
-        }
-        const float g00 = vA, g01 = 0.5f * vB, g11 = vC;
-        const float* T = st.T;
-        const float Sf[9] = {st.S[0], st.S[1], st.S[2], st.S[1], st.S[3], st.S[4], st.S[2], st.S[4], st.S[5]};
-        float GT[6];
+        float vmw[3], vs[3], vqr[4];
+        sgn_project_vjp(cam, st, v_xy, v_depth, v_conic, vmw, vs, vqr);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            GT[c] = g00 * T[c] + g01 * T[3 + c];
-            GT[3 + c] = g01 * T[c] + g11 * T[3 + c];
-        }
-        float vS[9];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) vS[3 * r + c] = T[r] * GT[c] + T[3 + r] * GT[3 + c];
-        float vT[6];
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                vT[3 * r + c] = 2.f * (GT[3 * r] * Sf[c] + GT[3 * r + 1] * Sf[3 + c] + GT[3 * r + 2] * Sf[6 + c]);
-        const float vJ00 = vT[0] * W[0] + vT[1] * W[1] + vT[2] * W[2];
-        const float vJ02 = vT[0] * W[8] + vT[1] * W[9] + vT[2] * W[10];
-        const float vJ11 = vT[3] * W[4] + vT[4] * W[5] + vT[5] * W[6];
-        const float vJ12 = vT[3] * W[8] + vT[4] * W[9] + vT[5] * W[10];
-        {
-            const float rz = 1.f / st.pv[2], rz2 = rz * rz, rz3 = rz2 * rz;
-            const float vtx = -fx * rz2 * vJ02;
-            const float vty = -fy * rz2 * vJ12;
-            const float vtz = -fx * rz2 * vJ00 - fy * rz2 * vJ11 + 2.f * fx * st.tx * rz3 * vJ02 + 2.f * fy * st.ty * rz3 * vJ12;
-            if (st.clampx == 0) vpv[0] += vtx; else vpv[2] += (st.clampx > 0 ? cam.limx : -cam.limx) * vtx;
-            if (st.clampy == 0) vpv[1] += vty; else vpv[2] += (st.clampy > 0 ? cam.limy : -cam.limy) * vty;
-            vpv[2] += vtz;
-        }
-        float vmw[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) vmw[c] = W[c] * vpv[0] + W[4 + c] * vpv[1] + W[8 + c] * vpv[2];
+        for (int c = 0; c < 3; ++c) gs[c] = vs[c] * st.s[c];  // through exp
         if (sg.has_pose) {
             const float* R = sg.R;
 #pragma unroll
             for (int c = 0; c < 3; ++c) gm[c] = R[c] * vmw[0] + R[3 + c] * vmw[1] + R[6 + c] * vmw[2];
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) gm[c] = vmw[c];
-        }
-        float M[9], vM[9];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) M[3 * r + c] = st.Rg[3 * r + c] * st.s[c];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                vM[3 * r + c] = 2.f * (vS[3 * r] * M[c] + vS[3 * r + 1] * M[3 + c] + vS[3 * r + 2] * M[6 + c]);
-        float vR[9];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float vs = st.Rg[c] * vM[c] + st.Rg[3 + c] * vM[3 + c] + st.Rg[6 + c] * vM[6 + c];
-            gs[c] = vs * st.s[c];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) vR[3 * r + c] = vM[3 * r + c] * st.s[c];
-        }
-        float vqn[4];
-        {
-            const float w = st.qn[0], x = st.qn[1], y = st.qn[2], z = st.qn[3];
-            vqn[0] = 2.f * (x * (vR[7] - vR[5]) + y * (vR[2] - vR[6]) + z * (vR[3] - vR[1]));
-            vqn[1] = 2.f * (-2.f * x * (vR[4] + vR[8]) + y * (vR[1] + vR[3]) + z * (vR[2] + vR[6]) + w * (vR[7] - vR[5]));
-            vqn[2] = 2.f * (x * (vR[1] + vR[3]) - 2.f * y * (vR[0] + vR[8]) + z * (vR[5] + vR[7]) + w * (vR[2] - vR[6]));
-            vqn[3] = 2.f * (x * (vR[2] + vR[6]) + y * (vR[5] + vR[7]) - 2.f * z * (vR[0] + vR[4]) + w * (vR[3] - vR[1]));
-        }
-        float vqr[4];
-        {
-            const float dot = vqn[0] * st.qn[0] + vqn[1] * st.qn[1] + vqn[2] * st.qn[2] + vqn[3] * st.qn[3];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) vqr[k] = (vqn[k] - st.qn[k] * dot) / st.qnorm;
-        }
-        if (sg.has_pose) {
             const float aw = sg.q[0], ax = sg.q[1], ay = sg.q[2], az = sg.q[3];
             gq[0] = aw * vqr[0] + ax * vqr[1] + ay * vqr[2] + az * vqr[3];
             gq[1] = -ax * vqr[0] + aw * vqr[1] + az * vqr[2] - ay * vqr[3];
             gq[2] = -ay * vqr[0] - az * vqr[1] + aw * vqr[2] + ax * vqr[3];
             gq[3] = -az * vqr[0] + ay * vqr[1] - ax * vqr[2] + aw * vqr[3];
         } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gm[c] = vmw[c];
 #pragma unroll
             for (int k = 0; k < 4; ++k) gq[k] = vqr[k];
         }
@@ -344,5 +344,133 @@ extern "C" int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_gr
         segs_dev, grads_dev, nseg, N, *cam, reinterpret_cast<const float4*>(records), radii,
         reinterpret_cast<const float4*>(v_records));
     SGN_CHECK_LAUNCH("project_bwd_kernel");
+    return SGN_OK;
+}
+
+// ================================================================================================
+// Level-1 entry points: gsplat 0.1.x function API (project_gaussians / spherical_harmonics) on plain
+// tensors, for the reference's unmodified model code (street_gaussians_ns/sgn_splatfacto.py:11-14,
+// 860-873, 939).  Same device functions as the fused path.
+// ================================================================================================
+__global__ void __launch_bounds__(PROJ_THREADS)
+l1_project_fwd_kernel(int N, const float* __restrict__ means, const float* __restrict__ scales, float glob_scale,
+                      const float* __restrict__ quats, const sgn_camera cam, float* __restrict__ xys,
+                      float* __restrict__ depths, int32_t* __restrict__ radii, float* __restrict__ conics,
+                      float* __restrict__ comp, int32_t* __restrict__ num_tiles_hit, float* __restrict__ cov3d) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    sgn_segment sg;
+    sg.has_pose = 0;
+    const float m[3] = {means[3 * g], means[3 * g + 1], means[3 * g + 2]};
+    const float sc[3] = {scales[3 * g], scales[3 * g + 1], scales[3 * g + 2]};
+    const float q[4] = {quats[4 * g], quats[4 * g + 1], quats[4 * g + 2], quats[4 * g + 3]};
+    SgnProj st;
+    const bool vis = sgn_project_exact(sg, cam, m, sc, q, st, false, glob_scale);
+    const bool clipped = st.pv[2] <= cam.clip_thresh;
+    xys[2 * g] = st.xy[0]; xys[2 * g + 1] = st.xy[1];
+    depths[g] = vis ? st.pv[2] : 0.f;
+    radii[g] = st.radius;
+    conics[3 * g] = st.conic[0]; conics[3 * g + 1] = st.conic[1]; conics[3 * g + 2] = st.conic[2];
+    num_tiles_hit[g] = vis ? (st.tmax[0] - st.tmin[0]) * (st.tmax[1] - st.tmin[1]) : 0;
+    float c = 0.f;
+    if (vis) {
+        const float det_orig = (st.a - 0.3f) * (st.c - 0.3f) - st.b * st.b;
+        const float det_blur = st.a * st.c - st.b * st.b;
+        c = sqrtf(fmaxf(0.f, det_orig / det_blur));
+    }
+    comp[g] = c;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cov3d[6 * g + k] = clipped ? 0.f : st.S[k];
+}
+
+extern "C" int sgn_l1_project_fwd(int N, const float* means, const float* scales, float glob_scale, const float* quats,
+                                  const sgn_camera* cam, float* xys, float* depths, int32_t* radii, float* conics,
+                                  float* compensation, int32_t* num_tiles_hit, float* cov3d, void* stream) {
+    SGN_REQUIRE(means && scales && quats && cam && xys && depths && radii && conics && compensation && num_tiles_hit && cov3d,
+                "sgn_l1_project_fwd: null pointer");
+    SGN_REQUIRE(cam->block_width >= 2 && cam->block_width <= 16, "block_width must be between 2 and 16 (got %d)", cam->block_width);
+    if (N == 0) return SGN_OK;
+    l1_project_fwd_kernel<<<(N + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, 0, (cudaStream_t)stream>>>(
+        N, means, scales, glob_scale, quats, *cam, xys, depths, radii, conics, compensation, num_tiles_hit, cov3d);
+    SGN_CHECK_LAUNCH("l1_project_fwd_kernel");
+    return SGN_OK;
+}
+
+__global__ void __launch_bounds__(PROJ_THREADS)
+l1_project_bwd_kernel(int N, const float* __restrict__ means, const float* __restrict__ scales, float glob_scale,
+                      const float* __restrict__ quats, const sgn_camera cam, const int32_t* __restrict__ radii,
+                      const float* __restrict__ v_xys, const float* __restrict__ v_depths, const float* __restrict__ v_conics,
+                      float* __restrict__ v_means, float* __restrict__ v_scales, float* __restrict__ v_quats) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    float gm[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+    if (radii[g] > 0) {
+        sgn_segment sg;
+        sg.has_pose = 0;
+        const float m[3] = {means[3 * g], means[3 * g + 1], means[3 * g + 2]};
+        const float sc[3] = {scales[3 * g], scales[3 * g + 1], scales[3 * g + 2]};
+        const float q[4] = {quats[4 * g], quats[4 * g + 1], quats[4 * g + 2], quats[4 * g + 3]};
+        SgnProj st;
+        if (sgn_project_exact(sg, cam, m, sc, q, st, false, glob_scale)) {
+            const float vxy[2] = {v_xys ? v_xys[2 * g] : 0.f, v_xys ? v_xys[2 * g + 1] : 0.f};
+            const float vc[3] = {v_conics ? v_conics[3 * g] : 0.f, v_conics ? v_conics[3 * g + 1] : 0.f,
+                                 v_conics ? v_conics[3 * g + 2] : 0.f};
+            float vs[3];
+            sgn_project_vjp(cam, st, vxy, v_depths ? v_depths[g] : 0.f, vc, gm, vs, gq);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gs[k] = vs[k] * glob_scale;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { v_means[3 * g + k] = gm[k]; v_scales[3 * g + k] = gs[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v_quats[4 * g + k] = gq[k];
+}
+
+extern "C" int sgn_l1_project_bwd(int N, const float* means, const float* scales, float glob_scale, const float* quats,
+                                  const sgn_camera* cam, const int32_t* radii, const float* v_xys, const float* v_depths,
+                                  const float* v_conics, float* v_means, float* v_scales, float* v_quats, void* stream) {
+    SGN_REQUIRE(means && scales && quats && cam && radii && v_means && v_scales && v_quats, "sgn_l1_project_bwd: null pointer");
+    if (N == 0) return SGN_OK;
+    l1_project_bwd_kernel<<<(N + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, 0, (cudaStream_t)stream>>>(
+        N, means, scales, glob_scale, quats, *cam, radii, v_xys, v_depths, v_conics, v_means, v_scales, v_quats);
+    SGN_CHECK_LAUNCH("l1_project_bwd_kernel");
+    return SGN_OK;
+}
+
+// gsplat spherical_harmonics(degrees_to_use, viewdirs[N,3], coeffs[N,K,3]) -> colors[N,3]
+__global__ void __launch_bounds__(PROJ_THREADS)
+l1_sh_kernel(int N, int K, int degree, const float* __restrict__ viewdirs, const float* __restrict__ coeffs,
+             const float* __restrict__ v_colors, float* __restrict__ colors, float* __restrict__ v_coeffs) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    float Y[16];
+    sgn_sh_basis(degree, viewdirs[3 * g], viewdirs[3 * g + 1], viewdirs[3 * g + 2], Y);
+    const int Kuse = min((degree + 1) * (degree + 1), K);
+    if (colors) {
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < Kuse; ++k)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) acc[ch] += Y[k] * coeffs[((size_t)g * K + k) * 3 + ch];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) colors[3 * g + ch] = acc[ch];
+    }
+    if (v_coeffs) {
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) v_coeffs[((size_t)g * K + k) * 3 + ch] = (k < Kuse) ? Y[k] * v_colors[3 * g + ch] : 0.f;
+    }
+}
+
+extern "C" int sgn_l1_sh(int N, int K, int degree, const float* viewdirs, const float* coeffs, const float* v_colors,
+                         float* colors, float* v_coeffs, void* stream) {
+    SGN_REQUIRE(viewdirs && (colors || v_coeffs), "sgn_l1_sh: null pointer");
+    SGN_REQUIRE(degree >= 0 && degree <= 3 && K >= 1 && K <= 16, "sgn_l1_sh: degree must be in [0,3], K in [1,16]");
+    SGN_REQUIRE(!colors || coeffs, "sgn_l1_sh: forward needs coeffs");
+    SGN_REQUIRE(!v_coeffs || v_colors, "sgn_l1_sh: backward needs v_colors");
+    if (N == 0) return SGN_OK;
+    l1_sh_kernel<<<(N + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, 0, (cudaStream_t)stream>>>(
+        N, K, degree, viewdirs, coeffs, v_colors, colors, v_coeffs);
+    SGN_CHECK_LAUNCH("l1_sh_kernel");
     return SGN_OK;
 }

@@ -56,8 +56,11 @@ __device__ __forceinline__ int sgn_f2i_sat(float x) {
 }
 
 // Returns st.visible.  `m`, `ls`, `q` are this Gaussian's raw parameters.
+// log_scales: `ls` holds log-scales (the model's parameters) -> exp is applied here; otherwise `ls` holds
+// activated scales (gsplat's project_gaussians argument) multiplied by glob_scale.
 __device__ __forceinline__ bool sgn_project_exact(const sgn_segment& sg, const sgn_camera& cam, const float m[3],
-                                                  const float ls[3], const float q[4], SgnProj& st) {
+                                                  const float ls[3], const float q[4], SgnProj& st,
+                                                  const bool log_scales = true, const float glob_scale = 1.f) {
     const float* W = cam.viewmat;
     st.visible = false;
     st.radius = 0;
@@ -91,7 +94,7 @@ __device__ __forceinline__ bool sgn_project_exact(const sgn_segment& sg, const s
         for (int k = 0; k < 4; ++k) st.qn[k] = st.qr[k] / st.qnorm;
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) st.s[k] = sgn_expf_exact(ls[k]);
+    for (int k = 0; k < 3; ++k) st.s[k] = log_scales ? sgn_expf_exact(ls[k]) : ls[k] * glob_scale;
     {
         const float w = st.qn[0], x = st.qn[1], y = st.qn[2], z = st.qn[3];
         float* R = st.Rg;
