@@ -110,6 +110,12 @@ def cpu_frame_fn(cfg: int):
     import numpy as np
     import street_gaussians_ns_b200.synthetic as syn
     from oracle import oracle_c  # the one place bench.py may execute oracle/: as the timed CPU baseline
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core it is allowed to
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    oracle_c.lib().sgn_oracle_set_threads(ncpu)
     fr = syn.config_frame(cfg)
     orc = oracle_c.Oracle(fr)
     H, W = fr.camera.height, fr.camera.width

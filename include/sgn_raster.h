@@ -57,7 +57,7 @@ typedef struct sgn_segment {
     int32_t F;        /* fourier_features_dim of features_dc (1..8)            (:239-247) */
     int32_t cls;      /* 0 background, 1 object                                 (:364-366) */
     int32_t has_pose; /* apply R,t,q  (object2world_gs, :404-417)                          */
-    int32_t pad0;
+    int32_t chunk0;   /* index of this segment's first 128-row chunk: sum over earlier segments of ceil(count/128) */
     float R[9];       /* object->world rotation, row-major (Box.rot cast to fp32, :411)    */
     float t[3];       /* Box.center cast to fp32 (:410)                                    */
     float q[4];       /* quaternion_from_matrix(rot), wxyz (:413)                          */
@@ -128,8 +128,9 @@ int sgn_upload(const void* host, size_t bytes, void* dev, void* stream);
  * (sgn_splatfacto.py:857-858,864), gsplat project_gaussians (:860-873), view directions +
  * spherical_harmonics + clamp (:934-940) and sigmoid(opacities) (:946-949).
  * Outputs: records[N,12] (layout above), radii[N] i32, num_tiles_hit[N] i32, tile_bbox[N] (4 x u16:
- * xmin,ymin,xmax,ymax in tiles). */
-int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, const sgn_camera* cam,
+ * xmin,ymin,xmax,ymax in tiles).  Work is split into 128-row chunks that never straddle segments:
+ * num_chunks = sum over segments of ceil(count/128), sgn_segment.chunk0 = the segment's first chunk. */
+int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, int num_chunks, const sgn_camera* cam,
                     float* records, int32_t* radii, int32_t* num_tiles_hit, uint16_t* tile_bbox,
                     void* stream);
 
@@ -137,7 +138,7 @@ int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, const sgn_came
  * ([0:2] v_xy, [2:5] v_conic, [5] v_opacity, [6:9] v_rgb, [9] v_depth), as accumulated by
  * sgn_blend_bwd.  Writes dense parameter gradients for every segment.
  * Replaces gsplat project_gaussians backward + compute_sh_backward + autograd of the glue. */
-int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N,
+int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N, int num_chunks,
                     const sgn_camera* cam, const float* records, const int32_t* radii,
                     const float* v_records, void* stream);
 

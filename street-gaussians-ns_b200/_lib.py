@@ -21,7 +21,7 @@ class SgnError(RuntimeError):
 class Segment(C.Structure):
     _fields_ = [
         ("row0", C.c_int32), ("count", C.c_int32), ("F", C.c_int32), ("cls", C.c_int32),
-        ("has_pose", C.c_int32), ("pad0", C.c_int32),
+        ("has_pose", C.c_int32), ("chunk0", C.c_int32),
         ("R", C.c_float * 9), ("t", C.c_float * 3), ("q", C.c_float * 4), ("idft", C.c_float * MAX_FOURIER),
         ("means", C.c_void_p), ("scales", C.c_void_p), ("quats", C.c_void_p),
         ("features_dc", C.c_void_p), ("features_rest", C.c_void_p), ("opacities", C.c_void_p),
@@ -102,8 +102,8 @@ def load():
     for f in ("sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera"):
         getattr(L, f).restype = sz
     L.sgn_upload.argtypes = [vp, sz, vp, vp]
-    L.sgn_project_fwd.argtypes = [vp, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp]
-    L.sgn_project_bwd.argtypes = [vp, vp, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp]
+    L.sgn_project_fwd.argtypes = [vp, i32, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp]
+    L.sgn_project_bwd.argtypes = [vp, vp, i32, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp]
     fl = C.c_float
     L.sgn_l1_project_fwd.argtypes = [i32, vp, vp, fl, vp, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp]
     L.sgn_l1_project_bwd.argtypes = [i32, vp, vp, fl, vp, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp]

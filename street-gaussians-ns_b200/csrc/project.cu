@@ -33,36 +33,82 @@ extern "C" int sgn_upload(const void* host, size_t bytes, void* dev, void* strea
 }
 
 // ------------------------------------------------------------------------------------------------
-// segment lookup: rows of a block may straddle sub-models; the row0 table lives in shared memory
+// Work decomposition: 128-row chunks that never straddle a sub-model (sgn_segment.chunk0 = first chunk
+// of the segment).  A chunk's slice of every parameter tensor is CONTIGUOUS in HBM (rows*12 B of means,
+// rows*180 B of features_rest, ...), so the block stages it into shared memory with coalesced 128-bit
+// loads and each thread then walks its own row at a bank-conflict-free odd word stride; the backward
+// stages the dense gradient rows the same way in the other direction.
 // ------------------------------------------------------------------------------------------------
 #define SGN_MAX_SEGMENTS 1024
-#define PROJ_THREADS 256
+#define PROJ_THREADS 256  // Level-1 kernels
+#define CH 128            // rows per chunk == threads per block of the fused kernels
+#define MAX_REST 45       // (4^2 - 1) * 3
+#define MAX_DC (3 * SGN_MAX_FOURIER)
 
-__device__ __forceinline__ int find_segment(const int* s_row0, int nseg, int g) {
+__device__ __forceinline__ int find_segment_by_chunk(const int* s_chunk0, int nseg, int c) {
     int lo = 0, hi = nseg - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (s_row0[mid] <= g) lo = mid; else hi = mid - 1;
+        if (s_chunk0[mid] <= c) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
 
-__global__ void __launch_bounds__(PROJ_THREADS)
-project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, int N, const sgn_camera cam,
+// global -> shared, n floats, all threads of the block participate
+__device__ __forceinline__ void coop_load(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const int n4 = n >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+        for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+}
+// shared -> global
+__device__ __forceinline__ void coop_store(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const int n4 = n >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = s4[i];
+        for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+__global__ void __launch_bounds__(CH)
+project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, const sgn_camera cam,
                    float4* __restrict__ records, int32_t* __restrict__ radii, int32_t* __restrict__ num_tiles_hit,
                    ushort4* __restrict__ tile_bbox) {
-    extern __shared__ int s_row0[];
-    for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_row0[i] = segs[i].row0;
+    extern __shared__ int s_chunk0[];
+    __shared__ __align__(16) float s_rest[CH * MAX_REST];
+    __shared__ __align__(16) float s_dc[CH * MAX_DC];
+    __shared__ __align__(16) float s_means[CH * 3];
+    __shared__ __align__(16) float s_scales[CH * 3];
+    for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_chunk0[i] = segs[i].chunk0;
     __syncthreads();
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= N) return;
-    const int si = find_segment(s_row0, nseg, g);
+    const int si = find_segment_by_chunk(s_chunk0, nseg, blockIdx.x);
     const sgn_segment& sg = segs[si];
-    const int i = g - sg.row0;
+    const int r0 = (blockIdx.x - sg.chunk0) * CH;
+    const int rows = min(CH, sg.count - r0);
+    const int K = (cam.sh_degree + 1) * (cam.sh_degree + 1);
+    const int nrest = (K - 1) * 3, ndc = sg.F * 3;
+    coop_load(s_means, sg.means + 3 * (size_t)r0, rows * 3);
+    coop_load(s_scales, sg.scales + 3 * (size_t)r0, rows * 3);
+    coop_load(s_dc, sg.features_dc + (size_t)r0 * ndc, rows * ndc);
+    if (cam.sh_degree > 0) coop_load(s_rest, sg.features_rest + (size_t)r0 * nrest, rows * nrest);
+    __syncthreads();
+    const int tid = threadIdx.x;
+    if (tid >= rows) return;
+    const int i = r0 + tid;
+    const size_t g = (size_t)sg.row0 + i;
 
-    float m[3], ls[3], q[4];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { m[k] = __ldg(sg.means + 3 * (size_t)i + k); ls[k] = __ldg(sg.scales + 3 * (size_t)i + k); }
+    const float m[3] = {s_means[3 * tid], s_means[3 * tid + 1], s_means[3 * tid + 2]};
+    const float ls[3] = {s_scales[3 * tid], s_scales[3 * tid + 1], s_scales[3 * tid + 2]};
+    float q[4];
     {
         const float4 qq = __ldg(reinterpret_cast<const float4*>(sg.quats) + i);
         q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
@@ -71,12 +117,11 @@ project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, int N, const 
     const bool vis = sgn_project_exact(sg, cam, m, ls, q, st);
 
     // colour: Fourier DC (scene graph :239-247), SH (sgn_splatfacto.py:933-940)
-    const int K = (cam.sh_degree + 1) * (cam.sh_degree + 1);
     float c0[3] = {0.f, 0.f, 0.f};
     for (int f = 0; f < sg.F; ++f) {
         const float w = sg.idft[f];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) c0[ch] += __ldg(sg.features_dc + ((size_t)i * sg.F + f) * 3 + ch) * w;
+        for (int ch = 0; ch < 3; ++ch) c0[ch] += s_dc[tid * ndc + f * 3 + ch] * w;
     }
     float rgb[3];
     int aux = 0;
@@ -88,10 +133,10 @@ project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, int N, const 
         sgn_sh_basis(cam.sh_degree_to_use, d[0], d[1], d[2], Y);
         const int Kuse = min((cam.sh_degree_to_use + 1) * (cam.sh_degree_to_use + 1), K);
         float acc[3] = {Y[0] * c0[0], Y[0] * c0[1], Y[0] * c0[2]};
-        const float* rest = sg.features_rest + (size_t)i * (K - 1) * 3;
+        const float* rest = s_rest + tid * nrest;
         for (int k = 1; k < Kuse; ++k) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) acc[ch] += Y[k] * __ldg(rest + (k - 1) * 3 + ch);
+            for (int ch = 0; ch < 3; ++ch) acc[ch] += Y[k] * rest[(k - 1) * 3 + ch];
         }
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
@@ -107,7 +152,7 @@ project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, int N, const 
     if (sg.cls == 1) aux |= SGN_AUX_OBJECT;
     if (vis) aux |= SGN_AUX_VISIBLE;
 
-    float4* rec = records + 3 * (size_t)g;
+    float4* rec = records + 3 * g;
     rec[0] = make_float4(st.xy[0], st.xy[1], st.conic[0], st.conic[1]);
     rec[1] = make_float4(st.conic[2], opac, rgb[0], rgb[1]);
     rec[2] = make_float4(rgb[2], vis ? st.pv[2] : 0.f, __int_as_float(aux), 0.f);
@@ -117,22 +162,21 @@ project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, int N, const 
                                 (unsigned short)st.tmax[0], (unsigned short)st.tmax[1]);
 }
 
-extern "C" int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, const sgn_camera* cam,
+extern "C" int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, int num_chunks, const sgn_camera* cam,
                                float* records, int32_t* radii, int32_t* num_tiles_hit, uint16_t* tile_bbox,
                                void* stream) {
     SGN_REQUIRE(segs_dev && cam && records && radii && num_tiles_hit && tile_bbox, "sgn_project_fwd: null pointer");
     SGN_REQUIRE(nseg >= 1 && nseg <= SGN_MAX_SEGMENTS, "sgn_project_fwd: nseg=%d out of range [1,%d]", nseg, SGN_MAX_SEGMENTS);
-    SGN_REQUIRE(N >= 0, "sgn_project_fwd: N < 0");
+    SGN_REQUIRE(N >= 0 && num_chunks >= 0, "sgn_project_fwd: negative size");
     SGN_REQUIRE(cam->block_width >= 2 && cam->block_width <= 16, "block_width must be between 2 and 16 (got %d)", cam->block_width);
     SGN_REQUIRE(cam->sh_degree >= 0 && cam->sh_degree <= 3 && cam->sh_degree_to_use >= 0 && cam->sh_degree_to_use <= cam->sh_degree,
                 "sh_degree must be in [0,3] and sh_degree_to_use <= sh_degree");
     SGN_REQUIRE((cam->width + cam->block_width - 1) / cam->block_width < 65536 && (cam->height + cam->block_width - 1) / cam->block_width < 65536,
                 "image too large for 16-bit tile coordinates");
     SGN_REQUIRE(sgn_aligned16(records), "records must be 16-byte aligned");
-    if (N == 0) return SGN_OK;
-    const int blocks = (N + PROJ_THREADS - 1) / PROJ_THREADS;
-    project_fwd_kernel<<<blocks, PROJ_THREADS, nseg * sizeof(int), (cudaStream_t)stream>>>(
-        segs_dev, nseg, N, *cam, reinterpret_cast<float4*>(records), radii, num_tiles_hit,
+    if (N == 0 || num_chunks == 0) return SGN_OK;
+    project_fwd_kernel<<<num_chunks, CH, nseg * sizeof(int), (cudaStream_t)stream>>>(
+        segs_dev, nseg, *cam, reinterpret_cast<float4*>(records), radii, num_tiles_hit,
         reinterpret_cast<ushort4*>(tile_bbox));
     SGN_CHECK_LAUNCH("project_fwd_kernel");
     return SGN_OK;
@@ -230,118 +274,130 @@ __device__ __forceinline__ void sgn_project_vjp(const sgn_camera& cam, const Sgn
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PROJ_THREADS)
-project_bwd_kernel(const sgn_segment* __restrict__ segs, const sgn_segment_grads* __restrict__ grads, int nseg, int N,
+__global__ void __launch_bounds__(CH)
+project_bwd_kernel(const sgn_segment* __restrict__ segs, const sgn_segment_grads* __restrict__ grads, int nseg,
                    const sgn_camera cam, const float4* __restrict__ records, const int32_t* __restrict__ radii,
                    const float4* __restrict__ v_records) {
-    extern __shared__ int s_row0[];
-    for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_row0[i] = segs[i].row0;
+    extern __shared__ int s_chunk0[];
+    __shared__ __align__(16) float s_rest[CH * MAX_REST];   // out: features_rest gradient rows
+    __shared__ __align__(16) float s_dc[CH * MAX_DC];       // out: features_dc gradient rows
+    __shared__ __align__(16) float s_means[CH * 3];         // in: means, then out: means gradient
+    __shared__ __align__(16) float s_scales[CH * 3];        // in: scales, then out: scales gradient
+    for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_chunk0[i] = segs[i].chunk0;
     __syncthreads();
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= N) return;
-    const int si = find_segment(s_row0, nseg, g);
+    const int si = find_segment_by_chunk(s_chunk0, nseg, blockIdx.x);
     const sgn_segment& sg = segs[si];
     const sgn_segment_grads& gr = grads[si];
-    const int i = g - sg.row0;
+    const int r0 = (blockIdx.x - sg.chunk0) * CH;
+    const int rows = min(CH, sg.count - r0);
     const int K = (cam.sh_degree + 1) * (cam.sh_degree + 1);
-
-    const float4 v0 = v_records[3 * (size_t)g], v1 = v_records[3 * (size_t)g + 1], v2 = v_records[3 * (size_t)g + 2];
-    const float v_xy[2] = {v0.x, v0.y};
-    const float v_conic[3] = {v0.z, v0.w, v1.x};
-    const float v_opac = v1.y;
-    const float v_rgb[3] = {v1.z, v1.w, v2.x};
-    const float v_depth = v2.y;
-    const float4 r1 = records[3 * (size_t)g + 1], r2 = records[3 * (size_t)g + 2];
-    const int aux = __float_as_int(r2.z);
-
-    // opacity: sigmoid backward
-    {
-        const float o = r1.y;
-        gr.opacities[i] = v_opac * o * (1.f - o);
-    }
-    float m[3], ls[3], q[4];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { m[k] = __ldg(sg.means + 3 * (size_t)i + k); ls[k] = __ldg(sg.scales + 3 * (size_t)i + k); }
-    {
-        const float4 qq = __ldg(reinterpret_cast<const float4*>(sg.quats) + i);
-        q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
-    }
-    SgnProj st;
-    const bool vis = sgn_project_exact(sg, cam, m, ls, q, st);
-
-    // colour backward (compute_sh_backward + clamp mask + Fourier DC)
-    {
-        float vc[3];
-        float* grest = gr.features_rest + (size_t)i * (K - 1) * 3;
-        if (cam.sh_degree > 0) {
-            float d[3] = {st.mw[0] - cam.cam_pos[0], st.mw[1] - cam.cam_pos[1], st.mw[2] - cam.cam_pos[2]};
-            const float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-            d[0] /= n; d[1] /= n; d[2] /= n;
-            float Y[16];
-            sgn_sh_basis(cam.sh_degree_to_use, d[0], d[1], d[2], Y);
-            const int Kuse = (cam.sh_degree_to_use + 1) * (cam.sh_degree_to_use + 1);
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) vc[ch] = (aux & (1 << ch)) ? v_rgb[ch] : 0.f;
-            for (int k = 1; k < K; ++k) {
-                const float y = (k < Kuse) ? Y[k] : 0.f;
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) grest[(k - 1) * 3 + ch] = y * vc[ch];
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) vc[ch] *= Y[0];
-        } else {
-            const float rgb[3] = {r1.z, r1.w, r2.x};
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) vc[ch] = v_rgb[ch] * rgb[ch] * (1.f - rgb[ch]);
-            for (int k = 1; k < K; ++k)
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) grest[(k - 1) * 3 + ch] = 0.f;
-        }
-        float* gdc = gr.features_dc + (size_t)i * sg.F * 3;
-        for (int f = 0; f < sg.F; ++f) {
-            const float w = sg.idft[f];
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) gdc[f * 3 + ch] = w * vc[ch];
-        }
-    }
-
+    const int nrest = (K - 1) * 3, ndc = sg.F * 3;
+    coop_load(s_means, sg.means + 3 * (size_t)r0, rows * 3);
+    coop_load(s_scales, sg.scales + 3 * (size_t)r0, rows * 3);
+    __syncthreads();
+    const int tid = threadIdx.x;
     float gm[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vis && radii[g] > 0) {
-        float vmw[3], vs[3], vqr[4];
-        sgn_project_vjp(cam, st, v_xy, v_depth, v_conic, vmw, vs, vqr);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) gs[c] = vs[c] * st.s[c];  // through exp
-        if (sg.has_pose) {
-            const float* R = sg.R;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) gm[c] = R[c] * vmw[0] + R[3 + c] * vmw[1] + R[6 + c] * vmw[2];
-            const float aw = sg.q[0], ax = sg.q[1], ay = sg.q[2], az = sg.q[3];
-            gq[0] = aw * vqr[0] + ax * vqr[1] + ay * vqr[2] + az * vqr[3];
-            gq[1] = -ax * vqr[0] + aw * vqr[1] + az * vqr[2] - ay * vqr[3];
-            gq[2] = -ay * vqr[0] - az * vqr[1] + aw * vqr[2] + ax * vqr[3];
-            gq[3] = -az * vqr[0] + ay * vqr[1] - ax * vqr[2] + aw * vqr[3];
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) gm[c] = vmw[c];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) gq[k] = vqr[k];
+    if (tid < rows) {
+        const int i = r0 + tid;
+        const size_t g = (size_t)sg.row0 + i;
+        const float4 v0 = v_records[3 * g], v1 = v_records[3 * g + 1], v2 = v_records[3 * g + 2];
+        const float v_xy[2] = {v0.x, v0.y};
+        const float v_conic[3] = {v0.z, v0.w, v1.x};
+        const float v_opac = v1.y;
+        const float v_rgb[3] = {v1.z, v1.w, v2.x};
+        const float v_depth = v2.y;
+        const float4 r1 = records[3 * g + 1], r2 = records[3 * g + 2];
+        const int aux = __float_as_int(r2.z);
+        {   // opacity: sigmoid backward
+            const float o = r1.y;
+            gr.opacities[i] = v_opac * o * (1.f - o);
         }
-    }
+        const float m[3] = {s_means[3 * tid], s_means[3 * tid + 1], s_means[3 * tid + 2]};
+        const float ls[3] = {s_scales[3 * tid], s_scales[3 * tid + 1], s_scales[3 * tid + 2]};
+        float q[4];
+        {
+            const float4 qq = __ldg(reinterpret_cast<const float4*>(sg.quats) + i);
+            q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
+        }
+        SgnProj st;
+        const bool vis = sgn_project_exact(sg, cam, m, ls, q, st);
+        // colour backward (compute_sh_backward + clamp mask + Fourier DC) into the staging rows
+        {
+            float vc[3];
+            float* grest = s_rest + tid * nrest;
+            if (cam.sh_degree > 0) {
+                float d[3] = {st.mw[0] - cam.cam_pos[0], st.mw[1] - cam.cam_pos[1], st.mw[2] - cam.cam_pos[2]};
+                const float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                d[0] /= n; d[1] /= n; d[2] /= n;
+                float Y[16];
+                sgn_sh_basis(cam.sh_degree_to_use, d[0], d[1], d[2], Y);
+                const int Kuse = (cam.sh_degree_to_use + 1) * (cam.sh_degree_to_use + 1);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { gr.means[3 * (size_t)i + k] = gm[k]; gr.scales[3 * (size_t)i + k] = gs[k]; }
-    reinterpret_cast<float4*>(gr.quats)[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
+                for (int ch = 0; ch < 3; ++ch) vc[ch] = (aux & (1 << ch)) ? v_rgb[ch] : 0.f;
+                for (int k = 1; k < K; ++k) {
+                    const float y = (k < Kuse) ? Y[k] : 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) grest[(k - 1) * 3 + ch] = y * vc[ch];
+                }
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) vc[ch] *= Y[0];
+            } else {
+                const float rgb[3] = {r1.z, r1.w, r2.x};
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) vc[ch] = v_rgb[ch] * rgb[ch] * (1.f - rgb[ch]);
+                for (int k = 0; k < nrest; ++k) grest[k] = 0.f;
+            }
+            float* gdc = s_dc + tid * ndc;
+            for (int f = 0; f < sg.F; ++f) {
+                const float w = sg.idft[f];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) gdc[f * 3 + ch] = w * vc[ch];
+            }
+        }
+        if (vis && radii[g] > 0) {
+            float vmw[3], vs[3], vqr[4];
+            sgn_project_vjp(cam, st, v_xy, v_depth, v_conic, vmw, vs, vqr);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gs[c] = vs[c] * st.s[c];  // through exp
+            if (sg.has_pose) {
+                const float* R = sg.R;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gm[c] = R[c] * vmw[0] + R[3 + c] * vmw[1] + R[6 + c] * vmw[2];
+                const float aw = sg.q[0], ax = sg.q[1], ay = sg.q[2], az = sg.q[3];
+                gq[0] = aw * vqr[0] + ax * vqr[1] + ay * vqr[2] + az * vqr[3];
+                gq[1] = -ax * vqr[0] + aw * vqr[1] + az * vqr[2] - ay * vqr[3];
+                gq[2] = -ay * vqr[0] - az * vqr[1] + aw * vqr[2] + ax * vqr[3];
+                gq[3] = -az * vqr[0] + ay * vqr[1] - ax * vqr[2] + aw * vqr[3];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gm[c] = vmw[c];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) gq[k] = vqr[k];
+            }
+        }
+        reinterpret_cast<float4*>(gr.quats)[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
+    }
+    __syncthreads();  // every thread has consumed its means / scales inputs
+    if (tid < rows) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s_means[3 * tid + k] = gm[k]; s_scales[3 * tid + k] = gs[k]; }
+    }
+    __syncthreads();
+    coop_store(gr.means + 3 * (size_t)r0, s_means, rows * 3);
+    coop_store(gr.scales + 3 * (size_t)r0, s_scales, rows * 3);
+    coop_store(gr.features_dc + (size_t)r0 * ndc, s_dc, rows * ndc);
+    if (nrest > 0) coop_store(gr.features_rest + (size_t)r0 * nrest, s_rest, rows * nrest);
 }
 
-extern "C" int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N,
+extern "C" int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N, int num_chunks,
                                const sgn_camera* cam, const float* records, const int32_t* radii,
                                const float* v_records, void* stream) {
     SGN_REQUIRE(segs_dev && grads_dev && cam && records && radii && v_records, "sgn_project_bwd: null pointer");
     SGN_REQUIRE(nseg >= 1 && nseg <= SGN_MAX_SEGMENTS, "sgn_project_bwd: nseg=%d out of range", nseg);
     SGN_REQUIRE(sgn_aligned16(records) && sgn_aligned16(v_records), "records / v_records must be 16-byte aligned");
-    if (N == 0) return SGN_OK;
-    const int blocks = (N + PROJ_THREADS - 1) / PROJ_THREADS;
-    project_bwd_kernel<<<blocks, PROJ_THREADS, nseg * sizeof(int), (cudaStream_t)stream>>>(
-        segs_dev, grads_dev, nseg, N, *cam, reinterpret_cast<const float4*>(records), radii,
+    if (N == 0 || num_chunks == 0) return SGN_OK;
+    project_bwd_kernel<<<num_chunks, CH, nseg * sizeof(int), (cudaStream_t)stream>>>(
+        segs_dev, grads_dev, nseg, *cam, reinterpret_cast<const float4*>(records), radii,
         reinterpret_cast<const float4*>(v_records));
     SGN_CHECK_LAUNCH("project_bwd_kernel");
     return SGN_OK;

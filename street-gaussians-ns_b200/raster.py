@@ -105,8 +105,10 @@ def _check_param(t: torch.Tensor, name: str, device) -> None:
         raise _lib.SgnError(f"{name} must be 16-byte aligned")
 
 
+CHUNK_ROWS = 128  # rows per thread block of the per-Gaussian kernels (project.cu)
+
 SEG_DTYPE = np.dtype([
-    ("row0", "<i4"), ("count", "<i4"), ("F", "<i4"), ("cls", "<i4"), ("has_pose", "<i4"), ("pad0", "<i4"),
+    ("row0", "<i4"), ("count", "<i4"), ("F", "<i4"), ("cls", "<i4"), ("has_pose", "<i4"), ("chunk0", "<i4"),
     ("R", "<f4", (9,)), ("t", "<f4", (3,)), ("q", "<f4", (4,)), ("idft", "<f4", (8,)),
     ("means", "<u8"), ("scales", "<u8"), ("quats", "<u8"), ("features_dc", "<u8"), ("features_rest", "<u8"),
     ("opacities", "<u8")])
@@ -135,12 +137,14 @@ class SegmentTable:
             counts = np.array([ps[0].shape[0] for ps in params], np.int64)
             host["count"] = counts
             host["row0"] = np.concatenate([[0], np.cumsum(counts)[:-1]])
+            chunks = (counts + CHUNK_ROWS - 1) // CHUNK_ROWS
+            host["chunk0"] = np.concatenate([[0], np.cumsum(chunks)[:-1]])
             host["F"] = [ps[3].shape[1] for ps in params]
             P = np.array(ptrs, np.uint64).reshape(n, 6)
             for c, nm in enumerate(PARAM_NAMES):
                 host[nm] = P[:, c]
             sizes = [[(t.numel() + 3) // 4 * 4 for t in ps] for ps in params]
-            st = dict(host=host, N=int(counts.sum()), sizes=sizes, shapes=[[tuple(t.shape) for t in ps] for ps in params])
+            st = dict(host=host, N=int(counts.sum()), num_chunks=int(chunks.sum()), sizes=sizes, shapes=[[tuple(t.shape) for t in ps] for ps in params])
             if len(_STATIC_CACHE) > 64:
                 _STATIC_CACHE.clear()
             _STATIC_CACHE[key] = st
@@ -153,6 +157,7 @@ class SegmentTable:
             host["idft"][i] = seg.idft_f32()
         self.host = host
         self.N = st["N"]
+        self.num_chunks = st["num_chunks"]
         self.nseg = n
         self.static = st
         self.dev = torch.from_numpy(host.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
@@ -179,7 +184,7 @@ def project_fwd(table: SegmentTable, cs: _lib.CameraStruct, device):
     tiles_hit = torch.empty(N, device=device, dtype=torch.int32)
     bbox = torch.empty(N, 4, device=device, dtype=torch.int16)
     with _timed("project_fwd"):
-        _lib.check(L.sgn_project_fwd(_ptr(table.dev), table.nseg, N, C.byref(cs), _ptr(records), _ptr(radii),
+        _lib.check(L.sgn_project_fwd(_ptr(table.dev), table.nseg, N, table.num_chunks, C.byref(cs), _ptr(records), _ptr(radii),
                                      _ptr(tiles_hit), _ptr(bbox), _stream()), "sgn_project_fwd")
     return records, radii, tiles_hit, bbox
 
@@ -311,8 +316,8 @@ def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, recor
             for c, n, shp in zip(chunks, st["flat_numel"], st["flat_shapes"])]
     gt = _grads_table(arena, st, device)
     with _timed("project_bwd"):
-        _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, C.byref(cs), _ptr(records), _ptr(radii),
-                                     _ptr(v_records), _stream()), "sgn_project_bwd")
+        _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, table.num_chunks, C.byref(cs), _ptr(records),
+                                     _ptr(radii), _ptr(v_records), _stream()), "sgn_project_bwd")
     return flat, arena
 
 
