@@ -209,13 +209,12 @@ def run_ours(args):
     vo = 0.1 * v
     leaves = [t for s in frc.segments for t in s.params.tensors()]
 
+    cot = {"rgb": w, "accumulation": v, "object_acc": vo}
+
     def step():
-        out, holder = raster.render_frame(frc, settings)
-        torch.autograd.backward([out["rgb"], out["accumulation"], out["object_acc"]],
-                                [w, v[..., None], vo[..., None]])
+        # the hot path straight through the C-ABI stages (same kernels as render_frame + backward())
+        out, holder = raster.forward_backward(frc, settings, cot)
         dp.allreduce_gradients(holder.grad_arena)  # camera-sharded DP: one SUM over the flat arena
-        for t in leaves:
-            t.grad = None
         return holder
 
     def barrier_sync():

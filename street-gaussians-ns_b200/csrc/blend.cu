@@ -438,13 +438,13 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
     // ---- per-pixel prologue: cotangents of the RAW blend outputs from those of the final outputs
     float T[PPL], tfv[PPL];
     float vr[PPL], vg[PPL], vb[PPL], vd[PPL];
-    float br[PPL], bgc[PPL], bb[PPL], bd[PPL];
+    float bv[PPL];  // running  sum_{later k} (c_k . v_out) * alpha_k * T_k  (gsplat's `buffer` dotted with v_out)
     int idx[PPL];
     int kmax = -1;
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
         T[s] = 1.f; tfv[s] = 0.f; vr[s] = vg[s] = vb[s] = vd[s] = 0.f;
-        br[s] = bgc[s] = bb[s] = bd[s] = 0.f;
+        bv[s] = 0.f;
         idx[s] = -1;
         const int i = i0 + 2 * s;
         if (j >= p.width || i >= p.height) continue;
@@ -533,14 +533,14 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
                 T[s] = Tk;
                 const float fac = vm ? alpha * Tk : 0.f;
                 cr = __fmaf_rn(fac, vr[s], cr); cg = __fmaf_rn(fac, vg[s], cg); cb = __fmaf_rn(fac, vb[s], cb);
-                float v_alpha = (B.z * Tk - br[s] * ra) * vr[s] + (B.w * Tk - bgc[s] * ra) * vg[s] + (Cc.x * Tk - bb[s] * ra) * vb[s];
-                br[s] = __fmaf_rn(B.z, fac, br[s]); bgc[s] = __fmaf_rn(B.w, fac, bgc[s]); bb[s] = __fmaf_rn(Cc.x, fac, bb[s]);
+                // v_alpha = sum_c (c*T - buffer_c*ra) * v_c + T_final*ra*v_acc  =  T*(c.v) + ra*(T_final*v_acc - buffer.v)
+                float dotc = __fmaf_rn(B.z, vr[s], __fmaf_rn(B.w, vg[s], Cc.x * vb[s]));
                 if (DEPTHG) {
                     cd = __fmaf_rn(fac, vd[s], cd);
-                    v_alpha += (Cc.y * Tk - bd[s] * ra) * vd[s];
-                    bd[s] = __fmaf_rn(Cc.y, fac, bd[s]);
+                    dotc = __fmaf_rn(Cc.y, vd[s], dotc);
                 }
-                v_alpha = __fmaf_rn(tfv[s], ra, v_alpha);
+                const float v_alpha = __fmaf_rn(Tk, dotc, ra * (tfv[s] - bv[s]));
+                bv[s] = __fmaf_rn(fac, dotc, bv[s]);
                 const float vs = valid ? -raw * v_alpha : 0.f;   // d/d sigma = -o*vis*v_alpha
                 S0 += vs;
                 const float vsy = vs * dy;

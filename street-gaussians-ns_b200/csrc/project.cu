@@ -79,36 +79,26 @@ __device__ __forceinline__ void coop_store(float* __restrict__ dst, const float*
     }
 }
 
+// Forward: one thread per row, direct loads (independent per-thread loads keep more requests in flight
+// than a stage-sync-compute split; measured).  Rows the camera does not see skip the colour work:
+// nothing downstream ever reads the colour of an invisible Gaussian.
 __global__ void __launch_bounds__(CH)
 project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, const sgn_camera cam,
                    float4* __restrict__ records, int32_t* __restrict__ radii, int32_t* __restrict__ num_tiles_hit,
                    ushort4* __restrict__ tile_bbox) {
     extern __shared__ int s_chunk0[];
-    __shared__ __align__(16) float s_rest[CH * MAX_REST];
-    __shared__ __align__(16) float s_dc[CH * MAX_DC];
-    __shared__ __align__(16) float s_means[CH * 3];
-    __shared__ __align__(16) float s_scales[CH * 3];
     for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_chunk0[i] = segs[i].chunk0;
     __syncthreads();
     const int si = find_segment_by_chunk(s_chunk0, nseg, blockIdx.x);
     const sgn_segment& sg = segs[si];
-    const int r0 = (blockIdx.x - sg.chunk0) * CH;
-    const int rows = min(CH, sg.count - r0);
-    const int K = (cam.sh_degree + 1) * (cam.sh_degree + 1);
-    const int nrest = (K - 1) * 3, ndc = sg.F * 3;
-    coop_load(s_means, sg.means + 3 * (size_t)r0, rows * 3);
-    coop_load(s_scales, sg.scales + 3 * (size_t)r0, rows * 3);
-    coop_load(s_dc, sg.features_dc + (size_t)r0 * ndc, rows * ndc);
-    if (cam.sh_degree > 0) coop_load(s_rest, sg.features_rest + (size_t)r0 * nrest, rows * nrest);
-    __syncthreads();
-    const int tid = threadIdx.x;
-    if (tid >= rows) return;
-    const int i = r0 + tid;
+    const int i = (blockIdx.x - sg.chunk0) * CH + threadIdx.x;
+    if (i >= sg.count) return;
     const size_t g = (size_t)sg.row0 + i;
+    const int K = (cam.sh_degree + 1) * (cam.sh_degree + 1);
 
-    const float m[3] = {s_means[3 * tid], s_means[3 * tid + 1], s_means[3 * tid + 2]};
-    const float ls[3] = {s_scales[3 * tid], s_scales[3 * tid + 1], s_scales[3 * tid + 2]};
-    float q[4];
+    float m[3], ls[3], q[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { m[k] = __ldg(sg.means + 3 * (size_t)i + k); ls[k] = __ldg(sg.scales + 3 * (size_t)i + k); }
     {
         const float4 qq = __ldg(reinterpret_cast<const float4*>(sg.quats) + i);
         q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
@@ -116,41 +106,44 @@ project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, const sgn_cam
     SgnProj st;
     const bool vis = sgn_project_exact(sg, cam, m, ls, q, st);
 
-    // colour: Fourier DC (scene graph :239-247), SH (sgn_splatfacto.py:933-940)
-    float c0[3] = {0.f, 0.f, 0.f};
-    for (int f = 0; f < sg.F; ++f) {
-        const float w = sg.idft[f];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) c0[ch] += s_dc[tid * ndc + f * 3 + ch] * w;
-    }
-    float rgb[3];
+    float rgb[3] = {0.f, 0.f, 0.f};
+    float opac = 0.f;
     int aux = 0;
-    if (cam.sh_degree > 0) {
-        float d[3] = {st.mw[0] - cam.cam_pos[0], st.mw[1] - cam.cam_pos[1], st.mw[2] - cam.cam_pos[2]};
-        const float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-        d[0] /= n; d[1] /= n; d[2] /= n;
-        float Y[16];
-        sgn_sh_basis(cam.sh_degree_to_use, d[0], d[1], d[2], Y);
-        const int Kuse = min((cam.sh_degree_to_use + 1) * (cam.sh_degree_to_use + 1), K);
-        float acc[3] = {Y[0] * c0[0], Y[0] * c0[1], Y[0] * c0[2]};
-        const float* rest = s_rest + tid * nrest;
-        for (int k = 1; k < Kuse; ++k) {
+    if (vis) {
+        // colour: Fourier DC (scene graph :239-247), SH (sgn_splatfacto.py:933-940)
+        float c0[3] = {0.f, 0.f, 0.f};
+        for (int f = 0; f < sg.F; ++f) {
+            const float w = sg.idft[f];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) acc[ch] += Y[k] * rest[(k - 1) * 3 + ch];
+            for (int ch = 0; ch < 3; ++ch) c0[ch] += __ldg(sg.features_dc + ((size_t)i * sg.F + f) * 3 + ch) * w;
         }
+        if (cam.sh_degree > 0) {
+            float d[3] = {st.mw[0] - cam.cam_pos[0], st.mw[1] - cam.cam_pos[1], st.mw[2] - cam.cam_pos[2]};
+            const float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            d[0] /= n; d[1] /= n; d[2] /= n;
+            float Y[16];
+            sgn_sh_basis(cam.sh_degree_to_use, d[0], d[1], d[2], Y);
+            const int Kuse = min((cam.sh_degree_to_use + 1) * (cam.sh_degree_to_use + 1), K);
+            float acc[3] = {Y[0] * c0[0], Y[0] * c0[1], Y[0] * c0[2]};
+            const float* rest = sg.features_rest + (size_t)i * (K - 1) * 3;
+            for (int k = 1; k < Kuse; ++k) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float pre = acc[ch] + 0.5f;
-            if (pre >= 0.f) aux |= (1 << ch);
-            rgb[ch] = pre > 0.f ? pre : 0.f;
+                for (int ch = 0; ch < 3; ++ch) acc[ch] += Y[k] * __ldg(rest + (k - 1) * 3 + ch);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float pre = acc[ch] + 0.5f;
+                if (pre >= 0.f) aux |= (1 << ch);
+                rgb[ch] = pre > 0.f ? pre : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) { rgb[ch] = 1.f / (1.f + expf(-c0[ch])); aux |= (1 << ch); }
         }
-    } else {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) { rgb[ch] = 1.f / (1.f + expf(-c0[ch])); aux |= (1 << ch); }
+        opac = 1.f / (1.f + expf(-__ldg(sg.opacities + i)));
+        aux |= SGN_AUX_VISIBLE;
     }
-    const float opac = 1.f / (1.f + expf(-__ldg(sg.opacities + i)));
     if (sg.cls == 1) aux |= SGN_AUX_OBJECT;
-    if (vis) aux |= SGN_AUX_VISIBLE;
 
     float4* rec = records + 3 * g;
     rec[0] = make_float4(st.xy[0], st.xy[1], st.conic[0], st.conic[1]);
@@ -297,7 +290,18 @@ project_bwd_kernel(const sgn_segment* __restrict__ segs, const sgn_segment_grads
     __syncthreads();
     const int tid = threadIdx.x;
     float gm[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
-    if (tid < rows) {
+    const bool row_vis = (tid < rows) && radii[(size_t)sg.row0 + r0 + tid] > 0;
+    if (tid < rows && !row_vis) {
+        // the rasterizer never touched this Gaussian: every cotangent is zero, so is every gradient
+        const int i = r0 + tid;
+        gr.opacities[i] = 0.f;
+        reinterpret_cast<float4*>(gr.quats)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* grest = s_rest + tid * nrest;
+        for (int k = 0; k < nrest; ++k) grest[k] = 0.f;
+        float* gdc = s_dc + tid * ndc;
+        for (int k = 0; k < ndc; ++k) gdc[k] = 0.f;
+    }
+    if (row_vis) {
         const int i = r0 + tid;
         const size_t g = (size_t)sg.row0 + i;
         const float4 v0 = v_records[3 * g], v1 = v_records[3 * g + 1], v2 = v_records[3 * g + 2];

@@ -95,6 +95,7 @@ class SceneGraphRasterModel(torch.nn.Module):
         self.xys = self.depths = self.radii = self.conics = self.num_tiles_hit = None
         self.last_size = None
         self._holder = None
+        self._frame_cache: dict = {}
 
     @staticmethod
     def get_object_model_name(object_id) -> str:
@@ -106,9 +107,25 @@ class SceneGraphRasterModel(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _frame(self, camera: Camera) -> Frame:
+        poses = self.poses_at(camera.time)
+        # box poses are static data per timestamp: reuse the Frame (and its staged segment table) while the
+        # parameter tensors are the same objects (densification replaces them, which invalidates the entry)
+        key = (camera.time, id(camera), tuple(id(p) for m in self.all_models.values() for p in m.gauss_params.values()),
+               tuple(id(p) for p in poses))
+        hit = self._frame_cache.get(key)
+        if hit is not None:
+            self.visible_model_names = hit[1]
+            return hit[0]
+        frame = self._build_frame(camera, poses)
+        if len(self._frame_cache) > 512:
+            self._frame_cache.clear()
+        self._frame_cache[key] = (frame, list(self.visible_model_names))
+        return frame
+
+    def _build_frame(self, camera: Camera, poses) -> Frame:
         segs = [Segment(self.all_models["background"].as_set(), CLS_BACKGROUND, name="background")]
         self.visible_model_names = ["background"]
-        for pose in self.poses_at(camera.time):
+        for pose in poses:
             name = self.get_object_model_name(pose.track_id)
             assert name not in self.visible_model_names
             sub = self.all_models[name]

@@ -148,13 +148,21 @@ class SegmentTable:
             if len(_STATIC_CACHE) > 64:
                 _STATIC_CACHE.clear()
             _STATIC_CACHE[key] = st
-        host = st["host"].copy()
-        host["cls"] = [s.cls for s in frame.segments]
-        host["has_pose"] = [int(s.has_pose) for s in frame.segments]
-        for i, seg in enumerate(frame.segments):
-            R, t, q = seg.pose_f32()
-            host["R"][i], host["t"][i], host["q"][i] = R, t, q
-            host["idft"][i] = seg.idft_f32()
+        dyn = getattr(frame, "_dyn_table", None)
+        if dyn is None or dyn[0] is not st:
+            host = st["host"].copy()
+            host["cls"] = [s.cls for s in frame.segments]
+            host["has_pose"] = [int(s.has_pose) for s in frame.segments]
+            for i, seg in enumerate(frame.segments):
+                R, t, q = seg.pose_f32()
+                host["R"][i], host["t"][i], host["q"][i] = R, t, q
+                host["idft"][i] = seg.idft_f32()
+            try:
+                frame._dyn_table = (st, host)  # poses of a Frame object do not change: reuse on re-render
+            except Exception:
+                pass
+        else:
+            host = dyn[1]
         self.host = host
         self.N = st["N"]
         self.num_chunks = st["num_chunks"]
@@ -300,7 +308,7 @@ def blend_bwd(cs, bo, records, sorted_ids, tile_bins, saved: Dict[str, torch.Ten
     return v_records, v_sky
 
 
-def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, records, radii, v_records):
+def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, records, radii, v_records, make_views: bool = True):
     """Dense parameter gradients, one flat arena (a single allocation, 16-byte aligned slices)."""
     L = _lib.load()
     device = records.device
@@ -311,9 +319,11 @@ def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, recor
         st["flat_shapes"] = [x for ss in st["shapes"] for x in ss]
         st["flat_numel"] = [int(np.prod(x)) for x in st["flat_shapes"]]
     arena = torch.empty(sum(flat_sizes), device=device, dtype=torch.float32)
-    chunks = arena.split_with_sizes(flat_sizes)
-    flat = [c[:n].view(shp) if n != c.shape[0] else c.view(shp)
-            for c, n, shp in zip(chunks, st["flat_numel"], st["flat_shapes"])]
+    flat = None
+    if make_views:
+        chunks = arena.split_with_sizes(flat_sizes)
+        flat = [c[:n].view(shp) if n != c.shape[0] else c.view(shp)
+                for c, n, shp in zip(chunks, st["flat_numel"], st["flat_shapes"])]
     gt = _grads_table(arena, st, device)
     with _timed("project_bwd"):
         _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, table.num_chunks, C.byref(cs), _ptr(records),
@@ -332,6 +342,8 @@ class _Holder:
         self.records = None
         self.v_records = None
         self.grad_arena = None
+        self.param_grads = None
+        self.v_sky = None
         self.M = 0
         self.post_backward = None
 
@@ -390,6 +402,41 @@ class _SceneGraphRasterize(torch.autograd.Function):
         if h.post_backward is not None:
             h.post_backward(h)
         return (None, None, None, v_sky, *flat)
+
+
+def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[str, Optional[torch.Tensor]],
+                     sky: Optional[torch.Tensor] = None, want_param_grads: bool = False):
+    """One frame, forward AND backward, straight through the C-ABI stages (no autograd graph).
+
+    ``cotangents`` maps output names (rgb, accumulation, depth, object_acc, background_acc) to their
+    cotangent tensors (missing / None = no gradient from that output).  Returns (outputs, holder);
+    ``holder.grad_arena`` is the flat dense gradient arena (what the data-parallel all-reduce and a
+    fused optimizer consume), ``holder.v_records[:, 0:2]`` the pixel-space mean gradients the
+    densification statistics read.  With ``want_param_grads`` the per-parameter views are returned in
+    ``holder.param_grads``.  Same kernels and same arithmetic as ``render_frame`` + ``backward()``."""
+    params = [seg.params.tensors() for seg in frame.segments]
+    device = params[0][0].device
+    cs = camera_struct(frame.camera, settings)
+    if sky is not None:
+        sky = sky.contiguous()
+    bo = blend_opts(settings, sky is not None)
+    table = SegmentTable(frame, params, device)
+    records, radii, tiles_hit, bbox = project_fwd(table, cs, device)
+    M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, tiles_hit, bbox)
+    cls_ids = cls_bins = None
+    if settings.class_streams:
+        cls_ids, cls_bins = class_lists(cs, M, sorted_ids, tile_bins)
+    out = blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky, cls_ids, cls_bins)
+    v = {k: cotangents.get(k) for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc")}
+    v_records, v_sky = blend_bwd(cs, bo, records, sorted_ids, tile_bins, out, sky, v, sky is not None, cls_ids, cls_bins)
+    flat, arena = project_bwd(table, params, cs, records, radii, v_records, make_views=want_param_grads)
+    holder = _Holder()
+    holder.records, holder.radii, holder.num_tiles_hit, holder.M = records, radii, tiles_hit, M
+    holder.xys, holder.conics, holder.depths = records[:, 0:2], records[:, 2:5], records[:, 9]
+    holder.v_records, holder.grad_arena, holder.v_sky = v_records, arena, v_sky
+    holder.param_grads = flat
+    res = {k: out[k] for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc") if k in out}
+    return res, holder
 
 
 def render_frame(frame: Frame, settings: Optional[RenderSettings] = None, sky: Optional[torch.Tensor] = None):

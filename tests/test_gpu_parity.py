@@ -71,8 +71,10 @@ def test_project_bit_exact_ints_and_records(scene):
     np.testing.assert_array_equal(rec[:, 0:2], fw.xys)
     np.testing.assert_array_equal(rec[:, 2:5], fw.conics)
     np.testing.assert_array_equal(rec[:, 9], fw.depths)
-    np.testing.assert_allclose(rec[:, 5], fw.opac, atol=1e-6)
-    np.testing.assert_allclose(rec[:, 6:9], fw.rgbs, atol=5e-6)
+    # colour / opacity are only produced for rows the camera sees (nothing reads them otherwise)
+    np.testing.assert_allclose(rec[vis, 5], fw.opac[vis], atol=1e-6)
+    np.testing.assert_allclose(rec[vis][:, 6:9], fw.rgbs[vis], atol=5e-6)
+    assert np.all(rec[~vis][:, 5:9] == 0)
     aux = rec[:, 10].view(np.int32)
     np.testing.assert_array_equal((aux >> 3) & 1, fw.cls)
     np.testing.assert_array_equal((aux >> 4) & 1, vis.astype(np.int32))
@@ -273,3 +275,22 @@ def test_full_size_properties_cfg3():
     g2 = frc.segments[0].params.means.grad
     assert rel_l2(g2.cpu().numpy(), 2 * g1.cpu().numpy()) < 1e-4  # atomics reorder sums: not bit-exact
     assert torch.isfinite(g2).all()
+
+
+def test_forward_backward_without_autograd_matches_autograd():
+    """raster.forward_backward (the C-ABI stages called back to back) == render_frame + backward()."""
+    fr = syn.make_frame(**SCENES["small_actors"])
+    frc = to_cuda(fr, requires_grad=True)
+    s = raster.RenderSettings()
+    H, W = fr.camera.height, fr.camera.width
+    w, v = syn.cotangents(H, W)
+    w, v = w.cuda(), v.cuda()
+    out, holder = raster.render_frame(frc, s)
+    torch.autograd.backward([out["rgb"], out["accumulation"], out["object_acc"]], [w, v[..., None], 0.1 * v[..., None]])
+    ref = torch.cat([t.grad.reshape(-1) for seg in frc.segments for t in seg.params.tensors()])
+    out2, h2 = raster.forward_backward(frc, s, {"rgb": w, "accumulation": v, "object_acc": 0.1 * v}, want_param_grads=True)
+    got = torch.cat([g.reshape(-1) for g in h2.param_grads])
+    for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc"):
+        assert torch.equal(out[k].detach().reshape(-1), out2[k].reshape(-1)), k
+    assert rel_l2(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5  # float atomics: summation order differs run to run
+    assert h2.grad_arena.numel() >= got.numel()
