@@ -31,6 +31,7 @@
 #define FULL 0xffffffffu
 #define LOG2E 1.4426950408889634f
 #define LN2 0.6931471805599453f
+#define LOG2_255 7.994353436858858f
 
 // saved per-pixel state is planar: slot 0 main, 1 object, 2 background
 #define SLOT_MAIN 0
@@ -93,12 +94,21 @@ __device__ __forceinline__ Staged gather_entry(const float4* __restrict__ record
     return s;
 }
 
+// Row reach of a staged entry: the largest |dy| (pixels) at which alpha >= 1/255 is still possible for
+// SOME dx, i.e. min_dx sigma(dx,dy) <= ln(255 o).  In staged units: dy^2 * (hc - bb^2/(4 ha)) <= log2(255 o).
+// Rows further away are skipped (warp-uniformly) by the accumulation kernels: a provable no-op.
+__device__ __forceinline__ float row_reach(const Staged& e) {
+    const float tau2 = LOG2_255 + e.B.y;
+    const float den = e.B.x - (e.A.w * e.A.w) / (4.f * e.A.z);
+    if (!(e.A.z > 0.f) || !(den > 0.f) || !(tau2 == tau2)) return 3.0e38f;  // degenerate conic: never cull
+    if (tau2 < 0.f) return -1.f;                                             // opacity < 1/255: no row can accept it
+    return sqrtf(tau2 / den) * 1.0001f + 0.01f;
+}
+
 // sigma*log2(e) for the pixel at (dx, dy) from the staged conic; identical in forward and backward
 __device__ __forceinline__ float sgn_sigma2(float hax2, float bdx, float hc, float dy) {
     return __fmaf_rn(dy, __fmaf_rn(hc, dy, bdx), hax2);
 }
-
-#define LOG2_255 7.994353436858858f
 
 __device__ __forceinline__ float fast_rcp(float x) {
     float y;
@@ -249,10 +259,11 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
 // accumulation-only pass over one class's per-tile sub-lists (objects-only / background-only render)
 template <int PPL>
 __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, int tile, int strip, const int2 range,
-                                              float4 (*sA)[32], float2 (*sB)[32]) {
+                                              float4 (*sA)[32], float4 (*sB)[32]) {
     const int32_t* __restrict__ ids = p.cls_ids[cls];
     const int slot = cls ? SLOT_OBJ : SLOT_BG;
     float* __restrict__ out_acc = cls ? p.obj_acc : p.bg_acc;
+    const float yc0 = (float)((tile / p.tiles_x) * SGN_TILE + strip * (2 * PPL)) + 1.0f;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int lane = threadIdx.x;
     const int j = tx * SGN_TILE + (lane & 15);
@@ -278,21 +289,23 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
     int buf = 0;
     bool finished = false;
     for (int base = range.x; base < range.y && !finished; base += 32) {
-        sA[buf][lane] = nxt.A; sB[buf][lane] = make_float2(nxt.B.x, nxt.B.y);
+        sA[buf][lane] = nxt.A; sB[buf][lane] = make_float4(nxt.B.x, nxt.B.y, row_reach(nxt) + 0.5f, 0.f);
         __syncwarp();
         if (base + 32 + lane < range.y) nxt = gather_entry(p.records, ids[base + 32 + lane]);
         const int n = min(32, range.y - base);
         for (int t = 0; t < n; ++t) {
             if (__all_sync(FULL, done == ALL)) { finished = true; break; }
             const float4 A = sA[buf][t];
-            const float2 B = sB[buf][t];
+            const float4 B = sB[buf][t];
             const float dx = A.x - px;
             const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
+            const float dyc = A.y - yc0;  // distance to the centre line of slot 0's row pair (warp-uniform)
             const float nlo = -B.y;
             const int k = base + t;
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
+                if (fabsf(dyc - (float)(2 * s)) > B.z) continue;  // the entry cannot reach this row pair
                 const float dy = dy0 - (float)(2 * s);
                 const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
                 const bool valid = (s2 >= nlo) && (s2 <= LOG2_255);
@@ -326,11 +339,9 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
     }
 }
 
-// blockIdx.y selects the class: 0 background, 1 object
-__global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p) {
+__global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p, const int cls) {
     __shared__ float4 sA[2][32];
-    __shared__ float2 sB[2][32];
-    const int cls = blockIdx.y;
+    __shared__ float4 sB[2][32];
     const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
     const int2 range = p.cls_bins[cls][tile];
     const int W = strips_for(range.y - range.x, p.split_acc);
@@ -342,6 +353,41 @@ __global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p) {
         default: acc_fwd_strip<1>(p, cls, tile, strip, range, sA, sB); break;
     }
 }
+
+// The object accumulation pass is independent of the main pass (and the background pass only needs the
+// main pass's flags), and every blend kernel ends in a tail during which most SMs idle.  The object pass
+// is therefore forked onto an auxiliary stream and joined back with events: same results, the tails overlap.
+#include <mutex>
+static cudaStream_t aux_stream() {
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!streams[dev]) {
+        if (cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
+    }
+    return streams[dev];
+}
+struct ForkJoin {
+    cudaStream_t main, aux;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+    ForkJoin(cudaStream_t m) : main(m), aux(aux_stream()) {
+        if (!aux) return;
+        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return;
+        if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) return;
+        ok = cudaEventRecord(fork, main) == cudaSuccess && cudaStreamWaitEvent(aux, fork, 0) == cudaSuccess;
+    }
+    cudaStream_t side() const { return ok ? aux : main; }
+    void finish() {
+        if (ok) { cudaEventRecord(join, aux); cudaStreamWaitEvent(main, join, 0); }
+    }
+    ~ForkJoin() {
+        if (fork) cudaEventDestroy(fork);
+        if (join) cudaEventDestroy(join);
+    }
+};
 
 static int check_cam(const sgn_camera* cam) {
     SGN_REQUIRE(cam, "null camera");
@@ -386,12 +432,18 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     SGN_REQUIRE(out->tile_depth, "sgn_blend_fwd: tile_depth is null");
     p.tile_depth = out->tile_depth;
     SGN_CHECK_CUDA(cudaMemsetAsync(out->tile_depth, 0, sizeof(int32_t) * 3 * (size_t)tiles, (cudaStream_t)stream));
-    if (opts->class_streams) blend_fwd_kernel<true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
-    else blend_fwd_kernel<false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
-    SGN_CHECK_LAUNCH("blend_fwd_kernel");
     if (opts->class_streams) {
-        acc_fwd_kernel<<<dim3(tiles * 8, 2), 32, 0, (cudaStream_t)stream>>>(p);
-        SGN_CHECK_LAUNCH("acc_fwd_kernel");
+        ForkJoin fj((cudaStream_t)stream);
+        acc_fwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 1);  // objects: independent of the main pass
+        SGN_CHECK_LAUNCH("acc_fwd_kernel<object>");
+        blend_fwd_kernel<true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        SGN_CHECK_LAUNCH("blend_fwd_kernel");
+        acc_fwd_kernel<<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p, 0);  // background: needs the main pass's flags
+        SGN_CHECK_LAUNCH("acc_fwd_kernel<background>");
+        fj.finish();
+    } else {
+        blend_fwd_kernel<false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        SGN_CHECK_LAUNCH("blend_fwd_kernel");
     }
     return SGN_OK;
 }
@@ -593,10 +645,11 @@ __global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
 // backward of the accumulation-only pass: out = 1 - T_final  =>  v_alpha_k = T_final * ra_k * v_out
 template <int PPL>
 __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, int tile, int strip, const int2 range,
-                                              float4 (*sA)[32], float4 (*sB)[32]) {
+                                              float4 (*sA)[32], float4 (*sB)[32], float (*sR)[32]) {
     const int32_t* __restrict__ ids = p.cls_ids[cls];
     const int slot = cls ? SLOT_OBJ : SLOT_BG;
     const float* __restrict__ v_out = cls ? p.v_obj : p.v_bg;
+    const float yc0 = (float)((tile / p.tiles_x) * SGN_TILE + strip * (2 * PPL)) + 1.0f;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int lane = threadIdx.x;
     const int j = tx * SGN_TILE + (lane & 15);
@@ -625,6 +678,7 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
     int buf = 0;
     for (int hi = hi0; hi > range.x; hi -= 32) {
         sA[buf][lane] = nxt.A; sB[buf][lane] = make_float4(nxt.B.x, nxt.B.y, nxt.C.z, nxt.C.w);
+        sR[buf][lane] = row_reach(nxt) + 0.5f;
         __syncwarp();
         if (hi - 33 - lane >= range.x) nxt = gather_entry(p.records, ids[hi - 33 - lane]);
         const int n = min(32, hi - range.x);
@@ -635,12 +689,14 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
             const float dx = A.x - px;
             const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
+            const float dyc = A.y - yc0, reach = sR[buf][t];
             const float nlo = -B.y;
             const float o = B.w;
             float S0 = 0.f, Sy = 0.f, Syy = 0.f;
             bool any = false;
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
+                if (fabsf(dyc - (float)(2 * s)) > reach) continue;
                 const float dy = dy0 - (float)(2 * s);
                 const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
                 const bool valid = (s2 >= nlo) && (s2 <= LOG2_255) && (k <= idx[s]);
@@ -675,15 +731,16 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
 __global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p, const int cls) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
+    __shared__ float sR[2][32];
     const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
     const int2 range = p.cls_bins[cls][tile];
     const int W = strips_for(p.tile_depth[(size_t)(cls ? SLOT_OBJ : SLOT_BG) * p.tiles + tile], p.split_acc);
     if (strip >= W) return;
     switch (W) {
-        case 1: acc_bwd_strip<8>(p, cls, tile, strip, range, sA, sB); break;
-        case 2: acc_bwd_strip<4>(p, cls, tile, strip, range, sA, sB); break;
-        case 4: acc_bwd_strip<2>(p, cls, tile, strip, range, sA, sB); break;
-        default: acc_bwd_strip<1>(p, cls, tile, strip, range, sA, sB); break;
+        case 1: acc_bwd_strip<8>(p, cls, tile, strip, range, sA, sB, sR); break;
+        case 2: acc_bwd_strip<4>(p, cls, tile, strip, range, sA, sB, sR); break;
+        case 4: acc_bwd_strip<2>(p, cls, tile, strip, range, sA, sB, sR); break;
+        default: acc_bwd_strip<1>(p, cls, tile, strip, range, sA, sB, sR); break;
     }
 }
 
@@ -724,16 +781,21 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.v_records = v_records;
     SGN_REQUIRE(in->tile_depth, "sgn_blend_bwd: tile_depth (saved by the forward) is null");
     p.tile_depth = in->tile_depth;
-    if (in->v_depth) blend_bwd_kernel<true><<<tiles * 8, 32, 0, stream>>>(p);
-    else blend_bwd_kernel<false><<<tiles * 8, 32, 0, stream>>>(p);
-    SGN_CHECK_LAUNCH("blend_bwd_kernel");
-    if (in->v_object_acc) {
-        acc_bwd_kernel<<<tiles * 8, 32, 0, stream>>>(p, 1);
-        SGN_CHECK_LAUNCH("acc_bwd_kernel<object>");
-    }
-    if (in->v_background_acc) {
-        acc_bwd_kernel<<<tiles * 8, 32, 0, stream>>>(p, 0);
-        SGN_CHECK_LAUNCH("acc_bwd_kernel<background>");
+    {
+        // all three kernels only accumulate (RED) into v_records: they may run concurrently
+        ForkJoin fj(stream);
+        if (in->v_object_acc) {
+            acc_bwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 1);
+            SGN_CHECK_LAUNCH("acc_bwd_kernel<object>");
+        }
+        if (in->v_background_acc) {
+            acc_bwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 0);
+            SGN_CHECK_LAUNCH("acc_bwd_kernel<background>");
+        }
+        if (in->v_depth) blend_bwd_kernel<true><<<tiles * 8, 32, 0, stream>>>(p);
+        else blend_bwd_kernel<false><<<tiles * 8, 32, 0, stream>>>(p);
+        SGN_CHECK_LAUNCH("blend_bwd_kernel");
+        fj.finish();
     }
     return SGN_OK;
 }
