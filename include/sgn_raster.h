@@ -109,6 +109,7 @@ typedef struct sgn_blend_opts {
      * channels come back as out = sum(c*alpha*T) + T_final*background[c] in rgb[...,0:3] and depth */
     int32_t raw_mode;
     float background[4];
+    int32_t row_skip; /* tuning: main kernels skip row pairs an entry cannot reach / that have fully terminated */
 } sgn_blend_opts;
 
 const char* sgn_last_error(void);

@@ -54,7 +54,7 @@ class BlendOpts(C.Structure):
         ("class_streams", C.c_int32), ("has_sky", C.c_int32), ("eval_clamp", C.c_int32),
         ("split_fwd_main", C.c_int32), ("split_fwd_acc", C.c_int32), ("split_bwd_main", C.c_int32),
         ("split_bwd_acc", C.c_int32),
-        ("raw_mode", C.c_int32), ("background", C.c_float * 4),
+        ("raw_mode", C.c_int32), ("background", C.c_float * 4), ("row_skip", C.c_int32),
     ]
 
 

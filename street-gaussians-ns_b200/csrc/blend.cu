@@ -125,7 +125,7 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // number of strips (warps) a tile is split into, from the length of the list it has to traverse
 __device__ __forceinline__ int strips_for(int len, int t1) { return len <= t1 ? 1 : (len <= 2 * t1 ? 2 : (len <= 4 * t1 ? 4 : 8)); }
 
-template <int PPL, bool CLS>
+template <int PPL, bool CLS, bool SKIP>
 __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int tile, int strip, const int2 range,
                                                 float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -150,10 +150,18 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
     if (range.x + lane < range.y) nxt = gather_entry(p.records, p.sorted_ids[range.x + lane]);
     int buf = 0;
     bool finished = false;
+    const float yc0 = (float)((tile / p.tiles_x) * SGN_TILE + strip * (2 * PPL)) + 1.0f;
+    unsigned slot_live = ALL;  // warp-uniform: row pairs that still have an unterminated pixel (refreshed per batch)
     for (int base = range.x; base < range.y && !finished; base += 32) {
-        sA[buf][lane] = nxt.A; sB[buf][lane] = nxt.B; sC[buf][lane] = nxt.C;
+        sA[buf][lane] = nxt.A; sB[buf][lane] = nxt.B;
+        sC[buf][lane] = make_float4(nxt.C.x, nxt.C.y, nxt.C.z, SKIP ? row_reach(nxt) + 0.5f : 0.f);
         __syncwarp();
         if (base + 32 + lane < range.y) nxt = gather_entry(p.records, p.sorted_ids[base + 32 + lane]);
+        if (SKIP) {
+            slot_live = 0;
+#pragma unroll
+            for (int s = 0; s < PPL; ++s) slot_live |= __any_sync(FULL, !((done >> s) & 1u)) ? (1u << s) : 0u;
+        }
         const int n = min(32, range.y - base);
         for (int t = 0; t < n; ++t) {
             if (__all_sync(FULL, done == ALL)) { finished = true; break; }
@@ -161,6 +169,7 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
             const float4 B = sB[buf][t];
             const float4 Cc = sC[buf][t];
             const bool isobj = CLS && (__float_as_int(Cc.z) < 0);
+            const float dyc = A.y - yc0;
             const float dx = A.x - px;
             const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
@@ -169,6 +178,9 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
             // straight-line, predicated: the PPL pixel chains are independent and interleave (ILP)
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
+                if (SKIP) {  // warp-uniform: the entry cannot reach this row pair, or all its pixels terminated
+                    if (!((slot_live >> s) & 1u) || fabsf(dyc - (float)(2 * s)) > Cc.w) continue;
+                }
                 const float dy = dy0 - (float)(2 * s);
                 const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
                 const bool valid = (s2 >= nlo) && (s2 <= LOG2_255);
@@ -239,7 +251,7 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
 
 // grid = tiles x 8 one-warp CTAs: block b -> strip b / tiles of tile b % tiles; strips beyond the
 // tile's split exit at once (registers are per CTA, so they cost nothing once gone)
-template <bool CLS>
+template <bool CLS, bool SKIP>
 __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
@@ -249,10 +261,10 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     const int W = strips_for(range.y - range.x, p.split_main);
     if (strip >= W) return;
     switch (W) {
-        case 1: blend_fwd_strip<8, CLS>(p, tile, strip, range, sA, sB, sC); break;
-        case 2: blend_fwd_strip<4, CLS>(p, tile, strip, range, sA, sB, sC); break;
-        case 4: blend_fwd_strip<2, CLS>(p, tile, strip, range, sA, sB, sC); break;
-        default: blend_fwd_strip<1, CLS>(p, tile, strip, range, sA, sB, sC); break;
+        case 1: blend_fwd_strip<8, CLS, SKIP>(p, tile, strip, range, sA, sB, sC); break;
+        case 2: blend_fwd_strip<4, CLS, SKIP>(p, tile, strip, range, sA, sB, sC); break;
+        case 4: blend_fwd_strip<2, CLS, SKIP>(p, tile, strip, range, sA, sB, sC); break;
+        default: blend_fwd_strip<1, CLS, SKIP>(p, tile, strip, range, sA, sB, sC); break;
     }
 }
 
@@ -436,13 +448,15 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
         ForkJoin fj((cudaStream_t)stream);
         acc_fwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 1);  // objects: independent of the main pass
         SGN_CHECK_LAUNCH("acc_fwd_kernel<object>");
-        blend_fwd_kernel<true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        if (opts->row_skip) blend_fwd_kernel<true, true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        else blend_fwd_kernel<true, false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("blend_fwd_kernel");
         acc_fwd_kernel<<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p, 0);  // background: needs the main pass's flags
         SGN_CHECK_LAUNCH("acc_fwd_kernel<background>");
         fj.finish();
     } else {
-        blend_fwd_kernel<false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        if (opts->row_skip) blend_fwd_kernel<false, true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        else blend_fwd_kernel<false, false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("blend_fwd_kernel");
     }
     return SGN_OK;
@@ -477,7 +491,7 @@ struct BlendBwdParams {
 };
 
 // DEPTHG: the depth output has a cotangent.
-template <int PPL, bool DEPTHG>
+template <int PPL, bool DEPTHG, bool SKIP>
 __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int tile, int strip, const int2 range,
                                                 float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -553,8 +567,13 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
     Staged nxt;
     if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, p.sorted_ids[hi0 - 1 - lane]);
     int buf = 0;
+    const float yc0 = (float)((tile / p.tiles_x) * SGN_TILE + strip * (2 * PPL)) + 1.0f;
+    int slot_kmax[PPL];  // warp-uniform: deepest contributing position of each row pair
+#pragma unroll
+    for (int s = 0; s < PPL; ++s) slot_kmax[s] = SKIP ? warp_max(idx[s]) : 0x7fffffff;
     for (int hi = hi0; hi > range.x; hi -= 32) {
         sA[buf][lane] = nxt.A; sB[buf][lane] = nxt.B; sC[buf][lane] = nxt.C;
+        const float my_reach = SKIP ? row_reach(nxt) + 0.5f : 0.f;
         __syncwarp();
         if (hi - 33 - lane >= range.x) nxt = gather_entry(p.records, p.sorted_ids[hi - 33 - lane]);
         const int n = min(32, hi - range.x);
@@ -563,6 +582,8 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             const float4 A = sA[buf][t];
             const float4 B = sB[buf][t];
             const float4 Cc = sC[buf][t];
+            const float reach = SKIP ? __shfl_sync(FULL, my_reach, t) : 0.f;
+            const float dyc = A.y - yc0;
             const float dx = A.x - px;
             const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
             const float dy0 = A.y - py0;
@@ -573,6 +594,9 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             // straight-line, predicated (see the forward)
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
+                if (SKIP) {  // warp-uniform: out of this row pair's reach, or deeper than any of its pixels blended
+                    if (k > slot_kmax[s] || fabsf(dyc - (float)(2 * s)) > reach) continue;
+                }
                 const float dy = dy0 - (float)(2 * s);
                 const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
                 const bool valid = (s2 >= nlo) && (s2 <= LOG2_255) && (k <= idx[s]);
@@ -625,7 +649,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
 
 // the prologue (v_sky, cotangent chain) must run for every pixel, so strips are always launched for the
 // whole tile: W strips of 16/W rows
-template <bool DEPTHG>
+template <bool DEPTHG, bool SKIP>
 __global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
@@ -635,10 +659,10 @@ __global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
     const int W = strips_for(p.tile_depth[tile], p.split_main);
     if (strip >= W) return;
     switch (W) {
-        case 1: blend_bwd_strip<8, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
-        case 2: blend_bwd_strip<4, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
-        case 4: blend_bwd_strip<2, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
-        default: blend_bwd_strip<1, DEPTHG>(p, tile, strip, range, sA, sB, sC); break;
+        case 1: blend_bwd_strip<8, DEPTHG, SKIP>(p, tile, strip, range, sA, sB, sC); break;
+        case 2: blend_bwd_strip<4, DEPTHG, SKIP>(p, tile, strip, range, sA, sB, sC); break;
+        case 4: blend_bwd_strip<2, DEPTHG, SKIP>(p, tile, strip, range, sA, sB, sC); break;
+        default: blend_bwd_strip<1, DEPTHG, SKIP>(p, tile, strip, range, sA, sB, sC); break;
     }
 }
 
@@ -792,8 +816,13 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
             acc_bwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 0);
             SGN_CHECK_LAUNCH("acc_bwd_kernel<background>");
         }
-        if (in->v_depth) blend_bwd_kernel<true><<<tiles * 8, 32, 0, stream>>>(p);
-        else blend_bwd_kernel<false><<<tiles * 8, 32, 0, stream>>>(p);
+        if (in->v_depth) {
+            if (opts->row_skip) blend_bwd_kernel<true, true><<<tiles * 8, 32, 0, stream>>>(p);
+            else blend_bwd_kernel<true, false><<<tiles * 8, 32, 0, stream>>>(p);
+        } else {
+            if (opts->row_skip) blend_bwd_kernel<false, true><<<tiles * 8, 32, 0, stream>>>(p);
+            else blend_bwd_kernel<false, false><<<tiles * 8, 32, 0, stream>>>(p);
+        }
         SGN_CHECK_LAUNCH("blend_bwd_kernel");
         fj.finish();
     }

@@ -250,6 +250,7 @@ def blend_opts(s: RenderSettings, has_sky: bool) -> _lib.BlendOpts:
     bo.split_fwd_acc = int(os.environ.get("SGN_SPLIT_FWD_ACC", "0"))
     bo.split_bwd_main = int(os.environ.get("SGN_SPLIT_BWD_MAIN", "0"))
     bo.split_bwd_acc = int(os.environ.get("SGN_SPLIT_BWD_ACC", "0"))
+    bo.row_skip = int(os.environ.get("SGN_ROW_SKIP", "1"))
     return bo
 
 
