@@ -129,11 +129,13 @@ int sgn_upload(const void* host, size_t bytes, void* dev, void* stream);
  * (sgn_splatfacto.py:857-858,864), gsplat project_gaussians (:860-873), view directions +
  * spherical_harmonics + clamp (:934-940) and sigmoid(opacities) (:946-949).
  * Outputs: records[N,12] (layout above), radii[N] i32, num_tiles_hit[N] i32, tile_bbox[N] (4 x u16:
- * xmin,ymin,xmax,ymax in tiles).  Work is split into 128-row chunks that never straddle segments:
+ * xmin,ymin,xmax,ymax in tiles), tiles_touched[N] i32 = number of AABB tiles the Gaussian can really
+ * reach (exact test, see sgn_bin_count), touch_mask[N] u32 = one bit per AABB tile when the AABB has at
+ * most 32 tiles.  Work is split into 128-row chunks that never straddle segments:
  * num_chunks = sum over segments of ceil(count/128), sgn_segment.chunk0 = the segment's first chunk. */
 int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, int num_chunks, const sgn_camera* cam,
                     float* records, int32_t* radii, int32_t* num_tiles_hit, uint16_t* tile_bbox,
-                    void* stream);
+                    int32_t* tiles_touched, uint32_t* touch_mask, void* stream);
 
 /* Backward of the above.  v_records[N,12] holds the per-Gaussian cotangents in record layout
  * ([0:2] v_xy, [2:5] v_conic, [5] v_opacity, [6:9] v_rgb, [9] v_depth), as accumulated by
@@ -161,20 +163,23 @@ int sgn_l1_sh(int N, int K, int degree, const float* viewdirs, const float* coef
 /* ---- binning: cumulative intersects, key emit, radix sort, tile bin edges ---------------------
  * Replaces the inside of gsplat rasterize_gaussians: compute_cumulative_intersects,
  * map_gaussian_to_intersects, torch.sort, get_tile_bin_edges. */
-/* step 1: per-Gaussian count of the AABB tiles it can actually reach (exact, conservative
- * ellipse-vs-tile test: a tile where no pixel centre can have alpha >= 1/255 is a no-op for every
- * stream and is dropped; gsplat's num_tiles_hit is NOT changed), inclusive scan -> cum[N];
- * the total M is also written to *total_dev (int64). */
+/* step 0 (only when the records do not come from sgn_project_fwd, e.g. the Level-1 rasterize path):
+ * per-Gaussian count of the AABB tiles it can actually reach.  Exact, conservative ellipse-vs-tile test:
+ * a tile where no pixel centre can have alpha >= 1/255 is a no-op for every stream and is dropped;
+ * gsplat's num_tiles_hit is NOT changed. */
+int sgn_bin_count(int N, const sgn_camera* cam, const float* records, const int32_t* radii,
+                  const uint16_t* tile_bbox, int32_t* tiles_touched, uint32_t* touch_mask, void* stream);
+/* step 1: stable depth order of the N rows (order[N], invisible rows last) and the inclusive scan of
+ * tiles_touched IN THAT ORDER (cum[N]); the total M is also written to *total_dev (int64). */
 size_t sgn_bin_scan_scratch_bytes(int N);
-int sgn_bin_scan(int N, const sgn_camera* cam, const float* records, const int32_t* radii,
-                 const uint16_t* tile_bbox, int32_t* cum, int64_t* total_dev,
-                 void* scratch, size_t scratch_bytes, void* stream);
-/* step 2: emit + sort + bin edges for M = total intersections (caller read total back, or passes
- * an upper bound capacity together with total_dev: entries beyond the true total are ignored). */
+int sgn_bin_scan(int N, const float* records, const int32_t* radii, const int32_t* tiles_touched,
+                 int32_t* order, int32_t* cum, int64_t* total_dev, void* scratch, size_t scratch_bytes, void* stream);
+/* step 2: emit (in depth order) + stable sort by tile id + bin edges for M = total intersections. */
 size_t sgn_bin_sort_scratch_bytes(int64_t M);
 int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, const int32_t* radii,
-                 const uint16_t* tile_bbox, const int32_t* cum, int32_t* sorted_ids /*[M]*/,
-                 int32_t* tile_bins /*[tiles,2]*/, void* scratch, size_t scratch_bytes, void* stream);
+                 const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* order, const int32_t* cum,
+                 int32_t* sorted_ids /*[M]*/, int32_t* tile_bins /*[tiles,2]*/, void* scratch, size_t scratch_bytes,
+                 void* stream);
 /* sorted_ids payload: bits 0-30 = Gaussian row (concatenated index space), bit 31 = object class.
  * step 3 (only for the class renders): per-tile class sub-lists, a stable partition of every tile's
  * list into background entries (class 0) and object entries (class 1) -- what the reference's

@@ -79,7 +79,7 @@ _lib = None
 
 EXPORTS = [
     "sgn_last_error", "sgn_abi_version", "sgn_launch_count", "sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera",
-    "sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_l1_project_fwd", "sgn_l1_project_bwd", "sgn_l1_sh", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
+    "sgn_upload", "sgn_bin_count", "sgn_project_fwd", "sgn_project_bwd", "sgn_l1_project_fwd", "sgn_l1_project_bwd", "sgn_l1_sh", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
     "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_bin_class_scratch_bytes", "sgn_bin_class_lists",
     "sgn_blend_fwd", "sgn_blend_bwd",
 ]
@@ -102,7 +102,7 @@ def load():
     for f in ("sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera"):
         getattr(L, f).restype = sz
     L.sgn_upload.argtypes = [vp, sz, vp, vp]
-    L.sgn_project_fwd.argtypes = [vp, i32, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp]
+    L.sgn_project_fwd.argtypes = [vp, i32, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp]
     L.sgn_project_bwd.argtypes = [vp, vp, i32, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp]
     fl = C.c_float
     L.sgn_l1_project_fwd.argtypes = [i32, vp, vp, fl, vp, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp]
@@ -112,10 +112,12 @@ def load():
         getattr(L, f).restype = C.c_int
     L.sgn_bin_scan_scratch_bytes.argtypes = [i32]
     L.sgn_bin_scan_scratch_bytes.restype = sz
-    L.sgn_bin_scan.argtypes = [i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_scan.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_count.argtypes = [i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp]
+    L.sgn_bin_count.restype = C.c_int
     L.sgn_bin_sort_scratch_bytes.argtypes = [i64]
     L.sgn_bin_sort_scratch_bytes.restype = sz
-    L.sgn_bin_sort.argtypes = [i32, i64, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_sort.argtypes = [i32, i64, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.sgn_bin_class_scratch_bytes.argtypes = [i32]
     L.sgn_bin_class_scratch_bytes.restype = sz
     L.sgn_bin_class_lists.argtypes = [C.POINTER(CameraStruct), i64, vp, vp, vp, vp, vp, sz, vp]

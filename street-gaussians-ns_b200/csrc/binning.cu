@@ -1,87 +1,25 @@
-// Tile binning: cumulative intersects, (tile|depth) key emit, radix sort, per-tile bin edges.
-// Semantics: gsplat 0.1.x rasterize_gaussians internals; sort order ==
-// stable sort of (tile_id << 32 | float_bits(depth)) with emission order as the tie break.
+// Tile binning: per-Gaussian touched-tile counts -> depth order -> key emit -> stable sort by tile ->
+// per-tile bin edges (-> class sub-lists).
+// Semantics: gsplat 0.1.x rasterize_gaussians internals: every tile's list is
+// ordered like a stable sort of (tile_id << 32 | float_bits(depth)) with emission order (Gaussian index)
+// as the tie break.  That order is produced in two cheaper stable steps instead of one 46-bit sort of
+// the M intersections:
+//   1. the N Gaussians are stably sorted by depth bits (32-bit keys, N elements);
+//   2. intersections are emitted in that order and stably sorted by their 14-bit tile id only.
+// Step 2 moves 12 B per entry twice instead of 24 B six times.
 #include <cub/cub.cuh>
 
-#include "sgn_common.cuh"
+#include "sgn_touch.cuh"
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------------
-// Exact (conservative) tile culling.
-//
-// gsplat lists a Gaussian in every tile of the AABB of its 3-sigma radius, but a pixel only ever
-// uses it when alpha = min(clamp, o*exp(-sigma)) >= 1/255, i.e. sigma <= tau = ln(255*o)
-// (SURVEY.md Appendix A.6).  A tile whose pixel centres ALL have sigma > tau is a no-op for every
-// stream, forward and backward, so it is dropped from the lists here (about half of the entries on
-// the synthetic street scenes).  num_tiles_hit -- the value gsplat reports -- is untouched.
-// The test minimises the (convex) quadratic form over the rectangle of the tile's pixel centres; a
-// margin covers float rounding in both this test and the blend kernels' own evaluation, so no pair
-// the blend would accept is ever dropped.  tests/ check "dropped => no valid pixel" against the oracle.
-struct TouchCtx {
-    float gx, gy, a, b, c, tau;
-    float nbc, nba;  // -b/c, -b/a: minimiser slopes along the rectangle edges
-    int always;      // degenerate conic: keep every AABB tile
-};
-
-__device__ __forceinline__ TouchCtx make_touch_ctx(const float4 r0, const float4 r1) {
-    TouchCtx t;
-    t.gx = r0.x; t.gy = r0.y; t.a = r0.z; t.b = r0.w; t.c = r1.x;
-    const float o = r1.y;
-    t.tau = __logf(255.f * o);
-    t.always = (!(t.a > 0.f && t.c > 0.f && __fsub_rn(__fmul_rn(t.a, t.c), __fmul_rn(t.b, t.b)) > 0.f) || !(t.tau == t.tau)) ? 1 : 0;
-    t.nbc = t.always ? 0.f : __fdiv_rn(-t.b, t.c);
-    t.nba = t.always ? 0.f : __fdiv_rn(-t.b, t.a);
-    return t;
-}
-
-__device__ __forceinline__ float touch_q(const TouchCtx& t, float dx, float dy, float& mag) {
-    // explicit, un-contractable operations: count_tiles_kernel and emit_keys_kernel must take
-    // bit-identical decisions
-    const float qa = __fmul_rn(__fmul_rn(0.5f * t.a, dx), dx), qc = __fmul_rn(__fmul_rn(0.5f * t.c, dy), dy);
-    const float qb = __fmul_rn(__fmul_rn(t.b, dx), dy);
-    const float s = __fadd_rn(qa, qc);
-    mag = __fadd_rn(s, fabsf(qb));
-    return __fadd_rn(s, qb);
-}
-
-// does the Gaussian reach any pixel centre of tile (tx,ty)?  (pixel centres: 16*tx+0.5 ... +15.5, clipped to the image)
-__device__ __forceinline__ bool tile_touched(const TouchCtx& t, int tx, int ty, int width, int height, int bw) {
-    if (t.always) return true;
-    if (t.tau < 0.f) return false;  // opacity < 1/255: alpha can never reach 1/255
-    const float x0 = __fsub_rn((float)(tx * bw) + 0.5f, t.gx), x1 = __fsub_rn(fminf((float)(tx * bw + bw), (float)width) - 0.5f, t.gx);
-    const float y0 = __fsub_rn((float)(ty * bw) + 0.5f, t.gy), y1 = __fsub_rn(fminf((float)(ty * bw + bw), (float)height) - 0.5f, t.gy);
-    if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;  // centre inside the rectangle
-    const float nbc = t.nbc, nba = t.nba;
-    float best = 3.4e38f, best_mag = 0.f, mag, q;
-    // edges x = x0, x = x1: minimise over dy
-    q = touch_q(t, x0, fminf(fmaxf(__fmul_rn(nbc, x0), y0), y1), mag); if (q < best) { best = q; best_mag = mag; }
-    q = touch_q(t, x1, fminf(fmaxf(__fmul_rn(nbc, x1), y0), y1), mag); if (q < best) { best = q; best_mag = mag; }
-    // edges y = y0, y = y1: minimise over dx
-    q = touch_q(t, fminf(fmaxf(__fmul_rn(nba, y0), x0), x1), y0, mag); if (q < best) { best = q; best_mag = mag; }
-    q = touch_q(t, fminf(fmaxf(__fmul_rn(nba, y1), x0), x1), y1, mag); if (q < best) { best = q; best_mag = mag; }
-    return best <= __fadd_rn(__fadd_rn(t.tau, 1e-3f), __fmul_rn(8e-6f, best_mag));
-}
-
-// Gaussians whose AABB spans more than COOP_AREA tiles are handled by the whole warp (32 tiles per
-// step) after the per-thread pass, so one huge splat does not serialise its warp.
-#define COOP_AREA 32
-
-__device__ __forceinline__ TouchCtx shfl_ctx(const TouchCtx& t, int src) {
-    TouchCtx r;
-    r.gx = __shfl_sync(0xffffffffu, t.gx, src); r.gy = __shfl_sync(0xffffffffu, t.gy, src);
-    r.a = __shfl_sync(0xffffffffu, t.a, src); r.b = __shfl_sync(0xffffffffu, t.b, src);
-    r.c = __shfl_sync(0xffffffffu, t.c, src); r.tau = __shfl_sync(0xffffffffu, t.tau, src);
-    r.nbc = __shfl_sync(0xffffffffu, t.nbc, src); r.nba = __shfl_sync(0xffffffffu, t.nba, src);
-    r.always = __shfl_sync(0xffffffffu, t.always, src);
-    return r;
-}
-
+// standalone touched-tile count (the fused path gets it from project_fwd; the Level-1 rasterize path,
+// which starts from plain xys/conics tensors, calls this)
 __global__ void __launch_bounds__(256)
 count_tiles_kernel(int N, int width, int height, int bw, const float4* __restrict__ records, const int32_t* __restrict__ radii,
-                   const ushort4* __restrict__ tile_bbox, int32_t* __restrict__ tiles_touched) {
+                   const ushort4* __restrict__ tile_bbox, int32_t* __restrict__ tiles_touched, uint32_t* __restrict__ touch_mask) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
     const bool vis = (g < N) && radii[g] > 0;
     ushort4 bb = make_ushort4(0, 0, 0, 0);
     TouchCtx t = {};
@@ -89,58 +27,89 @@ count_tiles_kernel(int N, int width, int height, int bw, const float4* __restric
         bb = tile_bbox[g];
         t = make_touch_ctx(records[3 * (size_t)g], records[3 * (size_t)g + 1]);
     }
-    const int bwid = bb.z - bb.x, area = bwid * (bb.w - bb.y);
-    int n = 0;
-    if (vis && area <= COOP_AREA) {
-        for (int ty = bb.y; ty < bb.w; ++ty)
-            for (int tx = bb.x; tx < bb.z; ++tx) n += tile_touched(t, tx, ty, width, height, bw) ? 1 : 0;
-    }
-    unsigned big = __ballot_sync(0xffffffffu, vis && area > COOP_AREA);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const TouchCtx c = shfl_ctx(t, src);
-        const int x0 = __shfl_sync(0xffffffffu, (int)bb.x, src), y0 = __shfl_sync(0xffffffffu, (int)bb.y, src);
-        const int w = __shfl_sync(0xffffffffu, bwid, src), ar = __shfl_sync(0xffffffffu, area, src);
-        int cnt = 0;
-        for (int base = 0; base < ar; base += 32) {
-            const int ti = base + lane;
-            const bool ok = (ti < ar) && tile_touched(c, x0 + ti % w, y0 + ti / w, width, height, bw);
-            cnt += __popc(__ballot_sync(0xffffffffu, ok));
-        }
-        if (lane == src) n = cnt;
-    }
-    if (g < N) tiles_touched[g] = n;
+    uint32_t mask;
+    const int n = count_touched_tiles(vis, t, bb, width, height, bw, mask);
+    if (g < N) { tiles_touched[g] = n; touch_mask[g] = mask; }
 }
+
+extern "C" int sgn_bin_count(int N, const sgn_camera* cam, const float* records, const int32_t* radii,
+                             const uint16_t* tile_bbox, int32_t* tiles_touched, uint32_t* touch_mask, void* stream) {
+    SGN_REQUIRE(cam && records && radii && tile_bbox && tiles_touched && touch_mask, "sgn_bin_count: null pointer");
+    if (N == 0) return SGN_OK;
+    count_tiles_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        N, cam->width, cam->height, cam->block_width, reinterpret_cast<const float4*>(records), radii,
+        reinterpret_cast<const ushort4*>(tile_bbox), tiles_touched, touch_mask);
+    SGN_CHECK_LAUNCH("count_tiles_kernel");
+    return SGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step 1: depth order + inclusive scan of the touched-tile counts in that order
+__global__ void __launch_bounds__(256)
+depth_keys_kernel(int N, const float4* __restrict__ records, const int32_t* __restrict__ radii, uint32_t* __restrict__ keys,
+                  int32_t* __restrict__ vals) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    // invisible rows sort last (no positive float has all bits set) and emit nothing
+    keys[g] = radii[g] > 0 ? (uint32_t)__float_as_int(records[3 * (size_t)g + 2].y) : 0xffffffffu;
+    vals[g] = g;
+}
+
+struct PermutedCount {
+    const int32_t* order;
+    const int32_t* counts;
+    __host__ __device__ int32_t operator()(int i) const { return counts[order[i]]; }
+};
 
 __global__ void write_total_kernel(const int32_t* __restrict__ cum, int N, int64_t* __restrict__ total) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *total = (N > 0) ? (int64_t)cum[N - 1] : 0;
 }
 
-extern "C" size_t sgn_bin_scan_scratch_bytes(int N) {
-    size_t temp = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, temp, (const int32_t*)nullptr, (int32_t*)nullptr, N > 0 ? N : 1);
-    return align_up(temp, 256) + 256 + align_up(sizeof(int32_t) * (size_t)(N > 0 ? N : 1), 256);
+struct ScanLayout {
+    size_t keys_in, keys_out, vals_in, temp, temp_bytes, total;
+};
+static ScanLayout scan_layout(int N) {
+    ScanLayout L;
+    const size_t n = (size_t)(N > 0 ? N : 1);
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)n, 0, 32);
+    cub::DeviceScan::InclusiveSum(nullptr, t2, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+    L.keys_in = 0;
+    L.keys_out = align_up(n * 4, 256);
+    L.vals_in = L.keys_out + align_up(n * 4, 256);
+    L.temp = L.vals_in + align_up(n * 4, 256);
+    L.temp_bytes = t1 > t2 ? t1 : t2;
+    L.total = L.temp + align_up(L.temp_bytes, 256) + 256;
+    return L;
 }
 
-extern "C" int sgn_bin_scan(int N, const sgn_camera* cam, const float* records, const int32_t* radii,
-                            const uint16_t* tile_bbox, int32_t* cum, int64_t* total_dev, void* scratch,
-                            size_t scratch_bytes, void* stream_) {
+extern "C" size_t sgn_bin_scan_scratch_bytes(int N) { return scan_layout(N).total; }
+
+extern "C" int sgn_bin_scan(int N, const float* records, const int32_t* radii, const int32_t* tiles_touched,
+                            int32_t* order, int32_t* cum, int64_t* total_dev, void* scratch, size_t scratch_bytes,
+                            void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    SGN_REQUIRE(cam && records && radii && tile_bbox && cum && total_dev && scratch, "sgn_bin_scan: null pointer");
-    if (scratch_bytes < sgn_bin_scan_scratch_bytes(N)) {
-        sgn_set_error("sgn_bin_scan: scratch too small (%zu < %zu)", scratch_bytes, sgn_bin_scan_scratch_bytes(N));
+    SGN_REQUIRE(records && radii && tiles_touched && order && cum && total_dev && scratch, "sgn_bin_scan: null pointer");
+    const ScanLayout L = scan_layout(N);
+    if (scratch_bytes < L.total) {
+        sgn_set_error("sgn_bin_scan: scratch too small (%zu < %zu)", scratch_bytes, L.total);
         return SGN_ERR_WORKSPACE;
     }
     if (N > 0) {
-        const size_t cnt_bytes = align_up(sizeof(int32_t) * (size_t)N, 256);
-        int32_t* touched = (int32_t*)scratch;
-        count_tiles_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, cam->width, cam->height, cam->block_width,
-                                                                reinterpret_cast<const float4*>(records), radii,
-                                                                reinterpret_cast<const ushort4*>(tile_bbox), touched);
-        SGN_CHECK_LAUNCH("count_tiles_kernel");
-        size_t temp = scratch_bytes - cnt_bytes;
-        SGN_CHECK_CUDA(cub::DeviceScan::InclusiveSum((char*)scratch + cnt_bytes, temp, touched, cum, N, stream));
+        char* base = (char*)scratch;
+        uint32_t* keys_in = (uint32_t*)(base + L.keys_in);
+        uint32_t* keys_out = (uint32_t*)(base + L.keys_out);
+        int32_t* vals_in = (int32_t*)(base + L.vals_in);
+        depth_keys_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, reinterpret_cast<const float4*>(records), radii, keys_in, vals_in);
+        SGN_CHECK_LAUNCH("depth_keys_kernel");
+        size_t temp = L.temp_bytes;
+        SGN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(base + L.temp, temp, keys_in, keys_out, vals_in, order, N, 0, 32, stream));
+        sgn_count_launch(1);
+        cub::CountingInputIterator<int> idx(0);
+        cub::TransformInputIterator<int32_t, PermutedCount, cub::CountingInputIterator<int>> it(idx, PermutedCount{order, tiles_touched});
+        temp = L.temp_bytes;
+        SGN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(base + L.temp, temp, it, cum, N, stream));
         sgn_count_launch(1);
     }
     write_total_kernel<<<1, 32, 0, stream>>>(cum, N, total_dev);
@@ -149,75 +118,76 @@ extern "C" int sgn_bin_scan(int N, const sgn_camera* cam, const float* records, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// key emit: one thread per Gaussian (map_gaussian_to_intersects), only tiles that pass tile_touched
+// step 2: key emit in depth order (thread i handles Gaussian order[i]), stable sort by tile, bin edges
 __global__ void __launch_bounds__(256)
 emit_keys_kernel(int N, int tiles_x, int width, int height, int bw, const float4* __restrict__ records,
-                 const int32_t* __restrict__ radii, const ushort4* __restrict__ tile_bbox, const int32_t* __restrict__ cum,
-                 uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+                 const int32_t* __restrict__ radii, const ushort4* __restrict__ tile_bbox,
+                 const uint32_t* __restrict__ touch_mask, const int32_t* __restrict__ order, const int32_t* __restrict__ cum,
+                 uint16_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool vis = (g < N) && radii[g] > 0;
+    const int g = (i < N) ? order[i] : 0;
+    const bool vis = (i < N) && radii[g] > 0;
     ushort4 bb = make_ushort4(0, 0, 0, 0);
     TouchCtx t = {};
-    uint32_t dbits = 0;
     int32_t payload = 0;
+    uint32_t mask = 0;
     int cur = 0, end = 0;
     if (vis) {
         bb = tile_bbox[g];
-        const float4 r0 = records[3 * (size_t)g], r1 = records[3 * (size_t)g + 1], r2 = records[3 * (size_t)g + 2];
-        t = make_touch_ctx(r0, r1);
-        dbits = (uint32_t)__float_as_int(r2.y);
         // payload: Gaussian row in the low 31 bits, object-class flag in bit 31 (no gather needed later)
-        payload = g | ((__float_as_int(r2.z) & SGN_AUX_OBJECT) ? (int32_t)0x80000000 : 0);
-        cur = (g == 0) ? 0 : cum[g - 1];
-        end = cum[g];
+        payload = g | ((__float_as_int(records[3 * (size_t)g + 2].z) & SGN_AUX_OBJECT) ? (int32_t)0x80000000 : 0);
+        mask = touch_mask[g];
+        cur = (i == 0) ? 0 : cum[i - 1];
+        end = cum[i];
     }
     const int bwid = bb.z - bb.x, area = bwid * (bb.w - bb.y);
     if (vis && area <= COOP_AREA) {
-        for (int ty = bb.y; ty < bb.w; ++ty) {
-            for (int tx = bb.x; tx < bb.z; ++tx) {
-                if (!tile_touched(t, tx, ty, width, height, bw)) continue;
-                if (cur >= end) break;  // cannot happen (same test as count_tiles_kernel); never overrun the slot range
-                keys[cur] = ((uint64_t)(ty * tiles_x + tx) << 32) | (uint64_t)dbits;
-                vals[cur] = payload;
-                ++cur;
-            }
+        // the projection kernel already decided every tile of a small AABB: replay its bit mask
+        while (mask && cur < end) {
+            const int bit = __ffs(mask) - 1;
+            mask &= mask - 1;
+            keys[cur] = (uint16_t)((bb.y + bit / bwid) * tiles_x + bb.x + bit % bwid);
+            vals[cur] = payload;
+            ++cur;
         }
     }
     unsigned big = __ballot_sync(0xffffffffu, vis && area > COOP_AREA);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const TouchCtx c = shfl_ctx(t, src);
-        const int x0 = __shfl_sync(0xffffffffu, (int)bb.x, src), y0 = __shfl_sync(0xffffffffu, (int)bb.y, src);
-        const int w = __shfl_sync(0xffffffffu, bwid, src), ar = __shfl_sync(0xffffffffu, area, src);
-        const uint32_t db = __shfl_sync(0xffffffffu, dbits, src);
-        const int32_t pl = __shfl_sync(0xffffffffu, payload, src);
-        int pos = __shfl_sync(0xffffffffu, cur, src);
-        const int lim = __shfl_sync(0xffffffffu, end, src);
-        for (int base = 0; base < ar; base += 32) {
-            const int ti = base + lane;
-            const int tx = x0 + ti % w, ty = y0 + ti / w;
-            const bool ok = (ti < ar) && tile_touched(c, tx, ty, width, height, bw);
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            const int my = pos + __popc(m & ((1u << lane) - 1u));
-            if (ok && my < lim) {
-                keys[my] = ((uint64_t)(ty * tiles_x + tx) << 32) | (uint64_t)db;
-                vals[my] = pl;
+    if (big) {
+        if (vis && area > COOP_AREA) t = make_touch_ctx(records[3 * (size_t)g], records[3 * (size_t)g + 1]);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const TouchCtx c = shfl_ctx(t, src);
+            const int x0 = __shfl_sync(0xffffffffu, (int)bb.x, src), y0 = __shfl_sync(0xffffffffu, (int)bb.y, src);
+            const int w = __shfl_sync(0xffffffffu, bwid, src), ar = __shfl_sync(0xffffffffu, area, src);
+            const int32_t pl = __shfl_sync(0xffffffffu, payload, src);
+            int pos = __shfl_sync(0xffffffffu, cur, src);
+            const int lim = __shfl_sync(0xffffffffu, end, src);
+            for (int base = 0; base < ar; base += 32) {
+                const int ti = base + lane;
+                const int tx = x0 + ti % w, ty = y0 + ti / w;
+                const bool ok = (ti < ar) && tile_touched(c, tx, ty, width, height, bw);
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                const int my = pos + __popc(m & ((1u << lane) - 1u));
+                if (ok && my < lim) {  // my >= lim cannot happen: same test as the counting pass
+                    keys[my] = (uint16_t)(ty * tiles_x + tx);
+                    vals[my] = pl;
+                }
+                pos += __popc(m);
             }
-            pos += __popc(m);
         }
     }
 }
 
 __global__ void __launch_bounds__(256)
-bin_edges_kernel(int64_t M, const uint64_t* __restrict__ keys_sorted, int32_t* __restrict__ tile_bins) {
+bin_edges_kernel(int64_t M, const uint16_t* __restrict__ keys_sorted, int32_t* __restrict__ tile_bins) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
-    const int32_t cur = (int32_t)(keys_sorted[i] >> 32);
+    const int32_t cur = (int32_t)keys_sorted[i];
     if (i == 0) tile_bins[2 * cur] = 0;
     else {
-        const int32_t prev = (int32_t)(keys_sorted[i - 1] >> 32);
+        const int32_t prev = (int32_t)keys_sorted[i - 1];
         if (prev != cur) {
             tile_bins[2 * prev + 1] = (int32_t)i;
             tile_bins[2 * cur] = (int32_t)i;
@@ -234,11 +204,11 @@ static SortLayout sort_layout(int64_t M) {
     SortLayout L;
     const size_t m = (size_t)(M > 0 ? M : 1);
     size_t temp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
-                                    (int32_t*)nullptr, (int64_t)m, 0, 64);
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int64_t)m, 0, 16);
     L.keys_in = 0;
-    L.keys_out = align_up(L.keys_in + m * 8, 256);
-    L.vals_in = align_up(L.keys_out + m * 8, 256);
+    L.keys_out = align_up(L.keys_in + m * 2, 256);
+    L.vals_in = align_up(L.keys_out + m * 2, 256);
     L.temp = align_up(L.vals_in + m * 4, 256);
     L.temp_bytes = temp;
     L.total = align_up(L.temp + temp, 256);
@@ -248,14 +218,16 @@ static SortLayout sort_layout(int64_t M) {
 extern "C" size_t sgn_bin_sort_scratch_bytes(int64_t M) { return sort_layout(M).total; }
 
 extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, const int32_t* radii,
-                            const uint16_t* tile_bbox, const int32_t* cum, int32_t* sorted_ids, int32_t* tile_bins,
-                            void* scratch, size_t scratch_bytes, void* stream_) {
+                            const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* order, const int32_t* cum,
+                            int32_t* sorted_ids, int32_t* tile_bins, void* scratch, size_t scratch_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    SGN_REQUIRE(cam && records && radii && tile_bbox && cum && tile_bins && scratch, "sgn_bin_sort: null pointer");
+    SGN_REQUIRE(cam && records && radii && tile_bbox && touch_mask && order && cum && tile_bins && scratch,
+                "sgn_bin_sort: null pointer");
     SGN_REQUIRE(M >= 0 && M < ((int64_t)1 << 31), "sgn_bin_sort: M=%lld out of the int32 range gsplat's cum_tiles_hit supports", (long long)M);
     const int bw = cam->block_width;
     const int tiles_x = (cam->width + bw - 1) / bw, tiles_y = (cam->height + bw - 1) / bw;
     const int tiles = tiles_x * tiles_y;
+    SGN_REQUIRE(tiles <= 65536, "sgn_bin_sort: more than 65536 tiles (16-bit tile keys)");
     SGN_CHECK_CUDA(cudaMemsetAsync(tile_bins, 0, sizeof(int32_t) * 2 * (size_t)tiles, stream));
     if (M == 0 || N == 0) return SGN_OK;
     SGN_REQUIRE(sorted_ids, "sgn_bin_sort: sorted_ids is null");
@@ -265,18 +237,18 @@ extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float
         return SGN_ERR_WORKSPACE;
     }
     char* base = (char*)scratch;
-    uint64_t* keys_in = (uint64_t*)(base + L.keys_in);
-    uint64_t* keys_out = (uint64_t*)(base + L.keys_out);
+    uint16_t* keys_in = (uint16_t*)(base + L.keys_in);
+    uint16_t* keys_out = (uint16_t*)(base + L.keys_out);
     int32_t* vals_in = (int32_t*)(base + L.vals_in);
     emit_keys_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, tiles_x, cam->width, cam->height, bw,
                                                           reinterpret_cast<const float4*>(records), radii,
-                                                          reinterpret_cast<const ushort4*>(tile_bbox), cum, keys_in, vals_in);
+                                                          reinterpret_cast<const ushort4*>(tile_bbox), touch_mask, order, cum,
+                                                          keys_in, vals_in);
     SGN_CHECK_LAUNCH("emit_keys_kernel");
     int tile_bits = 1;
     while ((1 << tile_bits) < tiles) ++tile_bits;
     size_t temp = L.temp_bytes;
-    SGN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(base + L.temp, temp, keys_in, keys_out, vals_in, sorted_ids, M, 0,
-                                                   32 + tile_bits, stream));
+    SGN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(base + L.temp, temp, keys_in, keys_out, vals_in, sorted_ids, M, 0, tile_bits, stream));
     sgn_count_launch(1);
     bin_edges_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, keys_out, tile_bins);
     SGN_CHECK_LAUNCH("bin_edges_kernel");

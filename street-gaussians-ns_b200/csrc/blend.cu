@@ -448,14 +448,14 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
         ForkJoin fj((cudaStream_t)stream);
         acc_fwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 1);  // objects: independent of the main pass
         SGN_CHECK_LAUNCH("acc_fwd_kernel<object>");
-        if (opts->row_skip) blend_fwd_kernel<true, true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        if (opts->row_skip & 1) blend_fwd_kernel<true, true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
         else blend_fwd_kernel<true, false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("blend_fwd_kernel");
         acc_fwd_kernel<<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p, 0);  // background: needs the main pass's flags
         SGN_CHECK_LAUNCH("acc_fwd_kernel<background>");
         fj.finish();
     } else {
-        if (opts->row_skip) blend_fwd_kernel<false, true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        if (opts->row_skip & 1) blend_fwd_kernel<false, true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
         else blend_fwd_kernel<false, false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
         SGN_CHECK_LAUNCH("blend_fwd_kernel");
     }
@@ -816,11 +816,14 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
             acc_bwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 0);
             SGN_CHECK_LAUNCH("acc_bwd_kernel<background>");
         }
+        // row skipping is a forward-only win (measured: the backward loses more ILP than it saves); bit 1 of
+        // row_skip forces it on for experiments
+        const bool skip = (opts->row_skip & 2) != 0;
         if (in->v_depth) {
-            if (opts->row_skip) blend_bwd_kernel<true, true><<<tiles * 8, 32, 0, stream>>>(p);
+            if (skip) blend_bwd_kernel<true, true><<<tiles * 8, 32, 0, stream>>>(p);
             else blend_bwd_kernel<true, false><<<tiles * 8, 32, 0, stream>>>(p);
         } else {
-            if (opts->row_skip) blend_bwd_kernel<false, true><<<tiles * 8, 32, 0, stream>>>(p);
+            if (skip) blend_bwd_kernel<false, true><<<tiles * 8, 32, 0, stream>>>(p);
             else blend_bwd_kernel<false, false><<<tiles * 8, 32, 0, stream>>>(p);
         }
         SGN_CHECK_LAUNCH("blend_bwd_kernel");

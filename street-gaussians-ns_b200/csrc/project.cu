@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "sgn_exact.cuh"
+#include "sgn_touch.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing + tiny ABI helpers
@@ -85,16 +86,20 @@ __device__ __forceinline__ void coop_store(float* __restrict__ dst, const float*
 __global__ void __launch_bounds__(CH)
 project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, const sgn_camera cam,
                    float4* __restrict__ records, int32_t* __restrict__ radii, int32_t* __restrict__ num_tiles_hit,
-                   ushort4* __restrict__ tile_bbox) {
+                   ushort4* __restrict__ tile_bbox, int32_t* __restrict__ tiles_touched, uint32_t* __restrict__ touch_mask) {
     extern __shared__ int s_chunk0[];
     for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_chunk0[i] = segs[i].chunk0;
     __syncthreads();
     const int si = find_segment_by_chunk(s_chunk0, nseg, blockIdx.x);
     const sgn_segment& sg = segs[si];
     const int i = (blockIdx.x - sg.chunk0) * CH + threadIdx.x;
-    if (i >= sg.count) return;
+    const bool active = i < sg.count;  // idle lanes of a tail chunk still take part in the warp-collective tile count
     const size_t g = (size_t)sg.row0 + i;
     const int K = (cam.sh_degree + 1) * (cam.sh_degree + 1);
+    bool vis = false;
+    ushort4 bb = make_ushort4(0, 0, 0, 0);
+    TouchCtx tc = {};
+    if (active) {
 
     float m[3], ls[3], q[4];
 #pragma unroll
@@ -104,7 +109,7 @@ project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, const sgn_cam
         q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
     }
     SgnProj st;
-    const bool vis = sgn_project_exact(sg, cam, m, ls, q, st);
+    vis = sgn_project_exact(sg, cam, m, ls, q, st);
 
     float rgb[3] = {0.f, 0.f, 0.f};
     float opac = 0.f;
@@ -151,14 +156,25 @@ project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, const sgn_cam
     rec[2] = make_float4(rgb[2], vis ? st.pv[2] : 0.f, __int_as_float(aux), 0.f);
     radii[g] = st.radius;
     num_tiles_hit[g] = vis ? (st.tmax[0] - st.tmin[0]) * (st.tmax[1] - st.tmin[1]) : 0;
-    tile_bbox[g] = make_ushort4((unsigned short)st.tmin[0], (unsigned short)st.tmin[1],
-                                (unsigned short)st.tmax[0], (unsigned short)st.tmax[1]);
+    bb = make_ushort4((unsigned short)st.tmin[0], (unsigned short)st.tmin[1],
+                      (unsigned short)st.tmax[0], (unsigned short)st.tmax[1]);
+    tile_bbox[g] = bb;
+    if (vis) tc = make_touch_ctx(make_float4(st.xy[0], st.xy[1], st.conic[0], st.conic[1]), make_float4(st.conic[2], opac, 0.f, 0.f));
+    }  // active
+    // tiles the Gaussian can really reach (exact ellipse-vs-tile test, sgn_touch.cuh); binning lists only those
+    uint32_t mask;
+    const int nt = count_touched_tiles(vis, tc, bb, cam.width, cam.height, cam.block_width, mask);
+    if (active) {
+        tiles_touched[g] = nt;
+        touch_mask[g] = mask;
+    }
 }
 
 extern "C" int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, int num_chunks, const sgn_camera* cam,
                                float* records, int32_t* radii, int32_t* num_tiles_hit, uint16_t* tile_bbox,
-                               void* stream) {
-    SGN_REQUIRE(segs_dev && cam && records && radii && num_tiles_hit && tile_bbox, "sgn_project_fwd: null pointer");
+                               int32_t* tiles_touched, uint32_t* touch_mask, void* stream) {
+    SGN_REQUIRE(segs_dev && cam && records && radii && num_tiles_hit && tile_bbox && tiles_touched && touch_mask,
+                "sgn_project_fwd: null pointer");
     SGN_REQUIRE(nseg >= 1 && nseg <= SGN_MAX_SEGMENTS, "sgn_project_fwd: nseg=%d out of range [1,%d]", nseg, SGN_MAX_SEGMENTS);
     SGN_REQUIRE(N >= 0 && num_chunks >= 0, "sgn_project_fwd: negative size");
     SGN_REQUIRE(cam->block_width >= 2 && cam->block_width <= 16, "block_width must be between 2 and 16 (got %d)", cam->block_width);
@@ -170,7 +186,7 @@ extern "C" int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, int
     if (N == 0 || num_chunks == 0) return SGN_OK;
     project_fwd_kernel<<<num_chunks, CH, nseg * sizeof(int), (cudaStream_t)stream>>>(
         segs_dev, nseg, *cam, reinterpret_cast<float4*>(records), radii, num_tiles_hit,
-        reinterpret_cast<ushort4*>(tile_bbox));
+        reinterpret_cast<ushort4*>(tile_bbox), tiles_touched, touch_mask);
     SGN_CHECK_LAUNCH("project_fwd_kernel");
     return SGN_OK;
 }

@@ -184,30 +184,49 @@ def _grads_table(arena: torch.Tensor, static: dict, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # stage wrappers (also used directly by tests and bench.py)
 # --------------------------------------------------------------------------------------------------
-def project_fwd(table: SegmentTable, cs: _lib.CameraStruct, device):
+class Projected:
+    """Outputs of the fused compose+project+SH kernel (also iterable as the legacy 4-tuple)."""
+
+    def __init__(self, records, radii, tiles_hit, bbox, tiles_touched, touch_mask):
+        self.records, self.radii, self.tiles_hit, self.bbox = records, radii, tiles_hit, bbox
+        self.tiles_touched, self.touch_mask = tiles_touched, touch_mask
+
+    def __iter__(self):
+        return iter((self.records, self.radii, self.tiles_hit, self.bbox))
+
+
+def project_fwd(table: SegmentTable, cs: _lib.CameraStruct, device) -> Projected:
     L = _lib.load()
     N = table.N
     records = torch.empty(N, _lib.RECORD_FLOATS, device=device, dtype=torch.float32)
-    radii = torch.empty(N, device=device, dtype=torch.int32)
-    tiles_hit = torch.empty(N, device=device, dtype=torch.int32)
+    ints = torch.empty(4, max(N, 1), device=device, dtype=torch.int32)  # radii, num_tiles_hit, tiles_touched, touch_mask
     bbox = torch.empty(N, 4, device=device, dtype=torch.int16)
     with _timed("project_fwd"):
-        _lib.check(L.sgn_project_fwd(_ptr(table.dev), table.nseg, N, table.num_chunks, C.byref(cs), _ptr(records), _ptr(radii),
-                                     _ptr(tiles_hit), _ptr(bbox), _stream()), "sgn_project_fwd")
-    return records, radii, tiles_hit, bbox
+        _lib.check(L.sgn_project_fwd(_ptr(table.dev), table.nseg, N, table.num_chunks, C.byref(cs), _ptr(records), _ptr(ints[0]),
+                                     _ptr(ints[1]), _ptr(bbox), _ptr(ints[2]), _ptr(ints[3]), _stream()), "sgn_project_fwd")
+    return Projected(records, ints[0][:N], ints[1][:N], bbox, ints[2][:N], ints[3][:N])
 
 
-def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit, bbox):
-    """Returns (M, sorted_ids[M], tile_bins[tiles,2]).  One host sync to read M (as gsplat does)."""
+def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit=None, bbox=None, proj: Optional[Projected] = None):
+    """Returns (M, sorted_ids[M], tile_bins[tiles,2]).  One host sync to read M (as gsplat does).
+    Pass ``proj`` (from project_fwd) or plain records/radii/bbox (the touched-tile count is then computed here)."""
     L = _lib.load()
     device = records.device
     N = records.shape[0]
-    cum = torch.empty(max(N, 1), device=device, dtype=torch.int32)
+    if proj is not None:
+        bbox, touched, mask = proj.bbox, proj.tiles_touched, proj.touch_mask
+    else:
+        touched = torch.empty(max(N, 1), device=device, dtype=torch.int32)
+        mask = torch.empty(max(N, 1), device=device, dtype=torch.int32)
+        with _timed("bin_count"):
+            _lib.check(L.sgn_bin_count(N, C.byref(cs), _ptr(records), _ptr(radii), _ptr(bbox), _ptr(touched), _ptr(mask),
+                                       _stream()), "sgn_bin_count")
+    oc = torch.empty(2, max(N, 1), device=device, dtype=torch.int32)  # order, cum
     total = torch.empty(1, device=device, dtype=torch.int64)
     sb = L.sgn_bin_scan_scratch_bytes(N)
     scratch = torch.empty(sb, device=device, dtype=torch.uint8)
     with _timed("bin_scan"):
-        _lib.check(L.sgn_bin_scan(N, C.byref(cs), _ptr(records), _ptr(radii), _ptr(bbox), _ptr(cum), _ptr(total),
+        _lib.check(L.sgn_bin_scan(N, _ptr(records), _ptr(radii), _ptr(touched), _ptr(oc[0]), _ptr(oc[1]), _ptr(total),
                                   _ptr(scratch), sb, _stream()), "sgn_bin_scan")
     M = int(total.item())
     bw = cs.block_width
@@ -217,8 +236,8 @@ def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit, bbox):
     sb2 = L.sgn_bin_sort_scratch_bytes(M)
     scratch2 = torch.empty(sb2, device=device, dtype=torch.uint8)
     with _timed("bin_sort"):
-        _lib.check(L.sgn_bin_sort(N, M, C.byref(cs), _ptr(records), _ptr(radii), _ptr(bbox), _ptr(cum), _ptr(sorted_ids),
-                                  _ptr(tile_bins), _ptr(scratch2), sb2, _stream()), "sgn_bin_sort")
+        _lib.check(L.sgn_bin_sort(N, M, C.byref(cs), _ptr(records), _ptr(radii), _ptr(bbox), _ptr(mask), _ptr(oc[0]), _ptr(oc[1]),
+                                  _ptr(sorted_ids), _ptr(tile_bins), _ptr(scratch2), sb2, _stream()), "sgn_bin_sort")
     return M, sorted_ids, tile_bins
 
 
@@ -250,7 +269,7 @@ def blend_opts(s: RenderSettings, has_sky: bool) -> _lib.BlendOpts:
     bo.split_fwd_acc = int(os.environ.get("SGN_SPLIT_FWD_ACC", "0"))
     bo.split_bwd_main = int(os.environ.get("SGN_SPLIT_BWD_MAIN", "0"))
     bo.split_bwd_acc = int(os.environ.get("SGN_SPLIT_BWD_ACC", "0"))
-    bo.row_skip = int(os.environ.get("SGN_ROW_SKIP", "1"))
+    bo.row_skip = int(os.environ.get("SGN_ROW_SKIP", "1"))  # forward only (measured: the backward loses ILP)
     return bo
 
 
@@ -369,8 +388,9 @@ class _SceneGraphRasterize(torch.autograd.Function):
             assert sky.shape == (cs.height, cs.width, 3)
         bo = blend_opts(settings, sky is not None)
         table = SegmentTable(frame, params, device)
-        records, radii, tiles_hit, bbox = project_fwd(table, cs, device)
-        M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, tiles_hit, bbox)
+        proj = project_fwd(table, cs, device)
+        records, radii, tiles_hit, bbox = proj
+        M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, proj=proj)
         obj_ids = obj_bins = None
         if settings.class_streams:
             obj_ids, obj_bins = class_lists(cs, M, sorted_ids, tile_bins)
@@ -422,8 +442,9 @@ def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[st
         sky = sky.contiguous()
     bo = blend_opts(settings, sky is not None)
     table = SegmentTable(frame, params, device)
-    records, radii, tiles_hit, bbox = project_fwd(table, cs, device)
-    M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, tiles_hit, bbox)
+    proj = project_fwd(table, cs, device)
+    records, radii, tiles_hit, bbox = proj
+    M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, proj=proj)
     cls_ids = cls_bins = None
     if settings.class_streams:
         cls_ids, cls_bins = class_lists(cs, M, sorted_ids, tile_bins)

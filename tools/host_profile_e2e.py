@@ -1,0 +1,52 @@
+"""cProfile of the host side of one e2e training step through the model API (developer tool)."""
+import cProfile
+import os
+import pstats
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import street_gaussians_ns_b200.synthetic as syn  # noqa: E402
+from street_gaussians_ns_b200.model import ActorPose, SceneGraphConfig, SceneGraphRasterModel  # noqa: E402
+
+dev = torch.device("cuda", 0)
+fr = syn.config_frame(3)
+bg = fr.segments[0].params.to(dev)
+actors = {s.name.replace("object_", ""): s.params.to(dev) for s in fr.segments[1:]}
+poses = [ActorPose(s.name.replace("object_", ""), s.rot, s.center, 21, list(range(85))) for s in fr.segments[1:]]
+model = SceneGraphRasterModel(bg, actors, SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0), poses_at=lambda t: poses).to(dev)
+model.train()
+model.step = 30000
+H, W = fr.camera.height, fr.camera.width
+gt_host = (torch.rand(H, W, 3) * 255).to(torch.uint8).pin_memory()
+params = list(model.parameters())
+
+
+def step():
+    gt = gt_host.to(dev, non_blocking=True).float() / 255.0
+    out = model.get_outputs(fr.camera)
+    loss = sum(model.get_loss_dict(out, {"image": gt}).values())
+    loss.backward()
+    v = float(loss.item())
+    for p in params:
+        p.grad = None
+    return v
+
+
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
+for _ in range(30):
+    step()
+torch.cuda.synchronize()
+print("e2e ms/step", (time.perf_counter() - t0) / 30 * 1e3)
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(30):
+    step()
+torch.cuda.synchronize()
+pr.disable()
+pstats.Stats(pr).sort_stats("tottime").print_stats(22)
