@@ -46,7 +46,7 @@ def test_argument_validation_without_gpu(lib):
     cs = mod.CameraStruct()
     cs.block_width, cs.width, cs.height, cs.sh_degree = 32, 64, 48, 3
     rc = L.sgn_project_fwd(ctypes.c_void_p(16), 1, 10, 1, ctypes.byref(cs), ctypes.c_void_p(16), ctypes.c_void_p(16),
-                           ctypes.c_void_p(16), ctypes.c_void_p(16), None)
+                           ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), None)
     assert rc == -1 and b"block_width" in L.sgn_last_error()
 
 
