@@ -29,6 +29,8 @@ def main():
     w, v = syn.cotangents(H, W)
     w, v = w.to(dev), v.to(dev)[..., None]
 
+    leaves = [t for sg in frc.segments for t in sg.params.tensors()]
+
     def step():
         out, holder = raster.render_frame(frc, s)
         outs, gr = [out["rgb"], out["accumulation"]], [w, v]
@@ -37,6 +39,8 @@ def main():
             if a.bg_grad:
                 outs.append(out["background_acc"]); gr.append(0.1 * v)
         torch.autograd.backward(outs, gr)
+        for t in leaves:
+            t.grad = None
         return out, holder
 
     for _ in range(3):
