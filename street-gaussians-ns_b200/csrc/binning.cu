@@ -61,12 +61,19 @@ struct PermutedCount {
     __host__ __device__ int32_t operator()(int i) const { return counts[order[i]]; }
 };
 
+// rank[g] = position of Gaussian g in depth order (inverse of `order`)
+__global__ void __launch_bounds__(256)
+inverse_perm_kernel(int N, const int32_t* __restrict__ order, int32_t* __restrict__ rank) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) rank[order[i]] = i;
+}
+
 __global__ void write_total_kernel(const int32_t* __restrict__ cum, int N, int64_t* __restrict__ total) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *total = (N > 0) ? (int64_t)cum[N - 1] : 0;
 }
 
 struct ScanLayout {
-    size_t keys_in, keys_out, vals_in, temp, temp_bytes, total;
+    size_t keys_in, keys_out, vals_in, vals_out, temp, temp_bytes, total;
 };
 static ScanLayout scan_layout(int N) {
     ScanLayout L;
@@ -78,7 +85,8 @@ static ScanLayout scan_layout(int N) {
     L.keys_in = 0;
     L.keys_out = align_up(n * 4, 256);
     L.vals_in = L.keys_out + align_up(n * 4, 256);
-    L.temp = L.vals_in + align_up(n * 4, 256);
+    L.vals_out = L.vals_in + align_up(n * 4, 256);
+    L.temp = L.vals_out + align_up(n * 4, 256);
     L.temp_bytes = t1 > t2 ? t1 : t2;
     L.total = L.temp + align_up(L.temp_bytes, 256) + 256;
     return L;
@@ -87,8 +95,8 @@ static ScanLayout scan_layout(int N) {
 extern "C" size_t sgn_bin_scan_scratch_bytes(int N) { return scan_layout(N).total; }
 
 extern "C" int sgn_bin_scan(int N, const float* records, const int32_t* radii, const int32_t* tiles_touched,
-                            int32_t* order, int32_t* cum, int64_t* total_dev, void* scratch, size_t scratch_bytes,
-                            void* stream_) {
+                            int32_t* order /* out: rank[g], the position of row g in depth order */, int32_t* cum,
+                            int64_t* total_dev, void* scratch, size_t scratch_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SGN_REQUIRE(records && radii && tiles_touched && order && cum && total_dev && scratch, "sgn_bin_scan: null pointer");
     const ScanLayout L = scan_layout(N);
@@ -103,14 +111,18 @@ extern "C" int sgn_bin_scan(int N, const float* records, const int32_t* radii, c
         int32_t* vals_in = (int32_t*)(base + L.vals_in);
         depth_keys_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, reinterpret_cast<const float4*>(records), radii, keys_in, vals_in);
         SGN_CHECK_LAUNCH("depth_keys_kernel");
+        int32_t* sorted_rows = (int32_t*)(base + L.vals_out);
         size_t temp = L.temp_bytes;
-        SGN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(base + L.temp, temp, keys_in, keys_out, vals_in, order, N, 0, 32, stream));
+        SGN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(base + L.temp, temp, keys_in, keys_out, vals_in, sorted_rows, N, 0, 32, stream));
         sgn_count_launch(1);
+        // counts scanned IN DEPTH ORDER: cum[r] = number of entries emitted by the first r+1 rows of that order
         cub::CountingInputIterator<int> idx(0);
-        cub::TransformInputIterator<int32_t, PermutedCount, cub::CountingInputIterator<int>> it(idx, PermutedCount{order, tiles_touched});
+        cub::TransformInputIterator<int32_t, PermutedCount, cub::CountingInputIterator<int>> it(idx, PermutedCount{sorted_rows, tiles_touched});
         temp = L.temp_bytes;
         SGN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(base + L.temp, temp, it, cum, N, stream));
         sgn_count_launch(1);
+        inverse_perm_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, sorted_rows, order);
+        SGN_CHECK_LAUNCH("inverse_perm_kernel");
     }
     write_total_kernel<<<1, 32, 0, stream>>>(cum, N, total_dev);
     SGN_CHECK_LAUNCH("write_total_kernel");
@@ -118,16 +130,16 @@ extern "C" int sgn_bin_scan(int N, const float* records, const int32_t* radii, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// step 2: key emit in depth order (thread i handles Gaussian order[i]), stable sort by tile, bin edges
+// step 2: key emit (thread g handles Gaussian g -- coalesced reads -- and writes its run of entries at the
+// offset of its depth rank, so the emitted sequence is in depth order), stable sort by tile, bin edges
 __global__ void __launch_bounds__(256)
 emit_keys_kernel(int N, int tiles_x, int width, int height, int bw, const float4* __restrict__ records,
                  const int32_t* __restrict__ radii, const ushort4* __restrict__ tile_bbox,
-                 const uint32_t* __restrict__ touch_mask, const int32_t* __restrict__ order, const int32_t* __restrict__ cum,
+                 const uint32_t* __restrict__ touch_mask, const int32_t* __restrict__ rank, const int32_t* __restrict__ cum,
                  uint16_t* __restrict__ keys, int32_t* __restrict__ vals) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int g = (i < N) ? order[i] : 0;
-    const bool vis = (i < N) && radii[g] > 0;
+    const bool vis = (g < N) && radii[g] > 0;
     ushort4 bb = make_ushort4(0, 0, 0, 0);
     TouchCtx t = {};
     int32_t payload = 0;
@@ -138,8 +150,9 @@ emit_keys_kernel(int N, int tiles_x, int width, int height, int bw, const float4
         // payload: Gaussian row in the low 31 bits, object-class flag in bit 31 (no gather needed later)
         payload = g | ((__float_as_int(records[3 * (size_t)g + 2].z) & SGN_AUX_OBJECT) ? (int32_t)0x80000000 : 0);
         mask = touch_mask[g];
-        cur = (i == 0) ? 0 : cum[i - 1];
-        end = cum[i];
+        const int r = rank[g];
+        cur = (r == 0) ? 0 : cum[r - 1];
+        end = cum[r];
     }
     const int bwid = bb.z - bb.x, area = bwid * (bb.w - bb.y);
     if (vis && area <= COOP_AREA) {
