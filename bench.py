@@ -54,52 +54,80 @@ def make_frames(cfg: int, n_ranks: int, rank: int):
 # clocks sampling (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region through NVML in a background thread
+    (spawning `nvidia-smi -lms` next to a sub-second timed region perturbs the driver and the measurement;
+    the queries are the same: clocks.sm, clocks.max.sm, clocks_event_reasons.*)."""
 
-    def __init__(self, gpu_index: int):
-        self.path = tempfile.mktemp(suffix=".csv")
-        self.proc = None
-        self.gpu = gpu_index
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
+    def __init__(self, gpu_index: int, interval_s: float = 0.01):
+        self.gpu, self.interval = gpu_index, interval_s
+        self.samples, self.reasons, self.smax = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
 
     def start(self):
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
-                stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._nv = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self._h = None
+            return
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _sample(self):
+        nv = self._nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in self.REASONS.items():
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self._stop.wait(self.interval)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": []}
+        if self._h is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, reasons, smax = [], set(), None
-        for line in open(self.path):
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1]))
-                smax = float(p[2])
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
+        self._stop.set()
+        self._thread.join(timeout=2)
+        sm = sorted(self.samples)
         if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.smax, "reasons": sorted(self.reasons), "samples": len(sm),
+                   "how": "NVML in-process, every 10 ms during both timed regions"}
         return out
+
+
+def host_threads() -> int:
+    """Threads the CPU arm may use: the affinity mask, capped by the cgroup CPU quota (a box can show 128
+    cores and grant 16; oversubscribing an OpenMP loop 8x makes the baseline slower, not faster)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(-(-int(quota) // int(period)))))
+    except Exception:
+        pass
+    return n
 
 
 # ------------------------------------------------------------------------------------------------
@@ -111,11 +139,7 @@ def cpu_frame_fn(cfg: int):
     import street_gaussians_ns_b200.synthetic as syn
     from oracle import oracle_c  # the one place bench.py may execute oracle/: as the timed CPU baseline
     # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core it is allowed to
-    try:
-        ncpu = len(os.sched_getaffinity(0))
-    except AttributeError:
-        ncpu = os.cpu_count() or 1
-    oracle_c.lib().sgn_oracle_set_threads(ncpu)
+    oracle_c.lib().sgn_oracle_set_threads(host_threads())
     fr = syn.config_frame(cfg)
     orc = oracle_c.Oracle(fr)
     H, W = fr.camera.height, fr.camera.width
