@@ -313,6 +313,25 @@ def run_ours(args):
     e2e_value = world / (float(t2.item()) / args.steps * 1e-3)
     clocks = sampler.stop() if sampler else None
 
+    # ---- secondary: the training step of SURVEY 8f rank 1 (render fwd+bwd + all-reduce + fused Adam) -------------
+    from street_gaussians_ns_b200.optim import FusedAdam
+    adam = FusedAdam([seg.params.tensors() for seg in frc.segments])
+    adam_ev = []
+    for _ in range(3):
+        adam.step(step().grad_arena)
+    barrier_sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h = step()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        adam.step(h.grad_arena)
+        a1.record()
+        adam_ev.append((a0, a1))
+    barrier_sync()
+    train_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    adam_ms = sum(a.elapsed_time(b) for a, b in adam_ev) / len(adam_ev)
+
     if rank == 0:
         N = sum(s.params.num_points for s in frc.segments)
         A = sum(s.params.num_points for s in frc.segments if s.cls == CLS_OBJECT)
@@ -348,7 +367,10 @@ def run_ours(args):
                         "note": "alpha-blend kernels are FP32/MUFU issue-bound, not HBM-bound (SURVEY.md 8d); "
                                 "all per-kernel fractions are in roofline_all",
                         "pair_evals_per_s": None}
-        total_alg = sum(alg.values())
+        per_kernel["adam"] = {"ms": round(adam_ms, 4), "alg_bytes": int(28 * adam.arena_elems),
+                              "GBps": round(28 * adam.arena_elems / adam_ms / 1e6, 1),
+                              "frac": round(28 * adam.arena_elems / adam_ms / 1e6 / peak, 4)}
+        total_alg = sum(v for k, v in alg.items())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -367,6 +389,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_all": per_kernel,
+            "training_step": {"what": "forward+backward + gradient all-reduce + fused Adam (SURVEY 8f rank 1), device-resident",
+                              "ms_per_step": round(train_ms, 4), "steps_per_s": round(world / (train_ms * 1e-3), 2),
+                              "adam_ms": round(adam_ms, 4)},
             "whole_step": {"alg_bytes": int(total_alg), "GBps": round(total_alg / ms_per_step / 1e6, 1),
                            "frac": round(total_alg / ms_per_step / 1e6 / peak, 4)},
         }

@@ -233,6 +233,25 @@ int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float
                   const int32_t* cls_ids /*[2,M] or NULL*/, const int32_t* cls_bins /*[2,tiles,2] or NULL*/,
                   const sgn_blend_bwd_in* in, float* v_records, void* stream);
 
+/* ---- fused multi-tensor Adam ------------------------------------------------------
+ * torch.optim.Adam semantics (betas, eps, no weight decay, no amsgrad) for every Gaussian parameter tensor in
+ * ONE launch; replaces the nine nerfstudio Adam optimizers over ~200 tensors (sgn_config.py:71-108).
+ * Gradients / exp_avg / exp_avg_sq are flat arenas with the gradient-arena layout of sgn_project_bwd
+ * (arena_offset in floats, multiples of 4); parameters are updated in place.  The host fills, per tensor and
+ * per step, step_size = lr / (1 - beta1^t) and inv_sqrt_bc2 = 1 / sqrt(1 - beta2^t). */
+typedef struct sgn_adam_tensor {
+    float* param;
+    int64_t arena_offset;
+    int64_t numel;
+    int32_t chunk0; /* first block of this tensor: sum over earlier tensors of ceil(numel / sgn_adam_chunk_elems()) */
+    float beta1, beta2, eps, step_size, inv_sqrt_bc2;
+    int32_t pad0;
+} sgn_adam_tensor;
+size_t sgn_sizeof_adam_tensor(void);
+int sgn_adam_chunk_elems(void);
+int sgn_adam_step(const sgn_adam_tensor* table_dev, int ntensors, int num_chunks, const float* grad_arena,
+                  float* exp_avg, float* exp_avg_sq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,14 @@ class BlendOpts(C.Structure):
     ]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [
+        ("param", C.c_void_p), ("arena_offset", C.c_int64), ("numel", C.c_int64), ("chunk0", C.c_int32),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step_size", C.c_float),
+        ("inv_sqrt_bc2", C.c_float), ("pad0", C.c_int32),
+    ]
+
+
 class BlendFwdOut(C.Structure):
     _fields_ = [
         ("rgb", C.c_void_p), ("accumulation", C.c_void_p), ("depth", C.c_void_p),
@@ -81,7 +89,7 @@ EXPORTS = [
     "sgn_last_error", "sgn_abi_version", "sgn_launch_count", "sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera",
     "sgn_upload", "sgn_bin_count", "sgn_project_fwd", "sgn_project_bwd", "sgn_l1_project_fwd", "sgn_l1_project_bwd", "sgn_l1_sh", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
     "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_bin_class_scratch_bytes", "sgn_bin_class_lists",
-    "sgn_blend_fwd", "sgn_blend_bwd",
+    "sgn_blend_fwd", "sgn_blend_bwd", "sgn_sizeof_adam_tensor", "sgn_adam_chunk_elems", "sgn_adam_step",
 ]
 
 
@@ -128,6 +136,11 @@ def load():
     for f in ("sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan", "sgn_bin_sort", "sgn_bin_class_lists",
               "sgn_blend_fwd", "sgn_blend_bwd"):
         getattr(L, f).restype = C.c_int
+    L.sgn_sizeof_adam_tensor.restype = sz
+    L.sgn_adam_chunk_elems.restype = C.c_int
+    L.sgn_adam_step.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.sgn_adam_step.restype = C.c_int
+    assert L.sgn_sizeof_adam_tensor() == C.sizeof(AdamTensor), "sgn_adam_tensor layout mismatch"
     assert L.sgn_sizeof_segment() == C.sizeof(Segment), "sgn_segment layout mismatch between header and ctypes"
     assert L.sgn_sizeof_segment_grads() == C.sizeof(SegmentGrads)
     assert L.sgn_sizeof_camera() == C.sizeof(CameraStruct), "sgn_camera layout mismatch"
