@@ -26,7 +26,7 @@ REFERENCE_LRS: Dict[str, float] = {
 
 ADAM_DTYPE = np.dtype([("param", "<u8"), ("arena_offset", "<i8"), ("numel", "<i8"), ("chunk0", "<i4"),
                        ("beta1", "<f4"), ("beta2", "<f4"), ("eps", "<f4"), ("step_size", "<f4"),
-                       ("inv_sqrt_bc2", "<f4"), ("pad0", "<i4")])
+                       ("inv_sqrt_bc2", "<f4"), ("pad0", "<i4"), ("pad1", "<i4")])  # 56 B: the C struct is 8-byte aligned
 assert ADAM_DTYPE.itemsize == C.sizeof(_lib.AdamTensor)
 
 
