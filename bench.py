@@ -60,8 +60,8 @@ class ClockSampler:
 
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index: int, interval_s: float = 0.01):
-        self.gpu, self.interval = gpu_index, interval_s
+    def __init__(self, gpu_index: int, interval_s: float = 0.05):
+        self.gpu, self.interval = gpu_index, float(os.environ.get("SGN_BENCH_CLOCK_INTERVAL", interval_s))
         self.samples, self.reasons, self.smax = [], set(), None
         self._stop = threading.Event()
         self._thread = None
@@ -77,6 +77,9 @@ class ClockSampler:
             self._nv = pynvml
             self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
+            self._h = None
+            return
+        if self.interval <= 0:  # debugging aid: SGN_BENCH_CLOCK_INTERVAL=0 disables the sampling thread
             self._h = None
             return
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -110,7 +113,7 @@ class ClockSampler:
         sm = sorted(self.samples)
         if sm:
             out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.smax, "reasons": sorted(self.reasons), "samples": len(sm),
-                   "how": "NVML in-process, every 10 ms during both timed regions"}
+                   "how": f"NVML in-process, every {int(self.interval * 1e3)} ms during both timed regions"}
         return out
 
 
