@@ -109,8 +109,15 @@ typedef struct sgn_blend_opts {
      * channels come back as out = sum(c*alpha*T) + T_final*background[c] in rgb[...,0:3] and depth */
     int32_t raw_mode;
     float background[4];
-    int32_t row_skip; /* tuning: main kernels skip row pairs an entry cannot reach / that have fully terminated */
+    int32_t tuning; /* SGN_TUNE_* bits: execution variants with identical results up to fp32 rounding */
 } sgn_blend_opts;
+
+/* main kernels skip row pairs an entry cannot reach / that have fully terminated (exact no-op) */
+#define SGN_TUNE_FWD_ROW_SKIP 1
+#define SGN_TUNE_BWD_ROW_SKIP 2
+/* Blackwell packed-FP32 (f32x2) slot bodies in the main forward / backward kernels */
+#define SGN_TUNE_FWD_PACKED 4
+#define SGN_TUNE_BWD_PACKED 8
 
 const char* sgn_last_error(void);
 int sgn_abi_version(void);
@@ -238,14 +245,14 @@ int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float
  * ONE launch; replaces the nine nerfstudio Adam optimizers over ~200 tensors (sgn_config.py:71-108).
  * Gradients / exp_avg / exp_avg_sq are flat arenas with the gradient-arena layout of sgn_project_bwd
  * (arena_offset in floats, multiples of 4); parameters are updated in place.  The host fills, per tensor and
- * per step, step_size = lr / (1 - beta1^t) and inv_sqrt_bc2 = 1 / sqrt(1 - beta2^t). */
+ * per step, step_size = lr / (1 - beta1^t) and sqrt_bc2 = sqrt(1 - beta2^t), both evaluated in double. */
 typedef struct sgn_adam_tensor {
     float* param;
     int64_t arena_offset;
     int64_t numel;
     int32_t chunk0; /* first block of this tensor: sum over earlier tensors of ceil(numel / sgn_adam_chunk_elems()) */
-    float beta1, beta2, eps, step_size, inv_sqrt_bc2;
-    int32_t pad0;
+    float beta1, beta2, eps, step_size, sqrt_bc2;
+    float one_minus_beta1, one_minus_beta2; /* rounded from double on the host, as torch passes them (1 - 0.999f != 0.001f) */
 } sgn_adam_tensor;
 size_t sgn_sizeof_adam_tensor(void);
 int sgn_adam_chunk_elems(void);

@@ -54,7 +54,7 @@ class BlendOpts(C.Structure):
         ("class_streams", C.c_int32), ("has_sky", C.c_int32), ("eval_clamp", C.c_int32),
         ("split_fwd_main", C.c_int32), ("split_fwd_acc", C.c_int32), ("split_bwd_main", C.c_int32),
         ("split_bwd_acc", C.c_int32),
-        ("raw_mode", C.c_int32), ("background", C.c_float * 4), ("row_skip", C.c_int32),
+        ("raw_mode", C.c_int32), ("background", C.c_float * 4), ("tuning", C.c_int32),
     ]
 
 
@@ -62,7 +62,7 @@ class AdamTensor(C.Structure):
     _fields_ = [
         ("param", C.c_void_p), ("arena_offset", C.c_int64), ("numel", C.c_int64), ("chunk0", C.c_int32),
         ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step_size", C.c_float),
-        ("inv_sqrt_bc2", C.c_float), ("pad0", C.c_int32),
+        ("sqrt_bc2", C.c_float), ("one_minus_beta1", C.c_float), ("one_minus_beta2", C.c_float),
     ]
 
 

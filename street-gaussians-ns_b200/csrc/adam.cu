@@ -29,7 +29,8 @@ adam_kernel(const sgn_adam_tensor* __restrict__ table, int ntensors, const float
     const float* __restrict__ g = grads + t.arena_offset;
     float* __restrict__ m = exp_avg + t.arena_offset;
     float* __restrict__ v = exp_avg_sq + t.arena_offset;
-    const float b1 = t.beta1, b2 = t.beta2, step_size = t.step_size, inv_sqrt_bc2 = t.inv_sqrt_bc2, eps = t.eps;
+    const float b1 = t.beta1, b2 = t.beta2, step_size = t.step_size, sqrt_bc2 = t.sqrt_bc2, eps = t.eps;
+    const float w1 = t.one_minus_beta1, w2 = t.one_minus_beta2;
     const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) && ((t.arena_offset & 3) == 0);
 #pragma unroll
     for (int it = 0; it < ADAM_CHUNK / (ADAM_THREADS * 4); ++it) {
@@ -43,9 +44,9 @@ adam_kernel(const sgn_adam_tensor* __restrict__ table, int ntensors, const float
             float* ga = (float*)&gg; float* ma = (float*)&mm; float* va = (float*)&vv; float* pa = (float*)&pp;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                ma[k] = ma[k] + (ga[k] - ma[k]) * (1.f - b1);
-                va[k] = va[k] * b2 + (1.f - b2) * ga[k] * ga[k];
-                const float denom = sqrtf(va[k]) * inv_sqrt_bc2 + eps;
+                ma[k] = ma[k] + w1 * (ga[k] - ma[k]);        // exp_avg.lerp_(grad, 1 - beta1)
+                va[k] = va[k] * b2 + w2 * ga[k] * ga[k];     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+                const float denom = sqrtf(va[k]) / sqrt_bc2 + eps;
                 pa[k] = pa[k] - step_size * (ma[k] / denom);
             }
             *reinterpret_cast<float4*>(m + e) = mm;
@@ -54,10 +55,10 @@ adam_kernel(const sgn_adam_tensor* __restrict__ table, int ntensors, const float
         } else {
             for (int k = 0; k < 4 && e + k < n; ++k) {
                 const float gk = g[e + k];
-                const float mk = m[e + k] + (gk - m[e + k]) * (1.f - b1);
-                const float vk = v[e + k] * b2 + (1.f - b2) * gk * gk;
+                const float mk = m[e + k] + w1 * (gk - m[e + k]);
+                const float vk = v[e + k] * b2 + w2 * gk * gk;
                 m[e + k] = mk; v[e + k] = vk;
-                p[e + k] = p[e + k] - step_size * (mk / (sqrtf(vk) * inv_sqrt_bc2 + eps));
+                p[e + k] = p[e + k] - step_size * (mk / (sqrtf(vk) / sqrt_bc2 + eps));
             }
         }
     }

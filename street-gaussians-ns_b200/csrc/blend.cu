@@ -76,6 +76,55 @@ __device__ __forceinline__ int warp_max(int v) {
     return v;
 }
 
+// Sums N per-lane values over the warp with N/2 + N/4 + ... shuffles instead of 5*N: at each butterfly
+// level a lane keeps one half of its values and ships the other half to its partner, so the values end
+// up spread over the lanes -- which is where the per-component atomics want them.  SHFL issues at a
+// quarter of the FP32 rate, and the backward's 10 x 5 shuffles per entry were its largest single cost.
+// Returns the warp total of the component multi_reduce_slot<N>(lane) names.
+template <int N>
+__device__ __forceinline__ float warp_multi_reduce(float (&v)[N], int lane) {
+    int n = N;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        if (n == 1) {
+            v[0] += __shfl_xor_sync(FULL, v[0], off);
+        } else {
+            const int half = (n + 1) / 2;
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float hi = (i + half < n) ? v[i + half] : 0.f;
+                const float send = up ? v[i] : hi;
+                const float keep = up ? hi : v[i];
+                v[i] = keep + __shfl_xor_sync(FULL, send, off);
+            }
+            n = half;
+        }
+    }
+    return v[0];
+}
+// component (0..N-1) whose total warp_multi_reduce leaves in this lane; -1 for a padding slot and for the
+// lanes that hold a duplicate of another lane's total (levels reached with one value left are plain sums)
+template <int N>
+__device__ __forceinline__ int multi_reduce_slot(int lane) {
+    int sizes[6];
+    sizes[0] = N;
+#pragma unroll
+    for (int l = 0; l < 5; ++l) sizes[l + 1] = sizes[l] > 1 ? (sizes[l] + 1) / 2 : 1;
+    int idx = 0;
+    bool ok = true;
+#pragma unroll
+    for (int l = 4; l >= 0; --l) {  // level l exchanges across lane bit (16 >> l)
+        if (sizes[l] > 1) {
+            if (lane & (16 >> l)) idx += sizes[l + 1];
+            ok = ok && (idx < sizes[l]);
+        } else if (lane & (16 >> l)) {
+            ok = false;
+        }
+    }
+    return ok ? idx : -1;
+}
+
 // One staged entry: A = (gx, gy, 0.5*a*log2e, b*log2e)  B = (0.5*c*log2e, log2(opacity), r, g)
 //                   C = (b, depth, id bits, opacity)
 // With s2 = sigma*log2e - log2(o):  o*exp(-sigma) = 2^(-s2);  sigma >= 0 <=> s2 >= -log2(o);
@@ -122,10 +171,36 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return y;
 }
 
+// Blackwell packed FP32: one FFMA2/FMUL2/FADD2 issues two IEEE fp32 operations on a register pair.
+// The slot loops below are FP32-issue bound, so the row-slot pairs (2p, 2p+1) of a lane are packed.
+struct f2 {
+    float x, y;
+};
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 d;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ f2 dup2(float v) { return f2{v, v}; }
+
 // number of strips (warps) a tile is split into, from the length of the list it has to traverse
 __device__ __forceinline__ int strips_for(int len, int t1) { return len <= t1 ? 1 : (len <= 2 * t1 ? 2 : (len <= 4 * t1 ? 4 : 8)); }
 
-template <int PPL, bool CLS, bool SKIP>
+template <int PPL, bool CLS, bool SKIP, bool PACK>
 __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int tile, int strip, const int2 range,
                                                 float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -152,6 +227,11 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
     bool finished = false;
     const float yc0 = (float)((tile / p.tiles_x) * SGN_TILE + strip * (2 * PPL)) + 1.0f;
     unsigned slot_live = ALL;  // warp-uniform: row pairs that still have an unterminated pixel (refreshed per batch)
+    constexpr bool PK = PACK && PPL >= 2;
+    constexpr int NP = PK ? PPL / 2 : 1;
+    f2 T2[NP], pr2[NP], pg2[NP], pb2[NP], pd2[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) { T2[q] = dup2(1.f); pr2[q] = pg2[q] = pb2[q] = pd2[q] = dup2(0.f); }
     for (int base = range.x; base < range.y && !finished; base += 32) {
         sA[buf][lane] = nxt.A; sB[buf][lane] = nxt.B;
         sC[buf][lane] = make_float4(nxt.C.x, nxt.C.y, nxt.C.z, SKIP ? row_reach(nxt) + 0.5f : 0.f);
@@ -175,6 +255,36 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
             const float dy0 = A.y - py0;
             const float nlo = -B.y;
             const int k = base + t;
+            if constexpr (PK) {
+                // packed row-slot pairs: a slot that is invalid or already terminated is masked once, at
+                // alpha (= 0): its T passes through unchanged (T * 1) and its weight is an exact zero.
+                // Weights and the four blended channels are kept negated (nw = -alpha*T), flipped in the epilogue.
+                const f2 dyb = f2{dy0, dy0 - 2.f};
+                const float nclamp = -p.clamp_fwd;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (SKIP) {
+                        if (!((slot_live >> (2 * q)) & 3u) || fabsf(dyc - (float)(4 * q + 1)) > Cc.w + 1.f) continue;
+                    }
+                    const f2 dy = add2(dyb, dup2(-(float)(4 * q)));
+                    const f2 s2 = fma2(dy, fma2(dup2(B.x), dy, dup2(bdx)), dup2(hax2));
+                    const bool a0 = (s2.x >= nlo) && (s2.x <= LOG2_255) && !((done >> (2 * q)) & 1u);
+                    const bool a1 = (s2.y >= nlo) && (s2.y <= LOG2_255) && !((done >> (2 * q + 1)) & 1u);
+                    const f2 nal = f2{a0 ? fmaxf(nclamp, -fast_ex2(-s2.x)) : 0.f, a1 ? fmaxf(nclamp, -fast_ex2(-s2.y)) : 0.f};
+                    const f2 om = add2(nal, dup2(1.f));
+                    const f2 nT = mul2(T2[q], om);
+                    const bool st0 = a0 && (nT.x <= T_STOP), st1 = a1 && (nT.y <= T_STOP);
+                    f2 nw = mul2(nal, T2[q]);
+                    nw.x = st0 ? 0.f : nw.x; nw.y = st1 ? 0.f : nw.y;
+                    pr2[q] = fma2(dup2(B.z), nw, pr2[q]); pg2[q] = fma2(dup2(B.w), nw, pg2[q]);
+                    pb2[q] = fma2(dup2(Cc.x), nw, pb2[q]); pd2[q] = fma2(dup2(Cc.y), nw, pd2[q]);
+                    T2[q].x = st0 ? T2[q].x : nT.x; T2[q].y = st1 ? T2[q].y : nT.y;
+                    idx[2 * q] = (a0 && !st0) ? k : idx[2 * q];
+                    idx[2 * q + 1] = (a1 && !st1) ? k : idx[2 * q + 1];
+                    done |= (st0 ? (1u << (2 * q)) : 0u) | (st1 ? (2u << (2 * q)) : 0u);
+                    if (CLS) objhit |= ((a0 && isobj) ? (1u << (2 * q)) : 0u) | ((a1 && isobj) ? (2u << (2 * q)) : 0u);
+                }
+            } else {
             // straight-line, predicated: the PPL pixel chains are independent and interleave (ILP)
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
@@ -198,8 +308,17 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
                 done |= stop ? (1u << s) : 0u;
                 if (CLS) objhit |= (act && isobj) ? (1u << s) : 0u;
             }
+            }
         }
         buf ^= 1;
+    }
+    if constexpr (PK) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            T[2 * q] = T2[q].x; T[2 * q + 1] = T2[q].y;
+            pr[2 * q] = -pr2[q].x; pr[2 * q + 1] = -pr2[q].y; pg[2 * q] = -pg2[q].x; pg[2 * q + 1] = -pg2[q].y;
+            pb[2 * q] = -pb2[q].x; pb[2 * q + 1] = -pb2[q].y; pd[2 * q] = -pd2[q].x; pd[2 * q + 1] = -pd2[q].y;
+        }
     }
     const size_t P = (size_t)p.width * p.height;
     {   // how deep this tile was traversed: the backward sizes its strips from it
@@ -251,7 +370,7 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
 
 // grid = tiles x 8 one-warp CTAs: block b -> strip b / tiles of tile b % tiles; strips beyond the
 // tile's split exit at once (registers are per CTA, so they cost nothing once gone)
-template <bool CLS, bool SKIP>
+template <bool CLS, bool SKIP, bool PACK>
 __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
@@ -261,10 +380,10 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     const int W = strips_for(range.y - range.x, p.split_main);
     if (strip >= W) return;
     switch (W) {
-        case 1: blend_fwd_strip<8, CLS, SKIP>(p, tile, strip, range, sA, sB, sC); break;
-        case 2: blend_fwd_strip<4, CLS, SKIP>(p, tile, strip, range, sA, sB, sC); break;
-        case 4: blend_fwd_strip<2, CLS, SKIP>(p, tile, strip, range, sA, sB, sC); break;
-        default: blend_fwd_strip<1, CLS, SKIP>(p, tile, strip, range, sA, sB, sC); break;
+        case 1: blend_fwd_strip<8, CLS, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
+        case 2: blend_fwd_strip<4, CLS, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
+        case 4: blend_fwd_strip<2, CLS, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
+        default: blend_fwd_strip<1, CLS, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
     }
 }
 
@@ -408,6 +527,17 @@ static int check_cam(const sgn_camera* cam) {
     return SGN_OK;
 }
 
+template <bool CLS>
+static void launch_blend_fwd(const BlendFwdParams& p, int tuning, cudaStream_t stream) {
+    const dim3 grid(p.tiles * 8), block(32);
+    switch (((tuning & SGN_TUNE_FWD_ROW_SKIP) ? 2 : 0) | ((tuning & SGN_TUNE_FWD_PACKED) ? 1 : 0)) {
+        case 0: blend_fwd_kernel<CLS, false, false><<<grid, block, 0, stream>>>(p); break;
+        case 1: blend_fwd_kernel<CLS, false, true><<<grid, block, 0, stream>>>(p); break;
+        case 2: blend_fwd_kernel<CLS, true, false><<<grid, block, 0, stream>>>(p); break;
+        default: blend_fwd_kernel<CLS, true, true><<<grid, block, 0, stream>>>(p); break;
+    }
+}
+
 extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
                              const int32_t* sorted_ids, const int32_t* tile_bins, int64_t M, const int32_t* cls_ids,
                              const int32_t* cls_bins, const float* sky, const sgn_blend_fwd_out* out, void* stream) {
@@ -448,15 +578,13 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
         ForkJoin fj((cudaStream_t)stream);
         acc_fwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 1);  // objects: independent of the main pass
         SGN_CHECK_LAUNCH("acc_fwd_kernel<object>");
-        if (opts->row_skip & 1) blend_fwd_kernel<true, true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
-        else blend_fwd_kernel<true, false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        launch_blend_fwd<true>(p, opts->tuning, (cudaStream_t)stream);
         SGN_CHECK_LAUNCH("blend_fwd_kernel");
         acc_fwd_kernel<<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p, 0);  // background: needs the main pass's flags
         SGN_CHECK_LAUNCH("acc_fwd_kernel<background>");
         fj.finish();
     } else {
-        if (opts->row_skip & 1) blend_fwd_kernel<false, true><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
-        else blend_fwd_kernel<false, false><<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p);
+        launch_blend_fwd<false>(p, opts->tuning, (cudaStream_t)stream);
         SGN_CHECK_LAUNCH("blend_fwd_kernel");
     }
     return SGN_OK;
@@ -491,7 +619,7 @@ struct BlendBwdParams {
 };
 
 // DEPTHG: the depth output has a cotangent.
-template <int PPL, bool DEPTHG, bool SKIP>
+template <int PPL, bool DEPTHG, bool SKIP, bool PACK>
 __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int tile, int strip, const int2 range,
                                                 float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -571,6 +699,19 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
     int slot_kmax[PPL];  // warp-uniform: deepest contributing position of each row pair
 #pragma unroll
     for (int s = 0; s < PPL; ++s) slot_kmax[s] = SKIP ? warp_max(idx[s]) : 0x7fffffff;
+    constexpr int NV = DEPTHG ? 10 : 9;
+    const int my_comp = multi_reduce_slot<NV>(lane);
+    constexpr bool PK = PACK && PPL >= 2;
+    constexpr int NP = PK ? PPL / 2 : 1;
+    f2 T2[NP], d2[NP], vr2[NP], vg2[NP], vb2[NP], vd2[NP];
+    if constexpr (PK) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            T2[q] = f2{T[2 * q], T[2 * q + 1]}; d2[q] = f2{tfv[2 * q], tfv[2 * q + 1]};
+            vr2[q] = f2{vr[2 * q], vr[2 * q + 1]}; vg2[q] = f2{vg[2 * q], vg[2 * q + 1]};
+            vb2[q] = f2{vb[2 * q], vb[2 * q + 1]}; vd2[q] = f2{vd[2 * q], vd[2 * q + 1]};
+        }
+    }
     for (int hi = hi0; hi > range.x; hi -= 32) {
         sA[buf][lane] = nxt.A; sB[buf][lane] = nxt.B; sC[buf][lane] = nxt.C;
         const float my_reach = SKIP ? row_reach(nxt) + 0.5f : 0.f;
@@ -591,6 +732,50 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             const float o = Cc.w;
             float S0 = 0.f, Sy = 0.f, Syy = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
             bool any = false;
+            if constexpr (PK) {
+                // packed row-slot pairs.  An invalid slot is masked ONCE, at the exponential (raw = 0): then
+                // alpha = 0, 1/(1-alpha) = 1, T and the running sums pass through unchanged and its gradient
+                // terms are exact zeros, so no further selects are needed.  The running value is
+                // d = T_final*v_acc - buffer.v, and the colour sums are kept negated (nfac = -alpha*T).
+                f2 S0p = dup2(0.f), Syp = dup2(0.f), Syyp = dup2(0.f);
+                f2 ncr = dup2(0.f), ncg = dup2(0.f), ncb = dup2(0.f), ncd = dup2(0.f);
+                const f2 dyb = f2{dy0, dy0 - 2.f};
+                const float nclamp = -p.clamp_bwd;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (SKIP) {
+                        if (k > max(slot_kmax[2 * q], slot_kmax[2 * q + 1]) || fabsf(dyc - (float)(4 * q + 1)) > reach + 1.f) continue;
+                    }
+                    const f2 dy = add2(dyb, dup2(-(float)(4 * q)));
+                    const f2 s2 = fma2(dy, fma2(dup2(B.x), dy, dup2(bdx)), dup2(hax2));
+                    const bool v0 = (s2.x >= nlo) && (s2.x <= LOG2_255) && (k <= idx[2 * q]);
+                    const bool v1 = (s2.y >= nlo) && (s2.y <= LOG2_255) && (k <= idx[2 * q + 1]);
+                    any = any || v0 || v1;
+                    const f2 nraw = f2{v0 ? -fast_ex2(-s2.x) : 0.f, v1 ? -fast_ex2(-s2.y) : 0.f};  // -o*exp(-sigma)
+                    const f2 nal = f2{fmaxf(nclamp, nraw.x), fmaxf(nclamp, nraw.y)};                 // -alpha
+                    const f2 om = add2(nal, dup2(1.f));
+                    const f2 ra = f2{fast_rcp(om.x), fast_rcp(om.y)};
+                    const f2 Tk = mul2(T2[q], ra);
+                    T2[q] = Tk;
+                    const f2 nfac = mul2(nal, Tk);
+                    ncr = fma2(nfac, vr2[q], ncr); ncg = fma2(nfac, vg2[q], ncg); ncb = fma2(nfac, vb2[q], ncb);
+                    f2 dotc = fma2(dup2(B.z), vr2[q], fma2(dup2(B.w), vg2[q], mul2(dup2(Cc.x), vb2[q])));
+                    if (DEPTHG) {
+                        ncd = fma2(nfac, vd2[q], ncd);
+                        dotc = fma2(dup2(Cc.y), vd2[q], dotc);
+                    }
+                    const f2 v_alpha = fma2(Tk, dotc, mul2(ra, d2[q]));
+                    d2[q] = fma2(nfac, dotc, d2[q]);
+                    const f2 vs = mul2(nraw, v_alpha);  // d/d sigma = -o*vis*v_alpha
+                    S0p = add2(S0p, vs);
+                    const f2 vsy = mul2(vs, dy);
+                    Syp = add2(Syp, vsy);
+                    Syyp = fma2(vsy, dy, Syyp);
+                }
+                S0 = S0p.x + S0p.y; Sy = Syp.x + Syp.y; Syy = Syyp.x + Syyp.y;
+                cr = -(ncr.x + ncr.y); cg = -(ncg.x + ncg.y); cb = -(ncb.x + ncb.y);
+                if (DEPTHG) cd = -(ncd.x + ncd.y);
+            } else {
             // straight-line, predicated (see the forward)
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
@@ -623,6 +808,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
                 Sy += vsy;
                 Syy = __fmaf_rn(vsy, dy, Syy);
             }
+            }
             if (!__any_sync(FULL, any)) continue;
             // true conic from the staged (log2e-scaled) one
             const float ca = A.z * (2.f * LN2), cbb = A.w * LN2, cc = B.x * (2.f * LN2);
@@ -632,16 +818,12 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             float l3 = dx * Sy;                     // v_conic.y
             float l4 = 0.5f * Syy;                  // v_conic.z
             float l5 = -S0 / o;                     // v_opacity = sum vis * v_alpha
-            l0 = warp_sum(l0); l1 = warp_sum(l1); l2 = warp_sum(l2); l3 = warp_sum(l3); l4 = warp_sum(l4); l5 = warp_sum(l5);
-            cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
-            if (DEPTHG) cd = warp_sum(cd);
-            // lanes 0..9 each own one component of the record-layout gradient
-            float mine = l0;
-            mine = lane == 1 ? l1 : mine; mine = lane == 2 ? l2 : mine; mine = lane == 3 ? l3 : mine;
-            mine = lane == 4 ? l4 : mine; mine = lane == 5 ? l5 : mine; mine = lane == 6 ? cr : mine;
-            mine = lane == 7 ? cg : mine; mine = lane == 8 ? cb : mine; mine = lane == 9 ? cd : mine;
-            if (lane < (DEPTHG ? 10 : 9))
-                atomicAdd(p.v_records + (size_t)(__float_as_int(Cc.z) & ID_MASK) * SGN_RECORD_FLOATS + lane, mine);
+            // one component of the record-layout gradient per lane pair
+            float comps[NV] = {l0, l1, l2, l3, l4, l5, cr, cg, cb};
+            if (DEPTHG) comps[NV - 1] = cd;
+            const float mine = warp_multi_reduce<NV>(comps, lane);
+            if (my_comp >= 0)
+                atomicAdd(p.v_records + (size_t)(__float_as_int(Cc.z) & ID_MASK) * SGN_RECORD_FLOATS + my_comp, mine);
         }
         buf ^= 1;
     }
@@ -649,7 +831,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
 
 // the prologue (v_sky, cotangent chain) must run for every pixel, so strips are always launched for the
 // whole tile: W strips of 16/W rows
-template <bool DEPTHG, bool SKIP>
+template <bool DEPTHG, bool SKIP, bool PACK>
 __global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
@@ -659,10 +841,10 @@ __global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
     const int W = strips_for(p.tile_depth[tile], p.split_main);
     if (strip >= W) return;
     switch (W) {
-        case 1: blend_bwd_strip<8, DEPTHG, SKIP>(p, tile, strip, range, sA, sB, sC); break;
-        case 2: blend_bwd_strip<4, DEPTHG, SKIP>(p, tile, strip, range, sA, sB, sC); break;
-        case 4: blend_bwd_strip<2, DEPTHG, SKIP>(p, tile, strip, range, sA, sB, sC); break;
-        default: blend_bwd_strip<1, DEPTHG, SKIP>(p, tile, strip, range, sA, sB, sC); break;
+        case 1: blend_bwd_strip<8, DEPTHG, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
+        case 2: blend_bwd_strip<4, DEPTHG, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
+        case 4: blend_bwd_strip<2, DEPTHG, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
+        default: blend_bwd_strip<1, DEPTHG, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
     }
 }
 
@@ -697,6 +879,7 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
     const int wkmax = warp_max(kmax);
     const int hi0 = min(range.y, wkmax + 1);
     if (hi0 <= range.x) return;
+    const int my_comp = multi_reduce_slot<6>(lane);
     Staged nxt;
     if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, ids[hi0 - 1 - lane]);
     int buf = 0;
@@ -742,11 +925,9 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
             float l3 = dx * Sy;
             float l4 = 0.5f * Syy;
             float l5 = -S0 / o;
-            l0 = warp_sum(l0); l1 = warp_sum(l1); l2 = warp_sum(l2); l3 = warp_sum(l3); l4 = warp_sum(l4); l5 = warp_sum(l5);
-            float mine = l0;
-            mine = lane == 1 ? l1 : mine; mine = lane == 2 ? l2 : mine; mine = lane == 3 ? l3 : mine;
-            mine = lane == 4 ? l4 : mine; mine = lane == 5 ? l5 : mine;
-            if (lane < 6) atomicAdd(p.v_records + (size_t)(__float_as_int(B.z) & ID_MASK) * SGN_RECORD_FLOATS + lane, mine);
+            float comps[6] = {l0, l1, l2, l3, l4, l5};
+            const float mine = warp_multi_reduce<6>(comps, lane);
+            if (my_comp >= 0) atomicAdd(p.v_records + (size_t)(__float_as_int(B.z) & ID_MASK) * SGN_RECORD_FLOATS + my_comp, mine);
         }
         buf ^= 1;
     }
@@ -816,15 +997,21 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
             acc_bwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 0);
             SGN_CHECK_LAUNCH("acc_bwd_kernel<background>");
         }
-        // row skipping is a forward-only win (measured: the backward loses more ILP than it saves); bit 1 of
-        // row_skip forces it on for experiments
-        const bool skip = (opts->row_skip & 2) != 0;
-        if (in->v_depth) {
-            if (skip) blend_bwd_kernel<true, true><<<tiles * 8, 32, 0, stream>>>(p);
-            else blend_bwd_kernel<true, false><<<tiles * 8, 32, 0, stream>>>(p);
-        } else {
-            if (skip) blend_bwd_kernel<false, true><<<tiles * 8, 32, 0, stream>>>(p);
-            else blend_bwd_kernel<false, false><<<tiles * 8, 32, 0, stream>>>(p);
+        // row skipping is a forward-only win (measured: the backward loses more ILP than it saves); SGN_TUNE_BWD_ROW_SKIP
+        // forces it on for experiments
+        const bool skip = (opts->tuning & SGN_TUNE_BWD_ROW_SKIP) != 0;
+        const bool pack = (opts->tuning & SGN_TUNE_BWD_PACKED) != 0;
+        const int variant = (in->v_depth ? 4 : 0) | (skip ? 2 : 0) | (pack ? 1 : 0);
+        const dim3 grid(tiles * 8), block(32);
+        switch (variant) {
+            case 0: blend_bwd_kernel<false, false, false><<<grid, block, 0, stream>>>(p); break;
+            case 1: blend_bwd_kernel<false, false, true><<<grid, block, 0, stream>>>(p); break;
+            case 2: blend_bwd_kernel<false, true, false><<<grid, block, 0, stream>>>(p); break;
+            case 3: blend_bwd_kernel<false, true, true><<<grid, block, 0, stream>>>(p); break;
+            case 4: blend_bwd_kernel<true, false, false><<<grid, block, 0, stream>>>(p); break;
+            case 5: blend_bwd_kernel<true, false, true><<<grid, block, 0, stream>>>(p); break;
+            case 6: blend_bwd_kernel<true, true, false><<<grid, block, 0, stream>>>(p); break;
+            default: blend_bwd_kernel<true, true, true><<<grid, block, 0, stream>>>(p); break;
         }
         SGN_CHECK_LAUNCH("blend_bwd_kernel");
         fj.finish();

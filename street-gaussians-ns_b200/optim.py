@@ -26,7 +26,7 @@ REFERENCE_LRS: Dict[str, float] = {
 
 ADAM_DTYPE = np.dtype([("param", "<u8"), ("arena_offset", "<i8"), ("numel", "<i8"), ("chunk0", "<i4"),
                        ("beta1", "<f4"), ("beta2", "<f4"), ("eps", "<f4"), ("step_size", "<f4"),
-                       ("inv_sqrt_bc2", "<f4"), ("pad0", "<i4"), ("pad1", "<i4")])  # 56 B: the C struct is 8-byte aligned
+                       ("sqrt_bc2", "<f4"), ("one_minus_beta1", "<f4"), ("one_minus_beta2", "<f4")])  # 56 B: the C struct is 8-byte aligned
 assert ADAM_DTYPE.itemsize == C.sizeof(_lib.AdamTensor)
 
 
@@ -52,6 +52,7 @@ class FusedAdam:
         tab["numel"] = [t.numel() for t in flat]
         tab["chunk0"] = np.concatenate([[0], np.cumsum(chunks)[:-1]])
         tab["beta1"], tab["beta2"], tab["eps"] = betas[0], betas[1], eps
+        tab["one_minus_beta1"], tab["one_minus_beta2"] = 1.0 - betas[0], 1.0 - betas[1]  # double, then rounded (torch)
         self.table = tab
         self.num_chunks = int(chunks.sum())
         self.arena_elems = int(sum(sizes))
@@ -71,7 +72,7 @@ class FusedAdam:
         bc2 = 1.0 - b2 ** self.step_count
         tab = self.table
         tab["step_size"] = [self.lrs[k] / bc1 for k in self.kinds]
-        tab["inv_sqrt_bc2"] = 1.0 / math.sqrt(bc2)
+        tab["sqrt_bc2"] = math.sqrt(bc2)
         dev_tab = torch.from_numpy(tab.view(np.uint8).reshape(-1)).to(self.device, non_blocking=True)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(self.L.sgn_adam_step(C.c_void_p(dev_tab.data_ptr()), len(tab), self.num_chunks,
