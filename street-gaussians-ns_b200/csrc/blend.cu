@@ -127,8 +127,8 @@ __device__ __forceinline__ int multi_reduce_slot(int lane) {
 
 // One staged entry: A = (gx, gy, 0.5*a*log2e, b*log2e)  B = (0.5*c*log2e, log2(opacity), r, g)
 //                   C = (b, depth, id bits, opacity)
-// With s2 = sigma*log2e - log2(o):  o*exp(-sigma) = 2^(-s2);  sigma >= 0 <=> s2 >= -log2(o);
-// alpha >= 1/255 <=> s2 <= log2(255).  Both tests only need s2, so validity is known before the MUFU result.
+// With sg = sigma*log2e:  o*exp(-sigma) = 2^(log2(o) - sg);  sigma >= 0 <=> sg >= 0;
+// alpha >= 1/255 <=> sg <= log2(255 o).  Both tests only need sg, so validity is known before the MUFU result.
 struct Staged {
     float4 A, B, C;
 };
@@ -154,9 +154,13 @@ __device__ __forceinline__ float row_reach(const Staged& e) {
     return sqrtf(tau2 / den) * 1.0001f + 0.01f;
 }
 
-// sigma*log2(e) for the pixel at (dx, dy) from the staged conic; identical in forward and backward
-__device__ __forceinline__ float sgn_sigma2(float hax2, float bdx, float hc, float dy) {
-    return __fmaf_rn(dy, __fmaf_rn(hc, dy, bdx), hax2);
+// Pins an alpha clamp (a kernel parameter in [0.5, 1]) in a register: ptxas otherwise re-reads it from the
+// constant bank (one LDC issue slot) inside every predicated slot body.  1 - (1 - x) is exact for
+// 0.5 <= x <= 2 (Sterbenz) and is not something ptxas rematerialises.
+__device__ __forceinline__ float in_register(float x) {
+    float y;
+    asm volatile("{.reg .f32 t; sub.rn.f32 t, 0f3F800000, %1; sub.rn.f32 %0, 0f3F800000, t;}" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ float fast_rcp(float x) {
@@ -208,17 +212,22 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
     const int j = tx * SGN_TILE + (lane & 15);
     const int i0 = ty * SGN_TILE + strip * (2 * PPL) + (lane >> 4);
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
-    constexpr unsigned ALL = (1u << PPL) - 1u;
-
-    float T[PPL], pr[PPL], pg[PPL], pb[PPL], pd[PPL];
+    // The slot loop is bound by the half-rate ALU pipe (compares, selects, min/max, bit logic), not by FMA
+    // (profiles/r01f): its bookkeeping is therefore arithmetic wherever possible.
+    //   * liveness lives in the slot's row offset: a pixel that has terminated (or lies outside the image)
+    //     gets the offset DEAD, which drives sigma out of range, so there is no per-slot `done` test;
+    //   * validity (0 <= sigma*log2e <= log2(255 o)) is ONE unsigned compare of the float's bits;
+    //   * an invalid slot is masked once (alpha = 0): T and the sums then pass through unchanged;
+    //   * "an object entry took part" is accumulated with an FMA (osum += objflag * alpha).
+    constexpr float DEAD = 1e18f;
+    float T[PPL], pr[PPL], pg[PPL], pb[PPL], pd[PPL], yoff[PPL], osum[PPL];
     int idx[PPL];
-    unsigned done = 0, objhit = 0;
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
-        T[s] = 1.f; pr[s] = pg[s] = pb[s] = pd[s] = 0.f;
+        T[s] = 1.f; pr[s] = pg[s] = pb[s] = pd[s] = 0.f; osum[s] = 0.f;
         idx[s] = -1;
         const bool inside = (j < p.width) && (i0 + 2 * s < p.height);
-        if (!inside) done |= 1u << s;
+        yoff[s] = inside ? (float)(2 * s) : DEAD;
     }
 
     Staged nxt;
@@ -226,12 +235,16 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
     int buf = 0;
     bool finished = false;
     const float yc0 = (float)((tile / p.tiles_x) * SGN_TILE + strip * (2 * PPL)) + 1.0f;
-    unsigned slot_live = ALL;  // warp-uniform: row pairs that still have an unterminated pixel (refreshed per batch)
+    unsigned slot_live = (1u << PPL) - 1u;  // warp-uniform: row pairs that still have an unterminated pixel (refreshed per batch)
     constexpr bool PK = PACK && PPL >= 2;
     constexpr int NP = PK ? PPL / 2 : 1;
-    f2 T2[NP], pr2[NP], pg2[NP], pb2[NP], pd2[NP];
+    f2 T2[NP], pr2[NP], pg2[NP], pb2[NP], pd2[NP], yoff2[NP], osum2[NP];
 #pragma unroll
-    for (int q = 0; q < NP; ++q) { T2[q] = dup2(1.f); pr2[q] = pg2[q] = pb2[q] = pd2[q] = dup2(0.f); }
+    for (int q = 0; q < NP; ++q) {
+        T2[q] = dup2(1.f); pr2[q] = pg2[q] = pb2[q] = pd2[q] = osum2[q] = dup2(0.f);
+        if (PK) yoff2[q] = f2{yoff[2 * q], yoff[2 * q + 1]};
+    }
+    const float clampf = in_register(p.clamp_fwd), nclamp = in_register(-p.clamp_fwd);
     for (int base = range.x; base < range.y && !finished; base += 32) {
         sA[buf][lane] = nxt.A; sB[buf][lane] = nxt.B;
         sC[buf][lane] = make_float4(nxt.C.x, nxt.C.y, nxt.C.z, SKIP ? row_reach(nxt) + 0.5f : 0.f);
@@ -240,74 +253,78 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
         if (SKIP) {
             slot_live = 0;
 #pragma unroll
-            for (int s = 0; s < PPL; ++s) slot_live |= __any_sync(FULL, !((done >> s) & 1u)) ? (1u << s) : 0u;
+            for (int s = 0; s < PPL; ++s) {
+                const float yo = PK ? ((s & 1) ? yoff2[s / 2].y : yoff2[s / 2].x) : yoff[s];
+                slot_live |= __any_sync(FULL, yo < 0.5f * DEAD) ? (1u << s) : 0u;
+            }
         }
         const int n = min(32, range.y - base);
         for (int t = 0; t < n; ++t) {
-            if (__all_sync(FULL, done == ALL)) { finished = true; break; }
+            if ((t & 7) == 0) {  // every pixel of the strip terminated: stop traversing (checked every 8 entries)
+                float ymin = DEAD;
+#pragma unroll
+                for (int s = 0; s < PPL; ++s) ymin = fminf(ymin, PK ? ((s & 1) ? yoff2[s / 2].y : yoff2[s / 2].x) : yoff[s]);
+                if (__all_sync(FULL, ymin >= 0.5f * DEAD)) { finished = true; break; }
+            }
             const float4 A = sA[buf][t];
             const float4 B = sB[buf][t];
             const float4 Cc = sC[buf][t];
-            const bool isobj = CLS && (__float_as_int(Cc.z) < 0);
+            const float objflag = (CLS && (__float_as_int(Cc.z) < 0)) ? 1.f : 0.f;
             const float dyc = A.y - yc0;
             const float dx = A.x - px;
-            const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
+            const float bdx = A.w * dx, ax2 = A.z * dx * dx;
             const float dy0 = A.y - py0;
-            const float nlo = -B.y;
+            // valid  <=>  0 <= sg <= log2(255 o)  <=>  bits(sg) < lim1   (sg = sigma*log2e; negative and NaN have huge bits)
+            const float span = LOG2_255 + B.y;
+            const unsigned lim1 = (unsigned)(max(__float_as_int(span), -1) + 1);  // 0 when span < 0 (negative floats are negative ints)
             const int k = base + t;
             if constexpr (PK) {
-                // packed row-slot pairs: a slot that is invalid or already terminated is masked once, at
-                // alpha (= 0): its T passes through unchanged (T * 1) and its weight is an exact zero.
-                // Weights and the four blended channels are kept negated (nw = -alpha*T), flipped in the epilogue.
-                const f2 dyb = f2{dy0, dy0 - 2.f};
-                const float nclamp = -p.clamp_fwd;
+                // packed row-slot pairs (f32x2); weights and the blended channels are kept negated (nw = -alpha*T)
+                const f2 dyb = dup2(dy0);
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     if (SKIP) {
                         if (!((slot_live >> (2 * q)) & 3u) || fabsf(dyc - (float)(4 * q + 1)) > Cc.w + 1.f) continue;
                     }
-                    const f2 dy = add2(dyb, dup2(-(float)(4 * q)));
-                    const f2 s2 = fma2(dy, fma2(dup2(B.x), dy, dup2(bdx)), dup2(hax2));
-                    const bool a0 = (s2.x >= nlo) && (s2.x <= LOG2_255) && !((done >> (2 * q)) & 1u);
-                    const bool a1 = (s2.y >= nlo) && (s2.y <= LOG2_255) && !((done >> (2 * q + 1)) & 1u);
-                    const f2 nal = f2{a0 ? fmaxf(nclamp, -fast_ex2(-s2.x)) : 0.f, a1 ? fmaxf(nclamp, -fast_ex2(-s2.y)) : 0.f};
-                    const f2 om = add2(nal, dup2(1.f));
-                    const f2 nT = mul2(T2[q], om);
-                    const bool st0 = a0 && (nT.x <= T_STOP), st1 = a1 && (nT.y <= T_STOP);
-                    f2 nw = mul2(nal, T2[q]);
-                    nw.x = st0 ? 0.f : nw.x; nw.y = st1 ? 0.f : nw.y;
+                    const f2 dy = f2{dy0 - yoff2[q].x, dy0 - yoff2[q].y};
+                    const f2 sg = fma2(dy, fma2(dup2(B.x), dy, dup2(bdx)), dup2(ax2));
+                    const bool v0 = __float_as_uint(sg.x) < lim1, v1 = __float_as_uint(sg.y) < lim1;
+                    const f2 nam = f2{v0 ? fmaxf(nclamp, -fast_ex2(B.y - sg.x)) : 0.f, v1 ? fmaxf(nclamp, -fast_ex2(B.y - sg.y)) : 0.f};
+                    const f2 nT = fma2(nam, T2[q], T2[q]);
+                    const bool st0 = nT.x <= T_STOP, st1 = nT.y <= T_STOP;
+                    const f2 nau = f2{st0 ? 0.f : nam.x, st1 ? 0.f : nam.y};
+                    const f2 nw = mul2(nau, T2[q]);
+                    T2[q] = fma2(nau, T2[q], T2[q]);
+                    yoff2[q].x = st0 ? DEAD : yoff2[q].x; yoff2[q].y = st1 ? DEAD : yoff2[q].y;
+                    idx[2 * q] = (nau.x < 0.f) ? k : idx[2 * q];
+                    idx[2 * q + 1] = (nau.y < 0.f) ? k : idx[2 * q + 1];
                     pr2[q] = fma2(dup2(B.z), nw, pr2[q]); pg2[q] = fma2(dup2(B.w), nw, pg2[q]);
                     pb2[q] = fma2(dup2(Cc.x), nw, pb2[q]); pd2[q] = fma2(dup2(Cc.y), nw, pd2[q]);
-                    T2[q].x = st0 ? T2[q].x : nT.x; T2[q].y = st1 ? T2[q].y : nT.y;
-                    idx[2 * q] = (a0 && !st0) ? k : idx[2 * q];
-                    idx[2 * q + 1] = (a1 && !st1) ? k : idx[2 * q + 1];
-                    done |= (st0 ? (1u << (2 * q)) : 0u) | (st1 ? (2u << (2 * q)) : 0u);
-                    if (CLS) objhit |= ((a0 && isobj) ? (1u << (2 * q)) : 0u) | ((a1 && isobj) ? (2u << (2 * q)) : 0u);
+                    if (CLS) osum2[q] = fma2(dup2(objflag), nam, osum2[q]);
+                    (void)dyb;
                 }
             } else {
-            // straight-line, predicated: the PPL pixel chains are independent and interleave (ILP)
+                // straight-line, predicated: the PPL pixel chains are independent and interleave (ILP)
 #pragma unroll
-            for (int s = 0; s < PPL; ++s) {
-                if (SKIP) {  // warp-uniform: the entry cannot reach this row pair, or all its pixels terminated
-                    if (!((slot_live >> s) & 1u) || fabsf(dyc - (float)(2 * s)) > Cc.w) continue;
+                for (int s = 0; s < PPL; ++s) {
+                    if (SKIP) {  // warp-uniform: the entry cannot reach this row pair, or all its pixels terminated
+                        if (!((slot_live >> s) & 1u) || fabsf(dyc - (float)(2 * s)) > Cc.w) continue;
+                    }
+                    const float dy = dy0 - yoff[s];
+                    const float sg = __fmaf_rn(dy, __fmaf_rn(B.x, dy, bdx), ax2);
+                    const bool valid = __float_as_uint(sg) < lim1;
+                    const float am = valid ? fminf(clampf, fast_ex2(B.y - sg)) : 0.f;
+                    const float nT = __fmaf_rn(-am, T[s], T[s]);
+                    const bool stop = nT <= T_STOP;  // only a valid entry can get here: T > T_STOP is invariant
+                    const float au = stop ? 0.f : am;
+                    const float w = au * T[s];
+                    T[s] = __fmaf_rn(-au, T[s], T[s]);
+                    yoff[s] = stop ? DEAD : yoff[s];
+                    idx[s] = (au > 0.f) ? k : idx[s];
+                    pr[s] = __fmaf_rn(B.z, w, pr[s]); pg[s] = __fmaf_rn(B.w, w, pg[s]);
+                    pb[s] = __fmaf_rn(Cc.x, w, pb[s]); pd[s] = __fmaf_rn(Cc.y, w, pd[s]);
+                    if (CLS) osum[s] = __fmaf_rn(objflag, am, osum[s]);
                 }
-                const float dy = dy0 - (float)(2 * s);
-                const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
-                const bool valid = (s2 >= nlo) && (s2 <= LOG2_255);
-                const float alpha = fminf(p.clamp_fwd, fast_ex2(-s2));
-                const float om = 1.f - alpha;
-                const bool act = valid && !((done >> s) & 1u);
-                const float nT = T[s] * om;
-                const bool stop = act && (nT <= T_STOP);
-                const bool upd = act && !stop;
-                const float w = upd ? alpha * T[s] : 0.f;
-                pr[s] = __fmaf_rn(B.z, w, pr[s]); pg[s] = __fmaf_rn(B.w, w, pg[s]);
-                pb[s] = __fmaf_rn(Cc.x, w, pb[s]); pd[s] = __fmaf_rn(Cc.y, w, pd[s]);
-                T[s] = upd ? nT : T[s];
-                idx[s] = upd ? k : idx[s];
-                done |= stop ? (1u << s) : 0u;
-                if (CLS) objhit |= (act && isobj) ? (1u << s) : 0u;
-            }
             }
         }
         buf ^= 1;
@@ -318,6 +335,7 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
             T[2 * q] = T2[q].x; T[2 * q + 1] = T2[q].y;
             pr[2 * q] = -pr2[q].x; pr[2 * q + 1] = -pr2[q].y; pg[2 * q] = -pg2[q].x; pg[2 * q + 1] = -pg2[q].y;
             pb[2 * q] = -pb2[q].x; pb[2 * q + 1] = -pb2[q].y; pd[2 * q] = -pd2[q].x; pd[2 * q + 1] = -pd2[q].y;
+            osum[2 * q] = -osum2[q].x; osum[2 * q + 1] = -osum2[q].y;
         }
     }
     const size_t P = (size_t)p.width * p.height;
@@ -361,7 +379,7 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
         p.final_T[SLOT_MAIN * P + pid] = T[s];
         p.final_idx[SLOT_MAIN * P + pid] = idx[s];
         if (CLS) {
-            const bool hit = (objhit >> s) & 1u;
+            const bool hit = osum[s] > 0.f;
             p.final_idx[SLOT_BG * P + pid] = hit ? BG_TODO : BG_SAME_AS_MAIN;
             if (!hit) { p.final_T[SLOT_BG * P + pid] = T[s]; p.bg_acc[pid] = alpha; }
         }
@@ -401,20 +419,22 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
     const int i0 = ty * SGN_TILE + strip * (2 * PPL) + (lane >> 4);
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
     constexpr unsigned ALL = (1u << PPL) - 1u;
-    float T[PPL];
+    constexpr float DEAD = 1e18f;  // row offset of a terminated / skipped pixel (see blend_fwd_strip)
+    float T[PPL], yoff[PPL];
     int idx[PPL];
-    unsigned done = 0, skip = 0;
+    unsigned skip = 0;
     const size_t P = (size_t)p.width * p.height;
 #pragma unroll
     for (int s = 0; s < PPL; ++s) {
-        T[s] = 1.f; idx[s] = -1;
+        T[s] = 1.f; idx[s] = -1; yoff[s] = (float)(2 * s);
         const int i = i0 + 2 * s;
-        if (!((j < p.width) && (i < p.height))) { done |= 1u << s; skip |= 1u << s; }
+        if (!((j < p.width) && (i < p.height))) { yoff[s] = DEAD; skip |= 1u << s; }
         else if (cls == 0 && p.final_idx[SLOT_BG * P + (size_t)i * p.width + j] != BG_TODO) {
-            done |= 1u << s; skip |= 1u << s;  // the main forward already wrote this pixel's background result
+            yoff[s] = DEAD; skip |= 1u << s;  // the main forward already wrote this pixel's background result
         }
     }
     if (__all_sync(FULL, skip == ALL)) return;
+    const float clampf = in_register(p.clamp_fwd);
     Staged nxt;
     if (range.x + lane < range.y) nxt = gather_entry(p.records, ids[range.x + lane]);
     int buf = 0;
@@ -425,29 +445,34 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
         if (base + 32 + lane < range.y) nxt = gather_entry(p.records, ids[base + 32 + lane]);
         const int n = min(32, range.y - base);
         for (int t = 0; t < n; ++t) {
-            if (__all_sync(FULL, done == ALL)) { finished = true; break; }
+            if ((t & 7) == 0) {
+                float ymin = DEAD;
+#pragma unroll
+                for (int s = 0; s < PPL; ++s) ymin = fminf(ymin, yoff[s]);
+                if (__all_sync(FULL, ymin >= 0.5f * DEAD)) { finished = true; break; }
+            }
             const float4 A = sA[buf][t];
             const float4 B = sB[buf][t];
             const float dx = A.x - px;
-            const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
+            const float bdx = A.w * dx, ax2 = A.z * dx * dx;
             const float dy0 = A.y - py0;
             const float dyc = A.y - yc0;  // distance to the centre line of slot 0's row pair (warp-uniform)
-            const float nlo = -B.y;
+            const float span = LOG2_255 + B.y;
+            const unsigned lim1 = (unsigned)(max(__float_as_int(span), -1) + 1);  // 0 when span < 0 (negative floats are negative ints)
             const int k = base + t;
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
                 if (fabsf(dyc - (float)(2 * s)) > B.z) continue;  // the entry cannot reach this row pair
-                const float dy = dy0 - (float)(2 * s);
-                const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
-                const bool valid = (s2 >= nlo) && (s2 <= LOG2_255);
-                const float alpha = fminf(p.clamp_fwd, fast_ex2(-s2));
-                const bool act = valid && !((done >> s) & 1u);
-                const float nT = T[s] * (1.f - alpha);
-                const bool stop = act && (nT <= T_STOP);
-                const bool upd = act && !stop;
-                T[s] = upd ? nT : T[s];
-                idx[s] = upd ? k : idx[s];
-                done |= stop ? (1u << s) : 0u;
+                // same arithmetic as blend_fwd_strip: a pixel without object entries gets the main pass's T bit for bit
+                const float dy = dy0 - yoff[s];
+                const float sg = __fmaf_rn(dy, __fmaf_rn(B.x, dy, bdx), ax2);
+                const bool valid = __float_as_uint(sg) < lim1;
+                const float am = valid ? fminf(clampf, fast_ex2(B.y - sg)) : 0.f;
+                const float nT = __fmaf_rn(-am, T[s], T[s]);
+                const bool stop = nT <= T_STOP;
+                T[s] = stop ? T[s] : nT;
+                yoff[s] = stop ? DEAD : yoff[s];
+                idx[s] = (valid && !stop) ? k : idx[s];
             }
         }
         buf ^= 1;
@@ -701,6 +726,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
     for (int s = 0; s < PPL; ++s) slot_kmax[s] = SKIP ? warp_max(idx[s]) : 0x7fffffff;
     constexpr int NV = DEPTHG ? 10 : 9;
     const int my_comp = multi_reduce_slot<NV>(lane);
+    const float clampb = in_register(p.clamp_bwd), nclamp = -clampb;
     constexpr bool PK = PACK && PPL >= 2;
     constexpr int NP = PK ? PPL / 2 : 1;
     f2 T2[NP], d2[NP], vr2[NP], vg2[NP], vb2[NP], vd2[NP];
@@ -726,38 +752,38 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             const float reach = SKIP ? __shfl_sync(FULL, my_reach, t) : 0.f;
             const float dyc = A.y - yc0;
             const float dx = A.x - px;
-            const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
+            const float bdx = A.w * dx, ax2 = A.z * dx * dx;
             const float dy0 = A.y - py0;
-            const float nlo = -B.y;
+            // valid  <=>  0 <= sg <= log2(255 o)  <=>  bits(sg) < lim1  (see blend_fwd_strip), and k <= idx
+            const unsigned lim1 = (unsigned)(max(__float_as_int(LOG2_255 + B.y), -1) + 1);
             const float o = Cc.w;
             float S0 = 0.f, Sy = 0.f, Syy = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
-            bool any = false;
+            float activity = 0.f;  // sum of alpha*T over the valid slots: non-zero iff some pixel of this lane took the entry
             if constexpr (PK) {
                 // packed row-slot pairs.  An invalid slot is masked ONCE, at the exponential (raw = 0): then
                 // alpha = 0, 1/(1-alpha) = 1, T and the running sums pass through unchanged and its gradient
                 // terms are exact zeros, so no further selects are needed.  The running value is
                 // d = T_final*v_acc - buffer.v, and the colour sums are kept negated (nfac = -alpha*T).
                 f2 S0p = dup2(0.f), Syp = dup2(0.f), Syyp = dup2(0.f);
-                f2 ncr = dup2(0.f), ncg = dup2(0.f), ncb = dup2(0.f), ncd = dup2(0.f);
+                f2 ncr = dup2(0.f), ncg = dup2(0.f), ncb = dup2(0.f), ncd = dup2(0.f), nact = dup2(0.f);
                 const f2 dyb = f2{dy0, dy0 - 2.f};
-                const float nclamp = -p.clamp_bwd;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     if (SKIP) {
                         if (k > max(slot_kmax[2 * q], slot_kmax[2 * q + 1]) || fabsf(dyc - (float)(4 * q + 1)) > reach + 1.f) continue;
                     }
                     const f2 dy = add2(dyb, dup2(-(float)(4 * q)));
-                    const f2 s2 = fma2(dy, fma2(dup2(B.x), dy, dup2(bdx)), dup2(hax2));
-                    const bool v0 = (s2.x >= nlo) && (s2.x <= LOG2_255) && (k <= idx[2 * q]);
-                    const bool v1 = (s2.y >= nlo) && (s2.y <= LOG2_255) && (k <= idx[2 * q + 1]);
-                    any = any || v0 || v1;
-                    const f2 nraw = f2{v0 ? -fast_ex2(-s2.x) : 0.f, v1 ? -fast_ex2(-s2.y) : 0.f};  // -o*exp(-sigma)
+                    const f2 sg = fma2(dy, fma2(dup2(B.x), dy, dup2(bdx)), dup2(ax2));
+                    const bool v0 = (__float_as_uint(sg.x) < lim1) && (k <= idx[2 * q]);
+                    const bool v1 = (__float_as_uint(sg.y) < lim1) && (k <= idx[2 * q + 1]);
+                    const f2 nraw = f2{v0 ? -fast_ex2(B.y - sg.x) : 0.f, v1 ? -fast_ex2(B.y - sg.y) : 0.f};  // -o*exp(-sigma)
                     const f2 nal = f2{fmaxf(nclamp, nraw.x), fmaxf(nclamp, nraw.y)};                 // -alpha
                     const f2 om = add2(nal, dup2(1.f));
                     const f2 ra = f2{fast_rcp(om.x), fast_rcp(om.y)};
                     const f2 Tk = mul2(T2[q], ra);
                     T2[q] = Tk;
                     const f2 nfac = mul2(nal, Tk);
+                    nact = add2(nact, nfac);
                     ncr = fma2(nfac, vr2[q], ncr); ncg = fma2(nfac, vg2[q], ncg); ncb = fma2(nfac, vb2[q], ncb);
                     f2 dotc = fma2(dup2(B.z), vr2[q], fma2(dup2(B.w), vg2[q], mul2(dup2(Cc.x), vb2[q])));
                     if (DEPTHG) {
@@ -775,6 +801,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
                 S0 = S0p.x + S0p.y; Sy = Syp.x + Syp.y; Syy = Syyp.x + Syyp.y;
                 cr = -(ncr.x + ncr.y); cg = -(ncg.x + ncg.y); cb = -(ncb.x + ncb.y);
                 if (DEPTHG) cd = -(ncd.x + ncd.y);
+                activity = nact.x + nact.y;
             } else {
             // straight-line, predicated (see the forward)
 #pragma unroll
@@ -783,16 +810,16 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
                     if (k > slot_kmax[s] || fabsf(dyc - (float)(2 * s)) > reach) continue;
                 }
                 const float dy = dy0 - (float)(2 * s);
-                const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
-                const bool valid = (s2 >= nlo) && (s2 <= LOG2_255) && (k <= idx[s]);
-                const float raw = fast_ex2(-s2);            // o * exp(-sigma)
-                const float alpha = fminf(p.clamp_bwd, raw);
+                const float sg = __fmaf_rn(dy, __fmaf_rn(B.x, dy, bdx), ax2);
+                const bool valid = (__float_as_uint(sg) < lim1) && (k <= idx[s]);
+                const float raw = fast_ex2(B.y - sg);       // o * exp(-sigma)
+                const float alpha = fminf(clampb, raw);
                 const float ra = fast_rcp(1.f - alpha);
                 const bool vm = valid;
-                any = any || valid;
                 const float Tk = vm ? T[s] * ra : T[s];
                 T[s] = Tk;
                 const float fac = vm ? alpha * Tk : 0.f;
+                activity += fac;
                 cr = __fmaf_rn(fac, vr[s], cr); cg = __fmaf_rn(fac, vg[s], cg); cb = __fmaf_rn(fac, vb[s], cb);
                 // v_alpha = sum_c (c*T - buffer_c*ra) * v_c + T_final*ra*v_acc  =  T*(c.v) + ra*(T_final*v_acc - buffer.v)
                 float dotc = __fmaf_rn(B.z, vr[s], __fmaf_rn(B.w, vg[s], Cc.x * vb[s]));
@@ -809,7 +836,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
                 Syy = __fmaf_rn(vsy, dy, Syy);
             }
             }
-            if (!__any_sync(FULL, any)) continue;
+            if (!__any_sync(FULL, activity != 0.f)) continue;
             // true conic from the staged (log2e-scaled) one
             const float ca = A.z * (2.f * LN2), cbb = A.w * LN2, cc = B.x * (2.f * LN2);
             float l0 = ca * dx * S0 + cbb * Sy;     // v_xy.x
@@ -880,6 +907,7 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
     const int hi0 = min(range.y, wkmax + 1);
     if (hi0 <= range.x) return;
     const int my_comp = multi_reduce_slot<6>(lane);
+    const float clampb = in_register(p.clamp_bwd);
     Staged nxt;
     if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, ids[hi0 - 1 - lane]);
     int buf = 0;
@@ -894,30 +922,28 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
             const float4 A = sA[buf][t];
             const float4 B = sB[buf][t];
             const float dx = A.x - px;
-            const float bdx = A.w * dx, hax2 = A.z * dx * dx - B.y;
+            const float bdx = A.w * dx, ax2 = A.z * dx * dx;
             const float dy0 = A.y - py0;
             const float dyc = A.y - yc0, reach = sR[buf][t];
-            const float nlo = -B.y;
+            const unsigned lim1 = (unsigned)(max(__float_as_int(LOG2_255 + B.y), -1) + 1);
             const float o = B.w;
             float S0 = 0.f, Sy = 0.f, Syy = 0.f;
-            bool any = false;
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
                 if (fabsf(dyc - (float)(2 * s)) > reach) continue;
                 const float dy = dy0 - (float)(2 * s);
-                const float s2 = sgn_sigma2(hax2, bdx, B.x, dy);
-                const bool valid = (s2 >= nlo) && (s2 <= LOG2_255) && (k <= idx[s]);
-                const float raw = fast_ex2(-s2);
-                const float alpha = fminf(p.clamp_bwd, raw);
+                const float sg = __fmaf_rn(dy, __fmaf_rn(B.x, dy, bdx), ax2);
+                const bool valid = (__float_as_uint(sg) < lim1) && (k <= idx[s]);
+                const float raw = fast_ex2(B.y - sg);
+                const float alpha = fminf(clampb, raw);
                 const float ra = fast_rcp(1.f - alpha);
-                any = any || valid;
                 const float vs = valid ? -raw * (tfv[s] * ra) : 0.f;
                 S0 += vs;
                 const float vsy = vs * dy;
                 Sy += vsy;
                 Syy = __fmaf_rn(vsy, dy, Syy);
             }
-            if (!__any_sync(FULL, any)) continue;
+            if (!__any_sync(FULL, S0 != 0.f)) continue;  // every term carries vs: all zero => nothing to add
             const float ca = A.z * (2.f * LN2), cbb = A.w * LN2, cc = B.x * (2.f * LN2);
             float l0 = ca * dx * S0 + cbb * Sy;
             float l1 = cbb * dx * S0 + cc * Sy;

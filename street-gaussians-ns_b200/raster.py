@@ -260,7 +260,7 @@ def class_lists(cs: _lib.CameraStruct, M: int, sorted_ids, tile_bins):
     return obj_ids, obj_bins
 
 
-DEFAULT_TUNING = 1 | 8  # measured on cfg3: packed forward is neutral (0.756 vs 0.766 ms), packed backward -7%
+DEFAULT_TUNING = 4 | 8  # measured on cfg3 (profiles/r01g_sweep_tuning.txt): packed f32x2 bodies, no row skipping in the main kernels
 
 
 def blend_opts(s: RenderSettings, has_sky: bool) -> _lib.BlendOpts:
