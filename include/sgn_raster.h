@@ -112,12 +112,13 @@ typedef struct sgn_blend_opts {
     int32_t tuning; /* SGN_TUNE_* bits: execution variants with identical results up to fp32 rounding */
 } sgn_blend_opts;
 
-/* main kernels skip row pairs an entry cannot reach / that have fully terminated (exact no-op) */
+/* main forward skips row pairs an entry cannot reach / that have fully terminated (exact no-op) */
 #define SGN_TUNE_FWD_ROW_SKIP 1
-#define SGN_TUNE_BWD_ROW_SKIP 2
 /* Blackwell packed-FP32 (f32x2) slot bodies in the main forward / backward kernels */
 #define SGN_TUNE_FWD_PACKED 4
 #define SGN_TUNE_BWD_PACKED 8
+/* the accumulation-only (object / background) kernels do NOT skip unreachable row pairs */
+#define SGN_TUNE_ACC_NO_ROW_SKIP 16
 
 const char* sgn_last_error(void);
 int sgn_abi_version(void);
@@ -212,8 +213,11 @@ typedef struct sgn_blend_fwd_out {
     float* final_T;        /* [3,H,W] planar: slot 0 main, 1 object, 2 background */
     int32_t* final_idx;    /* [3,H,W] */
     int32_t* tile_depth;   /* [3,tiles] entries traversed per tile (main, object, background pass); sizes the backward */
+    int32_t* sched;        /* scratch of sgn_blend_sched_ints(tiles) int32, or NULL: heavy-first work lists (longest tile
+                              lists are scheduled first; without it CTAs take the tiles in raster order) */
 } sgn_blend_fwd_out;
 
+size_t sgn_blend_sched_ints(int tiles);
 int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
                   const int32_t* sorted_ids, const int32_t* tile_bins, int64_t M,
                   const int32_t* cls_ids /*[2,M] or NULL*/, const int32_t* cls_bins /*[2,tiles,2] or NULL*/,
@@ -229,6 +233,7 @@ typedef struct sgn_blend_bwd_in {
     const float* final_T;
     const int32_t* final_idx;
     const int32_t* tile_depth;     /* [3,tiles] from the forward */
+    int32_t* sched;                /* scratch of sgn_blend_sched_ints(tiles) int32 (may be the forward's), or NULL */
     const float* sky;              /* [H,W,3] or NULL */
     float* v_sky;                  /* [H,W,3] or NULL: gradient to the sky colour */
 } sgn_blend_bwd_in;

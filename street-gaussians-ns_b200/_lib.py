@@ -71,6 +71,7 @@ class BlendFwdOut(C.Structure):
         ("rgb", C.c_void_p), ("accumulation", C.c_void_p), ("depth", C.c_void_p),
         ("object_acc", C.c_void_p), ("background_acc", C.c_void_p),
         ("raw", C.c_void_p), ("final_T", C.c_void_p), ("final_idx", C.c_void_p), ("tile_depth", C.c_void_p),
+        ("sched", C.c_void_p),
     ]
 
 
@@ -79,7 +80,7 @@ class BlendBwdIn(C.Structure):
         ("v_rgb", C.c_void_p), ("v_accumulation", C.c_void_p), ("v_depth", C.c_void_p),
         ("v_object_acc", C.c_void_p), ("v_background_acc", C.c_void_p),
         ("raw", C.c_void_p), ("final_T", C.c_void_p), ("final_idx", C.c_void_p), ("tile_depth", C.c_void_p),
-        ("sky", C.c_void_p), ("v_sky", C.c_void_p),
+        ("sched", C.c_void_p), ("sky", C.c_void_p), ("v_sky", C.c_void_p),
     ]
 
 
@@ -88,7 +89,7 @@ _lib = None
 EXPORTS = [
     "sgn_last_error", "sgn_abi_version", "sgn_launch_count", "sgn_sizeof_segment", "sgn_sizeof_segment_grads", "sgn_sizeof_camera",
     "sgn_upload", "sgn_bin_count", "sgn_project_fwd", "sgn_project_bwd", "sgn_l1_project_fwd", "sgn_l1_project_bwd", "sgn_l1_sh", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
-    "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_bin_class_scratch_bytes", "sgn_bin_class_lists",
+    "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_bin_class_scratch_bytes", "sgn_bin_class_lists", "sgn_blend_sched_ints",
     "sgn_blend_fwd", "sgn_blend_bwd", "sgn_sizeof_adam_tensor", "sgn_adam_chunk_elems", "sgn_adam_step",
 ]
 
@@ -129,6 +130,8 @@ def load():
     L.sgn_bin_class_scratch_bytes.argtypes = [i32]
     L.sgn_bin_class_scratch_bytes.restype = sz
     L.sgn_bin_class_lists.argtypes = [C.POINTER(CameraStruct), i64, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_blend_sched_ints.argtypes = [i32]
+    L.sgn_blend_sched_ints.restype = sz
     L.sgn_blend_fwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, i64, vp, vp, vp,
                                 C.POINTER(BlendFwdOut), vp]
     L.sgn_blend_bwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, i64, vp, vp,

@@ -46,6 +46,7 @@ struct BlendFwdParams {
     int width, height, tiles_x, tiles;
     int split_main, split_acc;  // list length up to which a tile is one strip (doubles per extra split)
     int32_t* tile_depth;  // [3][tiles] entries traversed per tile by the main / object / background pass (atomicMax)
+    const int32_t* sched;  // heavy-first work lists (sched_kernel) or null
     float clamp_fwd;
     int has_sky, eval_clamp, raw_mode;
     float bg[4];
@@ -204,6 +205,77 @@ __device__ __forceinline__ f2 dup2(float v) { return f2{v, v}; }
 // number of strips (warps) a tile is split into, from the length of the list it has to traverse
 __device__ __forceinline__ int strips_for(int len, int t1) { return len <= t1 ? 1 : (len <= 2 * t1 ? 2 : (len <= 4 * t1 ? 4 : 8)); }
 
+// ---- heavy-first scheduling ------------------------------------------------------------------
+// Per-tile lists range from empty to thousands of entries (behind dense actors) and a blend kernel ends
+// when its slowest warp does: with CTAs in raster order the SMs idle 12-40% of a kernel's duration
+// (profiles/r01f: sm__cycles_active vs elapsed).  One block per list kind (0 main, 1 object, 2
+// background: the slot numbering of final_T / tile_depth) counting-sorts the (tile, strip) work items
+// into 64 half-octave length buckets, longest first, with no empty items; CTA b takes item b and the
+// CTAs past the item count exit.  The order inside a bucket is arbitrary: it changes scheduling, never results.
+// Layout per kind: [0] item count, [1 + i] = tile << 3 | strip.
+#define SCHED_STRIDE(tiles) ((size_t)(tiles) * 8 + 1)
+extern "C" size_t sgn_blend_sched_ints(int tiles) { return 3 * SCHED_STRIDE(tiles > 0 ? tiles : 0); }
+
+__global__ void __launch_bounds__(1024)
+sched_kernel(int tiles, const int2* __restrict__ tile_bins, const int2* __restrict__ cls_bins0, const int2* __restrict__ cls_bins1,
+             const int32_t* __restrict__ tile_depth /* backward: lengths come from here */, int split_main, int split_acc,
+             int32_t* __restrict__ sched) {
+    const int kind = blockIdx.x;  // 0 main, 1 object, 2 background
+    const int2* bins = kind == SLOT_MAIN ? tile_bins : (kind == SLOT_OBJ ? cls_bins1 : cls_bins0);
+    const int split = kind == SLOT_MAIN ? split_main : split_acc;
+    int32_t* out = sched + kind * SCHED_STRIDE(tiles);
+    __shared__ int hist[64];
+    __shared__ int start[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    // every forward pass and the main backward write per-pixel results for tiles with empty lists too (background
+    // colour, zero accumulation, v_sky); only the accumulation backward has nothing to do there
+    const bool visit_empty = !tile_depth || kind == SLOT_MAIN;
+    auto length = [&](int t) {
+        if (tile_depth) return tile_depth[(size_t)kind * tiles + t];
+        const int2 r = bins[t];
+        return r.y - r.x;
+    };
+    auto bucket = [](int len) {
+        const int lg = 31 - __clz(len);                          // floor(log2 len), len >= 1
+        const int half = lg > 0 ? ((len >> (lg - 1)) & 1) : 0;  // upper half of the octave?
+        return 62 - min(2 * lg + half, 62);                     // longest lists -> bucket 0
+    };
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+        const int len = length(t);
+        if (len > 0 || visit_empty) atomicAdd(&hist[len > 0 ? bucket(len) : 63], len > 0 ? strips_for(len, split) : 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < 64; ++b) { start[b] = acc; acc += hist[b]; }
+        out[0] = acc;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+        const int len = length(t);
+        if (!(len > 0 || visit_empty)) continue;
+        const int W = len > 0 ? strips_for(len, split) : 1;
+        const int pos = atomicAdd(&start[len > 0 ? bucket(len) : 63], W);
+        for (int s = 0; s < W; ++s) out[1 + pos + s] = (t << 3) | s;
+    }
+}
+
+// CTA -> (tile, strip); false when there is nothing to do.  Without a schedule: strip-major raster order over
+// the tiles x 8 grid.  (A persistent form -- CTAs looping over the list -- was measured slower: the loop makes
+// ptxas hoist every parameter-derived value out of it, +35 registers.)
+__device__ __forceinline__ bool take_work(const int32_t* __restrict__ sched, int kind, int tiles, int& tile, int& strip) {
+    if (!sched) {
+        tile = blockIdx.x % tiles; strip = blockIdx.x / tiles;
+        return true;
+    }
+    const int32_t* w = sched + kind * SCHED_STRIDE(tiles);
+    if ((int)blockIdx.x >= w[0]) return false;
+    const int item = w[1 + blockIdx.x];
+    tile = item >> 3; strip = item & 7;
+    return true;
+}
+
 template <int PPL, bool CLS, bool SKIP, bool PACK>
 __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int tile, int strip, const int2 range,
                                                 float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
@@ -259,6 +331,9 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
             }
         }
         const int n = min(32, range.y - base);
+        // strips of long lists (PPL <= 2) are the kernel's critical path, and one entry is a ~70-cycle dependency
+        // chain: unrolled, consecutive entries (independent but for the one-FMA T chain) overlap
+#pragma unroll(PPL <= 2 ? 4 : 1)
         for (int t = 0; t < n; ++t) {
             if ((t & 7) == 0) {  // every pixel of the strip terminated: stop traversing (checked every 8 entries)
                 float ymin = DEAD;
@@ -386,14 +461,13 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
     }
 }
 
-// grid = tiles x 8 one-warp CTAs: block b -> strip b / tiles of tile b % tiles; strips beyond the
-// tile's split exit at once (registers are per CTA, so they cost nothing once gone)
 template <bool CLS, bool SKIP, bool PACK>
 __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
     __shared__ float4 sC[2][32];
-    const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
+    int tile, strip;
+    if (!take_work(p.sched, SLOT_MAIN, p.tiles, tile, strip)) return;
     const int2 range = p.tile_bins[tile];
     const int W = strips_for(range.y - range.x, p.split_main);
     if (strip >= W) return;
@@ -406,7 +480,7 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
 }
 
 // accumulation-only pass over one class's per-tile sub-lists (objects-only / background-only render)
-template <int PPL>
+template <int PPL, bool SKIP>
 __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, int tile, int strip, const int2 range,
                                               float4 (*sA)[32], float4 (*sB)[32]) {
     const int32_t* __restrict__ ids = p.cls_ids[cls];
@@ -444,6 +518,9 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
         __syncwarp();
         if (base + 32 + lane < range.y) nxt = gather_entry(p.records, ids[base + 32 + lane]);
         const int n = min(32, range.y - base);
+        // strips of long lists (PPL <= 2) are the kernel's critical path, and one entry is a ~70-cycle dependency
+        // chain: unrolled, consecutive entries (independent but for the one-FMA T chain) overlap
+#pragma unroll(PPL <= 2 ? 4 : 1)
         for (int t = 0; t < n; ++t) {
             if ((t & 7) == 0) {
                 float ymin = DEAD;
@@ -462,7 +539,7 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
             const int k = base + t;
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
-                if (fabsf(dyc - (float)(2 * s)) > B.z) continue;  // the entry cannot reach this row pair
+                if (SKIP && fabsf(dyc - (float)(2 * s)) > B.z) continue;  // the entry cannot reach this row pair
                 // same arithmetic as blend_fwd_strip: a pixel without object entries gets the main pass's T bit for bit
                 const float dy = dy0 - yoff[s];
                 const float sg = __fmaf_rn(dy, __fmaf_rn(B.x, dy, bdx), ax2);
@@ -495,18 +572,20 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
     }
 }
 
+template <bool SKIP>
 __global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p, const int cls) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
-    const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
+    int tile, strip;
+    if (!take_work(p.sched, cls ? SLOT_OBJ : SLOT_BG, p.tiles, tile, strip)) return;
     const int2 range = p.cls_bins[cls][tile];
     const int W = strips_for(range.y - range.x, p.split_acc);
     if (strip >= W) return;
     switch (W) {
-        case 1: acc_fwd_strip<8>(p, cls, tile, strip, range, sA, sB); break;
-        case 2: acc_fwd_strip<4>(p, cls, tile, strip, range, sA, sB); break;
-        case 4: acc_fwd_strip<2>(p, cls, tile, strip, range, sA, sB); break;
-        default: acc_fwd_strip<1>(p, cls, tile, strip, range, sA, sB); break;
+        case 1: acc_fwd_strip<8, SKIP>(p, cls, tile, strip, range, sA, sB); break;
+        case 2: acc_fwd_strip<4, SKIP>(p, cls, tile, strip, range, sA, sB); break;
+        case 4: acc_fwd_strip<2, SKIP>(p, cls, tile, strip, range, sA, sB); break;
+        default: acc_fwd_strip<1, SKIP>(p, cls, tile, strip, range, sA, sB); break;
     }
 }
 
@@ -599,13 +678,23 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     SGN_REQUIRE(out->tile_depth, "sgn_blend_fwd: tile_depth is null");
     p.tile_depth = out->tile_depth;
     SGN_CHECK_CUDA(cudaMemsetAsync(out->tile_depth, 0, sizeof(int32_t) * 3 * (size_t)tiles, (cudaStream_t)stream));
+    p.sched = out->sched;
+    if (out->sched) {
+        sched_kernel<<<opts->class_streams ? 3 : 1, 1024, 0, (cudaStream_t)stream>>>(tiles, p.tile_bins, p.cls_bins[0], p.cls_bins[1], nullptr,
+                                                                                  p.split_main, p.split_acc, out->sched);
+        SGN_CHECK_LAUNCH("sched_kernel");
+    }
     if (opts->class_streams) {
         ForkJoin fj((cudaStream_t)stream);
-        acc_fwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 1);  // objects: independent of the main pass
+        const bool acc_skip = !(opts->tuning & SGN_TUNE_ACC_NO_ROW_SKIP);
+        const unsigned acc_grid = tiles * 8;
+        if (acc_skip) acc_fwd_kernel<true><<<acc_grid, 32, 0, fj.side()>>>(p, 1);  // objects: independent of the main pass
+        else acc_fwd_kernel<false><<<acc_grid, 32, 0, fj.side()>>>(p, 1);
         SGN_CHECK_LAUNCH("acc_fwd_kernel<object>");
         launch_blend_fwd<true>(p, opts->tuning, (cudaStream_t)stream);
         SGN_CHECK_LAUNCH("blend_fwd_kernel");
-        acc_fwd_kernel<<<tiles * 8, 32, 0, (cudaStream_t)stream>>>(p, 0);  // background: needs the main pass's flags
+        if (acc_skip) acc_fwd_kernel<true><<<acc_grid, 32, 0, (cudaStream_t)stream>>>(p, 0);  // background: needs the main pass's flags
+        else acc_fwd_kernel<false><<<acc_grid, 32, 0, (cudaStream_t)stream>>>(p, 0);
         SGN_CHECK_LAUNCH("acc_fwd_kernel<background>");
         fj.finish();
     } else {
@@ -622,6 +711,7 @@ struct BlendBwdParams {
     int width, height, tiles_x, tiles;
     int split_main, split_acc;
     const int32_t* tile_depth;  // [3][tiles]
+    const int32_t* sched;  // heavy-first work lists (sched_kernel) or null
     float clamp_bwd;
     int has_sky, eval_clamp, raw_mode;
     float bg[4];
@@ -644,7 +734,9 @@ struct BlendBwdParams {
 };
 
 // DEPTHG: the depth output has a cotangent.
-template <int PPL, bool DEPTHG, bool SKIP, bool PACK>
+// (Measured and dropped: software-pipelining the reduction of entry t-1 under the arithmetic of entry t -- it
+// has to run unconditionally, which costs more than the overlap gains: 0.87 vs 0.82 ms on cfg3.)
+template <int PPL, bool DEPTHG, bool PACK>
 __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int tile, int strip, const int2 range,
                                                 float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -720,10 +812,6 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
     Staged nxt;
     if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, p.sorted_ids[hi0 - 1 - lane]);
     int buf = 0;
-    const float yc0 = (float)((tile / p.tiles_x) * SGN_TILE + strip * (2 * PPL)) + 1.0f;
-    int slot_kmax[PPL];  // warp-uniform: deepest contributing position of each row pair
-#pragma unroll
-    for (int s = 0; s < PPL; ++s) slot_kmax[s] = SKIP ? warp_max(idx[s]) : 0x7fffffff;
     constexpr int NV = DEPTHG ? 10 : 9;
     const int my_comp = multi_reduce_slot<NV>(lane);
     const float clampb = in_register(p.clamp_bwd), nclamp = -clampb;
@@ -740,7 +828,6 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
     }
     for (int hi = hi0; hi > range.x; hi -= 32) {
         sA[buf][lane] = nxt.A; sB[buf][lane] = nxt.B; sC[buf][lane] = nxt.C;
-        const float my_reach = SKIP ? row_reach(nxt) + 0.5f : 0.f;
         __syncwarp();
         if (hi - 33 - lane >= range.x) nxt = gather_entry(p.records, p.sorted_ids[hi - 33 - lane]);
         const int n = min(32, hi - range.x);
@@ -749,8 +836,6 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             const float4 A = sA[buf][t];
             const float4 B = sB[buf][t];
             const float4 Cc = sC[buf][t];
-            const float reach = SKIP ? __shfl_sync(FULL, my_reach, t) : 0.f;
-            const float dyc = A.y - yc0;
             const float dx = A.x - px;
             const float bdx = A.w * dx, ax2 = A.z * dx * dx;
             const float dy0 = A.y - py0;
@@ -769,9 +854,6 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
                 const f2 dyb = f2{dy0, dy0 - 2.f};
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
-                    if (SKIP) {
-                        if (k > max(slot_kmax[2 * q], slot_kmax[2 * q + 1]) || fabsf(dyc - (float)(4 * q + 1)) > reach + 1.f) continue;
-                    }
                     const f2 dy = add2(dyb, dup2(-(float)(4 * q)));
                     const f2 sg = fma2(dy, fma2(dup2(B.x), dy, dup2(bdx)), dup2(ax2));
                     const bool v0 = (__float_as_uint(sg.x) < lim1) && (k <= idx[2 * q]);
@@ -806,9 +888,6 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             // straight-line, predicated (see the forward)
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
-                if (SKIP) {  // warp-uniform: out of this row pair's reach, or deeper than any of its pixels blended
-                    if (k > slot_kmax[s] || fabsf(dyc - (float)(2 * s)) > reach) continue;
-                }
                 const float dy = dy0 - (float)(2 * s);
                 const float sg = __fmaf_rn(dy, __fmaf_rn(B.x, dy, bdx), ax2);
                 const bool valid = (__float_as_uint(sg) < lim1) && (k <= idx[s]);
@@ -848,9 +927,9 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             // one component of the record-layout gradient per lane pair
             float comps[NV] = {l0, l1, l2, l3, l4, l5, cr, cg, cb};
             if (DEPTHG) comps[NV - 1] = cd;
+            float* const dst = p.v_records + (size_t)(__float_as_int(Cc.z) & ID_MASK) * SGN_RECORD_FLOATS + (my_comp >= 0 ? my_comp : 0);
             const float mine = warp_multi_reduce<NV>(comps, lane);
-            if (my_comp >= 0)
-                atomicAdd(p.v_records + (size_t)(__float_as_int(Cc.z) & ID_MASK) * SGN_RECORD_FLOATS + my_comp, mine);
+            if (my_comp >= 0) atomicAdd(dst, mine);
         }
         buf ^= 1;
     }
@@ -858,25 +937,26 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
 
 // the prologue (v_sky, cotangent chain) must run for every pixel, so strips are always launched for the
 // whole tile: W strips of 16/W rows
-template <bool DEPTHG, bool SKIP, bool PACK>
+template <bool DEPTHG, bool PACK>
 __global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
     __shared__ float4 sC[2][32];
-    const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
+    int tile, strip;
+    if (!take_work(p.sched, SLOT_MAIN, p.tiles, tile, strip)) return;
     const int2 range = p.tile_bins[tile];
     const int W = strips_for(p.tile_depth[tile], p.split_main);
     if (strip >= W) return;
     switch (W) {
-        case 1: blend_bwd_strip<8, DEPTHG, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
-        case 2: blend_bwd_strip<4, DEPTHG, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
-        case 4: blend_bwd_strip<2, DEPTHG, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
-        default: blend_bwd_strip<1, DEPTHG, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
+        case 1: blend_bwd_strip<8, DEPTHG, PACK>(p, tile, strip, range, sA, sB, sC); break;
+        case 2: blend_bwd_strip<4, DEPTHG, PACK>(p, tile, strip, range, sA, sB, sC); break;
+        case 4: blend_bwd_strip<2, DEPTHG, PACK>(p, tile, strip, range, sA, sB, sC); break;
+        default: blend_bwd_strip<1, DEPTHG, PACK>(p, tile, strip, range, sA, sB, sC); break;
     }
 }
 
 // backward of the accumulation-only pass: out = 1 - T_final  =>  v_alpha_k = T_final * ra_k * v_out
-template <int PPL>
+template <int PPL, bool SKIP>
 __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, int tile, int strip, const int2 range,
                                               float4 (*sA)[32], float4 (*sB)[32], float (*sR)[32]) {
     const int32_t* __restrict__ ids = p.cls_ids[cls];
@@ -930,7 +1010,7 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
             float S0 = 0.f, Sy = 0.f, Syy = 0.f;
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
-                if (fabsf(dyc - (float)(2 * s)) > reach) continue;
+                if (SKIP && fabsf(dyc - (float)(2 * s)) > reach) continue;
                 const float dy = dy0 - (float)(2 * s);
                 const float sg = __fmaf_rn(dy, __fmaf_rn(B.x, dy, bdx), ax2);
                 const bool valid = (__float_as_uint(sg) < lim1) && (k <= idx[s]);
@@ -959,19 +1039,21 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
     }
 }
 
+template <bool SKIP>
 __global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p, const int cls) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
     __shared__ float sR[2][32];
-    const int tile = blockIdx.x % p.tiles, strip = blockIdx.x / p.tiles;
+    int tile, strip;
+    if (!take_work(p.sched, cls ? SLOT_OBJ : SLOT_BG, p.tiles, tile, strip)) return;
     const int2 range = p.cls_bins[cls][tile];
     const int W = strips_for(p.tile_depth[(size_t)(cls ? SLOT_OBJ : SLOT_BG) * p.tiles + tile], p.split_acc);
     if (strip >= W) return;
     switch (W) {
-        case 1: acc_bwd_strip<8>(p, cls, tile, strip, range, sA, sB, sR); break;
-        case 2: acc_bwd_strip<4>(p, cls, tile, strip, range, sA, sB, sR); break;
-        case 4: acc_bwd_strip<2>(p, cls, tile, strip, range, sA, sB, sR); break;
-        default: acc_bwd_strip<1>(p, cls, tile, strip, range, sA, sB, sR); break;
+        case 1: acc_bwd_strip<8, SKIP>(p, cls, tile, strip, range, sA, sB, sR); break;
+        case 2: acc_bwd_strip<4, SKIP>(p, cls, tile, strip, range, sA, sB, sR); break;
+        case 4: acc_bwd_strip<2, SKIP>(p, cls, tile, strip, range, sA, sB, sR); break;
+        default: acc_bwd_strip<1, SKIP>(p, cls, tile, strip, range, sA, sB, sR); break;
     }
 }
 
@@ -1012,32 +1094,35 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.v_records = v_records;
     SGN_REQUIRE(in->tile_depth, "sgn_blend_bwd: tile_depth (saved by the forward) is null");
     p.tile_depth = in->tile_depth;
+    p.sched = in->sched;
+    if (in->sched) {
+        sched_kernel<<<(in->v_object_acc || in->v_background_acc) ? 3 : 1, 1024, 0, stream>>>(
+            tiles, p.tile_bins, p.cls_bins[0], p.cls_bins[1], in->tile_depth, p.split_main, p.split_acc, in->sched);
+        SGN_CHECK_LAUNCH("sched_kernel");
+    }
     {
         // all three kernels only accumulate (RED) into v_records: they may run concurrently
         ForkJoin fj(stream);
+        const bool acc_skip = !(opts->tuning & SGN_TUNE_ACC_NO_ROW_SKIP);
+        const unsigned acc_grid = tiles * 8;
         if (in->v_object_acc) {
-            acc_bwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 1);
+            if (acc_skip) acc_bwd_kernel<true><<<acc_grid, 32, 0, fj.side()>>>(p, 1);
+            else acc_bwd_kernel<false><<<acc_grid, 32, 0, fj.side()>>>(p, 1);
             SGN_CHECK_LAUNCH("acc_bwd_kernel<object>");
         }
         if (in->v_background_acc) {
-            acc_bwd_kernel<<<tiles * 8, 32, 0, fj.side()>>>(p, 0);
+            if (acc_skip) acc_bwd_kernel<true><<<acc_grid, 32, 0, fj.side()>>>(p, 0);
+            else acc_bwd_kernel<false><<<acc_grid, 32, 0, fj.side()>>>(p, 0);
             SGN_CHECK_LAUNCH("acc_bwd_kernel<background>");
         }
-        // row skipping is a forward-only win (measured: the backward loses more ILP than it saves); SGN_TUNE_BWD_ROW_SKIP
-        // forces it on for experiments
-        const bool skip = (opts->tuning & SGN_TUNE_BWD_ROW_SKIP) != 0;
+
         const bool pack = (opts->tuning & SGN_TUNE_BWD_PACKED) != 0;
-        const int variant = (in->v_depth ? 4 : 0) | (skip ? 2 : 0) | (pack ? 1 : 0);
         const dim3 grid(tiles * 8), block(32);
-        switch (variant) {
-            case 0: blend_bwd_kernel<false, false, false><<<grid, block, 0, stream>>>(p); break;
-            case 1: blend_bwd_kernel<false, false, true><<<grid, block, 0, stream>>>(p); break;
-            case 2: blend_bwd_kernel<false, true, false><<<grid, block, 0, stream>>>(p); break;
-            case 3: blend_bwd_kernel<false, true, true><<<grid, block, 0, stream>>>(p); break;
-            case 4: blend_bwd_kernel<true, false, false><<<grid, block, 0, stream>>>(p); break;
-            case 5: blend_bwd_kernel<true, false, true><<<grid, block, 0, stream>>>(p); break;
-            case 6: blend_bwd_kernel<true, true, false><<<grid, block, 0, stream>>>(p); break;
-            default: blend_bwd_kernel<true, true, true><<<grid, block, 0, stream>>>(p); break;
+        switch ((in->v_depth ? 2 : 0) | (pack ? 1 : 0)) {
+            case 0: blend_bwd_kernel<false, false><<<grid, block, 0, stream>>>(p); break;
+            case 1: blend_bwd_kernel<false, true><<<grid, block, 0, stream>>>(p); break;
+            case 2: blend_bwd_kernel<true, false><<<grid, block, 0, stream>>>(p); break;
+            default: blend_bwd_kernel<true, true><<<grid, block, 0, stream>>>(p); break;
         }
         SGN_CHECK_LAUNCH("blend_bwd_kernel");
         fj.finish();

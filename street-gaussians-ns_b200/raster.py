@@ -12,6 +12,7 @@ CUDA library.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -260,6 +261,7 @@ def class_lists(cs: _lib.CameraStruct, M: int, sorted_ids, tile_bins):
     return obj_ids, obj_bins
 
 
+USE_TILE_ORDER = os.environ.get("SGN_TILE_ORDER", "1") != "0"
 DEFAULT_TUNING = 4 | 8  # measured on cfg3 (profiles/r01g_sweep_tuning.txt): packed f32x2 bodies, no row skipping in the main kernels
 
 
@@ -267,7 +269,6 @@ def blend_opts(s: RenderSettings, has_sky: bool) -> _lib.BlendOpts:
     bo = _lib.BlendOpts()
     bo.alpha_clamp_fwd, bo.alpha_clamp_bwd = s.alpha_clamp_fwd, s.alpha_clamp_bwd
     bo.class_streams, bo.has_sky, bo.eval_clamp = int(s.class_streams), int(has_sky), int(not s.training)
-    import os
     bo.split_fwd_main = int(os.environ.get("SGN_SPLIT_FWD_MAIN", "0"))
     bo.split_fwd_acc = int(os.environ.get("SGN_SPLIT_FWD_ACC", "0"))
     bo.split_bwd_main = int(os.environ.get("SGN_SPLIT_BWD_MAIN", "0"))
@@ -296,6 +297,9 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
     fo.background_acc = out["background_acc"].data_ptr() if bo.class_streams else None
     fo.raw, fo.final_T, fo.final_idx = out["raw"].data_ptr(), out["final_T"].data_ptr(), out["final_idx"].data_ptr()
     fo.tile_depth = out["tile_depth"].data_ptr()
+    if USE_TILE_ORDER:  # scratch for the heavy-first work lists (scheduling only), reused by the backward
+        out["sched"] = torch.empty(L.sgn_blend_sched_ints(tile_bins.shape[0]), device=device, dtype=torch.int32)
+        fo.sched = out["sched"].data_ptr()
     with _timed("blend_fwd"):
         _lib.check(L.sgn_blend_fwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins),
                                    max(sorted_ids.shape[0], 1), _ptr(obj_ids), _ptr(obj_bins), _ptr(sky), C.byref(fo), _stream()),
@@ -322,6 +326,7 @@ def blend_bwd(cs, bo, records, sorted_ids, tile_bins, saved: Dict[str, torch.Ten
     bi.v_background_acc = keep["background_acc"].data_ptr() if keep.get("background_acc") is not None else None
     bi.raw, bi.final_T, bi.final_idx = saved["raw"].data_ptr(), saved["final_T"].data_ptr(), saved["final_idx"].data_ptr()
     bi.tile_depth = saved["tile_depth"].data_ptr()
+    bi.sched = saved["sched"].data_ptr() if "sched" in saved else None
     bi.sky = sky.data_ptr() if sky is not None else None
     v_sky = torch.zeros(cs.height, cs.width, 3, device=device) if (want_v_sky and sky is not None) else None
     bi.v_sky = v_sky.data_ptr() if v_sky is not None else None
@@ -369,6 +374,7 @@ class _Holder:
         self.param_grads = None
         self.v_sky = None
         self.M = 0
+        self.tile_bins = self.tile_depth = None
         self.post_backward = None
 
 
@@ -461,6 +467,7 @@ def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[st
     holder.xys, holder.conics, holder.depths = records[:, 0:2], records[:, 2:5], records[:, 9]
     holder.v_records, holder.grad_arena, holder.v_sky = v_records, arena, v_sky
     holder.param_grads = flat
+    holder.tile_bins, holder.tile_depth = tile_bins, out["tile_depth"]  # diagnostics (tools/depth_stats.py)
     res = {k: out[k] for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc") if k in out}
     return res, holder
 
