@@ -78,6 +78,51 @@ class GaussianSubModel(torch.nn.Module):
         return GaussianSet(g["means"], g["scales"], g["quats"], g["features_dc"], g["features_rest"], g["opacities"])
 
 
+class _GradSink:
+    """Delivers the rasterizer's flat gradient arena to the model's ~200 parameter tensors.
+
+    torch.autograd with one leaf per parameter tensor costs ~1.5 ms of host time per step here (198
+    AccumulateGrad nodes + 198 views), more than half of the GPU time of the whole step.  Instead the
+    render has ONE differentiable input (an anchor), and after backward the sink points every
+    ``param.grad`` at its slice of a persistent arena that project_bwd overwrites in place.
+    Semantics match autograd's: a parameter whose ``.grad`` is None (after ``zero_grad()``) gets the new
+    gradient; if any gradient is still set (no zero_grad between backward calls) the new one is ADDED."""
+
+    def __init__(self):
+        self.key = None
+        self.arena = None
+        self.views: List[torch.Tensor] = []
+        self.params: List[torch.Tensor] = []
+
+    def bind(self, params: List[torch.Tensor]):
+        key = tuple(map(id, params))
+        if key != self.key:
+            self.key, self.params, self.arena, self.views = key, list(params), None, []
+
+    def target(self, static: dict, device):
+        sizes, _, _ = raster.arena_layout(static)
+        total = sum(sizes)
+        if self.arena is None or self.arena.numel() != total or self.arena.device != device:
+            self.arena = torch.empty(total, device=device, dtype=torch.float32)
+            self.views = raster.arena_views(self.arena, static)
+        for p in self.params:
+            if p.grad is not None:
+                return None  # accumulate: render into a temporary arena, add in publish()
+        return self.arena
+
+    def publish(self, arena: torch.Tensor, static: dict):
+        if arena is self.arena:
+            for p, v in zip(self.params, self.views):
+                p.grad = v
+            return
+        for p, v, pv in zip(self.params, raster.arena_views(arena, static), self.views):
+            if p.grad is None:
+                pv.copy_(v)
+                p.grad = pv
+            else:
+                p.grad.add_(v)
+
+
 class SceneGraphRasterModel(torch.nn.Module):
     def __init__(self, background: GaussianSet, actors: Dict[str, GaussianSet], config: Optional[SceneGraphConfig] = None,
                  poses_at: Optional[Callable[[float], List[ActorPose]]] = None,
@@ -96,6 +141,8 @@ class SceneGraphRasterModel(torch.nn.Module):
         self.last_size = None
         self._holder = None
         self._frame_cache: dict = {}
+        self._grad_sink = _GradSink()
+        self._anchor = None
 
     @staticmethod
     def get_object_model_name(object_id) -> str:
@@ -154,7 +201,16 @@ class SceneGraphRasterModel(torch.nn.Module):
         H, W = camera.height, camera.width
         self.last_size = (H, W)
         sky = self.env_map(camera, self.training) if (self.config.use_sky_sphere and self.env_map is not None) else None
-        out, holder = raster.render_frame(frame, self._settings(class_streams=True), sky=sky)
+        sink = anchor = None
+        if torch.is_grad_enabled():
+            flat = [t for seg in frame.segments for t in seg.params.tensors()]
+            if all(t.requires_grad and t.is_leaf for t in flat):  # the normal case: the model's own nn.Parameters
+                sink = self._grad_sink
+                sink.bind(flat)
+                if self._anchor is None or self._anchor.device != flat[0].device:
+                    self._anchor = torch.zeros(1, device=flat[0].device, requires_grad=True)
+                anchor = self._anchor
+        out, holder = raster.render_frame(frame, self._settings(class_streams=True), sky=sky, grad_sink=sink, anchor=anchor)
         self._holder = holder
         self._publish_side_effects(frame, holder)
         if holder.M == 0:

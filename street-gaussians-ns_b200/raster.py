@@ -337,22 +337,31 @@ def blend_bwd(cs, bo, records, sorted_ids, tile_bins, saved: Dict[str, torch.Ten
     return v_records, v_sky
 
 
-def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, records, radii, v_records, make_views: bool = True):
-    """Dense parameter gradients, one flat arena (a single allocation, 16-byte aligned slices)."""
+def arena_layout(static: dict):
+    """(padded sizes, shapes, numels) of the flat gradient arena, in segment-major parameter order."""
+    if static.get("flat_sizes") is None:
+        static["flat_sizes"] = [x for ss in static["sizes"] for x in ss]
+        static["flat_shapes"] = [x for ss in static["shapes"] for x in ss]
+        static["flat_numel"] = [int(np.prod(x)) for x in static["flat_shapes"]]
+    return static["flat_sizes"], static["flat_shapes"], static["flat_numel"]
+
+
+def arena_views(arena: torch.Tensor, static: dict) -> List[torch.Tensor]:
+    sizes, shapes, numels = arena_layout(static)
+    chunks = arena.split_with_sizes(sizes)
+    return [c[:n].view(shp) if n != c.shape[0] else c.view(shp) for c, n, shp in zip(chunks, numels, shapes)]
+
+
+def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, records, radii, v_records, make_views: bool = True,
+                out: Optional[torch.Tensor] = None):
+    """Dense parameter gradients, one flat arena (a single allocation, 16-byte aligned slices; ``out`` reuses one)."""
     L = _lib.load()
     device = records.device
     st = table.static
-    flat_sizes = st.get("flat_sizes")
-    if flat_sizes is None:
-        flat_sizes = st["flat_sizes"] = [x for ss in st["sizes"] for x in ss]
-        st["flat_shapes"] = [x for ss in st["shapes"] for x in ss]
-        st["flat_numel"] = [int(np.prod(x)) for x in st["flat_shapes"]]
-    arena = torch.empty(sum(flat_sizes), device=device, dtype=torch.float32)
-    flat = None
-    if make_views:
-        chunks = arena.split_with_sizes(flat_sizes)
-        flat = [c[:n].view(shp) if n != c.shape[0] else c.view(shp)
-                for c, n, shp in zip(chunks, st["flat_numel"], st["flat_shapes"])]
+    flat_sizes, _, _ = arena_layout(st)
+    arena = out if out is not None else torch.empty(sum(flat_sizes), device=device, dtype=torch.float32)
+    assert arena.numel() == sum(flat_sizes) and arena.dtype == torch.float32 and arena.is_contiguous()
+    flat = arena_views(arena, st) if make_views else None
     gt = _grads_table(arena, st, device)
     with _timed("project_bwd"):
         _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, table.num_chunks, C.byref(cs), _ptr(records),
@@ -376,6 +385,9 @@ class _Holder:
         self.M = 0
         self.tile_bins = self.tile_depth = None
         self.post_backward = None
+        # model path: an object with target(static) -> arena-or-None and publish(arena, static); the parameter
+        # gradients are then delivered through it instead of through 6 x segments autograd leaves
+        self.grad_sink = None
 
 
 class _SceneGraphRasterize(torch.autograd.Function):
@@ -385,9 +397,13 @@ class _SceneGraphRasterize(torch.autograd.Function):
         # which cotangents exist (depth / background_acc have none in training)
         ctx.set_materialize_grads(False)
         nseg = len(frame.segments)
-        assert len(flat) == 6 * nseg
-        params = [list(flat[6 * i: 6 * i + 6]) for i in range(nseg)]
-        device = flat[0].device
+        if holder.grad_sink is not None:  # flat = (anchor,): only there so that autograd calls backward
+            assert len(flat) == 1
+            params = [list(seg.params.tensors()) for seg in frame.segments]
+        else:
+            assert len(flat) == 6 * nseg
+            params = [list(flat[6 * i: 6 * i + 6]) for i in range(nseg)]
+        device = params[0][0].device
         for seg, ps in zip(frame.segments, params):
             K = (settings.sh_degree + 1) ** 2
             if ps[4].shape[1] != K - 1:
@@ -424,8 +440,15 @@ class _SceneGraphRasterize(torch.autograd.Function):
         vd = {k: t for k, t in zip(names, v)}
         v_records, v_sky = blend_bwd(ctx.cs, ctx.bo, ctx.records, ctx.sorted_ids, ctx.tile_bins, ctx.saved, ctx.sky, vd,
                                      ctx.sky_needs_grad, ctx.obj_ids, ctx.obj_bins)
-        flat, arena = project_bwd(ctx.table, ctx.params, ctx.cs, ctx.records, ctx.radii, v_records)
         h = ctx.holder
+        sink = h.grad_sink
+        if sink is not None:
+            _, arena = project_bwd(ctx.table, ctx.params, ctx.cs, ctx.records, ctx.radii, v_records, make_views=False,
+                                   out=sink.target(ctx.table.static, v_records.device))
+            sink.publish(arena, ctx.table.static)
+            flat = (None,)
+        else:
+            flat, arena = project_bwd(ctx.table, ctx.params, ctx.cs, ctx.records, ctx.radii, v_records)
         h.v_records, h.grad_arena = v_records, arena
         # the reference reads ``self.xys.grad`` after backward (densification statistics,
         # sgn_splatfacto.py:520-524): xys is a view of the record array, its gradient a view of v_records
@@ -472,11 +495,16 @@ def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[st
     return res, holder
 
 
-def render_frame(frame: Frame, settings: Optional[RenderSettings] = None, sky: Optional[torch.Tensor] = None):
-    """Render one camera.  Returns (outputs dict, holder).  Segment parameters must be CUDA tensors."""
+def render_frame(frame: Frame, settings: Optional[RenderSettings] = None, sky: Optional[torch.Tensor] = None,
+                 grad_sink=None, anchor: Optional[torch.Tensor] = None):
+    """Render one camera.  Returns (outputs dict, holder).  Segment parameters must be CUDA tensors.
+
+    With ``grad_sink`` (+ ``anchor``, a 1-element leaf that requires grad) the parameter gradients are handed
+    to the sink after backward instead of flowing through one autograd leaf per parameter tensor."""
     settings = settings or RenderSettings()
     holder = _Holder()
-    flat = [t for seg in frame.segments for t in seg.params.tensors()]
+    holder.grad_sink = grad_sink
+    flat = [anchor] if grad_sink is not None else [t for seg in frame.segments for t in seg.params.tensors()]
     outs = _SceneGraphRasterize.apply(frame, settings, holder, sky, *flat)
     names = ["rgb", "accumulation", "depth", "object_acc", "background_acc"][: len(outs)]
     out = {k: t for k, t in zip(names, outs)}

@@ -1,0 +1,100 @@
+"""Level-2 surface (SceneGraphRasterModel.get_outputs / get_loss_dict, the reference's nerfstudio Model methods on
+the hot path, street_gaussians_ns/sgn_splatfacto_scene_graph.py:305-391) against the autograd path of
+raster.render_frame on the same frame: outputs identical, parameter gradients delivered through the gradient sink
+equal to the per-leaf autograd gradients, and torch's accumulate-unless-zeroed semantics."""
+import numpy as np
+import pytest
+import torch
+
+import street_gaussians_ns_b200.synthetic as syn
+from street_gaussians_ns_b200 import raster
+from street_gaussians_ns_b200.model import ActorPose, SceneGraphConfig, SceneGraphRasterModel
+from street_gaussians_ns_b200.scene import PARAM_NAMES, Frame, Segment
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def setup():
+    fr = syn.make_frame(n_background=20000, n_actors=4, n_per_actor=1500, width=320, height=240, seed=3,
+                        actor_shift=np.array([1.0, 0.0, -1.0]))
+    dev = torch.device("cuda", 0)
+    bg = fr.segments[0].params.to(dev)
+    actors = {s.name.replace("object_", ""): s.params.to(dev) for s in fr.segments[1:]}
+    poses = [ActorPose(s.name.replace("object_", ""), s.rot, s.center, 21, list(range(85))) for s in fr.segments[1:]]
+    model = SceneGraphRasterModel(bg, actors, SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0),
+                                  poses_at=lambda t: poses).to(dev)
+    model.train()
+    model.step = 30000
+    gt = torch.rand(fr.camera.height, fr.camera.width, 3, generator=torch.Generator().manual_seed(2)).to(dev)
+    return fr, model, gt
+
+
+def _loss(model, out, gt):
+    return sum(model.get_loss_dict(out, {"image": gt}).values())
+
+
+def _model_grads(model):
+    # PARAM_NAMES order (a ParameterDict built from a plain dict iterates its keys SORTED)
+    return torch.cat([model.all_models[name].gauss_params[k].grad.reshape(-1) for name in model.visible_model_names
+                      for k in PARAM_NAMES])
+
+
+def test_model_matches_render_frame_autograd(setup):
+    fr, model, gt = setup
+    for p in model.parameters():
+        p.grad = None
+    out = model.get_outputs(fr.camera)
+    loss = _loss(model, out, gt)
+    loss.backward()
+    got = _model_grads(model).clone()
+    # the same frame through the per-leaf autograd path
+    frame = model._frame(fr.camera)
+    frc = Frame(fr.camera, [Segment(type(s.params)(*[t.detach().clone().requires_grad_(True) for t in s.params.tensors()]),
+                                    s.cls, s.rot, s.center, s.idft, s.name) for s in frame.segments])
+    out2, h2 = raster.render_frame(frc, model._settings(class_streams=True))
+    for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc"):
+        assert torch.equal(out[k].detach(), out2[k].detach()), k
+    loss2 = _loss(model, out2, gt)
+    loss2.backward()
+    ref = torch.cat([t.grad.reshape(-1) for seg in frc.segments for t in seg.params.tensors()])
+    assert float(loss) == pytest.approx(float(loss2), rel=1e-6)
+    assert rel_l2(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    # side effects the densification reads (sgn_splatfacto.py:513-541)
+    assert model.xys.grad is not None and model.xys.grad.shape == model.xys.shape
+    sub = model.all_models[model.visible_model_names[1]]
+    assert sub.xys.grad.shape[0] == sub.num_points and sub.radii.shape[0] == sub.num_points
+    assert model._holder.grad_arena.numel() >= got.numel()
+
+
+def test_gradients_accumulate_unless_zeroed(setup):
+    fr, model, gt = setup
+    for p in model.parameters():
+        p.grad = None
+    _loss(model, model.get_outputs(fr.camera), gt).backward()
+    g1 = _model_grads(model).clone()
+    _loss(model, model.get_outputs(fr.camera), gt).backward()  # no zero_grad: torch semantics = sum
+    g2 = _model_grads(model).clone()
+    assert rel_l2(g2.cpu().numpy(), 2 * g1.cpu().numpy()) < 1e-4
+    for p in model.parameters():
+        p.grad = None
+    _loss(model, model.get_outputs(fr.camera), gt).backward()
+    assert rel_l2(_model_grads(model).cpu().numpy(), g1.cpu().numpy()) < 1e-5
+
+
+def test_eval_outputs_and_no_grad(setup):
+    fr, model, gt = setup
+    model.eval()
+    try:
+        with torch.no_grad():
+            out = model.get_outputs(fr.camera)
+        for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc", "background_rgb", "object_rgb"):
+            assert k in out and torch.isfinite(out[k]).all(), k
+        assert float(out["rgb"].min()) >= 0.0 and float(out["rgb"].max()) <= 1.0  # eval clamp (sgn_splatfacto.py:974-975)
+        assert not out["rgb"].requires_grad
+    finally:
+        model.train()
