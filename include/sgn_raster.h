@@ -245,6 +245,29 @@ int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float
                   const int32_t* cls_ids /*[2,M] or NULL*/, const int32_t* cls_bins /*[2,tiles,2] or NULL*/,
                   const sgn_blend_bwd_in* in, float* v_records, void* stream);
 
+/* ---- loss epilogue ------------------------------------------------------------------
+ * The image-space loss terms of the reference that re-read the rasterizer's outputs right after the render, and
+ * their cotangents: L1 = w_l1 * mean|gt - rgb| (sgn_splatfacto.py:1079-1084; with mask: both sides times mask,
+ * :1073-1076), sky = w_sky * mean(sky_mask * accumulation) (:1090-1093), entropy = w_entropy * mean(-(oa log oa +
+ * (1-oa) log(1-oa))) with oa = clamp(object_acc, 1e-5, 1-1e-5) (sgn_splatfacto_scene_graph.py:386-389).
+ * A term whose inputs are NULL is 0 / gets no cotangent.  gt is the float image or the uint8 one (gt = u8 / 255). */
+typedef struct sgn_loss_in {
+    const float* rgb;           /* [H,W,3] or NULL */
+    const uint8_t* gt_u8;       /* [H,W,3] exactly one of gt_u8 / gt_f32 when rgb is given */
+    const float* gt_f32;
+    const float* mask;          /* [H,W,1] or NULL */
+    const float* accumulation;  /* [H,W,1] or NULL */
+    const uint8_t* sky_mask;    /* [H,W] 1 = sky (semantic == SKY) or NULL */
+    const float* object_acc;    /* [H,W,1] or NULL */
+    float w_l1, w_sky, w_entropy;
+} sgn_loss_in;
+size_t sgn_loss_scratch_bytes(void);
+/* losses[3] (device) = {L1, sky, entropy} terms, already weighted */
+int sgn_loss_fwd(int H, int W, const sgn_loss_in* in, float* losses, void* scratch, size_t scratch_bytes, void* stream);
+/* cotangents of the outputs for incoming gradients grad_losses[3] (device scalars; NULL = all ones); each output may be NULL */
+int sgn_loss_bwd(int H, int W, const sgn_loss_in* in, const float* grad_losses, float* v_rgb, float* v_accumulation,
+                 float* v_object_acc, void* stream);
+
 /* ---- fused multi-tensor Adam ------------------------------------------------------
  * torch.optim.Adam semantics (betas, eps, no weight decay, no amsgrad) for every Gaussian parameter tensor in
  * ONE launch; replaces the nine nerfstudio Adam optimizers over ~200 tensors (sgn_config.py:71-108).

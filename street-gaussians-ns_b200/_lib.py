@@ -66,6 +66,14 @@ class AdamTensor(C.Structure):
     ]
 
 
+class LossIn(C.Structure):
+    _fields_ = [
+        ("rgb", C.c_void_p), ("gt_u8", C.c_void_p), ("gt_f32", C.c_void_p), ("mask", C.c_void_p),
+        ("accumulation", C.c_void_p), ("sky_mask", C.c_void_p), ("object_acc", C.c_void_p),
+        ("w_l1", C.c_float), ("w_sky", C.c_float), ("w_entropy", C.c_float),
+    ]
+
+
 class BlendFwdOut(C.Structure):
     _fields_ = [
         ("rgb", C.c_void_p), ("accumulation", C.c_void_p), ("depth", C.c_void_p),
@@ -91,6 +99,7 @@ EXPORTS = [
     "sgn_upload", "sgn_bin_count", "sgn_project_fwd", "sgn_project_bwd", "sgn_l1_project_fwd", "sgn_l1_project_bwd", "sgn_l1_sh", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
     "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_bin_class_scratch_bytes", "sgn_bin_class_lists", "sgn_blend_sched_ints",
     "sgn_blend_fwd", "sgn_blend_bwd", "sgn_sizeof_adam_tensor", "sgn_adam_chunk_elems", "sgn_adam_step",
+    "sgn_loss_scratch_bytes", "sgn_loss_fwd", "sgn_loss_bwd",
 ]
 
 
@@ -139,6 +148,11 @@ def load():
     for f in ("sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan", "sgn_bin_sort", "sgn_bin_class_lists",
               "sgn_blend_fwd", "sgn_blend_bwd"):
         getattr(L, f).restype = C.c_int
+    L.sgn_loss_scratch_bytes.restype = sz
+    L.sgn_loss_fwd.argtypes = [i32, i32, C.POINTER(LossIn), vp, vp, sz, vp]
+    L.sgn_loss_fwd.restype = C.c_int
+    L.sgn_loss_bwd.argtypes = [i32, i32, C.POINTER(LossIn), vp, vp, vp, vp, vp]
+    L.sgn_loss_bwd.restype = C.c_int
     L.sgn_sizeof_adam_tensor.restype = sz
     L.sgn_adam_chunk_elems.restype = C.c_int
     L.sgn_adam_step.argtypes = [vp, i32, i32, vp, vp, vp, vp]

@@ -20,6 +20,7 @@ SOURCES = {
     "project.cu": ["--fmad=false"],
     "binning.cu": [],
     "blend.cu": ["--use_fast_math"],
+    "loss.cu": [],
     "adam.cu": ["--fmad=false"],  # keep torch.optim.Adam's rounding sequence (no contraction)
 }
 

@@ -40,7 +40,7 @@ void sgn_count_launch(int n);
         }                                                                                        \
     } while (0)
 
-static inline bool sgn_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static __host__ __device__ inline bool sgn_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // aux word of the projected record
 #define SGN_AUX_CLAMP_MASK 0x7

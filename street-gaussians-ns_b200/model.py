@@ -56,6 +56,7 @@ class SceneGraphConfig:
     alpha_clamp_fwd: float = 0.999
     alpha_clamp_bwd: float = 0.99
     render_background_acc: bool = True
+    fused_loss: bool = True  # L1 / sky / entropy terms through the fused loss epilogue (loss.py) instead of torch ops
 
 
 class GaussianSubModel(torch.nn.Module):
@@ -277,26 +278,52 @@ class SceneGraphRasterModel(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:
-        """sgn_splatfacto.py:1042-1094 + scene graph :376-391."""
+        """sgn_splatfacto.py:1042-1094 + scene graph :376-391.  ``batch["image"]`` may be the float image or the
+        uint8 one the data loader holds (converted as the reference does: ``.float() / 255``)."""
         c = self.config
-        gt_img = batch["image"]
-        rgb = outputs["rgb"]
-        if "mask" in batch:
-            gt_img = gt_img * batch["mask"]
-            rgb = rgb * batch["mask"]
+        want_sky = "semantic" in batch and c.sky_acc_loss_mult > 0
+        want_ent = c.object_acc_entropy_loss_mult > 0.0 and self.step > c.stop_split_at
+        fused = c.fused_loss and outputs["rgb"].is_cuda
         losses = {}
-        Ll1 = torch.abs(gt_img - rgb).mean()
-        losses["Ll1"] = (1 - c.ssim_lambda) * Ll1
+
+        def float_pair():  # (gt, rgb) as the torch ops consume them
+            gt_img, rgb = batch["image"], outputs["rgb"]
+            if gt_img.dtype == torch.uint8:
+                gt_img = gt_img.float() / 255.0
+            if "mask" in batch:
+                gt_img, rgb = gt_img * batch["mask"], rgb * batch["mask"]
+            return gt_img, rgb
+
+        if fused:
+            # one forward + one backward kernel for the three image-space terms (loss.py)
+            from .loss import fused_image_losses
+            l1, sky, ent = fused_image_losses(
+                outputs["rgb"], batch["image"], accumulation=outputs["accumulation"] if want_sky else None,
+                object_acc=outputs["object_acc"] if want_ent else None, mask=batch.get("mask"),
+                sky_mask=(batch["semantic"] == 2) if want_sky else None,  # SemanticType.SKY (data/utils/data_utils.py:26-29)
+                w_l1=1 - c.ssim_lambda, w_sky=c.sky_acc_loss_mult if want_sky else 0.0,
+                w_entropy=c.object_acc_entropy_loss_mult if want_ent else 0.0)
+            losses["Ll1"] = l1
+        else:
+            gt_img, rgb = float_pair()
+            losses["Ll1"] = (1 - c.ssim_lambda) * torch.abs(gt_img - rgb).mean()
         if c.ssim_lambda > 0:
+            gt_img, rgb = float_pair()
             simloss = 1 - ssim(gt_img.permute(2, 0, 1)[None, ...], rgb.permute(2, 0, 1)[None, ...])
             losses["simloss"] = c.ssim_lambda * simloss
-        if "semantic" in batch and c.sky_acc_loss_mult > 0:
-            sky_mask = (batch["semantic"] == 2)  # SemanticType.SKY (data/utils/data_utils.py:26-29)
-            losses["sky_accumulation"] = c.sky_acc_loss_mult * (sky_mask * outputs["accumulation"]).mean()
-        if c.object_acc_entropy_loss_mult > 0.0 and self.step > c.stop_split_at:
-            oa = torch.clamp(outputs["object_acc"], min=1e-5, max=1 - 1e-5)
-            losses["object_acc_entropy_loss"] = c.object_acc_entropy_loss_mult * -(
-                oa * torch.log(oa) + (1.0 - oa) * torch.log(1.0 - oa)).mean()
+        if want_sky:
+            if fused:
+                losses["sky_accumulation"] = sky
+            else:
+                sky_mask = (batch["semantic"] == 2)
+                losses["sky_accumulation"] = c.sky_acc_loss_mult * (sky_mask * outputs["accumulation"]).mean()
+        if want_ent:
+            if fused:
+                losses["object_acc_entropy_loss"] = ent
+            else:
+                oa = torch.clamp(outputs["object_acc"], min=1e-5, max=1 - 1e-5)
+                losses["object_acc_entropy_loss"] = c.object_acc_entropy_loss_mult * -(
+                    oa * torch.log(oa) + (1.0 - oa) * torch.log(1.0 - oa)).mean()
         return losses
 
 

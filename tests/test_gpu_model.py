@@ -98,3 +98,40 @@ def test_eval_outputs_and_no_grad(setup):
         assert not out["rgb"].requires_grad
     finally:
         model.train()
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_fused_loss_epilogue_matches_torch(setup, u8):
+    """loss.py against the reference's torch expressions (sgn_splatfacto.py:1079-1093,
+    scene graph :386-389): loss values and the cotangents that reach rgb / accumulation / object_acc."""
+    fr, model, gt = setup
+    H, W = fr.camera.height, fr.camera.width
+    g = torch.Generator().manual_seed(11)
+    dev = gt.device
+    rgb0 = torch.rand(H, W, 3, generator=g).to(dev)
+    acc0 = torch.rand(H, W, 1, generator=g).to(dev)
+    obj0 = torch.rand(H, W, 1, generator=g).to(dev)
+    obj0[:4] = 0.0          # clamp region: no gradient
+    obj0[4:8] = 1.0
+    semantic = (torch.rand(H, W, 1, generator=g) > 0.7).to(dev).long() * 2
+    mask = (torch.rand(H, W, 1, generator=g) > 0.2).float().to(dev)
+    image = (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).to(dev) if u8 else gt
+    res = {}
+    for fused in (False, True):
+        model.config.fused_loss = fused
+        for with_mask in (False, True):
+            rgb, acc, obj = (t.clone().requires_grad_(True) for t in (rgb0, acc0, obj0))
+            batch = {"image": image, "semantic": semantic}
+            if with_mask:
+                batch["mask"] = mask
+            losses = model.get_loss_dict({"rgb": rgb, "accumulation": acc, "object_acc": obj}, batch)
+            assert set(losses) == {"Ll1", "sky_accumulation", "object_acc_entropy_loss"}
+            (2.0 * losses["Ll1"] + 0.5 * losses["sky_accumulation"] + 3.0 * losses["object_acc_entropy_loss"]).backward()
+            res[(fused, with_mask)] = ({k: float(v) for k, v in losses.items()}, rgb.grad, acc.grad, obj.grad)
+    model.config.fused_loss = True
+    for with_mask in (False, True):
+        (l0, *g0), (l1, *g1) = res[(False, with_mask)], res[(True, with_mask)]
+        for k in l0:
+            assert l1[k] == pytest.approx(l0[k], rel=2e-6), k
+        for a, b in zip(g0, g1):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-12)

@@ -25,7 +25,7 @@ ring = torch.zeros(1).pin_memory()
 
 
 def step():
-    gt = gt_host.to(dev, non_blocking=True).float() / 255.0
+    gt = gt_host.to(dev, non_blocking=True)
     out = model.get_outputs(fr.camera)
     loss = sum(model.get_loss_dict(out, {"image": gt}).values())
     loss.backward()
