@@ -268,6 +268,23 @@ int sgn_loss_fwd(int H, int W, const sgn_loss_in* in, float* losses, void* scrat
 int sgn_loss_bwd(int H, int W, const sgn_loss_in* in, const float* grad_losses, float* v_rgb, float* v_accumulation,
                  float* v_object_acc, void* stream);
 
+/* ---- densification statistics -------------------------------------------------------
+ * What each sub-model's `after_train` accumulates after backward (sgn_splatfacto.py:513-541), for all visible
+ * sub-models of the frame in one launch: grads = ||v_records[:,0:2]||; on a sub-model's first call
+ * xys_grad_norm = grads, vis_counts = 1, max_2Dsize = 0 (then the max below); afterwards, for rows with
+ * radii > 0: xys_grad_norm += grads, vis_counts += 1; max_2Dsize = max(max_2Dsize, radii / max(H, W)). */
+typedef struct sgn_densify_segment {
+    int32_t row0, count;  /* rows of this sub-model in the frame's row space */
+    int32_t first;        /* 1: the sub-model's statistics are being created by this call */
+    int32_t pad;
+    float* xys_grad_norm; /* [count] */
+    float* vis_counts;    /* [count] */
+    float* max_2Dsize;    /* [count] */
+} sgn_densify_segment;
+size_t sgn_sizeof_densify_segment(void);
+int sgn_densify_stats(const sgn_densify_segment* table_dev, int nseg, int N, const float* v_records /*[N,12]*/,
+                      const int32_t* radii /*[N]*/, int height, int width, void* stream);
+
 /* ---- fused multi-tensor Adam ------------------------------------------------------
  * torch.optim.Adam semantics (betas, eps, no weight decay, no amsgrad) for every Gaussian parameter tensor in
  * ONE launch; replaces the nine nerfstudio Adam optimizers over ~200 tensors (sgn_config.py:71-108).

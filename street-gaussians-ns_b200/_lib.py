@@ -66,6 +66,13 @@ class AdamTensor(C.Structure):
     ]
 
 
+class DensifySegment(C.Structure):
+    _fields_ = [
+        ("row0", C.c_int32), ("count", C.c_int32), ("first", C.c_int32), ("pad", C.c_int32),
+        ("xys_grad_norm", C.c_void_p), ("vis_counts", C.c_void_p), ("max_2Dsize", C.c_void_p),
+    ]
+
+
 class LossIn(C.Structure):
     _fields_ = [
         ("rgb", C.c_void_p), ("gt_u8", C.c_void_p), ("gt_f32", C.c_void_p), ("mask", C.c_void_p),
@@ -99,7 +106,7 @@ EXPORTS = [
     "sgn_upload", "sgn_bin_count", "sgn_project_fwd", "sgn_project_bwd", "sgn_l1_project_fwd", "sgn_l1_project_bwd", "sgn_l1_sh", "sgn_bin_scan_scratch_bytes", "sgn_bin_scan",
     "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_bin_class_scratch_bytes", "sgn_bin_class_lists", "sgn_blend_sched_ints",
     "sgn_blend_fwd", "sgn_blend_bwd", "sgn_sizeof_adam_tensor", "sgn_adam_chunk_elems", "sgn_adam_step",
-    "sgn_loss_scratch_bytes", "sgn_loss_fwd", "sgn_loss_bwd",
+    "sgn_loss_scratch_bytes", "sgn_loss_fwd", "sgn_loss_bwd", "sgn_sizeof_densify_segment", "sgn_densify_stats",
 ]
 
 
@@ -108,11 +115,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("SGN_RASTER_LIB", LIB_PATH)  # developer A/B of two builds of the same ABI (tools/)
+    if not os.path.exists(path):
         raise SgnError(
-            f"{LIB_PATH} is missing. Build it with `python street-gaussians-ns_b200/build.py` "
+            f"{path} is missing. Build it with `python street-gaussians-ns_b200/build.py` "
             "(or __graft_entry__.build()). There is no CPU fallback for the rasterizer.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
     L.sgn_last_error.restype = C.c_char_p
     L.sgn_abi_version.restype = C.c_int
@@ -148,6 +156,9 @@ def load():
     for f in ("sgn_upload", "sgn_project_fwd", "sgn_project_bwd", "sgn_bin_scan", "sgn_bin_sort", "sgn_bin_class_lists",
               "sgn_blend_fwd", "sgn_blend_bwd"):
         getattr(L, f).restype = C.c_int
+    L.sgn_sizeof_densify_segment.restype = sz
+    L.sgn_densify_stats.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp]
+    L.sgn_densify_stats.restype = C.c_int
     L.sgn_loss_scratch_bytes.restype = sz
     L.sgn_loss_fwd.argtypes = [i32, i32, C.POINTER(LossIn), vp, vp, sz, vp]
     L.sgn_loss_fwd.restype = C.c_int

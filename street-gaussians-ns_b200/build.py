@@ -21,6 +21,7 @@ SOURCES = {
     "binning.cu": [],
     "blend.cu": ["--use_fast_math"],
     "loss.cu": [],
+    "densify.cu": ["--fmad=false"],
     "adam.cu": ["--fmad=false"],  # keep torch.optim.Adam's rounding sequence (no contraction)
 }
 

@@ -156,13 +156,20 @@ emit_keys_kernel(int N, int tiles_x, int width, int height, int bw, const float4
     }
     const int bwid = bb.z - bb.x, area = bwid * (bb.w - bb.y);
     if (vis && area <= COOP_AREA) {
-        // the projection kernel already decided every tile of a small AABB: replay its bit mask
-        while (mask && cur < end) {
-            const int bit = __ffs(mask) - 1;
-            mask &= mask - 1;
-            keys[cur] = (uint16_t)((bb.y + bit / bwid) * tiles_x + bb.x + bit % bwid);
-            vals[cur] = payload;
-            ++cur;
+        // the projection kernel already decided every tile of a small AABB: replay its bit mask, one AABB row
+        // at a time (no per-tile division by the AABB width)
+        const unsigned row_bits = bwid >= 32 ? 0xffffffffu : ((1u << bwid) - 1u);
+        for (int ty = bb.y; ty < bb.w && mask && cur < end; ++ty) {
+            unsigned rm = mask & row_bits;
+            mask = bwid >= 32 ? 0u : (mask >> bwid);
+            const int base = ty * tiles_x + bb.x;
+            while (rm && cur < end) {
+                const int bit = __ffs(rm) - 1;
+                rm &= rm - 1;
+                keys[cur] = (uint16_t)(base + bit);
+                vals[cur] = payload;
+                ++cur;
+            }
         }
     }
     unsigned big = __ballot_sync(0xffffffffu, vis && area > COOP_AREA);

@@ -987,7 +987,7 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
     const int hi0 = min(range.y, wkmax + 1);
     if (hi0 <= range.x) return;
     const int my_comp = multi_reduce_slot<6>(lane);
-    const float clampb = in_register(p.clamp_bwd);
+    const float clampb = in_register(p.clamp_bwd), nclamp = -clampb;
     Staged nxt;
     if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, ids[hi0 - 1 - lane]);
     int buf = 0;
@@ -1008,6 +1008,27 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
             const unsigned lim1 = (unsigned)(max(__float_as_int(LOG2_255 + B.y), -1) + 1);
             const float o = B.w;
             float S0 = 0.f, Sy = 0.f, Syy = 0.f;
+            if constexpr (PPL >= 2) {  // packed row-slot pairs (f32x2), as in blend_bwd_strip
+                f2 S0p = dup2(0.f), Syp = dup2(0.f), Syyp = dup2(0.f);
+                const f2 dyb = f2{dy0, dy0 - 2.f};
+#pragma unroll
+                for (int q = 0; q < PPL / 2; ++q) {
+                    if (SKIP && fabsf(dyc - (float)(4 * q + 1)) > reach + 1.f) continue;
+                    const f2 dy = add2(dyb, dup2(-(float)(4 * q)));
+                    const f2 sg = fma2(dy, fma2(dup2(B.x), dy, dup2(bdx)), dup2(ax2));
+                    const bool v0 = (__float_as_uint(sg.x) < lim1) && (k <= idx[2 * q]);
+                    const bool v1 = (__float_as_uint(sg.y) < lim1) && (k <= idx[2 * q + 1]);
+                    const f2 nraw = f2{v0 ? -fast_ex2(B.y - sg.x) : 0.f, v1 ? -fast_ex2(B.y - sg.y) : 0.f};
+                    const f2 om = add2(f2{fmaxf(nclamp, nraw.x), fmaxf(nclamp, nraw.y)}, dup2(1.f));
+                    const f2 ra = f2{fast_rcp(om.x), fast_rcp(om.y)};
+                    const f2 vs = mul2(nraw, mul2(f2{tfv[2 * q], tfv[2 * q + 1]}, ra));
+                    S0p = add2(S0p, vs);
+                    const f2 vsy = mul2(vs, dy);
+                    Syp = add2(Syp, vsy);
+                    Syyp = fma2(vsy, dy, Syyp);
+                }
+                S0 = S0p.x + S0p.y; Sy = Syp.x + Syp.y; Syy = Syyp.x + Syyp.y;
+            } else {
 #pragma unroll
             for (int s = 0; s < PPL; ++s) {
                 if (SKIP && fabsf(dyc - (float)(2 * s)) > reach) continue;
@@ -1022,6 +1043,7 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
                 const float vsy = vs * dy;
                 Sy += vsy;
                 Syy = __fmaf_rn(vsy, dy, Syy);
+            }
             }
             if (!__any_sync(FULL, S0 != 0.f)) continue;  // every term carries vs: all zero => nothing to add
             const float ca = A.z * (2.f * LN2), cbb = A.w * LN2, cc = B.x * (2.f * LN2);

@@ -49,14 +49,21 @@ __device__ __forceinline__ bool tile_touched(const TouchCtx& t, int tx, int ty, 
     const float x0 = __fsub_rn((float)(tx * bw) + 0.5f, t.gx), x1 = __fsub_rn(fminf((float)(tx * bw + bw), (float)width) - 0.5f, t.gx);
     const float y0 = __fsub_rn((float)(ty * bw) + 0.5f, t.gy), y1 = __fsub_rn(fminf((float)(ty * bw + bw), (float)height) - 0.5f, t.gy);
     if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;  // centre inside the rectangle
-    const float nbc = t.nbc, nba = t.nba;
+    // The centre lies outside the rectangle, so the minimum of the convex form over it sits on an edge FACING the
+    // centre: for an interior minimum on the edge y = y1 the gradient there is (0, g) with g < 0, and convexity
+    // (0 = q(centre) >= q(p) - g*p_y) forces p_y < 0, i.e. the centre above that edge; likewise for the other three.
+    // At most one vertical and one horizontal edge qualify.
     float best = 3.4e38f, best_mag = 0.f, mag, q;
-    // edges x = x0, x = x1: minimise over dy
-    q = touch_q(t, x0, fminf(fmaxf(__fmul_rn(nbc, x0), y0), y1), mag); if (q < best) { best = q; best_mag = mag; }
-    q = touch_q(t, x1, fminf(fmaxf(__fmul_rn(nbc, x1), y0), y1), mag); if (q < best) { best = q; best_mag = mag; }
-    // edges y = y0, y = y1: minimise over dx
-    q = touch_q(t, fminf(fmaxf(__fmul_rn(nba, y0), x0), x1), y0, mag); if (q < best) { best = q; best_mag = mag; }
-    q = touch_q(t, fminf(fmaxf(__fmul_rn(nba, y1), x0), x1), y1, mag); if (q < best) { best = q; best_mag = mag; }
+    if (x0 > 0.f || x1 < 0.f) {  // vertical edge nearest the centre: minimise over dy
+        const float xe = x0 > 0.f ? x0 : x1;
+        q = touch_q(t, xe, fminf(fmaxf(__fmul_rn(t.nbc, xe), y0), y1), mag);
+        best = q; best_mag = mag;
+    }
+    if (y0 > 0.f || y1 < 0.f) {  // horizontal edge nearest the centre: minimise over dx
+        const float ye = y0 > 0.f ? y0 : y1;
+        q = touch_q(t, fminf(fmaxf(__fmul_rn(t.nba, ye), x0), x1), ye, mag);
+        if (q < best) { best = q; best_mag = mag; }
+    }
     return best <= __fadd_rn(__fadd_rn(t.tau, 1e-3f), __fmul_rn(8e-6f, best_mag));
 }
 

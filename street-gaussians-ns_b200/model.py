@@ -69,6 +69,8 @@ class GaussianSubModel(torch.nn.Module):
              ("means", "scales", "quats", "features_dc", "features_rest", "opacities")})
         self.xys = self.depths = self.radii = self.conics = self.num_tiles_hit = None
         self.last_size = None
+        # densification statistics (sgn_splatfacto.py:513-541), created by the first after_train
+        self.xys_grad_norm = self.vis_counts = self.max_2Dsize = None
 
     @property
     def num_points(self) -> int:
@@ -265,6 +267,36 @@ class SceneGraphRasterModel(torch.nn.Module):
             row += n
         d["_slices"] = slices
         holder.post_backward = self._split_xys_grad(slices)
+
+    def after_train(self, step: int) -> None:
+        """The ``after_train`` callbacks of all visible sub-models (sgn_splatfacto.py:513-541; the scene graph
+        registers one per sub-model, :127-137) as one launch of ``sgn_densify_stats`` over the frame's rows:
+        running ||xys.grad|| sums, visibility counts and the max screen-space radius ratio, per sub-model."""
+        assert step == self.step
+        h = self._holder
+        if h is None or h.v_records is None or self.step >= self.config.stop_split_at:
+            return
+        import ctypes as C
+        from . import _lib
+        L = _lib.load()
+        slices = self.__dict__.get("_slices") or []
+        if not slices:
+            return
+        tab = (_lib.DensifySegment * len(slices))()
+        dev = h.v_records.device
+        for j, (sub, sl) in enumerate(slices):
+            n = sl.stop - sl.start
+            first = sub.xys_grad_norm is None or sub.xys_grad_norm.shape[0] != n
+            if first:
+                d = sub.__dict__
+                d["xys_grad_norm"], d["vis_counts"], d["max_2Dsize"] = (torch.empty(n, device=dev) for _ in range(3))
+            tab[j].row0, tab[j].count, tab[j].first = sl.start, n, int(first)
+            tab[j].xys_grad_norm, tab[j].vis_counts = sub.xys_grad_norm.data_ptr(), sub.vis_counts.data_ptr()
+            tab[j].max_2Dsize = sub.max_2Dsize.data_ptr()
+        raw = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(dev, non_blocking=True)
+        H, W = self.last_size
+        _lib.check(L.sgn_densify_stats(raster._ptr(raw), len(slices), h.v_records.shape[0], raster._ptr(h.v_records),
+                                       raster._ptr(h.radii), H, W, raster._stream()), "sgn_densify_stats")
 
     @staticmethod
     def _split_xys_grad(slices):

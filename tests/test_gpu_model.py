@@ -135,3 +135,44 @@ def test_fused_loss_epilogue_matches_torch(setup, u8):
             assert l1[k] == pytest.approx(l0[k], rel=2e-6), k
         for a, b in zip(g0, g1):
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-12)
+
+
+def test_after_train_statistics_match_reference_expressions(setup):
+    """sgn_densify_stats against the torch statements of every sub-model's after_train
+    (sgn_splatfacto.py:513-541), over two steps (creation, then accumulation on visible rows)."""
+    fr, model, gt = setup
+    model.step = 100  # < stop_split_at: statistics are still collected
+    try:
+        for sub in model.all_models.values():
+            sub.xys_grad_norm = sub.vis_counts = sub.max_2Dsize = None
+        ref = {}
+        for it in range(2):
+            for p in model.parameters():
+                p.grad = None
+            _loss(model, model.get_outputs(fr.camera), gt).backward()
+            model.after_train(model.step)
+            for name in model.visible_model_names:
+                sub = model.all_models[name]
+                vis = (sub.radii > 0).flatten()
+                grads = sub.xys.grad.detach().norm(dim=-1)
+                if name not in ref:
+                    r = dict(g=grads.clone(), c=torch.ones_like(grads), m=torch.zeros_like(sub.radii, dtype=torch.float32))
+                    ref[name] = r
+                else:
+                    r = ref[name]
+                    r["c"][vis] = r["c"][vis] + 1
+                    r["g"][vis] = grads[vis] + r["g"][vis]
+                r["m"][vis] = torch.maximum(r["m"][vis], sub.radii.detach()[vis] / float(max(model.last_size)))
+        for name, r in ref.items():
+            sub = model.all_models[name]
+            assert torch.equal(sub.vis_counts, r["c"]), name
+            assert torch.allclose(sub.max_2Dsize, r["m"], rtol=2e-6, atol=0), name   # radii * (1/max) vs torch's own rounding
+            assert torch.allclose(sub.xys_grad_norm, r["g"], rtol=2e-6, atol=1e-12), name
+        bgm = model.all_models["background"]
+        assert float(bgm.vis_counts.max()) == 2.0 and float(bgm.vis_counts.min()) == 1.0 and float(bgm.xys_grad_norm.sum()) > 0
+        model.step = model.config.stop_split_at  # statistics frozen after refinement stops (:516-518)
+        before = model.all_models["background"].vis_counts.clone()
+        model.after_train(model.step)
+        assert torch.equal(model.all_models["background"].vis_counts, before)
+    finally:
+        model.step = 30000
