@@ -82,6 +82,10 @@ class ClockSampler:
         if self.interval <= 0:  # debugging aid: SGN_BENCH_CLOCK_INTERVAL=0 disables the sampling thread
             self._h = None
             return
+        try:
+            self._sample()  # the first NVML clock query initialises driver state (tens of ms): keep it out of the timed region
+        except Exception:
+            pass
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 
@@ -97,12 +101,11 @@ class ClockSampler:
                 self.reasons.add(name)
 
     def _run(self):
-        while not self._stop.is_set():
+        while not self._stop.wait(self.interval):
             try:
                 self._sample()
             except Exception:
                 pass
-            self._stop.wait(self.interval)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": []}
@@ -262,11 +265,16 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier_sync()
     e0.record()
+    marks = []
     for _ in range(args.steps):
         holder = step()
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
     e1.record()
     barrier_sync()
     ms = e0.elapsed_time(e1)
+    per_step = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))  # diagnostic: spread of the K steps
     launches = L.sgn_launch_count() - launches0
     stage_ms = raster.TIMER.mean_ms()
     raster.TIMER = None
@@ -392,13 +400,25 @@ def run_ours(args):
                         "note": "alpha-blend kernels are FP32/MUFU issue-bound, not HBM-bound (SURVEY.md 8d); "
                                 "all per-kernel fractions are in roofline_all",
                         "pair_evals_per_s": None}
+            try:  # (pixel, Gaussian) pairs the traversals actually evaluate: 256 x entries traversed per tile and pass
+                td = holder.tile_depth.sum(dim=1).tolist()
+                fwd_pairs = 256.0 * sum(td)
+                bwd_pairs = 256.0 * (td[0] + (td[1] if cot.get("object_acc") is not None else 0) +
+                                     (td[2] if cot.get("background_acc") is not None else 0))
+                pairs = {"blend_fwd": fwd_pairs, "blend_bwd": bwd_pairs}.get(dom)
+                if pairs:
+                    roofline["pair_evals_per_s"] = pairs / (per_kernel[dom]["ms"] * 1e-3)
+                    roofline["entries_traversed"] = {"main": td[0], "object": td[1], "background": td[2], "listed": int(M)}
+            except Exception:
+                pass
         per_kernel["adam"] = {"ms": round(adam_ms, 4), "alg_bytes": int(28 * adam.arena_elems),
                               "GBps": round(28 * adam.arena_elems / adam_ms / 1e6, 1),
                               "frac": round(28 * adam.arena_elems / adam_ms / 1e6 / peak, 4)}
         total_alg = sum(v for k, v in alg.items())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_max": per_step[-1],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_config(args.cfg), "N_gaussians": N, "N_actor_gaussians": A,
                        "M_intersections": M, "N_visible": n_vis, "parallelism": f"camera-sharded dp{world}",
@@ -439,8 +459,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cfg", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -224,9 +224,12 @@ sched_kernel(int tiles, const int2* __restrict__ tile_bins, const int2* __restri
     const int2* bins = kind == SLOT_MAIN ? tile_bins : (kind == SLOT_OBJ ? cls_bins1 : cls_bins0);
     const int split = kind == SLOT_MAIN ? split_main : split_acc;
     int32_t* out = sched + kind * SCHED_STRIDE(tiles);
-    __shared__ int hist[64];
+    // per-warp histograms / cursors: the tiles of a frame fall into a handful of length buckets, and 9600 shared-memory
+    // atomics on ~10 addresses serialise (15 us); privatised per warp they contend 32-way at most
+    __shared__ int hist[32][64];
     __shared__ int start[64];
-    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) (&hist[0][0])[i] = 0;
     __syncthreads();
     // every forward pass and the main backward write per-pixel results for tiles with empty lists too (background
     // colour, zero accumulation, v_sky); only the accumulation backward has nothing to do there
@@ -237,18 +240,25 @@ sched_kernel(int tiles, const int2* __restrict__ tile_bins, const int2* __restri
         return r.y - r.x;
     };
     auto bucket = [](int len) {
+        if (len <= 0) return 63;
         const int lg = 31 - __clz(len);                          // floor(log2 len), len >= 1
         const int half = lg > 0 ? ((len >> (lg - 1)) & 1) : 0;  // upper half of the octave?
         return 62 - min(2 * lg + half, 62);                     // longest lists -> bucket 0
     };
     for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
         const int len = length(t);
-        if (len > 0 || visit_empty) atomicAdd(&hist[len > 0 ? bucket(len) : 63], len > 0 ? strips_for(len, split) : 1);
+        if (len > 0 || visit_empty) atomicAdd(&hist[warp][bucket(len)], len > 0 ? strips_for(len, split) : 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {  // bucket b: exclusive offsets of the warps inside the bucket, bucket total in start[b]
+        int acc = 0;
+        for (int w = 0; w < 32; ++w) { const int c = hist[w][threadIdx.x]; hist[w][threadIdx.x] = acc; acc += c; }
+        start[threadIdx.x] = acc;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int b = 0; b < 64; ++b) { start[b] = acc; acc += hist[b]; }
+        for (int b = 0; b < 64; ++b) { const int c = start[b]; start[b] = acc; acc += c; }
         out[0] = acc;
     }
     __syncthreads();
@@ -256,7 +266,8 @@ sched_kernel(int tiles, const int2* __restrict__ tile_bins, const int2* __restri
         const int len = length(t);
         if (!(len > 0 || visit_empty)) continue;
         const int W = len > 0 ? strips_for(len, split) : 1;
-        const int pos = atomicAdd(&start[len > 0 ? bucket(len) : 63], W);
+        const int bk = bucket(len);
+        const int pos = start[bk] + atomicAdd(&hist[warp][bk], W);
         for (int s = 0; s < W; ++s) out[1 + pos + s] = (t << 3) | s;
     }
 }
