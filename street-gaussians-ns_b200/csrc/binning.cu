@@ -61,11 +61,12 @@ struct PermutedCount {
     __host__ __device__ int32_t operator()(int i) const { return counts[order[i]]; }
 };
 
-// rank[g] = position of Gaussian g in depth order (inverse of `order`)
+// start[g] = where the run of Gaussian g begins in the depth-ordered entry sequence: the exclusive scan value of its
+// depth rank, scattered back to row order so that the emit kernel reads it coalesced (no rank -> cum gathers)
 __global__ void __launch_bounds__(256)
-inverse_perm_kernel(int N, const int32_t* __restrict__ order, int32_t* __restrict__ rank) {
+start_offsets_kernel(int N, const int32_t* __restrict__ rows_by_depth, const int32_t* __restrict__ cum, int32_t* __restrict__ start) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) rank[order[i]] = i;
+    if (i < N) start[rows_by_depth[i]] = (i == 0) ? 0 : cum[i - 1];
 }
 
 __global__ void write_total_kernel(const int32_t* __restrict__ cum, int N, int64_t* __restrict__ total) {
@@ -121,8 +122,8 @@ extern "C" int sgn_bin_scan(int N, const float* records, const int32_t* radii, c
         temp = L.temp_bytes;
         SGN_CHECK_CUDA(cub::DeviceScan::InclusiveSum(base + L.temp, temp, it, cum, N, stream));
         sgn_count_launch(1);
-        inverse_perm_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, sorted_rows, order);
-        SGN_CHECK_LAUNCH("inverse_perm_kernel");
+        start_offsets_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, sorted_rows, cum, order);
+        SGN_CHECK_LAUNCH("start_offsets_kernel");
     }
     write_total_kernel<<<1, 32, 0, stream>>>(cum, N, total_dev);
     SGN_CHECK_LAUNCH("write_total_kernel");
@@ -135,7 +136,7 @@ extern "C" int sgn_bin_scan(int N, const float* records, const int32_t* radii, c
 __global__ void __launch_bounds__(256)
 emit_keys_kernel(int N, int tiles_x, int width, int height, int bw, const float4* __restrict__ records,
                  const int32_t* __restrict__ radii, const ushort4* __restrict__ tile_bbox,
-                 const uint32_t* __restrict__ touch_mask, const int32_t* __restrict__ rank, const int32_t* __restrict__ cum,
+                 const uint32_t* __restrict__ touch_mask, const int32_t* __restrict__ start, int end,
                  uint16_t* __restrict__ keys, int32_t* __restrict__ vals) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -144,15 +145,13 @@ emit_keys_kernel(int N, int tiles_x, int width, int height, int bw, const float4
     TouchCtx t = {};
     int32_t payload = 0;
     uint32_t mask = 0;
-    int cur = 0, end = 0;
+    int cur = 0;  // `end` (= M) only guards the buffers: the counts come from the same test as the counting pass
     if (vis) {
         bb = tile_bbox[g];
         // payload: Gaussian row in the low 31 bits, object-class flag in bit 31 (no gather needed later)
         payload = g | ((__float_as_int(records[3 * (size_t)g + 2].z) & SGN_AUX_OBJECT) ? (int32_t)0x80000000 : 0);
         mask = touch_mask[g];
-        const int r = rank[g];
-        cur = (r == 0) ? 0 : cum[r - 1];
-        end = cum[r];
+        cur = start[g];
     }
     const int bwid = bb.z - bb.x, area = bwid * (bb.w - bb.y);
     if (vis && area <= COOP_AREA) {
@@ -183,7 +182,7 @@ emit_keys_kernel(int N, int tiles_x, int width, int height, int bw, const float4
             const int w = __shfl_sync(0xffffffffu, bwid, src), ar = __shfl_sync(0xffffffffu, area, src);
             const int32_t pl = __shfl_sync(0xffffffffu, payload, src);
             int pos = __shfl_sync(0xffffffffu, cur, src);
-            const int lim = __shfl_sync(0xffffffffu, end, src);
+            const int lim = end;
             for (int base = 0; base < ar; base += 32) {
                 const int ti = base + lane;
                 const int tx = x0 + ti % w, ty = y0 + ti / w;
@@ -262,7 +261,7 @@ extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float
     int32_t* vals_in = (int32_t*)(base + L.vals_in);
     emit_keys_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, tiles_x, cam->width, cam->height, bw,
                                                           reinterpret_cast<const float4*>(records), radii,
-                                                          reinterpret_cast<const ushort4*>(tile_bbox), touch_mask, order, cum,
+                                                          reinterpret_cast<const ushort4*>(tile_bbox), touch_mask, order, (int)M,
                                                           keys_in, vals_in);
     SGN_CHECK_LAUNCH("emit_keys_kernel");
     int tile_bits = 1;
