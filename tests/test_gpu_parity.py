@@ -43,6 +43,12 @@ SCENES = {
     "cfg1_50k_640x480": dict(n_background=50000, n_actors=0, width=640, height=480, seed=0),
     "ragged_edge": dict(n_background=8000, n_actors=2, n_per_actor=500, width=200, height=136, seed=9,
                         actor_shift=np.array([1.5, 0.0, 0.0])),
+    # odd image size (no multiple of 16 in either direction), many small actors, rotated camera of the Waymo rig
+    "odd_many_actors": dict(n_background=12000, n_actors=9, n_per_actor=300, width=333, height=177, seed=21,
+                            actor_shift=np.array([0.5, 0.0, -2.0]), c2w=syn.waymo_rig(4)[6]),
+    # dense overlap: long per-tile lists on a small image, so tiles split into 2/4/8 strips and pixels saturate
+    "dense_small_image": dict(n_background=60000, n_actors=3, n_per_actor=4000, width=96, height=80, seed=5,
+                              actor_shift=np.array([1.0, 0.0, 2.0]), fourier_dim=1),
 }
 
 
