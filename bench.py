@@ -405,6 +405,21 @@ def run_ours(args):
                         "note": "alpha-blend kernels are FP32/MUFU issue-bound, not HBM-bound (SURVEY.md 8d); "
                                 "all per-kernel fractions are in roofline_all",
                         "pair_evals_per_s": None}
+            try:  # what actually bounds it: pipe utilisation of the stage's main kernel from the committed ncu capture
+                prof = json.load(open(os.path.join(ROOT, "profiles", "r01j_ncu_step_v10.json")))
+                want = {"blend_bwd": "blend_bwd_kernel", "blend_fwd": "blend_fwd_kernel"}.get(dom, dom + "_kernel")
+                for k in prof["kernels"]:
+                    if want in k["kernel"]:
+                        pct = lambda key: float(k[key].split()[0])  # noqa: E731
+                        roofline["ncu"] = {
+                            "source": "profiles/r01j_ncu_step_v10.json (one step under ncu --set full; not a timing)",
+                            "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                            "fma_pipe_pct": pct("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                            "alu_pipe_pct": pct("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                            "dram_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}
+                        break
+            except Exception:
+                pass
             try:  # (pixel, Gaussian) pairs the traversals actually evaluate: 256 x entries traversed per tile and pass
                 td = holder.tile_depth.sum(dim=1).tolist()
                 fwd_pairs = 256.0 * sum(td)
