@@ -139,7 +139,8 @@ __device__ __forceinline__ Staged gather_entry(const float4* __restrict__ record
     const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
     Staged s;
     s.A = make_float4(r0.x, r0.y, 0.5f * LOG2E * r0.z, LOG2E * r0.w);
-    s.B = make_float4(0.5f * LOG2E * r1.x, __log2f(r1.y), r1.z, r1.w);
+    // an opacity that is not a positive number (NaN logits upstream) gets log2 = -inf: no pixel accepts the entry
+    s.B = make_float4(0.5f * LOG2E * r1.x, r1.y > 0.f ? __log2f(r1.y) : __int_as_float(0xff800000) /* -inf */, r1.z, r1.w);
     s.C = make_float4(r2.x, r2.y, __int_as_float(id), r1.y);
     return s;
 }
