@@ -261,7 +261,7 @@ def class_lists(cs: _lib.CameraStruct, M: int, sorted_ids, tile_bins):
     return obj_ids, obj_bins
 
 
-USE_TILE_ORDER = os.environ.get("SGN_TILE_ORDER", "1") != "0"
+HEAVY_FIRST = os.environ.get("SGN_HEAVY_FIRST", "1") != "0"
 DEFAULT_TUNING = 4 | 8  # measured on cfg3 (profiles/r01g_sweep_tuning.txt): packed f32x2 bodies, no row skipping in the main kernels
 
 
@@ -297,7 +297,7 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
     fo.background_acc = out["background_acc"].data_ptr() if bo.class_streams else None
     fo.raw, fo.final_T, fo.final_idx = out["raw"].data_ptr(), out["final_T"].data_ptr(), out["final_idx"].data_ptr()
     fo.tile_depth = out["tile_depth"].data_ptr()
-    if USE_TILE_ORDER:  # scratch for the heavy-first work lists (scheduling only), reused by the backward
+    if HEAVY_FIRST:  # scratch for the heavy-first work lists (scheduling only), reused by the backward
         out["sched"] = torch.empty(L.sgn_blend_sched_ints(tile_bins.shape[0]), device=device, dtype=torch.int32)
         fo.sched = out["sched"].data_ptr()
     with _timed("blend_fwd"):
