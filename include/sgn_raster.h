@@ -288,12 +288,15 @@ int sgn_densify_stats(const sgn_densify_segment* table_dev, int nseg, int N, con
 /* ---- fused multi-tensor Adam ------------------------------------------------------
  * torch.optim.Adam semantics (betas, eps, no weight decay, no amsgrad) for every Gaussian parameter tensor in
  * ONE launch; replaces the nine nerfstudio Adam optimizers over ~200 tensors (sgn_config.py:71-108).
- * Gradients / exp_avg / exp_avg_sq are flat arenas with the gradient-arena layout of sgn_project_bwd
- * (arena_offset in floats, multiples of 4); parameters are updated in place.  The host fills, per tensor and
+ * Gradients / exp_avg / exp_avg_sq are flat arenas of 16-byte aligned slices (offsets in floats, multiples of 4):
+ * the gradient arena has the layout sgn_project_bwd wrote for the frame, the moment arenas cover every tensor of
+ * the model; parameters are updated in place.  The table lists the tensors that have a gradient this step.  The host fills, per tensor and
  * per step, step_size = lr / (1 - beta1^t) and sqrt_bc2 = sqrt(1 - beta2^t), both evaluated in double. */
 typedef struct sgn_adam_tensor {
     float* param;
-    int64_t arena_offset;
+    int64_t arena_offset; /* of the tensor's moments in exp_avg / exp_avg_sq */
+    int64_t grad_offset;  /* of its gradient in grad_arena: the arena of a frame only holds the sub-models visible in that
+                             frame (torch.optim.Adam skips parameters whose .grad is None: no decay, no step count) */
     int64_t numel;
     int32_t chunk0; /* first block of this tensor: sum over earlier tensors of ceil(numel / sgn_adam_chunk_elems()) */
     float beta1, beta2, eps, step_size, sqrt_bc2;
@@ -303,6 +306,53 @@ size_t sgn_sizeof_adam_tensor(void);
 int sgn_adam_chunk_elems(void);
 int sgn_adam_step(const sgn_adam_tensor* table_dev, int ntensors, int num_chunks, const float* grad_arena,
                   float* exp_avg, float* exp_avg_sq, void* stream);
+
+/* ---- refinement: split / duplicate / cull ---------------------------------------------
+ * What `SplatfactoModel.refinement_after` does to ONE sub-model every `refine_every` steps
+ * (sgn_splatfacto.py:550-646 with cull_gaussians :648-672, split_gaussians :674-710, dup_gaussians :712-720 and the
+ * optimizer surgery dup_in_optim / remove_from_optim :459-511), as two launches instead of ~120 torch statements
+ * with eight host syncs per sub-model:
+ *   sgn_refine_decide: per row, from the running statistics of sgn_densify_stats, the log-scales and the opacity
+ *     logit -> flags (SGN_RF_* bits, csrc/sgn_refine_rules.cuh) and four 0/1 marks the caller prefix-sums;
+ *   sgn_refine_apply: rebuilds the six parameter tensors and their Adam moments in the reference's row order
+ *     [surviving old rows | split samples, sample-major | duplicates]: a split sample's mean is
+ *     mean + R(q) (exp(scale) * z), split rows shrink by 1/1.6 in log space, new rows start with zero moments.
+ * Both are HBM-bound streaming passes (decide: 32 B read per row; apply: 3 x 4 B read + written per element). */
+typedef struct sgn_refine_config {
+    int32_t densify;         /* 1: split + duplicate + cull (do_densification, :563-619); 0: cull only (:620-621) */
+    int32_t n_split_samples; /* config.n_split_samples (2) */
+    int32_t use_screen_size; /* step < stop_screen_size_at (:575, :662) */
+    int32_t cull_big;        /* step > refine_every * reset_alpha_every (:659) */
+    float max_size;          /* (float)max(last_size) (:570) */
+    float densify_grad_thresh, densify_size_thresh, split_screen_size;
+    float cull_alpha_thresh, cull_scale_thresh, cull_screen_size;
+    float inv_size_fac;      /* fp32 reciprocal of size_fac = 1.6 (:694-695) */
+} sgn_refine_config;
+
+/* Source / destination of the rebuild: the six parameter tensors in gradient-arena order (means, scales, quats,
+ * features_dc, features_rest, opacities) and, when an Adam state exists, exp_avg (m) and exp_avg_sq (v) per tensor
+ * (all NULL = no optimizer state).  width[k] = floats per row of tensor k (3, 3, 4, 3F, 3(K-1), 1). */
+typedef struct sgn_refine_tensors {
+    const float* src[6];
+    float* dst[6];
+    const float* src_m[6];
+    float* dst_m[6];
+    const float* src_v[6];
+    float* dst_v[6];
+    int32_t width[6];
+} sgn_refine_tensors;
+size_t sgn_sizeof_refine_config(void);
+size_t sgn_sizeof_refine_tensors(void);
+/* flags[n] u8; marks[4,n] i32 = {survives, split samples survive, duplicate survives, is split} per row.
+ * xys_grad_norm / vis_counts may be NULL when !cfg->densify, max_2Dsize when !cfg->use_screen_size. */
+int sgn_refine_decide(int n, const sgn_refine_config* cfg, const float* scales /*[n,3]*/, const float* opacities /*[n,1]*/,
+                      const float* xys_grad_norm, const float* vis_counts, const float* max_2Dsize, uint8_t* flags,
+                      int32_t* marks, void* stream);
+/* scan[4,n] = inclusive prefix sums of marks along the rows; totals[4] (HOST) = their last column; samples =
+ * [n_split_samples * totals[3], 3] standard-normal draws (torch.randn, :680), NULL when totals[3] == 0.
+ * Destinations hold totals[0] + n_split_samples * totals[1] + totals[2] rows. */
+int sgn_refine_apply(int n, const sgn_refine_config* cfg, const sgn_refine_tensors* tensors, const uint8_t* flags,
+                     const int32_t* scan, const int32_t* totals, const float* samples, void* stream);
 
 #ifdef __cplusplus
 }

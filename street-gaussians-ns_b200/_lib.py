@@ -60,7 +60,7 @@ class BlendOpts(C.Structure):
 
 class AdamTensor(C.Structure):
     _fields_ = [
-        ("param", C.c_void_p), ("arena_offset", C.c_int64), ("numel", C.c_int64), ("chunk0", C.c_int32),
+        ("param", C.c_void_p), ("arena_offset", C.c_int64), ("grad_offset", C.c_int64), ("numel", C.c_int64), ("chunk0", C.c_int32),
         ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step_size", C.c_float),
         ("sqrt_bc2", C.c_float), ("one_minus_beta1", C.c_float), ("one_minus_beta2", C.c_float),
     ]
@@ -71,6 +71,26 @@ class DensifySegment(C.Structure):
         ("row0", C.c_int32), ("count", C.c_int32), ("first", C.c_int32), ("pad", C.c_int32),
         ("xys_grad_norm", C.c_void_p), ("vis_counts", C.c_void_p), ("max_2Dsize", C.c_void_p),
     ]
+
+
+class RefineConfig(C.Structure):
+    _fields_ = [
+        ("densify", C.c_int32), ("n_split_samples", C.c_int32), ("use_screen_size", C.c_int32), ("cull_big", C.c_int32),
+        ("max_size", C.c_float), ("densify_grad_thresh", C.c_float), ("densify_size_thresh", C.c_float),
+        ("split_screen_size", C.c_float), ("cull_alpha_thresh", C.c_float), ("cull_scale_thresh", C.c_float),
+        ("cull_screen_size", C.c_float), ("inv_size_fac", C.c_float),
+    ]
+
+
+class RefineTensors(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p * 6), ("dst", C.c_void_p * 6), ("src_m", C.c_void_p * 6), ("dst_m", C.c_void_p * 6),
+        ("src_v", C.c_void_p * 6), ("dst_v", C.c_void_p * 6), ("width", C.c_int32 * 6),
+    ]
+
+
+# flag bits of sgn_refine_decide (csrc/sgn_refine_rules.cuh)
+RF_SPLIT, RF_DUP, RF_KEEP_ORIG, RF_KEEP_SPLIT, RF_KEEP_DUP, RF_HIGH_GRAD, RF_ALPHA, RF_TOOBIG = (1 << i for i in range(8))
 
 
 class LossIn(C.Structure):
@@ -107,6 +127,7 @@ EXPORTS = [
     "sgn_bin_sort_scratch_bytes", "sgn_bin_sort", "sgn_bin_class_scratch_bytes", "sgn_bin_class_lists", "sgn_blend_sched_ints",
     "sgn_blend_fwd", "sgn_blend_bwd", "sgn_sizeof_adam_tensor", "sgn_adam_chunk_elems", "sgn_adam_step",
     "sgn_loss_scratch_bytes", "sgn_loss_fwd", "sgn_loss_bwd", "sgn_sizeof_densify_segment", "sgn_densify_stats",
+    "sgn_sizeof_refine_config", "sgn_sizeof_refine_tensors", "sgn_refine_decide", "sgn_refine_apply",
 ]
 
 
@@ -168,6 +189,14 @@ def load():
     L.sgn_adam_chunk_elems.restype = C.c_int
     L.sgn_adam_step.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.sgn_adam_step.restype = C.c_int
+    L.sgn_sizeof_refine_config.restype = sz
+    L.sgn_sizeof_refine_tensors.restype = sz
+    L.sgn_refine_decide.argtypes = [i32, C.POINTER(RefineConfig), vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sgn_refine_decide.restype = C.c_int
+    L.sgn_refine_apply.argtypes = [i32, C.POINTER(RefineConfig), C.POINTER(RefineTensors), vp, vp, C.POINTER(C.c_int32), vp, vp]
+    L.sgn_refine_apply.restype = C.c_int
+    assert L.sgn_sizeof_refine_config() == C.sizeof(RefineConfig), "sgn_refine_config layout mismatch"
+    assert L.sgn_sizeof_refine_tensors() == C.sizeof(RefineTensors), "sgn_refine_tensors layout mismatch"
     assert L.sgn_sizeof_adam_tensor() == C.sizeof(AdamTensor), "sgn_adam_tensor layout mismatch"
     assert L.sgn_sizeof_segment() == C.sizeof(Segment), "sgn_segment layout mismatch between header and ctypes"
     assert L.sgn_sizeof_segment_grads() == C.sizeof(SegmentGrads)

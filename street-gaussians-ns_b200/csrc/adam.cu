@@ -26,12 +26,12 @@ adam_kernel(const sgn_adam_tensor* __restrict__ table, int ntensors, const float
     const long long e0 = (long long)(blockIdx.x - t.chunk0) * ADAM_CHUNK;
     const long long n = t.numel;
     float* __restrict__ p = t.param;
-    const float* __restrict__ g = grads + t.arena_offset;
+    const float* __restrict__ g = grads + t.grad_offset;
     float* __restrict__ m = exp_avg + t.arena_offset;
     float* __restrict__ v = exp_avg_sq + t.arena_offset;
     const float b1 = t.beta1, b2 = t.beta2, step_size = t.step_size, sqrt_bc2 = t.sqrt_bc2, eps = t.eps;
     const float w1 = t.one_minus_beta1, w2 = t.one_minus_beta2;
-    const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) && ((t.arena_offset & 3) == 0);
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) && ((t.arena_offset & 3) == 0) && ((t.grad_offset & 3) == 0);
 #pragma unroll
     for (int it = 0; it < ADAM_CHUNK / (ADAM_THREADS * 4); ++it) {
         const long long e = e0 + ((long long)it * ADAM_THREADS + threadIdx.x) * 4;

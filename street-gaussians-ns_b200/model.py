@@ -25,8 +25,9 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import raster
-from .scene import CLS_BACKGROUND, CLS_OBJECT, Camera, Frame, GaussianSet, Segment, fourier_time, idft_basis
+from . import raster, refine
+from .refine import RefineSettings
+from .scene import PARAM_NAMES, CLS_BACKGROUND, CLS_OBJECT, Camera, Frame, GaussianSet, Segment, fourier_time, idft_basis
 
 
 @dataclass
@@ -57,6 +58,11 @@ class SceneGraphConfig:
     alpha_clamp_bwd: float = 0.99
     render_background_acc: bool = True
     fused_loss: bool = True  # L1 / sky / entropy terms through the fused loss epilogue (loss.py) instead of torch ops
+    # refinement (sgn_splatfacto.py:550-646): the sub-model configs of sgn_config.py:46-66 (background / object template)
+    refine: RefineSettings = field(default_factory=lambda: RefineSettings(cull_alpha_thresh=0.02))
+    object_refine: RefineSettings = field(default_factory=lambda: RefineSettings(cull_alpha_thresh=0.005))
+    num_train_data: int = 0      # Model.num_train_data: refinement waits until every image was seen after an opacity reset (:563-566)
+    refine_record: bool = False  # fill sub.refine_record_dict (the reference's logging counters; one extra read-back per sub-model)
 
 
 class GaussianSubModel(torch.nn.Module):
@@ -71,6 +77,7 @@ class GaussianSubModel(torch.nn.Module):
         self.last_size = None
         # densification statistics (sgn_splatfacto.py:513-541), created by the first after_train
         self.xys_grad_norm = self.vis_counts = self.max_2Dsize = None
+        self.refine_record_dict: dict = {}
 
     @property
     def num_points(self) -> int:
@@ -298,6 +305,74 @@ class SceneGraphRasterModel(torch.nn.Module):
         _lib.check(L.sgn_densify_stats(raster._ptr(raw), len(slices), h.v_records.shape[0], raster._ptr(h.v_records),
                                        raster._ptr(h.radii), H, W, raster._stream()), "sgn_densify_stats")
 
+    # ------------------------------------------------------------------------------------------
+    def refinement_after(self, optimizers, step: int, generator: Optional[torch.Generator] = None, sync_stats: bool = True) -> None:
+        """The ``refinement_after`` callbacks of all sub-models (sgn_splatfacto.py:550-646; the scene graph registers one
+        per sub-model, :127-137): split / duplicate / cull / opacity reset, with the optimizer state carried along
+        (dup_in_optim / remove_from_optim, :459-511).  ``optimizers`` is a ``FusedAdam`` built over
+        ``self.optimizer_params()``, or the reference's form -- an object (or dict) mapping the six group names to
+        ``torch.optim.Adam`` instances whose ``param_groups[0]["params"][i]`` is sub-model i's tensor -- or None.
+
+        Two phases so that nothing is copied twice: decide every sub-model (one read-back of four counts each), then
+        lay out the new tensors / moment arenas and let ``sgn_refine_apply`` write each sub-model's rows into them."""
+        assert step == self.step
+        names = list(self.all_models._modules)
+        subs = [self.all_models[n] for n in names]
+        adapter = _optimizer_adapter(optimizers, len(subs))
+        if sync_stats:
+            from . import dp
+            for sub in subs:  # replicas rendered different cameras: identical decisions need identical statistics (SURVEY 8e)
+                if sub.xys_grad_norm is not None:
+                    dp.allreduce_densification_stats(sub.xys_grad_norm, sub.vis_counts, sub.max_2Dsize)
+        plans, resets = [], []
+        for name, sub in zip(names, subs):
+            st = self.config.refine if name == "background" else self.config.object_refine
+            densify, cull_only, reset = refine.phase(st, step, self.config.num_train_data)
+            sub.__dict__["refine_record_dict"] = {}
+            if step <= st.warmup_length or sub.xys_grad_norm is None:  # :552-555
+                plans.append(None), resets.append(None)
+                continue
+            plan = None
+            if densify or cull_only:
+                size = sub.last_size or self.last_size
+                cfg = refine.make_config(st, step, size, densify)
+                g = sub.gauss_params
+                plan = refine.plan_submodel(g["scales"].data, g["opacities"].data, sub.xys_grad_norm if densify else None,
+                                            sub.vis_counts if densify else None, sub.max_2Dsize if cfg.use_screen_size else None,
+                                            cfg, generator)
+                if self.config.refine_record:
+                    sub.__dict__["refine_record_dict"] = plan.record()
+                if not plan.changed:
+                    plan = None
+            plans.append(plan), resets.append(st if reset else None)
+            d = sub.__dict__
+            d["xys_grad_norm"] = d["vis_counts"] = d["max_2Dsize"] = None  # :644-646
+        old = [[sub.gauss_params[k].data for k in PARAM_NAMES] for sub in subs]
+        new = [o if p is None else [torch.empty((p.out_rows,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype) for t in o]
+               for o, p in zip(old, plans)]
+        if any(p is not None for p in plans):
+            src_m, dst_m = adapter.relayout(new, [p is not None for p in plans])
+            for i, p in enumerate(plans):
+                if p is not None:
+                    refine.apply_plan(p, old[i], new[i], src_m[i], dst_m[i])
+                    for k, t in zip(PARAM_NAMES, new[i]):
+                        subs[i].gauss_params[k] = torch.nn.Parameter(t)
+            adapter.commit([[sub.gauss_params[k] for k in PARAM_NAMES] for sub in subs], [p is not None for p in plans])
+            self._frame_cache.clear()
+        for i, st in enumerate(resets):
+            if st is not None:  # opacity reset on the survivors (:629-642)
+                subs[i].gauss_params["opacities"].data.clamp_(max=refine.opacity_reset_logit(st))
+                adapter.zero_moments(i, 5)
+
+    def optimizer_params(self) -> List[List[torch.Tensor]]:
+        """Per sub-model (all_models order: background, then objects), the six tensors in gradient-arena order: what
+        ``FusedAdam`` is built over.  ``present_submodels()`` names the ones in the last frame's gradient arena."""
+        return [[sub.gauss_params[k] for k in PARAM_NAMES] for sub in self.all_models._modules.values()]
+
+    def present_submodels(self) -> List[int]:
+        index = {n: i for i, n in enumerate(self.all_models._modules)}
+        return [index[n] for n in self.visible_model_names]
+
     @staticmethod
     def _split_xys_grad(slices):
         """After ``loss.backward()``: ``sub.xys.grad`` for every visible sub-model, as the reference's
@@ -357,6 +432,116 @@ class SceneGraphRasterModel(torch.nn.Module):
                 losses["object_acc_entropy_loss"] = c.object_acc_entropy_loss_mult * -(
                     oa * torch.log(oa) + (1.0 - oa) * torch.log(1.0 - oa)).mean()
         return losses
+
+
+class _NoOptimizer:
+    """refinement_after(None, ...): parameters only."""
+
+    def relayout(self, new, changed):
+        return [None] * len(new), [None] * len(new)
+
+    def commit(self, params, changed):
+        pass
+
+    def zero_moments(self, sub: int, k: int):
+        pass
+
+
+class _FusedAdamAdapter(_NoOptimizer):
+    """Moments live in two flat arenas: ``relayout`` allocates the arenas of the new layout, hands out views of the old
+    and new ones for the sub-models that change (sgn_refine_apply writes the new ones) and block-copies the rest."""
+
+    def __init__(self, opt):
+        self.opt = opt
+
+    def relayout(self, new, changed):
+        opt = self.opt
+        old_params = opt._params
+        old_m, old_v, old_off = opt.rebuild(new)
+        src, dst = [], []
+        for i, ch in enumerate(changed):
+            if ch:
+                pairs = []
+                for k in range(6):
+                    t, o = old_params[6 * i + k], int(old_off[6 * i + k])
+                    pairs.append((old_m[o:o + t.numel()].view(t.shape), old_v[o:o + t.numel()].view(t.shape)))
+                src.append(pairs), dst.append([opt.moment_views(6 * i + k) for k in range(6)])
+            else:  # same tensors, new offsets: one block copy per arena
+                a, b = int(old_off[6 * i]), int(opt.offsets[6 * i])
+                size = int(opt.sizes[6 * i:6 * i + 6].sum())
+                opt.exp_avg[b:b + size].copy_(old_m[a:a + size])
+                opt.exp_avg_sq[b:b + size].copy_(old_v[a:a + size])
+                src.append(None), dst.append(None)
+        return src, dst
+
+    def commit(self, params, changed):
+        self.opt.rebuild_pointers(params)
+
+    def zero_moments(self, sub: int, k: int):
+        m, v = self.opt.moment_views(6 * sub + k)
+        m.zero_(), v.zero_()
+
+
+class _TorchAdamGroupsAdapter(_NoOptimizer):
+    """The reference's form (nerfstudio ``Optimizers``): one torch.optim.Adam per group name, sub-model i's tensor at
+    ``param_groups[0]["params"][i]`` (sgn_splatfacto.py:459-511 index it with ``_model_idx_in_scene_graph``)."""
+
+    def __init__(self, groups):
+        self.groups = groups
+        self._new_state = {}
+
+    def _state(self, k: int, i: int):
+        opt = self.groups[PARAM_NAMES[k]]
+        return opt, opt.state.get(opt.param_groups[0]["params"][i], {})
+
+    def relayout(self, new, changed):
+        src, dst = [], []
+        for i, ch in enumerate(changed):
+            if not ch:
+                src.append(None), dst.append(None)
+                continue
+            states = [self._state(k, i)[1] for k in range(6)]
+            if not all("exp_avg" in st for st in states):  # never stepped: nothing to carry
+                src.append(None), dst.append(None)
+                continue
+            src.append([(st["exp_avg"], st["exp_avg_sq"]) for st in states])
+            dst.append([(torch.empty_like(t), torch.empty_like(t)) for t in new[i]])
+            self._new_state[i] = dst[-1]
+        return src, dst
+
+    def commit(self, params, changed):
+        for i, ch in enumerate(changed):
+            if not ch:
+                continue
+            for k in range(6):
+                opt, st = self._state(k, i)
+                plist = opt.param_groups[0]["params"]
+                opt.state.pop(plist[i], None)
+                if i in self._new_state:
+                    st = dict(st)
+                    st["exp_avg"], st["exp_avg_sq"] = self._new_state[i][k]
+                plist[i] = params[i][k]
+                if st:
+                    opt.state[params[i][k]] = st
+        self._new_state = {}
+
+    def zero_moments(self, sub: int, k: int):
+        _, st = self._state(k, sub)
+        if "exp_avg" in st:
+            st["exp_avg"] = torch.zeros_like(st["exp_avg"])
+            st["exp_avg_sq"] = torch.zeros_like(st["exp_avg_sq"])
+
+
+def _optimizer_adapter(optimizers, num_submodels: int):
+    from .optim import FusedAdam
+    if optimizers is None:
+        return _NoOptimizer()
+    if isinstance(optimizers, FusedAdam):
+        assert optimizers.num_segments == num_submodels, "FusedAdam must be built over model.optimizer_params()"
+        return _FusedAdamAdapter(optimizers)
+    groups = getattr(optimizers, "optimizers", optimizers)
+    assert all(k in groups for k in PARAM_NAMES), f"expected Adam optimizers for the groups {PARAM_NAMES}"
+    return _TorchAdamGroupsAdapter(groups)
 
 
 def _gauss_window(size: int, sigma: float, device, dtype):

@@ -2,15 +2,22 @@
 
 Drop-in for the nine ``torch.optim.Adam`` instances nerfstudio builds from
 street_gaussians_ns/sgn_config.py:71-108 for the Gaussian parameter groups: same update rule (dense, eps 1e-15,
-betas (0.9, 0.999)), one kernel launch for all ~200 tensors.  Moments live in two flat arenas that share
-the layout of ``holder.grad_arena`` (raster.project_bwd), so a training step is
+betas (0.9, 0.999)), one kernel launch for all ~200 tensors.  Moments live in two flat arenas laid out like the
+gradient arena of a frame in which every sub-model is visible (raster.project_bwd), so a training step is
 ``forward_backward -> (all-reduce arena) -> FusedAdam.step(arena)``.
+
+Two torch.optim.Adam behaviours the scene graph depends on are kept:
+
+* a parameter without a gradient is skipped -- no moment decay, no step count.  The gradient arena of a frame only
+  holds the sub-models visible in it (an actor is in view for a fraction of the frames), so ``step`` takes the
+  list of sub-models the arena covers and every tensor keeps its own step count, as torch keeps ``state["step"]``;
+* the refinement step replaces parameters and edits their moments (sgn_splatfacto.py:459-511): ``rebuild`` moves the
+  optimizer onto the new tensors (refine.py fills the new moment arenas).
 """
 from __future__ import annotations
 
 import ctypes as C
-import math
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -24,57 +31,121 @@ REFERENCE_LRS: Dict[str, float] = {
     "opacities": 0.05,
 }
 
-ADAM_DTYPE = np.dtype([("param", "<u8"), ("arena_offset", "<i8"), ("numel", "<i8"), ("chunk0", "<i4"),
+ADAM_DTYPE = np.dtype([("param", "<u8"), ("arena_offset", "<i8"), ("grad_offset", "<i8"), ("numel", "<i8"), ("chunk0", "<i4"),
                        ("beta1", "<f4"), ("beta2", "<f4"), ("eps", "<f4"), ("step_size", "<f4"),
-                       ("sqrt_bc2", "<f4"), ("one_minus_beta1", "<f4"), ("one_minus_beta2", "<f4")])  # 56 B: the C struct is 8-byte aligned
-assert ADAM_DTYPE.itemsize == C.sizeof(_lib.AdamTensor)
+                       ("sqrt_bc2", "<f4"), ("one_minus_beta1", "<f4"), ("one_minus_beta2", "<f4")])
+assert ADAM_DTYPE.itemsize == C.sizeof(_lib.AdamTensor) == 64
+
+
+def padded(numel: int) -> int:
+    """Arena slices are 16-byte aligned: every tensor occupies a multiple of 4 floats."""
+    return (numel + 3) // 4 * 4
 
 
 class FusedAdam:
-    """``params``: per segment, the six parameter tensors in PARAM_NAMES order (the order of the gradient arena)."""
+    """``params``: per sub-model (segment), the six parameter tensors in PARAM_NAMES order (the order of the gradient arena)."""
 
     def __init__(self, params: Sequence[Sequence[torch.Tensor]], lrs: Dict[str, float] = None, betas=(0.9, 0.999),
-                 eps: float = 1e-15):
-        self.L = _lib.load()
+                 eps: float = 1e-15, chunk_elems: Optional[int] = None):
+        self._chunk = chunk_elems if chunk_elems is not None else _lib.load().sgn_adam_chunk_elems()
         self.lrs = dict(REFERENCE_LRS if lrs is None else lrs)
         self.betas, self.eps = betas, eps
-        self.step_count = 0
+        self.step_count = 0  # calls of step(); the bias correction uses the per-tensor counts below
+        self._install(params)
+        self.exp_avg = torch.zeros(self.arena_elems, device=self.device)
+        self.exp_avg_sq = torch.zeros(self.arena_elems, device=self.device)
+        self.steps = np.zeros(len(self._params), np.int64)  # torch.optim.Adam keeps state["step"] per parameter
+
+    # ---- layout ---------------------------------------------------------------------------------------------
+    def _install(self, params: Sequence[Sequence[torch.Tensor]]) -> None:
+        assert all(len(ps) == 6 for ps in params), "six parameter tensors per sub-model, in PARAM_NAMES order"
         flat = [t for ps in params for t in ps]
         self.kinds = [PARAM_NAMES[i % 6] for i in range(len(flat))]
         self.device = flat[0].device
-        sizes = [(t.numel() + 3) // 4 * 4 for t in flat]
-        offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
-        chunk = self.L.sgn_adam_chunk_elems()
-        chunks = np.array([(t.numel() + chunk - 1) // chunk for t in flat], np.int64)
+        self.sizes = np.array([padded(t.numel()) for t in flat], np.int64)
+        self.offsets = np.concatenate([[0], np.cumsum(self.sizes)[:-1]]).astype(np.int64)
+        self.chunks = np.array([(t.numel() + self._chunk - 1) // self._chunk for t in flat], np.int64)
         tab = np.zeros(len(flat), ADAM_DTYPE)
         tab["param"] = [t.data_ptr() for t in flat]
-        tab["arena_offset"] = offsets
+        tab["arena_offset"] = tab["grad_offset"] = self.offsets
         tab["numel"] = [t.numel() for t in flat]
-        tab["chunk0"] = np.concatenate([[0], np.cumsum(chunks)[:-1]])
-        tab["beta1"], tab["beta2"], tab["eps"] = betas[0], betas[1], eps
-        tab["one_minus_beta1"], tab["one_minus_beta2"] = 1.0 - betas[0], 1.0 - betas[1]  # double, then rounded (torch)
+        tab["chunk0"] = np.concatenate([[0], np.cumsum(self.chunks)[:-1]])
+        b1, b2 = self.betas
+        tab["beta1"], tab["beta2"], tab["eps"] = b1, b2, self.eps
+        tab["one_minus_beta1"], tab["one_minus_beta2"] = 1.0 - b1, 1.0 - b2  # double, then rounded (torch)
         self.table = tab
-        self.num_chunks = int(chunks.sum())
-        self.arena_elems = int(sum(sizes))
-        self.exp_avg = torch.zeros(self.arena_elems, device=self.device)
-        self.exp_avg_sq = torch.zeros(self.arena_elems, device=self.device)
+        self.num_chunks = int(self.chunks.sum())
+        self.arena_elems = int(self.sizes.sum())
+        self.num_segments = len(params)
         self._params = flat  # keep the tensors (and their storage) alive
+        self._lr_vec = np.array([self.lrs[k] for k in self.kinds], np.float64)
 
     def set_lr(self, kind: str, lr: float) -> None:
         """Schedulers (e.g. the exponential decay of the means lr, sgn_config.py:85-90) update rates here."""
         self.lrs[kind] = lr
+        self._lr_vec = np.array([self.lrs[k] for k in self.kinds], np.float64)
 
-    def step(self, grad_arena: torch.Tensor) -> None:
-        assert grad_arena.numel() >= self.arena_elems and grad_arena.is_cuda
-        self.step_count += 1
+    def moment_views(self, tensor_index: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """exp_avg / exp_avg_sq of one tensor, shaped like the parameter (views of the arenas)."""
+        t = self._params[tensor_index]
+        o = int(self.offsets[tensor_index])
+        return self.exp_avg[o:o + t.numel()].view(t.shape), self.exp_avg_sq[o:o + t.numel()].view(t.shape)
+
+    # ---- the step -------------------------------------------------------------------------------------------
+    def step_table(self, present: Optional[Sequence[int]] = None) -> np.ndarray:
+        """Advance the step counts of the tensors that have a gradient and return their sgn_adam_tensor rows.
+        ``present``: indices of the sub-models whose gradients the arena holds, in arena order (None = all)."""
+        if present is None:
+            idx = slice(None)
+            tab = self.table  # grad_offset == arena_offset, chunk0 as installed
+        else:
+            present = list(present)
+            assert len(set(present)) == len(present) and all(0 <= s < self.num_segments for s in present), present
+            idx = (np.asarray(present, np.int64)[:, None] * 6 + np.arange(6)[None, :]).reshape(-1)
+            tab = self.table[idx]
+            sz, ch = self.sizes[idx], self.chunks[idx]
+            tab["grad_offset"] = np.concatenate([[0], np.cumsum(sz)[:-1]])
+            tab["chunk0"] = np.concatenate([[0], np.cumsum(ch)[:-1]])
+        self.steps[idx] += 1
+        st = self.steps[idx].astype(np.float64)
         b1, b2 = self.betas
-        bc1 = 1.0 - b1 ** self.step_count
-        bc2 = 1.0 - b2 ** self.step_count
-        tab = self.table
-        tab["step_size"] = [self.lrs[k] / bc1 for k in self.kinds]
-        tab["sqrt_bc2"] = math.sqrt(bc2)
-        dev_tab = torch.from_numpy(tab.view(np.uint8).reshape(-1)).to(self.device, non_blocking=True)
+        tab["step_size"] = self._lr_vec[idx] / (1.0 - b1 ** st)   # lr / bias_correction1, in double like torch
+        tab["sqrt_bc2"] = np.sqrt(1.0 - b2 ** st)
+        return tab
+
+    def step(self, grad_arena: torch.Tensor, present: Optional[Sequence[int]] = None) -> None:
+        assert grad_arena.is_cuda, "FusedAdam runs on the CUDA library only"
+        self.step_count += 1
+        tab = self.step_table(present)
+        need = int(tab["grad_offset"][-1] + padded(int(tab["numel"][-1]))) if len(tab) else 0
+        assert grad_arena.numel() >= need, (grad_arena.numel(), need)
+        if len(tab) == 0:
+            return
+        num_chunks = self.num_chunks if present is None else int(tab["chunk0"][-1] + (int(tab["numel"][-1]) + self._chunk - 1) // self._chunk)
+        dev_tab = torch.from_numpy(np.ascontiguousarray(tab).view(np.uint8).reshape(-1)).to(self.device, non_blocking=True)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(self.L.sgn_adam_step(C.c_void_p(dev_tab.data_ptr()), len(tab), self.num_chunks,
-                                        C.c_void_p(grad_arena.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
-                                        C.c_void_p(self.exp_avg_sq.data_ptr()), stream), "sgn_adam_step")
+        L = _lib.load()
+        _lib.check(L.sgn_adam_step(C.c_void_p(dev_tab.data_ptr()), len(tab), num_chunks,
+                                   C.c_void_p(grad_arena.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
+                                   C.c_void_p(self.exp_avg_sq.data_ptr()), stream), "sgn_adam_step")
+
+    # ---- refinement (sgn_splatfacto.py:459-511) ---------------------------------------------------------------
+    def rebuild(self, params: Sequence[Sequence[torch.Tensor]]) -> Tuple[torch.Tensor, torch.Tensor, np.ndarray]:
+        """Move the optimizer onto new parameter tensors (same sub-models, new row counts).  Allocates new, ZEROED
+        moment arenas for the new layout and returns the OLD ``(exp_avg, exp_avg_sq, offsets)`` so that the caller
+        (refine.py) can carry the surviving rows' moments over; step counts are kept (the reference moves
+        ``param_state`` -- including ``step`` -- to the new parameter)."""
+        assert len(params) == self.num_segments
+        old = (self.exp_avg, self.exp_avg_sq, self.offsets.copy())
+        self._install(params)
+        self.exp_avg = torch.zeros(self.arena_elems, device=self.device)
+        self.exp_avg_sq = torch.zeros(self.arena_elems, device=self.device)
+        return old
+
+    def rebuild_pointers(self, params: Sequence[Sequence[torch.Tensor]]) -> None:
+        """The layout is unchanged but the tensors were re-wrapped (``nn.Parameter(t)`` shares storage): refresh the
+        pointer column and the keep-alive list."""
+        flat = [t for ps in params for t in ps]
+        assert [t.numel() for t in flat] == [int(x) for x in self.table["numel"]]
+        self.table["param"] = [t.data_ptr() for t in flat]
+        self._params = flat
