@@ -177,7 +177,7 @@ PHASES = [
     ("densify+3samples", 7400, {"n_split_samples": 3}),
     ("reset-only", 3100, {}),                           # opacity reset, no structural change
     ("cull-only", 25000, {}),                           # past stop_split_at
-    ("nothing", 3200, {}),
+    ("nothing", 3130, {}),                              # 130 <= num_train_data + refine_every: not every image seen since the reset
 ]
 
 
