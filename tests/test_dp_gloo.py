@@ -43,6 +43,70 @@ def _worker(rank: int, world: int, port: int, q):
     dist.destroy_process_group()
 
 
+def _refine_worker(rank: int, world: int, port: int, q, patch: bool = True):
+    """Every replica saw a different camera, so its densification statistics differ; after the SUM/SUM/MAX
+    all-reduce and with equal seeds the replicas must take IDENTICAL split / duplicate / cull decisions."""
+    from street_gaussians_ns_b200 import refine
+    from tests.host_harness import use_host_backend
+    from tests.test_refine import build_model
+    if patch:
+        use_host_backend(refine)  # CPU stand-in for the two CUDA entry points (tests only; a spawned process of its own)
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    model, _ = build_model(seed=0)
+    model.step = 3400
+    ranks = [rank] if world > 1 else [0, 1]  # the single process plays both replicas' statistics
+    for sub in model.all_models.values():
+        n = sub.num_points
+        per_rank = []
+        for r in ranks:
+            g = torch.Generator().manual_seed(100 + r)
+            vis = torch.randint(1, 5, (n,), generator=g).float()
+            per_rank.append((torch.rand(n, generator=g) * vis * 2.5e-6, vis, torch.rand(n, generator=g) * 0.2))
+        d = sub.__dict__
+        d["xys_grad_norm"] = sum(p[0] for p in per_rank)
+        d["vis_counts"] = sum(p[1] for p in per_rank)
+        d["max_2Dsize"] = torch.stack([p[2] for p in per_rank]).max(dim=0).values
+    model.refinement_after(None, 3400, generator=torch.Generator().manual_seed(7), sync_stats=True)
+    q.put((rank, [sub.gauss_params["means"].detach().numpy().copy() for sub in model.all_models.values()],
+           [sub.gauss_params["scales"].detach().numpy().copy() for sub in model.all_models.values()]))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_replicas_take_identical_refinement_decisions_world2(monkeypatch):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_refine_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict((r, (m, sc)) for r, m, sc in (q.get(timeout=300) for _ in range(2)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    import queue as _q
+    single = _q.Queue()
+    from street_gaussians_ns_b200 import refine
+    from tests.host_harness import load_refine_harness
+    H = load_refine_harness()
+    monkeypatch.setattr(refine, "_backend", lambda: H)
+    monkeypatch.setattr(refine, "_require_cuda", lambda t, what: None)
+    _refine_worker(0, 1, 0, single, patch=False)   # one process with the summed statistics
+    _, means, scales = single.get()
+    for a, b, c in zip(got[0][0], got[1][0], means):
+        assert a.shape == b.shape == c.shape and a.shape[0] > 0
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)
+    for a, b, c in zip(got[0][1], got[1][1], scales):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)
+
+
 def test_camera_assignment():
     seen = [dp.camera_for_rank(s, r, 4, 425) for s in range(3) for r in range(4)]
     assert seen == list(range(12))  # distinct cameras within and across steps

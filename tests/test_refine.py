@@ -11,9 +11,7 @@ restatement of the reference (oracle/oracle_refine.py; street_gaussians_ns/sgn_s
   * random sub-models through every phase of the schedule: tensors, row order, Adam moments, record counters;
   * the model-level two-phase path with FusedAdam arenas and with the reference's per-group torch.optim.Adam form.
 """
-import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -28,19 +26,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def harness():
-    src = os.path.join(ROOT, "tests", "host_harness", "refine_host.cpp")
-    out = os.path.join(ROOT, "tests", "host_harness", "librefine_host.so")
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(
-            os.path.join(ROOT, "street-gaussians-ns_b200", "csrc", "sgn_refine_rules.cuh"))):
-        subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src], check=True)
-    H = C.CDLL(out)
-    vp, i32 = C.c_void_p, C.c_int
-    H.sgn_refine_decide.argtypes = [i32, C.POINTER(_lib.RefineConfig), vp, vp, vp, vp, vp, vp, vp, vp]
-    H.sgn_refine_apply.argtypes = [i32, C.POINTER(_lib.RefineConfig), C.POINTER(_lib.RefineTensors), vp, vp, C.POINTER(C.c_int32), vp, vp]
-    H.sgn_sizeof_refine_config.restype = H.sgn_sizeof_refine_tensors.restype = C.c_size_t
-    assert H.sgn_sizeof_refine_config() == C.sizeof(_lib.RefineConfig)
-    assert H.sgn_sizeof_refine_tensors() == C.sizeof(_lib.RefineTensors)
-    return H
+    from tests.host_harness import load_refine_harness
+    return load_refine_harness()
 
 
 @pytest.fixture()
