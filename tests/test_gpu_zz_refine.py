@@ -151,7 +151,7 @@ def test_training_continues_after_refinement():
         loss.backward()
         model.after_train(step)
         opt.step(model._holder.grad_arena, present=model.present_submodels())
-        return float(loss)
+        return float(loss.detach())
 
     before = [train_step(695 + i) for i in range(5)]
     counts0 = [sub.num_points for sub in model.all_models.values()]
