@@ -177,3 +177,11 @@ def test_training_continues_after_refinement():
         assert torch.isfinite(m1).all() and not torch.equal(m1, m0)
     bgm = model.all_models["background"]
     assert bgm.vis_counts is not None and bgm.vis_counts.shape[0] == counts1[0]  # statistics restarted at the new size
+
+
+def test_cuda_matches_golden_refine():
+    """The committed known-answer vectors (tests/golden/refine_case.npz, generated by tests/golden/make_golden_refine.py)."""
+    from tests.test_refine import check_against_golden, product_on_golden
+    res = product_on_golden(torch.device("cuda", 0))
+    torch.cuda.synchronize()
+    check_against_golden(*res, tol=1e-5)

@@ -319,3 +319,58 @@ def test_fused_adam_step_table_skips_absent_submodels():
     t1 = opt.step_table(present=[1])
     np.testing.assert_allclose(t1["step_size"][0], 1.6e-4 / (1 - 0.9 ** 2), rtol=1e-6)   # its second step only now
     np.testing.assert_allclose(t1["sqrt_bc2"][0], np.sqrt(1 - 0.999 ** 2), rtol=1e-6)
+
+
+# --------------------------------------------------------------------------------------------------
+# committed known-answer vectors (tests/golden/refine_case.npz)
+# --------------------------------------------------------------------------------------------------
+def product_on_golden(device):
+    """The product path (refine.plan_submodel / apply_plan) on the fixture's inputs, with the fixture's split samples."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_refine as mg
+    gold = np.load(mg.OUT)
+    t = lambda k: torch.from_numpy(gold[k].copy()).to(device)  # noqa: E731
+    params = [t("in_" + k) for k in PARAM_NAMES]
+    moments = [(t("in_m_" + k), t("in_v_" + k)) for k in PARAM_NAMES]
+    settings = refine.RefineSettings(**mg.CONFIG)
+    cfg = refine.make_config(settings, mg.STEP, mg.SIZE, True)
+    plan = refine.plan_submodel(params[1], params[5], t("xys_grad_norm"), t("vis_counts"), t("max_2Dsize"), cfg)
+    plan.samples = t("samples")[: cfg.n_split_samples * plan.totals[3]].contiguous()
+    new = [torch.empty((plan.out_rows,) + tuple(p.shape[1:]), device=device) for p in params]
+    new_m = [(torch.empty_like(a), torch.empty_like(a)) for a in new]
+    refine.apply_plan(plan, params, new, moments, new_m)
+    return gold, plan, new, new_m
+
+
+def check_against_golden(gold, plan, new, new_m, tol):
+    for k, name in enumerate(PARAM_NAMES):
+        want = gold["out_" + name]
+        got = new[k].cpu().numpy()
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        if name in ("means", "scales"):
+            np.testing.assert_allclose(got, want, rtol=tol, atol=tol, err_msg=name)
+        else:
+            np.testing.assert_array_equal(got, want, err_msg=name)
+        np.testing.assert_array_equal(new_m[k][0].cpu().numpy(), gold["out_m_" + name], err_msg=name + " exp_avg")
+        np.testing.assert_array_equal(new_m[k][1].cpu().numpy(), gold["out_v_" + name], err_msg=name + " exp_avg_sq")
+    rec = plan.record()
+    got = [rec["high_grads_count"], rec["refine_splits_count"], rec["refine_dups_count"], rec["refine_culls_alpha_count"]]
+    assert got == [int(x) for x in gold["counts"][:4]]
+
+
+def test_oracle_reproduces_golden_refine():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_refine as mg
+    gold = np.load(mg.OUT)
+    out = mg.run_oracle({k: gold[k] for k in gold.files})
+    for k, v in out.items():
+        if k in ("out_means", "out_scales"):
+            np.testing.assert_allclose(v, gold[k], rtol=1e-6, atol=1e-6, err_msg=k)  # vector exp/log may differ by an ulp across hosts
+        else:
+            np.testing.assert_array_equal(v, gold[k], err_msg=k)
+
+
+def test_rules_match_golden_refine(host_backend):
+    check_against_golden(*product_on_golden(torch.device("cpu")), tol=2e-6)
