@@ -63,6 +63,9 @@ class SceneGraphConfig:
     object_refine: RefineSettings = field(default_factory=lambda: RefineSettings(cull_alpha_thresh=0.005))
     num_train_data: int = 0      # Model.num_train_data: refinement waits until every image was seen after an opacity reset (:563-566)
     refine_record: bool = False  # fill sub.refine_record_dict (the reference's logging counters; one extra read-back per sub-model)
+    # data parallel: gradients are delivered in an arena that has the layout of ALL sub-models (the
+    # optimizer's), so that replicas which see different actors can sum their arenas with one all-reduce
+    full_gradient_arena: bool = False
 
 
 class GaussianSubModel(torch.nn.Module):
@@ -120,6 +123,10 @@ class _GradSink:
                 return None  # accumulate: render into a temporary arena, add in publish()
         return self.arena
 
+    def grad_offsets(self, static: dict):
+        """Where project_bwd puts the frame's slices inside ``target()``'s arena: None = back to back (the frame's layout)."""
+        return None
+
     def publish(self, arena: torch.Tensor, static: dict):
         if arena is self.arena:
             for p, v in zip(self.params, self.views):
@@ -131,6 +138,69 @@ class _GradSink:
                 p.grad = pv
             else:
                 p.grad.add_(v)
+
+
+class _FullArenaSink(_GradSink):
+    """Data-parallel form of the sink: the persistent arena has the layout of ALL sub-models (the optimizer's layout,
+    ``FusedAdam(model.optimizer_params())``), whatever subset is in view.  Replicas render different cameras at
+    different timestamps and therefore see different sets of actors; only with a common layout can ONE all-reduce sum
+    their gradients.  The slices of sub-models that are not in this replica's frame are zeroed (their sum over the
+    replicas is then the other replicas' gradient), the frame's slices are written in place by project_bwd through
+    per-tensor offsets."""
+
+    def __init__(self):
+        super().__init__()
+        self.model_key = None
+        self.sizes = self.offsets = None   # per tensor of the whole model (floats, padded to 4)
+        self.present: List[int] = []
+        self.all_views: List[torch.Tensor] = []
+        self.all_shapes: List[tuple] = []
+
+    def bind_model(self, all_params: List[List[torch.Tensor]], present: List[int]):
+        key = tuple(id(t) for ps in all_params for t in ps)
+        if key != self.model_key:
+            flat = [t for ps in all_params for t in ps]
+            self.model_key, self.arena, self.all_views = key, None, []
+            self.all_shapes = [tuple(t.shape) for t in flat]
+            self.sizes = np.array([(t.numel() + 3) // 4 * 4 for t in flat], np.int64)
+            self.offsets = np.concatenate([[0], np.cumsum(self.sizes)[:-1]]).astype(np.int64)
+        self.present = list(present)
+        self.params = [t for i in self.present for t in all_params[i]]
+        self.key = tuple(map(id, self.params))
+
+    def _tensor_ids(self):
+        return [6 * i + k for i in self.present for k in range(6)]
+
+    def grad_offsets(self, static: dict):
+        return self.offsets[self._tensor_ids()]
+
+    def target(self, static: dict, device):
+        total = int(self.sizes.sum())
+        if self.arena is None or self.arena.numel() != total or self.arena.device != device:
+            self.arena = torch.zeros(total, device=device, dtype=torch.float32)
+            chunks = self.arena.split_with_sizes([int(x) for x in self.sizes])
+            self.all_views = [c[:int(np.prod(shp))].view(shp) for c, shp in zip(chunks, self.all_shapes)]
+        self.views = [self.all_views[t] for t in self._tensor_ids()]
+        for p in self.params:
+            if p.grad is not None:
+                return None  # accumulate: render into a temporary arena (frame layout), add in publish()
+        # zero the sub-models that are not in this frame (runs of absent sub-models are contiguous in the arena);
+        # after an all-reduce they hold the other replicas' gradients
+        nsub = len(self.sizes) // 6
+        here = set(self.present)
+        i = 0
+        while i < nsub:
+            if i in here:
+                i += 1
+                continue
+            j = i
+            while j < nsub and j not in here:
+                j += 1
+            lo = int(self.offsets[6 * i])
+            hi = int(self.offsets[6 * (j - 1) + 5] + self.sizes[6 * (j - 1) + 5])
+            self.arena[lo:hi].zero_()
+            i = j
+        return self.arena
 
 
 class SceneGraphRasterModel(torch.nn.Module):
@@ -151,7 +221,7 @@ class SceneGraphRasterModel(torch.nn.Module):
         self.last_size = None
         self._holder = None
         self._frame_cache: dict = {}
-        self._grad_sink = _GradSink()
+        self._grad_sink = _FullArenaSink() if self.config.full_gradient_arena else _GradSink()
         self._anchor = None
 
     @staticmethod
@@ -216,7 +286,10 @@ class SceneGraphRasterModel(torch.nn.Module):
             flat = [t for seg in frame.segments for t in seg.params.tensors()]
             if all(t.requires_grad and t.is_leaf for t in flat):  # the normal case: the model's own nn.Parameters
                 sink = self._grad_sink
-                sink.bind(flat)
+                if isinstance(sink, _FullArenaSink):
+                    sink.bind_model(self.optimizer_params(), self.present_submodels())
+                else:
+                    sink.bind(flat)
                 if self._anchor is None or self._anchor.device != flat[0].device:
                     self._anchor = torch.zeros(1, device=flat[0].device, requires_grad=True)
                 anchor = self._anchor
@@ -320,10 +393,7 @@ class SceneGraphRasterModel(torch.nn.Module):
         subs = [self.all_models[n] for n in names]
         adapter = _optimizer_adapter(optimizers, len(subs))
         if sync_stats:
-            from . import dp
-            for sub in subs:  # replicas rendered different cameras: identical decisions need identical statistics
-                if sub.xys_grad_norm is not None:
-                    dp.allreduce_densification_stats(sub.xys_grad_norm, sub.vis_counts, sub.max_2Dsize)
+            self._sync_densification_stats(subs)
         plans, resets = [], []
         for name, sub in zip(names, subs):
             st = self.config.refine if name == "background" else self.config.object_refine
@@ -363,6 +433,34 @@ class SceneGraphRasterModel(torch.nn.Module):
             if st is not None:  # opacity reset on the survivors (:629-642)
                 subs[i].gauss_params["opacities"].data.clamp_(max=refine.opacity_reset_logit(st))
                 adapter.zero_moments(i, 5)
+
+    def _sync_densification_stats(self, subs) -> None:
+        """Replicas rendered different cameras: identical split / cull decisions need identical statistics.
+        SUM / SUM / MAX per sub-model; a replica that has not seen a sub-model since the last refinement contributes
+        zeros, and a sub-model nobody saw stays without statistics (the collectives are the same on every replica)."""
+        import torch.distributed as dist
+        from . import dp
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        dev = self.device
+        has = torch.tensor([float(sub.xys_grad_norm is not None) for sub in subs], device=dev)
+        dist.all_reduce(has, op=dist.ReduceOp.MAX)
+        for sub, h in zip(subs, has.tolist()):
+            if not h:
+                continue
+            if sub.xys_grad_norm is None:
+                d = sub.__dict__
+                d["xys_grad_norm"], d["vis_counts"], d["max_2Dsize"] = (torch.zeros(sub.num_points, device=dev) for _ in range(3))
+                d["last_size"] = sub.last_size or self.last_size
+            dp.allreduce_densification_stats(sub.xys_grad_norm, sub.vis_counts, sub.max_2Dsize)
+
+    def zero_gradient_arena(self) -> torch.Tensor:
+        """Data parallel: this replica rendered nothing (early-out) but the others did -- its contribution to the
+        all-reduce is an all-zero arena in the common layout."""
+        sink = self._grad_sink
+        assert isinstance(sink, _FullArenaSink), "only with SceneGraphConfig(full_gradient_arena=True)"
+        sink.bind_model(self.optimizer_params(), [])
+        return sink.target(None, self.device)
 
     def optimizer_params(self) -> List[List[torch.Tensor]]:
         """Per sub-model (all_models order: background, then objects), the six tensors in gradient-arena order: what

@@ -92,9 +92,11 @@ class FusedAdam:
         return self.exp_avg[o:o + t.numel()].view(t.shape), self.exp_avg_sq[o:o + t.numel()].view(t.shape)
 
     # ---- the step -------------------------------------------------------------------------------------------
-    def step_table(self, present: Optional[Sequence[int]] = None) -> np.ndarray:
+    def step_table(self, present: Optional[Sequence[int]] = None, full_layout: bool = False) -> np.ndarray:
         """Advance the step counts of the tensors that have a gradient and return their sgn_adam_tensor rows.
-        ``present``: indices of the sub-models whose gradients the arena holds, in arena order (None = all)."""
+        ``present``: indices of the sub-models that have a gradient this step (None = all).  The gradient arena
+        either holds exactly those, back to back in that order (a frame's arena, the default), or has the optimizer's
+        own layout with the absent sub-models' slices unused (``full_layout``: the data-parallel arena, model.py)."""
         if present is None:
             idx = slice(None)
             tab = self.table  # grad_offset == arena_offset, chunk0 as installed
@@ -104,7 +106,8 @@ class FusedAdam:
             idx = (np.asarray(present, np.int64)[:, None] * 6 + np.arange(6)[None, :]).reshape(-1)
             tab = self.table[idx]
             sz, ch = self.sizes[idx], self.chunks[idx]
-            tab["grad_offset"] = np.concatenate([[0], np.cumsum(sz)[:-1]])
+            if not full_layout:
+                tab["grad_offset"] = np.concatenate([[0], np.cumsum(sz)[:-1]])
             tab["chunk0"] = np.concatenate([[0], np.cumsum(ch)[:-1]])
         self.steps[idx] += 1
         st = self.steps[idx].astype(np.float64)
@@ -113,11 +116,11 @@ class FusedAdam:
         tab["sqrt_bc2"] = np.sqrt(1.0 - b2 ** st)
         return tab
 
-    def step(self, grad_arena: torch.Tensor, present: Optional[Sequence[int]] = None) -> None:
+    def step(self, grad_arena: torch.Tensor, present: Optional[Sequence[int]] = None, full_layout: bool = False) -> None:
         assert grad_arena.is_cuda, "FusedAdam runs on the CUDA library only"
         self.step_count += 1
-        tab = self.step_table(present)
-        need = int(tab["grad_offset"][-1] + padded(int(tab["numel"][-1]))) if len(tab) else 0
+        tab = self.step_table(present, full_layout)
+        need = int((tab["grad_offset"] + tab["numel"]).max()) if len(tab) else 0
         assert grad_arena.numel() >= need, (grad_arena.numel(), need)
         if len(tab) == 0:
             return

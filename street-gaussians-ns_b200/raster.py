@@ -353,16 +353,25 @@ def arena_views(arena: torch.Tensor, static: dict) -> List[torch.Tensor]:
 
 
 def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, records, radii, v_records, make_views: bool = True,
-                out: Optional[torch.Tensor] = None):
-    """Dense parameter gradients, one flat arena (a single allocation, 16-byte aligned slices; ``out`` reuses one)."""
+                out: Optional[torch.Tensor] = None, out_offsets: Optional[np.ndarray] = None):
+    """Dense parameter gradients, one flat arena (a single allocation, 16-byte aligned slices; ``out`` reuses one).
+    ``out_offsets`` (floats, one per parameter tensor of the frame, multiples of 4) places the slices inside a larger
+    ``out`` -- the data-parallel arena that has the layout of ALL sub-models (model._FullArenaSink)."""
     L = _lib.load()
     device = records.device
     st = table.static
     flat_sizes, _, _ = arena_layout(st)
     arena = out if out is not None else torch.empty(sum(flat_sizes), device=device, dtype=torch.float32)
-    assert arena.numel() == sum(flat_sizes) and arena.dtype == torch.float32 and arena.is_contiguous()
+    assert arena.dtype == torch.float32 and arena.is_contiguous()
+    if out_offsets is not None:
+        assert out is not None and not make_views and len(out_offsets) == len(flat_sizes)
+        off = np.asarray(out_offsets, np.int64)
+        assert (off % 4 == 0).all() and int((off + np.asarray(flat_sizes, np.int64)).max()) <= arena.numel()
+        gt = torch.from_numpy((np.uint64(arena.data_ptr()) + (off * 4).astype(np.uint64)).view(np.uint8)).to(device, non_blocking=True)
+    else:
+        assert arena.numel() == sum(flat_sizes)
+        gt = _grads_table(arena, st, device)
     flat = arena_views(arena, st) if make_views else None
-    gt = _grads_table(arena, st, device)
     with _timed("project_bwd"):
         _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, table.num_chunks, C.byref(cs), _ptr(records),
                                      _ptr(radii), _ptr(v_records), _stream()), "sgn_project_bwd")
@@ -443,8 +452,10 @@ class _SceneGraphRasterize(torch.autograd.Function):
         h = ctx.holder
         sink = h.grad_sink
         if sink is not None:
+            target = sink.target(ctx.table.static, v_records.device)
+            offsets = sink.grad_offsets(ctx.table.static) if target is not None else None  # None: the frame's own layout
             _, arena = project_bwd(ctx.table, ctx.params, ctx.cs, ctx.records, ctx.radii, v_records, make_views=False,
-                                   out=sink.target(ctx.table.static, v_records.device))
+                                   out=target, out_offsets=offsets)
             sink.publish(arena, ctx.table.static)
             flat = (None,)
         else:

@@ -1,0 +1,87 @@
+"""One training iteration of the scene-graph model on the fused path (BASELINE.json configs 4 and 5).
+
+What nerfstudio's ``Trainer.train_iteration`` plus the model's training callbacks do per step for the reference
+(SURVEY.md 3.1): ``step_cb`` -> zero_grad -> ``get_outputs`` -> ``get_loss_dict`` -> backward -> optimizer step ->
+``after_train`` (densification statistics, sgn_splatfacto.py:513-541) -> every ``refine_every`` steps ``refinement_after``
+(:550-646).  nerfstudio's engine itself (config system, data managers, viewer, checkpoints) is out of scope; this is
+the sequence of hot-path calls it makes, so that a step -- and a data-parallel step -- can be run, tested and timed.
+
+Data parallel: every replica holds all parameters and renders its own camera; the dense gradient
+arena is summed with ONE all-reduce and divided by the world size, then every replica applies the same Adam update.
+Replicas see different actors (different timestamps), so the arena has the layout of ALL sub-models
+(``SceneGraphConfig.full_gradient_arena``) and Adam steps the UNION of the sub-models in view on any replica -- a
+parameter that no replica rendered has no gradient and is skipped, as torch.optim.Adam skips ``grad is None``.  The
+union is computed on the host from the cameras of all replicas (the camera assignment is deterministic,
+``dp.camera_for_rank``): no extra collective.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import dp
+from .model import SceneGraphRasterModel, _FullArenaSink
+from .optim import FusedAdam
+from .scene import Camera
+
+
+class TrainStep:
+    def __init__(self, model: SceneGraphRasterModel, optimizer: FusedAdam, refine_every: Optional[int] = None,
+                 group: Optional[dist.ProcessGroup] = None):
+        self.model, self.optimizer, self.group = model, optimizer, group
+        self.refine_every = refine_every if refine_every is not None else model.config.refine.refine_every
+        assert optimizer.num_segments == len(model.all_models), "build FusedAdam over model.optimizer_params()"
+
+    def world_size(self) -> int:
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def submodels_in_view(self, camera: Camera) -> List[int]:
+        """Indices (all_models order) of the sub-models a render of ``camera`` lists: the background and every actor with
+        a box at the camera's timestamp and at least one Gaussian (scene graph :332-352)."""
+        m = self.model
+        index = {n: i for i, n in enumerate(m.all_models._modules)}
+        seen = [0]
+        for pose in m.poses_at(camera.time):
+            name = m.get_object_model_name(pose.track_id)
+            if m.all_models[name].num_points > 0:
+                seen.append(index[name])
+        return seen
+
+    def __call__(self, step: int, camera: Camera, batch: Dict[str, torch.Tensor],
+                 all_cameras: Optional[Sequence[Camera]] = None) -> Dict[str, torch.Tensor]:
+        """``all_cameras``: this step's cameras of ALL replicas (rank order), needed when the world size is > 1."""
+        m, opt = self.model, self.optimizer
+        world = self.world_size()
+        full = isinstance(m._grad_sink, _FullArenaSink)
+        if world > 1:
+            assert full, "data parallel needs SceneGraphConfig(full_gradient_arena=True): replicas see different actors"
+            assert all_cameras is not None and len(all_cameras) == world
+        m.step = step                                     # step_cb (sgn_splatfacto.py:754-755)
+        for p in m.parameters():                          # Optimizers.zero_grad_all()
+            p.grad = None
+        out = m.get_outputs(camera)
+        losses = m.get_loss_dict(out, batch)
+        total = sum(losses.values())
+        rendered = isinstance(total, torch.Tensor) and total.requires_grad
+        if rendered:
+            total.backward()
+            arena = m._holder.grad_arena
+        else:
+            # nothing in view on this replica (the reference's early-out, sgn_splatfacto.py:878-886): no gradient here
+            if world == 1:
+                return losses
+            arena = m.zero_gradient_arena()
+        if world > 1:
+            dp.allreduce_gradients(arena, average=True, group=self.group)
+            present = sorted(set(i for cam in all_cameras for i in self.submodels_in_view(cam)))
+        else:
+            present = m.present_submodels()
+        everything = len(present) == opt.num_segments and (full or present == list(range(opt.num_segments)))
+        opt.step(arena, present=None if everything else present, full_layout=full)
+        if rendered:
+            m.after_train(step)                           # AFTER_TRAIN_ITERATION callbacks, in the reference's order
+        if self.refine_every > 0 and step % self.refine_every == 0:
+            m.refinement_after(opt, step)
+        return losses

@@ -57,17 +57,22 @@ def _refine_worker(rank: int, world: int, port: int, q, patch: bool = True):
     model, _ = build_model(seed=0)
     model.step = 3400
     ranks = [rank] if world > 1 else [0, 1]  # the single process plays both replicas' statistics
-    for sub in model.all_models.values():
+    for si, sub in enumerate(model.all_models.values()):
         n = sub.num_points
         per_rank = []
         for r in ranks:
+            if si > 0 and (si - 1) % 2 != r:
+                continue  # actor si-1 was never in view on replica r since the last refinement: no statistics there
             g = torch.Generator().manual_seed(100 + r)
             vis = torch.randint(1, 5, (n,), generator=g).float()
             per_rank.append((torch.rand(n, generator=g) * vis * 2.5e-6, vis, torch.rand(n, generator=g) * 0.2))
         d = sub.__dict__
-        d["xys_grad_norm"] = sum(p[0] for p in per_rank)
-        d["vis_counts"] = sum(p[1] for p in per_rank)
-        d["max_2Dsize"] = torch.stack([p[2] for p in per_rank]).max(dim=0).values
+        if per_rank:
+            d["xys_grad_norm"] = sum(p[0] for p in per_rank)
+            d["vis_counts"] = sum(p[1] for p in per_rank)
+            d["max_2Dsize"] = torch.stack([p[2] for p in per_rank]).max(dim=0).values
+        else:
+            d["xys_grad_norm"] = d["vis_counts"] = d["max_2Dsize"] = None
     model.refinement_after(None, 3400, generator=torch.Generator().manual_seed(7), sync_stats=True)
     q.put((rank, [sub.gauss_params["means"].detach().numpy().copy() for sub in model.all_models.values()],
            [sub.gauss_params["scales"].detach().numpy().copy() for sub in model.all_models.values()]))

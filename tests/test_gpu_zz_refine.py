@@ -185,3 +185,68 @@ def test_cuda_matches_golden_refine():
     res = product_on_golden(torch.device("cuda", 0))
     torch.cuda.synchronize()
     check_against_golden(*res, tol=1e-5)
+
+
+def _alternating_scene(full_arena: bool):
+    """Background + 3 actors; actor 1 has a box only at even timestamps (an actor is in view for part of the frames)."""
+    from street_gaussians_ns_b200.training import TrainStep
+    fr = syn.make_frame(n_background=20000, n_actors=3, n_per_actor=1500, width=320, height=240, seed=3,
+                        actor_shift=np.array([1.0, 0.0, -1.0]))
+    dev = torch.device("cuda", 0)
+    bg = fr.segments[0].params.to(dev)
+    actors = {s.name.replace("object_", ""): s.params.to(dev) for s in fr.segments[1:]}
+    poses = [ActorPose(s.name.replace("object_", ""), s.rot, s.center, 21, list(range(85))) for s in fr.segments[1:]]
+
+    def poses_at(t):
+        return poses if int(t) % 2 == 0 else [poses[0], poses[2]]
+
+    cfg = SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0, full_gradient_arena=full_arena)
+    model = SceneGraphRasterModel(bg, actors, cfg, poses_at=poses_at).to(dev)
+    model.train()
+    opt = FusedAdam(model.optimizer_params())
+    cams = [syn.make_camera(320, 240, time=float(t)) for t in range(2)]
+    gt = (torch.rand(240, 320, 3, generator=torch.Generator().manual_seed(2)) * 0.5 + 0.25).to(dev)
+    return model, opt, TrainStep(model, opt, refine_every=0), cams, gt
+
+
+@pytest.mark.parametrize("full_arena", [False, True])
+def test_train_step_skips_actors_that_are_not_in_view(full_arena):
+    """TrainStep (training.py) over frames in which actor 1 comes and goes: in the frames without it its parameters, moments
+    and step count stay untouched (torch.optim.Adam skips parameters without a gradient), in both arena layouts."""
+    model, opt, step_fn, cams, gt = _alternating_scene(full_arena)
+    a1 = model.all_models["object_1"]
+    for it in range(6):
+        before = [a1.gauss_params[k].detach().clone() for k in PARAM_NAMES]
+        m_before = opt.moment_views(6 * 2 + 0)[0].clone()   # all_models order: background, object_0, object_1, object_2
+        losses = step_fn(1000 + it, cams[it % 2], {"image": gt})
+        assert all(torch.isfinite(v) for v in losses.values())
+        same = all(torch.equal(a1.gauss_params[k].detach(), b) for k, b in zip(PARAM_NAMES, before))
+        if it % 2 == 1:
+            assert model.present_submodels() == [0, 1, 3]
+            assert same and torch.equal(opt.moment_views(12)[0], m_before)
+            assert a1.gauss_params["means"].grad is None
+        else:
+            assert model.present_submodels() == [0, 1, 2, 3]
+            assert not same
+    assert list(opt.steps[12:18]) == [3] * 6 and list(opt.steps[:12]) == [6] * 12 and list(opt.steps[18:]) == [6] * 6
+
+
+def test_full_arena_layout_trains_like_the_frame_layout():
+    """Same scene, same steps, once with the frame-layout gradient arena and once with the data-parallel (all sub-models)
+    layout: the same gradients land at different offsets, the parameters follow the same trajectory (up to the
+    summation-order noise of the backward's atomics)."""
+    results = []
+    for full in (False, True):
+        model, opt, step_fn, cams, gt = _alternating_scene(full)
+        for it in range(4):
+            step_fn(1000 + it, cams[it % 2], {"image": gt})
+        torch.cuda.synchronize()
+        results.append({n: {k: sub.gauss_params[k].detach().clone() for k in PARAM_NAMES} for n, sub in model.all_models.items()})
+        if full:
+            sink = model._grad_sink
+            assert sink.arena.numel() == opt.arena_elems  # the optimizer's layout
+    for name in results[0]:
+        for k in PARAM_NAMES:
+            a, b = results[0][name][k], results[1][name][k]
+            bad = ((a - b).abs() > 1e-4 + 1e-3 * b.abs()).float().mean().item()
+            assert bad < 2e-3, (name, k, bad)

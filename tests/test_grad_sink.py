@@ -58,3 +58,42 @@ def test_sink_overwrites_when_zeroed_and_accumulates_otherwise():
     sink.bind(params2)
     assert sink.arena is None and backward(1.0) is True and sink.arena is not old
     assert all(p.grad is not None for p in params2)
+
+
+def test_full_arena_sink_places_a_frame_inside_the_model_layout():
+    """Data-parallel sink: the arena has the layout of ALL sub-models; a frame that sees sub-models [0, 2] writes their
+    slices through per-tensor offsets, the absent sub-model's slice is zeroed (it may hold the other replicas' sum)."""
+    import numpy as np
+    from street_gaussians_ns_b200.model import _FullArenaSink
+    shapes6 = lambda n, F: [(n, 3), (n, 3), (n, 4), (n, F, 3), (n, 15, 3), (n, 1)]  # noqa: E731
+    model_params = [[torch.zeros(s, requires_grad=True) for s in shapes6(n, F)] for n, F in ((5, 1), (3, 5), (2, 5))]
+    sink = _FullArenaSink()
+    sink.bind_model(model_params, [0, 2])
+    sizes = np.array([(p.numel() + 3) // 4 * 4 for ps in model_params for p in ps])
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    assert list(sink.grad_offsets(None)) == list(offs[[0, 1, 2, 3, 4, 5, 12, 13, 14, 15, 16, 17]])
+    arena = sink.target(None, torch.device("cpu"))
+    assert arena.numel() == sizes.sum() and float(arena.abs().sum()) == 0.0
+    arena.fill_(3.0)                                   # "all-reduce result of the previous step"
+    again = sink.target(None, torch.device("cpu"))     # next step: same arena, the absent sub-model's slice zeroed
+    assert again is arena
+    lo, hi = int(offs[6]), int(offs[12])
+    assert float(arena[lo:hi].abs().sum()) == 0.0 and float(arena[:lo].min()) == 3.0 and float(arena[hi:].min()) == 3.0
+    sink.publish(arena, None)
+    for i in (0, 2):
+        for k, p in enumerate(model_params[i]):
+            assert p.grad is not None and p.grad.shape == p.shape
+            assert p.grad.data_ptr() == arena.data_ptr() + 4 * int(offs[6 * i + k])
+    assert all(p.grad is None for p in model_params[1])
+    # grads still set -> accumulate through a temporary arena in the FRAME's layout, like the plain sink
+    assert sink.target(None, torch.device("cpu")) is None
+    # a replica that rendered nothing contributes zeros in the common layout
+    for ps in model_params:
+        for p in ps:
+            p.grad = None
+    sink.bind_model(model_params, [])
+    z = sink.target(None, torch.device("cpu"))
+    assert z is arena and float(z.abs().sum()) == 0.0
+    # different order of the visible sub-models (annotation order): offsets follow the frame's order
+    sink.bind_model(model_params, [0, 2, 1])
+    assert list(sink.grad_offsets(None)[6:12]) == list(offs[12:18])
