@@ -90,6 +90,26 @@ class GaussianSubModel(torch.nn.Module):
         g = self.gauss_params
         return GaussianSet(g["means"], g["scales"], g["quats"], g["features_dc"], g["features_rest"], g["opacities"])
 
+    def load_state_dict(self, state_dict, **kwargs):  # type: ignore[override]
+        """Checkpoints hold whatever number of Gaussians refinement had reached: resize the parameters to the
+        checkpoint's row count before loading, and accept the pre-ParameterDict key names
+        (sgn_splatfacto.py:425-438)."""
+        state_dict = dict(state_dict)
+        if "means" in state_dict:
+            for k in PARAM_NAMES:
+                state_dict[f"gauss_params.{k}"] = state_dict.pop(k)
+        if "gauss_params.means" in state_dict:
+            rows = state_dict["gauss_params.means"].shape[0]
+            for k in PARAM_NAMES:
+                old = self.gauss_params[k]
+                want = state_dict.get(f"gauss_params.{k}")
+                shape = (rows,) + (tuple(want.shape[1:]) if want is not None else tuple(old.shape[1:]))
+                if tuple(old.shape) != shape:
+                    self.gauss_params[k] = torch.nn.Parameter(torch.zeros(shape, device=old.device, dtype=old.dtype))
+            d = self.__dict__
+            d["xys_grad_norm"] = d["vis_counts"] = d["max_2Dsize"] = None  # statistics of the old rows are meaningless
+        return super().load_state_dict(state_dict, **kwargs)
+
 
 class _GradSink:
     """Delivers the rasterizer's flat gradient arena to the model's ~200 parameter tensors.
@@ -227,6 +247,18 @@ class SceneGraphRasterModel(torch.nn.Module):
     @staticmethod
     def get_object_model_name(object_id) -> str:
         return f"object_{object_id}"
+
+    def load_state_dict(self, state_dict, **kwargs):  # type: ignore[override]
+        """``SplatfactoSceneGraphModel.load_state_dict`` (scene graph :393-401): every sub-model takes the keys under
+        ``all_models.<name>.`` (and resizes itself to the checkpoint's row count), the rest loads non-strictly."""
+        state_dict = dict(state_dict)
+        for name, sub in self.all_models.items():
+            prefix = f"all_models.{name}."
+            own = {k[len(prefix):]: state_dict.pop(k) for k in list(state_dict) if k.startswith(prefix)}
+            if own:
+                sub.load_state_dict(own, **kwargs)
+        self._frame_cache.clear()
+        return torch.nn.Module.load_state_dict(self, state_dict, strict=False)
 
     @property
     def device(self):

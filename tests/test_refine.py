@@ -374,3 +374,26 @@ def test_oracle_reproduces_golden_refine():
 
 def test_rules_match_golden_refine(host_backend):
     check_against_golden(*product_on_golden(torch.device("cpu")), tol=2e-6)
+
+
+def test_checkpoint_with_a_different_number_of_gaussians_loads():
+    """Refinement changes the row counts; a checkpoint taken later must load into a freshly built model
+    (sgn_splatfacto.py:425-438, scene graph :393-401), including the pre-ParameterDict key names."""
+    big, _ = build_model(seed=0)
+    small, _ = build_model(seed=5)
+    for sub in small.all_models.values():   # a model "before refinement": fewer rows everywhere
+        for k in PARAM_NAMES:
+            sub.gauss_params[k] = torch.nn.Parameter(sub.gauss_params[k].data[:50].clone())
+    ckpt = {k: v.clone() for k, v in big.state_dict().items()}
+    assert "all_models.background.gauss_params.means" in ckpt and "all_models.object_a.gauss_params.features_dc" in ckpt
+    small.load_state_dict(ckpt)
+    for name in big.all_models:
+        for k in PARAM_NAMES:
+            assert torch.equal(small.all_models[name].gauss_params[k], big.all_models[name].gauss_params[k]), (name, k)
+            assert isinstance(small.all_models[name].gauss_params[k], torch.nn.Parameter)
+        assert small.all_models[name].xys_grad_norm is None
+    # old key names (means, scales, ... directly on the sub-model)
+    sub = small.all_models["object_b"]
+    legacy = {k: torch.full_like(big.all_models["object_a"].gauss_params[k], 0.5) for k in PARAM_NAMES}
+    sub.load_state_dict(legacy)
+    assert sub.num_points == big.all_models["object_a"].num_points and float(sub.gauss_params["quats"].detach().min()) == 0.5
