@@ -117,20 +117,41 @@ class FusedAdam:
         return tab
 
     def step(self, grad_arena: torch.Tensor, present: Optional[Sequence[int]] = None, full_layout: bool = False) -> None:
-        assert grad_arena.is_cuda, "FusedAdam runs on the CUDA library only"
         self.step_count += 1
-        tab = self.step_table(present, full_layout)
-        need = int((tab["grad_offset"] + tab["numel"]).max()) if len(tab) else 0
-        assert grad_arena.numel() >= need, (grad_arena.numel(), need)
+        self.launch(self.step_table(present, full_layout), grad_arena)
+
+    def launch(self, tab: np.ndarray, grad_arena: torch.Tensor) -> None:
+        """One ``sgn_adam_step`` over the rows of ``tab`` (from step_table, possibly cut by rows_in_range)."""
+        assert grad_arena.is_cuda, "FusedAdam runs on the CUDA library only"
         if len(tab) == 0:
             return
-        num_chunks = self.num_chunks if present is None else int(tab["chunk0"][-1] + (int(tab["numel"][-1]) + self._chunk - 1) // self._chunk)
+        need = int((tab["grad_offset"] + tab["numel"]).max())
+        assert grad_arena.numel() >= need, (grad_arena.numel(), need)
+        num_chunks = int(tab["chunk0"][-1] + (int(tab["numel"][-1]) + self._chunk - 1) // self._chunk)
         dev_tab = torch.from_numpy(np.ascontiguousarray(tab).view(np.uint8).reshape(-1)).to(self.device, non_blocking=True)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         L = _lib.load()
         _lib.check(L.sgn_adam_step(C.c_void_p(dev_tab.data_ptr()), len(tab), num_chunks,
                                    C.c_void_p(grad_arena.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
                                    C.c_void_p(self.exp_avg_sq.data_ptr()), stream), "sgn_adam_step")
+
+    def rows_in_range(self, tab: np.ndarray, lo: int, hi: int) -> np.ndarray:
+        """The part of a step's table that falls into floats [lo, hi) of the arena (full layout: gradient and
+        moment offsets coincide): tensors are cut at the range's ends, so that a step can be issued range by range
+        while the all-reduce of the next range is still in flight (dp.allreduce_and_step).  ``lo`` / ``hi`` must be
+        multiples of 4 floats (16-byte slices)."""
+        assert lo % 4 == 0 and hi % 4 == 0 and np.array_equal(tab["grad_offset"], tab["arena_offset"])
+        a = np.maximum(tab["arena_offset"], lo)
+        b = np.minimum(tab["arena_offset"] + tab["numel"], hi)
+        keep = a < b
+        out = tab[keep].copy()
+        a, b = a[keep], b[keep]
+        out["param"] = out["param"] + ((a - out["arena_offset"]) * 4).astype(np.uint64)
+        out["arena_offset"] = out["grad_offset"] = a
+        out["numel"] = b - a
+        ch = (out["numel"] + self._chunk - 1) // self._chunk
+        out["chunk0"] = np.concatenate([[0], np.cumsum(ch)[:-1]]) if len(out) else []
+        return out
 
     # ---- refinement (sgn_splatfacto.py:459-511) ---------------------------------------------------------------
     def rebuild(self, params: Sequence[Sequence[torch.Tensor]]) -> Tuple[torch.Tensor, torch.Tensor, np.ndarray]:

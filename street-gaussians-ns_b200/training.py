@@ -29,8 +29,11 @@ from .scene import Camera
 
 class TrainStep:
     def __init__(self, model: SceneGraphRasterModel, optimizer: FusedAdam, refine_every: Optional[int] = None,
-                 group: Optional[dist.ProcessGroup] = None):
+                 group: Optional[dist.ProcessGroup] = None, pipeline_chunks: int = 0):
+        """``pipeline_chunks`` > 0 (data parallel only): all-reduce and Adam are pipelined over that many ranges of the
+        arena (dp.allreduce_and_step) instead of running one after the other."""
         self.model, self.optimizer, self.group = model, optimizer, group
+        self.pipeline_chunks = pipeline_chunks
         self.refine_every = refine_every if refine_every is not None else model.config.refine.refine_every
         assert optimizer.num_segments == len(model.all_models), "build FusedAdam over model.optimizer_params()"
 
@@ -74,12 +77,16 @@ class TrainStep:
                 return losses
             arena = m.zero_gradient_arena()
         if world > 1:
-            dp.allreduce_gradients(arena, average=True, group=self.group)
             present = sorted(set(i for cam in all_cameras for i in self.submodels_in_view(cam)))
         else:
             present = m.present_submodels()
         everything = len(present) == opt.num_segments and (full or present == list(range(opt.num_segments)))
-        opt.step(arena, present=None if everything else present, full_layout=full)
+        if world > 1 and self.pipeline_chunks > 0:
+            dp.allreduce_and_step(arena, opt, None if everything else present, self.pipeline_chunks, self.group)
+        else:
+            if world > 1:
+                dp.allreduce_gradients(arena, average=True, group=self.group)
+            opt.step(arena, present=None if everything else present, full_layout=full)
         if rendered:
             m.after_train(step)                           # AFTER_TRAIN_ITERATION callbacks, in the reference's order
         if self.refine_every > 0 and step % self.refine_every == 0:

@@ -112,6 +112,81 @@ def test_replicas_take_identical_refinement_decisions_world2(monkeypatch):
         np.testing.assert_array_equal(a, c)
 
 
+def _cpu_adam_launch(opt):
+    """Test stand-in for FusedAdam.launch: applies the rows of a table with the kernel's arithmetic (adam.cu) to CPU
+    tensors, addressing parameters through the table's raw pointers exactly as the kernel does."""
+    import ctypes
+
+    def launch(tab, grad_arena):
+        g_all, m_all, v_all = grad_arena.numpy(), opt.exp_avg.numpy(), opt.exp_avg_sq.numpy()
+        for r in tab:
+            n = int(r["numel"])
+            p = np.ctypeslib.as_array((ctypes.c_float * n).from_address(int(r["param"])))
+            g = g_all[int(r["grad_offset"]):int(r["grad_offset"]) + n]
+            m = m_all[int(r["arena_offset"]):int(r["arena_offset"]) + n]
+            v = v_all[int(r["arena_offset"]):int(r["arena_offset"]) + n]
+            m += r["one_minus_beta1"] * (g - m)
+            v *= r["beta2"]
+            v += r["one_minus_beta2"] * g * g
+            p -= r["step_size"] * (m / (np.sqrt(v) / r["sqrt_bc2"] + r["eps"]))
+    return launch
+
+
+def _pipeline_worker(rank: int, world: int, port: int, q):
+    from street_gaussians_ns_b200.optim import FusedAdam
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shapes = lambda n, F: [(n, 3), (n, 3), (n, 4), (n, F, 3), (n, 15, 3), (n, 1)]  # noqa: E731
+    results = []
+    for mode in ("serial", "pipelined"):
+        g = torch.Generator().manual_seed(1)
+        params = [[torch.randn(s, generator=g) for s in shapes(n, F)] for n, F in ((301, 1), (57, 5), (40, 5))]
+        opt = FusedAdam(params, chunk_elems=256)
+        opt.launch = _cpu_adam_launch(opt)
+        gr = torch.Generator().manual_seed(10 + rank)   # every replica has its own gradients
+        for it in range(3):
+            arena = torch.randn(opt.arena_elems, generator=gr)
+            present = None if it == 1 else [0, 2]
+            if mode == "serial":
+                dp.allreduce_gradients(arena, average=True)
+                opt.step(arena, present=present, full_layout=True)
+            else:
+                dp.allreduce_and_step(arena, opt, present, chunks=3)
+        results.append(([t.clone() for ps in params for t in ps], opt.exp_avg.clone(), list(opt.steps)))
+    (pa, ma, sa), (pb, mb, sb) = results
+    ok = all(torch.equal(a, b) for a, b in zip(pa, pb)) and torch.equal(ma, mb) and sa == sb
+    q.put((rank, ok, sa, float(sum(t.abs().sum() for t in pa))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_allreduce_and_adam_equals_serial_world2():
+    """dp.allreduce_and_step (all-reduce of range k+1 in flight while Adam runs on range k) gives bit-identical parameters,
+    moments and step counts to all-reduce-then-step, on both replicas; tensors are cut at range ends."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in got)
+    assert got[0][2] == got[1][2] == [3] * 6 + [1] * 6 + [3] * 6     # sub-model 1 only had a gradient in step 1
+    assert got[0][3] == got[1][3] and got[0][3] > 0                   # replicas end up with identical parameters
+
+
+def test_chunk_bounds_cover_the_arena():
+    for total, chunks in ((10_000_000, 4), (4096, 4), (1000, 8), (8, 3)):
+        b = dp.chunk_bounds(total, chunks)
+        assert b[0][0] == 0 and b[-1][1] == total and all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
+        assert all(lo % 4 == 0 for lo, _ in b) and all(hi > lo for lo, hi in b)
+
+
 def test_camera_assignment():
     seen = [dp.camera_for_rank(s, r, 4, 425) for s in range(3) for r in range(4)]
     assert seen == list(range(12))  # distinct cameras within and across steps

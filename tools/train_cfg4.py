@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--refine-every", type=int, default=100)
     ap.add_argument("--start-step", type=int, default=600, help="past warmup_length so that refinement is live")
     ap.add_argument("--actor-range", type=float, default=45.0)
+    ap.add_argument("--pipeline-chunks", type=int, default=0, help="> 0: all-reduce and Adam pipelined over that many arena ranges")
     args = ap.parse_args()
 
     import numpy as np
@@ -82,7 +83,7 @@ def main():
     model = SceneGraphRasterModel(bg, actors, cfg, poses_at=poses_at).to(dev)
     model.train()
     opt = FusedAdam(model.optimizer_params())
-    step_fn = TrainStep(model, opt, refine_every=args.refine_every)
+    step_fn = TrainStep(model, opt, refine_every=args.refine_every, pipeline_chunks=args.pipeline_chunks)
     g = torch.Generator().manual_seed(5)
     gt = (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).to(dev)  # get_loss_dict consumes uint8 directly
     counts0 = [sub.num_points for sub in model.all_models.values()]
