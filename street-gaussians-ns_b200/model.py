@@ -432,7 +432,8 @@ class SceneGraphRasterModel(torch.nn.Module):
             densify, cull_only, reset = refine.phase(st, step, self.config.num_train_data)
             sub.__dict__["refine_record_dict"] = {}
             if step <= st.warmup_length or sub.xys_grad_norm is None:  # :552-555
-                plans.append(None), resets.append(None)
+                plans.append(None)
+                resets.append(None)
                 continue
             plan = None
             if densify or cull_only:
@@ -446,7 +447,8 @@ class SceneGraphRasterModel(torch.nn.Module):
                     sub.__dict__["refine_record_dict"] = plan.record()
                 if not plan.changed:
                     plan = None
-            plans.append(plan), resets.append(st if reset else None)
+            plans.append(plan)
+            resets.append(st if reset else None)
             d = sub.__dict__
             d["xys_grad_norm"] = d["vis_counts"] = d["max_2Dsize"] = None  # :644-646
         old = [[sub.gauss_params[k].data for k in PARAM_NAMES] for sub in subs]
@@ -595,13 +597,15 @@ class _FusedAdamAdapter(_NoOptimizer):
                 for k in range(6):
                     t, o = old_params[6 * i + k], int(old_off[6 * i + k])
                     pairs.append((old_m[o:o + t.numel()].view(t.shape), old_v[o:o + t.numel()].view(t.shape)))
-                src.append(pairs), dst.append([opt.moment_views(6 * i + k) for k in range(6)])
+                src.append(pairs)
+                dst.append([opt.moment_views(6 * i + k) for k in range(6)])
             else:  # same tensors, new offsets: one block copy per arena
                 a, b = int(old_off[6 * i]), int(opt.offsets[6 * i])
                 size = int(opt.sizes[6 * i:6 * i + 6].sum())
                 opt.exp_avg[b:b + size].copy_(old_m[a:a + size])
                 opt.exp_avg_sq[b:b + size].copy_(old_v[a:a + size])
-                src.append(None), dst.append(None)
+                src.append(None)
+                dst.append(None)
         return src, dst
 
     def commit(self, params, changed):
@@ -609,7 +613,8 @@ class _FusedAdamAdapter(_NoOptimizer):
 
     def zero_moments(self, sub: int, k: int):
         m, v = self.opt.moment_views(6 * sub + k)
-        m.zero_(), v.zero_()
+        m.zero_()
+        v.zero_()
 
 
 class _TorchAdamGroupsAdapter(_NoOptimizer):
@@ -627,12 +632,10 @@ class _TorchAdamGroupsAdapter(_NoOptimizer):
     def relayout(self, new, changed):
         src, dst = [], []
         for i, ch in enumerate(changed):
-            if not ch:
-                src.append(None), dst.append(None)
-                continue
-            states = [self._state(k, i)[1] for k in range(6)]
-            if not all("exp_avg" in st for st in states):  # never stepped: nothing to carry
-                src.append(None), dst.append(None)
+            states = [self._state(k, i)[1] for k in range(6)] if ch else []
+            if not ch or not all("exp_avg" in st for st in states):  # unchanged, or never stepped: nothing to carry
+                src.append(None)
+                dst.append(None)
                 continue
             src.append([(st["exp_avg"], st["exp_avg_sq"]) for st in states])
             dst.append([(torch.empty_like(t), torch.empty_like(t)) for t in new[i]])

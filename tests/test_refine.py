@@ -397,3 +397,31 @@ def test_checkpoint_with_a_different_number_of_gaussians_loads():
     legacy = {k: torch.full_like(big.all_models["object_a"].gauss_params[k], 0.5) for k in PARAM_NAMES}
     sub.load_state_dict(legacy)
     assert sub.num_points == big.all_models["object_a"].num_points and float(sub.gauss_params["quats"].detach().min()) == 0.5
+
+
+def test_fused_adam_relayout_keeps_untouched_submodels(host_backend):
+    """One actor has no statistics (never in view since the last refinement): its tensors stay, but its moments move to
+    new offsets inside the rebuilt arenas because the sub-models before it changed size."""
+    from street_gaussians_ns_b200.optim import FusedAdam
+    step = 3400
+    model, states = build_model(seed=2)
+    model.step = step
+    quiet = model.all_models["object_a"]
+    d = quiet.__dict__
+    d["xys_grad_norm"] = d["vis_counts"] = d["max_2Dsize"] = None
+    opt = FusedAdam(model.optimizer_params(), chunk_elems=4096)
+    g = torch.Generator().manual_seed(3)
+    opt.exp_avg.copy_(torch.randn(opt.arena_elems, generator=g))
+    opt.exp_avg_sq.copy_(torch.rand(opt.arena_elems, generator=g))
+    before_p = [quiet.gauss_params[k].data.clone() for k in PARAM_NAMES]
+    before_m = [tuple(x.clone() for x in opt.moment_views(6 + j)) for j in range(6)]
+    old_offset = int(opt.offsets[6])
+    ptrs = [quiet.gauss_params[k].data_ptr() for k in PARAM_NAMES]
+    model.refinement_after(opt, step, generator=torch.Generator().manual_seed(1), sync_stats=False)
+    assert model.all_models["background"].num_points != states[0].params["means"].shape[0]  # the arena before it changed
+    assert int(opt.offsets[6]) != old_offset
+    for j, k in enumerate(PARAM_NAMES):
+        assert quiet.gauss_params[k].data_ptr() == ptrs[j] and torch.equal(quiet.gauss_params[k].data, before_p[j])
+        m, v = opt.moment_views(6 + j)
+        assert torch.equal(m, before_m[j][0]) and torch.equal(v, before_m[j][1]), k
+        assert int(opt.table["param"][6 + j]) == ptrs[j]
