@@ -373,7 +373,7 @@ def run_ours(args):
     refinement = None
     if rank == 0:
         try:
-            refinement = measure_refinement(frc, adam, H, W, dev)
+            refinement = measure_refinement(frc, adam, H, W, dev, cpu_baseline=world == 1 and not args.no_cpu_baseline)
         except Exception as e:  # a secondary metric must never cost the bench line
             refinement = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
@@ -487,7 +487,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def measure_refinement(frc, adam, H, W, dev, reps: int = 5):
+def measure_refinement(frc, adam, H, W, dev, reps: int = 5, cpu_baseline: bool = True):
     """Secondary: one refinement of the background sub-model -- decide, prefix sums + the one read-back,
     apply (parameters + both Adam moments rebuilt in the reference's row order) -- on seeded statistics under which
     ~9 % of the rows exceed the gradient threshold.  The inputs are not modified (new tensors are written)."""
@@ -526,7 +526,29 @@ def measure_refinement(frc, adam, H, W, dev, reps: int = 5):
         del new, new_m
     width = sum(int(np.prod(t.shape[1:])) for t in params)
     read_rows = int(((plan.flags & (_lib.RF_KEEP_ORIG | _lib.RF_KEEP_SPLIT | _lib.RF_KEEP_DUP)) != 0).sum())
-    return {"what": "split / duplicate / cull of the background sub-model incl. both Adam moments (decide -> scan + read-back -> apply)",
+    cpu = None
+    if cpu_baseline:
+        # the reference's refinement IS torch code (sgn_splatfacto.py:550-720): its restatement runs on the host cores on
+        # the same inputs (one call; the second place bench.py executes oracle/, as a CPU baseline only)
+        try:
+            from oracle import oracle_refine as orc
+            names = orc.PARAMS
+            old_threads = torch.get_num_threads()
+            torch.set_num_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1
+            st_cpu = orc.SubModelState({k: t.cpu().clone() for k, t in zip(names, params)},
+                                       {k: (m.cpu().clone(), v.cpu().clone()) for k, (m, v) in zip(names, moments)},
+                                       xgn.cpu(), vis.cpu(), m2d.cpu())
+            ocfg = orc.RefineConfig(**{k: getattr(st, k) for k in orc.RefineConfig.__dataclass_fields__})
+            t0 = time.perf_counter()
+            orc.refinement_after(st_cpu, ocfg, step, (H, W), 0)
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            cpu = {"value": round(cpu_ms, 2), "unit": "ms per refinement of this sub-model", "cores": host_threads(), "kind": "port",
+                   "sample": "1 call on the same inputs: the reference's torch statements (oracle/oracle_refine.py) on the host cores",
+                   "rows_out": int(st_cpu.params["means"].shape[0]), "rows_out_match": int(st_cpu.params["means"].shape[0]) == plan.out_rows}
+            torch.set_num_threads(old_threads)
+        except Exception as e:
+            cpu = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return {"cpu_baseline": cpu, "what": "split / duplicate / cull of the background sub-model incl. both Adam moments (decide -> scan + read-back -> apply)",
             "rows_in": n, "rows_out": plan.out_rows, "kept": plan.totals[0], "split_rows": plan.totals[3],
             "duplicates": plan.totals[2], "decide_ms": round(t_decide / reps, 4), "apply_ms": round(t_apply / reps, 4),
             "wall_ms": round(sorted(wall)[len(wall) // 2], 4),

@@ -425,3 +425,17 @@ def test_fused_adam_relayout_keeps_untouched_submodels(host_backend):
         m, v = opt.moment_views(6 + j)
         assert torch.equal(m, before_m[j][0]) and torch.equal(v, before_m[j][1]), k
         assert int(opt.table["param"][6 + j]) == ptrs[j]
+
+
+@pytest.mark.parametrize("F,rest,samps", [(8, 15, 4), (1, 0, 2), (3, 3, 1)])
+def test_row_widths_and_sample_counts(host_backend, F, rest, samps):
+    """Widest Fourier basis (SGN_MAX_FOURIER = 8), sh_degree 0 (features_rest has zero columns), sh_degree 1, and 1 / 2 / 4
+    split samples: the per-element rebuild walks whatever column layout the six tensors have."""
+    st = make_state(700, F, seed=40 + F)
+    st.params["features_rest"] = st.params["features_rest"][:, :rest].contiguous()
+    st.moments["features_rest"] = tuple(x[:, :rest].contiguous() for x in st.moments["features_rest"])
+    cfg = orc.RefineConfig(stop_split_at=25000, cull_alpha_thresh=0.02, cull_scale_thresh=0.2, n_split_samples=samps)
+    new_p, new_m, plan = run_product(clone_state(st), cfg, 3400, (240, 320), 50, seed=6)
+    ost, _ = run_oracle(st, cfg, 3400, (240, 320), 50, seed=6)
+    assert plan.totals[3] > 10 and plan.out_rows == ost.params["means"].shape[0]
+    assert_same(new_p, new_m, ost, f"F={F} rest={rest} samps={samps}")
