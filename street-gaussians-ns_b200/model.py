@@ -177,7 +177,7 @@ class _FullArenaSink(_GradSink):
         self.all_shapes: List[tuple] = []
 
     def bind_model(self, all_params: List[List[torch.Tensor]], present: List[int]):
-        key = tuple(id(t) for ps in all_params for t in ps)
+        key = tuple((id(t), t.shape[0]) for ps in all_params for t in ps)  # ids can be recycled after a refinement
         if key != self.model_key:
             flat = [t for ps in all_params for t in ps]
             self.model_key, self.arena, self.all_views = key, None, []
