@@ -7,8 +7,11 @@ Whole-tensor statements in the reference's ORDER (the order matters: ``split_gau
 place before ``dups`` is evaluated, :696 then :582), on whatever device the tensors live on: the CPU tests run it on
 CPU, the GPU test runs it on the GPU so that exp / log / sigmoid are the very CUDA functions the reference would call.
 
-Parity status: the reference has no tests for this step; the restatement is pinned by hand-built cases with known
-answers (tests/test_refine.py) -- "parity unpinned" in the sense of DESIGN.md section 4.
+Parity status: PINNED.  This step is pure torch in the reference, so the reference's own code runs in the build
+container: tests/golden/make_golden_reference.py executes ``SplatfactoModel.refinement_after`` itself (imported through
+tests/golden/reference_loader.py) through every phase of the schedule with a live torch.optim.Adam state and commits
+inputs, captured split samples and outputs as tests/golden/reference_vectors.npz; tests/test_reference_vectors.py holds
+this restatement (and the product) to those vectors.  Hand-built known-answer cases are in tests/test_refine.py.
 """
 from __future__ import annotations
 
