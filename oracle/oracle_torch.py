@@ -134,8 +134,10 @@ def compose(frame, dtype=torch.float64, requires_grad: bool = True):
     return leaves, cat
 
 
-def project(cat, camera, block_width=16, clip_thresh=0.01, use_spec_exp=True):
-    """gsplat project_gaussians on the composed tensors (Appendix A.1-A.4)."""
+def project(cat, camera, block_width=16, clip_thresh=0.01, use_spec_exp=True, scales_are_linear=False):
+    """gsplat project_gaussians on the composed tensors (Appendix A.1-A.4).  ``scales_are_linear``: cat["scales"] already
+    went through exp, as in the reference's call (sgn_splatfacto.py:857-862) -- used when this function serves the
+    gsplat slot under the reference's own glue (tests/golden/reference_glue.py)."""
     dtype = cat["means"].dtype
     W = torch.from_numpy(camera.viewmat().copy()).to(dtype)  # [3,4]
     fx, fy, cx, cy = camera.fx, camera.fy, camera.cx, camera.cy
@@ -147,7 +149,10 @@ def project(cat, camera, block_width=16, clip_thresh=0.01, use_spec_exp=True):
     not_clipped = z > clip_thresh
     q = cat["quats"]
     qn = q / q.norm(dim=-1, keepdim=True)
-    s = expf_spec(cat["scales"]) if use_spec_exp else torch.exp(cat["scales"])
+    if scales_are_linear:
+        s = cat["scales"]
+    else:
+        s = expf_spec(cat["scales"]) if use_spec_exp else torch.exp(cat["scales"])
     Rg = quat_to_rotmat(qn)
     M = Rg * s[:, None, :]
     S = M @ M.transpose(1, 2)

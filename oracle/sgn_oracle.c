@@ -12,9 +12,14 @@
  *   blend fwd / bwd      : gsplat rasterize_forward / rasterize_backward
  *   project / SH bwd     : gsplat project_gaussians_backward / compute_sh_backward (Appendix A.7-A.8)
  *
- * PARITY UNPINNED: the reference ships no tests and gsplat is absent from the container, so this
- * oracle is pinned only by (a) closed-form known answers, (b) a float64 autograd restatement
- * (oracle/oracle_torch.py) and (c) finite differences -- see tests/test_oracle_*.py.
+ * PARITY: the reference ships no tests and gsplat is absent from the container, so gsplat's KERNEL
+ * ARITHMETIC here (projection, SH, binning, blend, and their backward: SURVEY.md Appendix A) is a restatement --
+ * "parity unpinned" for those -- pinned only by (a) closed-form known answers, (b) a float64 autograd restatement
+ * (oracle/oracle_torch.py) and (c) finite differences -- see tests/test_oracle.py.  Everything AROUND those kernels
+ * (scene-graph compose, camera, pre-ops, view directions, SH schedule, the four rasterize calls, post-ops, side
+ * effects, the backward chain) is pinned to the reference's own code: tests/test_reference_glue.py runs the reference's
+ * get_outputs + autograd on the CPU with this restatement in gsplat's slots and this file reproduces its outputs and
+ * every gradient tensor (tests/golden/reference_glue_tiny.npz).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
  * call into this file.  It is never on the product path.

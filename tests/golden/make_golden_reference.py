@@ -7,7 +7,9 @@ tests/golden/reference_loader.py -- read its header for what is stubbed and why)
              phase of the schedule; the standard-normal draws of ``split_gaussians`` are captured and stored;
   loss_*     ``SplatfactoSceneGraphModel.get_loss_dict`` (:1042-1094 + scene graph :376-391): L1 (with and without
              mask), sky accumulation, object-accumulation entropy (the SSIM term is not in the fixture);
-  idft_*     ``IDFT`` and ``get_fourier_features`` (scene graph :420-433, :239-247).
+  idft_*     ``IDFT`` and ``get_fourier_features`` (scene graph :420-433, :239-247);
+  view_*     what ``get_outputs`` (:793-873) hands to gsplat's ``project_gaussians``: world->camera matrix, intrinsics,
+             image size, block width, ``exp(scales)``, unit quaternions (the call itself is intercepted).
 
 This is the one part of the path where the reference itself -- not a restatement -- can run in the build container
 (pure torch, no gsplat / nerfstudio arithmetic), so these vectors PIN the refinement oracle, the product's row rules,
@@ -24,6 +26,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))  # repo root: the seeded synthetic camera rig
 import reference_loader as rl  # noqa: E402
 
 OUT = os.path.join(HERE, "reference_vectors.npz")
@@ -148,6 +151,69 @@ def fourier_vectors(base, graph):
     return out
 
 
+class _Captured(Exception):
+    pass
+
+
+def view_vectors(base):
+    """Runs the reference's ``get_outputs`` (sgn_splatfacto.py:793-873) up to its ``project_gaussians`` call and captures
+    the arguments it passes: the world->camera matrix built from an OpenGL camera_to_worlds (:822-836), the intrinsics,
+    image size, block width, glob_scale, and the pre-ops ``exp(scales)`` / ``quats / ||quats||`` (:857-864)."""
+    import street_gaussians_ns_b200.synthetic as syn
+    Cameras = sys.modules["nerfstudio.cameras.cameras"].Cameras
+    rig = syn.waymo_rig(4)
+    g = torch.Generator().manual_seed(3)
+    rand_rot, _ = np.linalg.qr(torch.randn(3, 3, generator=g).numpy().astype(np.float64))
+    poses = [np.concatenate([np.eye(3), np.zeros((3, 1))], axis=1), rig[7], rig[13],
+             np.concatenate([rand_rot, np.array([[1.5], [-0.7], [3.25]])], axis=1)]
+    n = 40
+    params = {"means": torch.randn(n, 3, generator=g), "scales": torch.randn(n, 3, generator=g) - 3, "quats": torch.randn(n, 4, generator=g),
+              "features_dc": torch.randn(n, 1, 3, generator=g), "features_rest": torch.randn(n, 15, 3, generator=g),
+              "opacities": torch.randn(n, 1, generator=g)}
+    out = {"view_in_" + k: v.numpy() for k, v in params.items()}
+    captured = {}
+
+    def capture(means, scales, glob_scale, quats, viewmat, fx, fy, cx, cy, H, W, block_width, *rest):
+        captured.update(means=means, scales=scales, glob_scale=glob_scale, quats=quats, viewmat=viewmat, fx=fx, fy=fy, cx=cx, cy=cy,
+                        H=H, W=W, block_width=block_width)
+        raise _Captured()
+
+    m = rl.bare_model(base, params)
+    m.back_color = torch.zeros(3)
+    m.crop_box = None
+    m.train()
+    real = base.project_gaussians
+    base.project_gaussians = capture
+    try:
+        for i, c2w in enumerate(poses):
+            W, H = (1920, 1280) if i % 2 == 0 else (640, 480)
+            f = np.float32(2055.0 * W / 1920.0)
+            cam = Cameras()
+            cam.shape = (1,)
+            cam.camera_to_worlds = torch.from_numpy(c2w.astype(np.float32))[None]
+            cam.fx, cam.fy = torch.tensor([[f]]), torch.tensor([[f * np.float32(1.01)]])
+            cam.cx, cam.cy = torch.tensor([[W / 2.0 + 0.25]]), torch.tensor([[H / 2.0 - 0.5]])
+            cam.width, cam.height = torch.tensor([[W]]), torch.tensor([[H]])
+            cam.rescale_output_resolution = lambda s: None
+            try:
+                m.get_outputs(cam)
+                raise AssertionError("the reference did not reach project_gaussians")
+            except _Captured:
+                pass
+            out[f"view_c2w_{i}"] = c2w.astype(np.float32)
+            out[f"view_viewmat_{i}"] = captured["viewmat"].detach().numpy().copy()
+            out[f"view_scalars_{i}"] = np.array([captured["fx"], captured["fy"], captured["cx"], captured["cy"], captured["H"], captured["W"],
+                                                 captured["block_width"], captured["glob_scale"]], np.float64)
+            assert m.last_size == (H, W)
+    finally:
+        base.project_gaussians = real
+    out["view_num_cameras"] = np.array(len(poses))
+    out["view_exp_scales"] = captured["scales"].detach().numpy().copy()
+    out["view_unit_quats"] = captured["quats"].detach().numpy().copy()
+    assert torch.equal(captured["means"], m.gauss_params["means"])
+    return out
+
+
 def build():
     base, graph = rl.load()
     d = refine_inputs()
@@ -156,6 +222,7 @@ def build():
         d.update({f"refine_{label}_{k}": v for k, v in res.items()})
     d.update(loss_vectors(base, graph))
     d.update(fourier_vectors(base, graph))
+    d.update(view_vectors(base))
     return d
 
 
