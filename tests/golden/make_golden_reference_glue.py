@@ -6,6 +6,7 @@ autograd backward produce on a tiny seeded scene when gsplat's three calls are s
           (xys, depths, radii, conics, num_tiles_hit per model), and the parameter gradients of the fixed linear loss
           sum(w*rgb) + sum(v*accumulation) + sum(u*object_acc) for every sub-model;
   eval    eval mode with a sky image: sky blend, clamp(0,1), background_rgb / object_rgb;
+  sched   training at step 1500 (SH degree 1 of 3 by the schedule), rotated camera of the rig, 70x50 image (ragged tiles);
   empty   camera turned away from everything: the base model's early-out dict (sgn_splatfacto.py:878-886); the scene-graph
           wrapper itself raises in this situation (recorded).
 
@@ -30,6 +31,14 @@ OUTPUTS = ("rgb", "accumulation", "depth", "object_acc", "background_acc")
 
 def scene():
     return syn.make_frame(**SCENE)
+
+
+SCHED_STEP = 1500  # training: n = min(step // sh_degree_interval, sh_degree) = 1 (sgn_splatfacto.py:936-938)
+SCENE2 = dict(n_background=2500, n_actors=3, n_per_actor=250, width=70, height=50, seed=21, actor_shift=np.array([0.5, 0.0, -2.0]))
+
+
+def scene2():
+    return syn.make_frame(c2w=syn.waymo_rig(4)[6], **SCENE2)
 
 
 def cotangents(H, W):
@@ -75,6 +84,13 @@ def build():
         out = m.get_outputs(cam)
     for k in OUTPUTS + ("sky", "background_rgb", "object_rgb"):
         d["eval_" + k] = out[k].numpy()
+    # ---- SH-degree schedule, rotated rig camera, ragged image size -------------------------------------------------------
+    fr3 = scene2()
+    m, cam = rg.build_reference_model(fr3, training=True, step=SCHED_STEP)
+    out = m.get_outputs(cam)
+    for k in OUTPUTS:
+        d["sched_" + k] = out[k].detach().numpy()
+    d["sched_radii"] = m.radii.numpy()
     # ---- nothing visible ------------------------------------------------------------------------------------------
     fr2 = scene()
     fr2.camera = away_camera()

@@ -111,6 +111,29 @@ def test_oracle_eval_and_sky_post_ops_reproduce_the_reference_glue(oracle_run):
         assert np.abs(rgb_c.numpy() - GOLD[key])[frag == 0].max() <= 1e-5, key
 
 
+def test_sh_schedule_rotated_camera_ragged_image():
+    """Second scene: the SH degree the training schedule selects at step 1500 (1 of 3), a yawed camera of the rig, an image
+    whose size is no multiple of the tile."""
+    fr = mg.scene2()
+    orc = oracle_c.Oracle(fr, sh_degree_to_use=min(mg.SCHED_STEP // 1000, 3))
+    fw = orc.forward()
+    assert fw.M > 0
+    alpha = 1 - fw.final_T
+    rgb, _, depth = oracle_c.post_ops(torch.from_numpy(fw.img), torch.from_numpy(alpha), None, True)
+    ok = fw.fragile == 0
+    assert ok.mean() > 0.99
+    assert np.abs(rgb.numpy() - GOLD["sched_rgb"])[ok].max() <= 1e-5
+    assert np.abs(alpha - GOLD["sched_accumulation"][..., 0])[ok].max() <= 1e-5
+    d, dr = depth.numpy()[..., 0], GOLD["sched_depth"][..., 0]
+    assert (np.abs(d - dr) / np.maximum(dr, 1.0))[ok].max() <= 1e-4
+    assert np.abs((1 - fw.obj_T) - GOLD["sched_object_acc"][..., 0])[fw.fragile_obj == 0].max() <= 1e-5
+    assert np.abs((1 - fw.bg_T) - GOLD["sched_background_acc"][..., 0])[fw.fragile_bg == 0].max() <= 1e-5
+    np.testing.assert_array_equal(fw.radii, GOLD["sched_radii"])
+    # and degree 3 would NOT have matched: the schedule is really exercised
+    full = oracle_c.Oracle(fr).forward()
+    assert np.abs(np.minimum(full.img[..., :3], 1.0) - GOLD["sched_rgb"]).max() > 1e-3
+
+
 def test_nothing_in_view():
     """The base model's early-out (sgn_splatfacto.py:878-886): rgb = background colour (zeros), accumulation 0, depth 0.
     The reference's scene-graph wrapper itself raises an AssertionError in this situation (:944, recorded in the fixture);
