@@ -8,6 +8,7 @@ tests/golden/reference_loader.py -- read its header for what is stubbed and why)
   loss_*     ``SplatfactoSceneGraphModel.get_loss_dict`` (:1042-1094 + scene graph :376-391): L1 (with and without
              mask), sky accumulation, object-accumulation entropy (the SSIM term is not in the fixture);
   idft_*     ``IDFT`` and ``get_fourier_features`` (scene graph :420-433, :239-247);
+  stats_*    ``after_train`` (:513-541): the running densification statistics over two steps;
   view_*     what ``get_outputs`` (:793-873) hands to gsplat's ``project_gaussians``: world->camera matrix, intrinsics,
              image size, block width, ``exp(scales)``, unit quaternions (the call itself is intercepted).
 
@@ -151,6 +152,30 @@ def fourier_vectors(base, graph):
     return out
 
 
+def after_train_vectors(base):
+    """``SplatfactoModel.after_train`` (sgn_splatfacto.py:513-541) twice on one sub-model: the first call creates the
+    running statistics, the second accumulates on the rows that were visible."""
+    g = torch.Generator().manual_seed(14)
+    n = 300
+    out = {"stats_size": np.array([240, 320])}
+    m = rl.bare_model(base, {"means": torch.zeros(n, 3), "scales": torch.zeros(n, 3), "quats": torch.ones(n, 4),
+                             "features_dc": torch.zeros(n, 1, 3), "features_rest": torch.zeros(n, 15, 3), "opacities": torch.zeros(n, 1)},
+                      step=1000)
+    m.last_size = (240, 320)
+    for call in range(2):
+        radii = (torch.rand(n, generator=g) * 40).to(torch.int32) * (torch.rand(n, generator=g) > 0.35).to(torch.int32)
+        grad = torch.randn(n, 2, generator=g) * 1e-4
+        m.xys = torch.zeros(n, 2, requires_grad=True)
+        m.xys.grad = grad.clone()
+        m.radii = radii.clone()
+        m.after_train(1000)
+        out[f"stats_radii_{call}"], out[f"stats_xys_grad_{call}"] = radii.numpy(), grad.numpy()
+        out[f"stats_xys_grad_norm_{call}"] = m.xys_grad_norm.numpy().copy()
+        out[f"stats_vis_counts_{call}"] = m.vis_counts.numpy().copy()
+        out[f"stats_max_2Dsize_{call}"] = m.max_2Dsize.numpy().copy()
+    return out
+
+
 class _Captured(Exception):
     pass
 
@@ -223,6 +248,7 @@ def build():
     d.update(loss_vectors(base, graph))
     d.update(fourier_vectors(base, graph))
     d.update(view_vectors(base))
+    d.update(after_train_vectors(base))
     return d
 
 
