@@ -16,9 +16,7 @@ Prints ONE JSON line on rank 0.
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import threading
 import time
 

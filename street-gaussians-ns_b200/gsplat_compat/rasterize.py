@@ -2,14 +2,13 @@
 
 N-channel colours are blended four channels per traversal (the fused main kernel carries rgb + depth,
 i.e. four generic channels); binning happens once per call."""
-import ctypes as C
 from typing import Optional
 
 import torch
 from torch.autograd import Function
 
 from .. import _lib, raster
-from ._common import need_cuda, ptr, stream
+from ._common import need_cuda
 
 
 def rasterize_gaussians(xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height: int, img_width: int,

@@ -1,5 +1,4 @@
 """gsplat.sh (call site street_gaussians_ns/sgn_splatfacto.py:939, :292-293)."""
-import ctypes as C
 
 import torch
 from torch.autograd import Function

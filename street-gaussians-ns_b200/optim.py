@@ -17,7 +17,7 @@ Two torch.optim.Adam behaviours the scene graph depends on are kept:
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -34,7 +34,6 @@ def main():
     ap.add_argument("--pipeline-chunks", type=int, default=0, help="> 0: all-reduce and Adam pipelined over that many arena ranges")
     args = ap.parse_args()
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
