@@ -183,3 +183,33 @@ def test_cuda_model_reproduces_the_reference_glue(oracle_run):
                 assert np.abs(got).max() == 0.0, (name, k)
             else:
                 assert rel_l2(got, ref) <= 5e-3, (name, k, rel_l2(got, ref))
+
+
+@pytest.mark.gpu
+def test_cuda_model_eval_reproduces_the_reference_glue(oracle_run):
+    """Eval mode with a sky image: rgb * alpha + sky * (1 - alpha), clamp(0, 1), and the per-class colour renders
+    ``background_rgb`` (over the sky) / ``object_rgb`` (over nothing) of scene graph :367-372."""
+    from street_gaussians_ns_b200.model import ActorPose, SceneGraphConfig, SceneGraphRasterModel
+    fr, orc, fw = oracle_run
+    dev = torch.device("cuda", 0)
+    H, W = fr.camera.height, fr.camera.width
+    sky = mg.sky_image(H, W).to(dev)
+    bg = fr.segments[0].params.to(dev)
+    actors = {s.name.replace("object_", ""): s.params.to(dev) for s in fr.segments[1:]}
+    poses = [ActorPose(s.name.replace("object_", ""), s.rot, s.center, int(fr.camera.time), list(range(85))) for s in fr.segments[1:]]
+    model = SceneGraphRasterModel(bg, actors, SceneGraphConfig(use_sky_sphere=True), poses_at=lambda t: poses,
+                                  sky=lambda camera, training: sky).to(dev)
+    model.eval()
+    model.step = 30000
+    with torch.no_grad():
+        out = model.get_outputs(fr.camera)
+    torch.cuda.synchronize()
+    ok = fw.fragile == 0
+    assert np.abs(out["rgb"].cpu().numpy() - GOLD["eval_rgb"])[ok].max() <= 1e-4
+    assert np.abs(out["accumulation"].cpu().numpy() - GOLD["eval_accumulation"])[ok].max() <= 1e-4
+    np.testing.assert_array_equal(out["sky"].cpu().numpy(), GOLD["eval_sky"])
+    pr = orc.project()
+    colors4 = np.concatenate([pr["rgbs"], pr["depths"][:, None]], axis=1)
+    for cls, key in ((0, "background_rgb"), (1, "object_rgb")):
+        _, _, _, frag = orc.blend(pr, fw.sorted_ids, fw.tile_bins, colors4, cls_filter=cls)
+        assert np.abs(out[key].cpu().numpy() - GOLD["eval_" + key])[frag == 0].max() <= 1e-4, key
