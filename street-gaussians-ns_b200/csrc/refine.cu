@@ -45,9 +45,19 @@ refine_apply_kernel(int n, int row_width, const sgn_refine_config cfg, const sgn
                     const uint8_t* __restrict__ flags, const int32_t* __restrict__ scan, const refine_totals totals,
                     const float* __restrict__ samples) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (long long)n * row_width) return;
-    const long long i = e / row_width;
-    const int c = (int)(e - i * row_width);
+    const long long total = (long long)n * row_width;
+    if (e >= total) return;
+    long long i;
+    int c;
+    if (total < (1ll << 32)) {  // the usual case: a 32-bit divide instead of the 64-bit software routine
+        const unsigned e32 = (unsigned)e, w32 = (unsigned)row_width;
+        const unsigned i32 = e32 / w32;
+        i = i32;
+        c = (int)(e32 - i32 * w32);
+    } else {
+        i = e / row_width;
+        c = (int)(e - i * row_width);
+    }
     sgn_refine_apply_elem(i, c, n, cfg, t, flags, scan, totals.v, samples);
 }
 
