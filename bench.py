@@ -369,7 +369,7 @@ def run_ours(args):
     adam_ms = sum(a.elapsed_time(b) for a, b in adam_ev) / len(adam_ev)
 
     refinement = None
-    if rank == 0:
+    if rank == 0 and world == 1:  # a single-GPU measurement; ranks of a multi-GPU run leave together
         try:
             refinement = measure_refinement(frc, adam, H, W, dev, cpu_baseline=world == 1 and not args.no_cpu_baseline)
         except Exception as e:  # a secondary metric must never cost the bench line
