@@ -213,3 +213,36 @@ def test_cuda_model_eval_reproduces_the_reference_glue(oracle_run):
     for cls, key in ((0, "background_rgb"), (1, "object_rgb")):
         _, _, _, frag = orc.blend(pr, fw.sorted_ids, fw.tile_bins, colors4, cls_filter=cls)
         assert np.abs(out[key].cpu().numpy() - GOLD["eval_" + key])[frag == 0].max() <= 1e-4, key
+
+
+@pytest.mark.skipif(not rl.available(), reason="the reference source is only mounted in the build container")
+@pytest.mark.parametrize("seed,training,with_sky,step", [(31, True, False, 30000), (32, False, True, 30000), (33, True, True, 2500)])
+def test_more_scenes_live_against_the_reference_glue(seed, training, with_sky, step):
+    """No fixture: where the reference is mounted, fresh seeded scenes go through the reference's get_outputs (oracle in
+    gsplat's slots) and through the C oracle, in training / eval mode, with / without a sky, at different SH-schedule steps."""
+    import reference_glue as rg
+    import street_gaussians_ns_b200.synthetic as syn
+    fr = syn.make_frame(n_background=1200, n_actors=2, n_per_actor=200, width=64, height=48, seed=seed,
+                        actor_shift=np.array([1.75, 0.4, 2.0]))
+    H, W = fr.camera.height, fr.camera.width
+    sky = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(seed)) if with_sky else None
+    m, cam = rg.build_reference_model(fr, training=training, step=step, sky=sky)
+    if training:
+        out = {k: v.detach() for k, v in m.get_outputs(cam).items()}
+    else:
+        with torch.no_grad():
+            out = m.get_outputs(cam)
+    n = min(step // 1000, 3) if training else 3
+    orc = oracle_c.Oracle(fr, sh_degree_to_use=n)
+    fw = orc.forward()
+    alpha = 1 - fw.final_T
+    rgb, _, depth = oracle_c.post_ops(torch.from_numpy(fw.img), torch.from_numpy(alpha), sky, training)
+    ok = fw.fragile == 0
+    assert ok.mean() > 0.98
+    assert np.abs(rgb.numpy() - out["rgb"].numpy())[ok].max() <= 1e-5
+    assert np.abs(alpha - out["accumulation"].numpy()[..., 0])[ok].max() <= 1e-5
+    d, dr = depth.numpy()[..., 0], out["depth"].numpy()[..., 0]
+    assert (np.abs(d - dr) / np.maximum(dr, 1.0))[ok].max() <= 1e-4
+    assert np.abs((1 - fw.obj_T) - out["object_acc"].numpy()[..., 0])[fw.fragile_obj == 0].max() <= 1e-5
+    assert np.abs((1 - fw.bg_T) - out["background_acc"].numpy()[..., 0])[fw.fragile_bg == 0].max() <= 1e-5
+    np.testing.assert_array_equal(fw.radii, m.radii.numpy())

@@ -439,3 +439,46 @@ def test_row_widths_and_sample_counts(host_backend, F, rest, samps):
     ost, _ = run_oracle(st, cfg, 3400, (240, 320), 50, seed=6)
     assert plan.totals[3] > 10 and plan.out_rows == ost.params["means"].shape[0]
     assert_same(new_p, new_m, ost, f"F={F} rest={rest} samps={samps}")
+
+
+def test_special_values_follow_torch_semantics(host_backend):
+    """Rows with never-seen statistics (vis_counts = 0 -> 0/0 and x/0), infinite / NaN statistics, overflowing and
+    underflowing scales, saturated opacities: every comparison must come out as torch's does (NaN compares false)."""
+    n = 64
+    st = make_state(n, 1, seed=8)
+    inf, nan = float("inf"), float("nan")
+    st.vis_counts[:8] = 0.0                     # never visible: xys_grad_norm / 0
+    st.xys_grad_norm[:4] = 0.0                  # 0 / 0 = NaN  -> not a high gradient
+    st.xys_grad_norm[8:10] = inf
+    st.xys_grad_norm[10:12] = nan
+    st.max_2Dsize[12:14] = nan
+    st.max_2Dsize[14:16] = inf
+    st.params["scales"][16:18] = 100.0          # exp overflows to inf
+    st.params["scales"][18:20] = -120.0         # exp underflows to 0 (log(0 / 1.6) = -inf for a split row)
+    st.params["opacities"][20:22] = 200.0       # sigmoid == 1
+    st.params["opacities"][22:24] = -200.0      # sigmoid == 0
+    st.params["opacities"][24] = nan
+    cfg = orc.RefineConfig(stop_split_at=25000, cull_alpha_thresh=0.02, cull_scale_thresh=0.2)
+    for step in (700, 3400, 25000):
+        new_p, new_m, plan = run_product(clone_state(st), cfg, step, (240, 320), 50, seed=2)
+        ost, _ = run_oracle(clone_state(st), cfg, step, (240, 320), 50, seed=2)
+        for k, name in enumerate(PARAM_NAMES):
+            a, b = new_p[k], ost.params[name]
+            assert a.shape == b.shape, (step, name, a.shape, b.shape)
+            if name in ("means", "scales"):
+                torch.testing.assert_close(a, b, rtol=2e-6, atol=2e-6, equal_nan=True)
+            else:
+                assert torch.equal(torch.nan_to_num(a, nan=12345.0), torch.nan_to_num(b, nan=12345.0)), (step, name)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3])
+def test_tiny_submodels(host_backend, n):
+    st = make_state(max(n, 1), 5, seed=50 + n)
+    if n == 0:
+        st = orc.SubModelState({k: v[:0].contiguous() for k, v in st.params.items()},
+                               {k: (a[:0].contiguous(), b[:0].contiguous()) for k, (a, b) in st.moments.items()},
+                               st.xys_grad_norm[:0], st.vis_counts[:0], st.max_2Dsize[:0])
+    cfg = orc.RefineConfig(stop_split_at=25000, cull_alpha_thresh=0.02, cull_scale_thresh=0.2)
+    new_p, new_m, plan = run_product(clone_state(st), cfg, 3400, (240, 320), 50, seed=1)
+    ost, _ = run_oracle(st, cfg, 3400, (240, 320), 50, seed=1)
+    assert_same(new_p, new_m, ost, f"n={n}")
