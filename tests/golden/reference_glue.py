@@ -159,7 +159,7 @@ def build_reference_model(frame, training: bool, step: int = 30000, sky=None, nu
     annos = []
     for i, seg in enumerate(frame.segments):
         params = {k: getattr(seg.params, k).detach().clone() for k in PARAMS}
-        sub_cfg = base.SplatfactoModelConfig(use_sky_sphere=False)
+        sub_cfg = base.SplatfactoModelConfig(use_sky_sphere=False, fourier_features_dim=int(params["features_dc"].shape[1]))
         sub = rl.bare_model(base, params, sub_cfg, step=step, idx=i)
         sub.xys = sub.depths = sub.radii = sub.conics = sub.num_tiles_hit = sub.last_size = None
         name = "background" if i == 0 else seg.name
@@ -168,6 +168,8 @@ def build_reference_model(frame, training: bool, step: int = 30000, sky=None, nu
             track = name[len("object_"):]
             annos.append(types.SimpleNamespace(trackId=track, frame=int(frame.camera.time), center=np.asarray(seg.center, np.float64),
                                                rot=np.asarray(seg.rot, np.float64)))
+    # the reference sizes features_dc by config.fourier_features_dim (sgn_splatfacto.py:272-289): keep config and data consistent
+    m.config.fourier_features_dim = max([int(s.params.features_dc.shape[1]) for s in frame.segments[1:]] or [1])
     m.object_annos = _Annotations(annos, {a.trackId: list(range(num_frames)) for a in annos})
     m.bbox_optimizer = types.SimpleNamespace(apply_to_bbox=lambda anno: None)
     m.visible_model_names = list(m.all_models.keys())

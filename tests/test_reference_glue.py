@@ -216,14 +216,16 @@ def test_cuda_model_eval_reproduces_the_reference_glue(oracle_run):
 
 
 @pytest.mark.skipif(not rl.available(), reason="the reference source is only mounted in the build container")
-@pytest.mark.parametrize("seed,training,with_sky,step", [(31, True, False, 30000), (32, False, True, 30000), (33, True, True, 2500)])
-def test_more_scenes_live_against_the_reference_glue(seed, training, with_sky, step):
+@pytest.mark.parametrize("seed,training,with_sky,step,fourier_dim", [(31, True, False, 30000, 5), (32, False, True, 30000, 5),
+                                                                       (33, True, True, 2500, 5), (34, False, False, 30000, 1)])
+def test_more_scenes_live_against_the_reference_glue(seed, training, with_sky, step, fourier_dim):
     """No fixture: where the reference is mounted, fresh seeded scenes go through the reference's get_outputs (oracle in
-    gsplat's slots) and through the C oracle, in training / eval mode, with / without a sky, at different SH-schedule steps."""
+    gsplat's slots) and through the C oracle, in training / eval mode, with / without a sky, at different SH-schedule steps,
+    with time-Fourier (F = 5) and static (F = 1) actor colour."""
     import reference_glue as rg
     import street_gaussians_ns_b200.synthetic as syn
     fr = syn.make_frame(n_background=1200, n_actors=2, n_per_actor=200, width=64, height=48, seed=seed,
-                        actor_shift=np.array([1.75, 0.4, 2.0]))
+                        actor_shift=np.array([1.75, 0.4, 2.0]), fourier_dim=fourier_dim)
     H, W = fr.camera.height, fr.camera.width
     sky = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(seed)) if with_sky else None
     m, cam = rg.build_reference_model(fr, training=training, step=step, sky=sky)
