@@ -24,7 +24,7 @@ import types
 
 import torch
 
-REFERENCE_ROOT = "/root/reference"
+REFERENCE_ROOT = os.environ.get("SGN_REFERENCE_ROOT", "/root/reference")  # only mounted in the build container
 
 
 def available() -> bool:
