@@ -12,8 +12,11 @@
  *   - structs (sgn_camera, sgn_segment, ...) are plain host structs passed by pointer; segment
  *     tables are staged to a caller-provided device buffer with sgn_upload().
  *   - every function returns 0 on success, a negative sgn_status otherwise; the message is
- *     available from sgn_last_error() (thread local).  No exceptions cross the ABI, no global
- *     state, no allocation inside the library: scratch sizes are queried, buffers are passed in.
+ *     available from sgn_last_error() (thread local).  No exceptions cross the ABI, no allocation
+ *     inside the library: scratch sizes are queried, buffers are passed in.  The only process-wide state is a launch
+ *     counter and one lazily created auxiliary stream per device, onto which sgn_blend_fwd / sgn_blend_bwd fork the
+ *     object-class pass (event fork / join around it: calls from several host threads on different streams stay
+ *     correctly ordered, they merely share that side stream).
  *   - there is NO CPU fallback: a missing device or a failed launch is an error.
  */
 #ifndef SGN_RASTER_H_
