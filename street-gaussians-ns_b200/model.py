@@ -418,39 +418,49 @@ class SceneGraphRasterModel(torch.nn.Module):
         ``self.optimizer_params()``, or the reference's form -- an object (or dict) mapping the six group names to
         ``torch.optim.Adam`` instances whose ``param_groups[0]["params"][i]`` is sub-model i's tensor -- or None.
 
-        Two phases so that nothing is copied twice: decide every sub-model (one read-back of four counts each), then
-        lay out the new tensors / moment arenas and let ``sgn_refine_apply`` write each sub-model's rows into them."""
+        Two phases so that nothing is copied twice and the host waits once: decide every sub-model (all launches first,
+        then ONE read-back of all the counts), then lay out the new tensors / moment arenas and let ``sgn_refine_apply``
+        write each sub-model's rows into them."""
         assert step == self.step
         names = list(self.all_models._modules)
         subs = [self.all_models[n] for n in names]
         adapter = _optimizer_adapter(optimizers, len(subs))
         if sync_stats:
             self._sync_densification_stats(subs)
-        plans, resets = [], []
+        # phase 1: every sub-model's decision pass is launched, then ALL totals come back with one read-back
+        decided, resets = [], []
         for name, sub in zip(names, subs):
             st = self.config.refine if name == "background" else self.config.object_refine
             densify, cull_only, reset = refine.phase(st, step, self.config.num_train_data)
             sub.__dict__["refine_record_dict"] = {}
             if step <= st.warmup_length or sub.xys_grad_norm is None:  # :552-555
-                plans.append(None)
+                decided.append(None)
                 resets.append(None)
                 continue
-            plan = None
+            entry = None
             if densify or cull_only:
                 size = sub.last_size or self.last_size
                 cfg = refine.make_config(st, step, size, densify)
                 g = sub.gauss_params
-                plan = refine.plan_submodel(g["scales"].data, g["opacities"].data, sub.xys_grad_norm if densify else None,
-                                            sub.vis_counts if densify else None, sub.max_2Dsize if cfg.use_screen_size else None,
-                                            cfg, generator)
+                flags, scan = refine.decide_submodel(g["scales"].data, g["opacities"].data, sub.xys_grad_norm if densify else None,
+                                                     sub.vis_counts if densify else None,
+                                                     sub.max_2Dsize if cfg.use_screen_size else None, cfg)
+                entry = (flags, scan, cfg)
+            decided.append(entry)
+            resets.append(st if reset else None)
+            d = sub.__dict__
+            d["xys_grad_norm"] = d["vis_counts"] = d["max_2Dsize"] = None  # :644-646
+        totals = iter(refine.read_totals([e[1] for e in decided if e is not None]))
+        plans = []
+        for sub, entry in zip(subs, decided):  # split samples are drawn in sub-model order, as the reference's callbacks run
+            plan = None
+            if entry is not None:
+                plan = refine.finish_plan(entry[0], entry[1], next(totals), entry[2], generator)
                 if self.config.refine_record:
                     sub.__dict__["refine_record_dict"] = plan.record()
                 if not plan.changed:
                     plan = None
             plans.append(plan)
-            resets.append(st if reset else None)
-            d = sub.__dict__
-            d["xys_grad_norm"] = d["vis_counts"] = d["max_2Dsize"] = None  # :644-646
         old = [[sub.gauss_params[k].data for k in PARAM_NAMES] for sub in subs]
         new = [o if p is None else [torch.empty((p.out_rows,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype) for t in o]
                for o, p in zip(old, plans)]

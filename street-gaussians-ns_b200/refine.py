@@ -125,12 +125,9 @@ class Plan:
         return out
 
 
-def plan_submodel(scales: torch.Tensor, opacities: torch.Tensor, xys_grad_norm: Optional[torch.Tensor],
-                  vis_counts: Optional[torch.Tensor], max_2dsize: Optional[torch.Tensor], cfg: _lib.RefineConfig,
-                  generator: Optional[torch.Generator] = None) -> Plan:
-    """``sgn_refine_decide`` + prefix sums + the one host read-back + the split samples.  The samples are drawn
-    as the reference draws them -- ``torch.randn((samps * n_splits, 3), device=...)`` (:680) -- so equal seeds give
-    equal draws (data-parallel replicas seed identically and take identical decisions)."""
+def decide_submodel(scales: torch.Tensor, opacities: torch.Tensor, xys_grad_norm: Optional[torch.Tensor],
+                    vis_counts: Optional[torch.Tensor], max_2dsize: Optional[torch.Tensor], cfg: _lib.RefineConfig):
+    """``sgn_refine_decide`` + the prefix sums of its four mark rows; nothing is read back.  Returns (flags, scan)."""
     L = _backend()
     n = int(scales.shape[0])
     dev = scales.device
@@ -143,12 +140,34 @@ def plan_submodel(scales: torch.Tensor, opacities: torch.Tensor, xys_grad_norm: 
     marks = torch.empty((4, n), dtype=torch.int32, device=dev)
     _lib.check(L.sgn_refine_decide(n, C.byref(cfg), _p(scales), _p(opacities), _p(xys_grad_norm), _p(vis_counts), _p(max_2dsize),
                                    _p(flags), _p(marks), _stream(scales)), "sgn_refine_decide")
-    scan = torch.cumsum(marks, dim=1, dtype=torch.int32)
-    totals = [int(x) for x in scan[:, -1].tolist()] if n else [0, 0, 0, 0]
+    return flags, torch.cumsum(marks, dim=1, dtype=torch.int32)
+
+
+def read_totals(scans: Sequence[torch.Tensor]) -> List[List[int]]:
+    """The four totals (survivors, surviving split rows, surviving duplicates, split rows) of every scan: ONE read-back
+    for any number of sub-models (the reference syncs eight times per sub-model)."""
+    live = [s for s in scans if s.shape[1] > 0]
+    vals = torch.stack([s[:, -1] for s in live]).tolist() if live else []
+    it = iter(vals)
+    return [[int(x) for x in next(it)] if s.shape[1] > 0 else [0, 0, 0, 0] for s in scans]
+
+
+def finish_plan(flags: torch.Tensor, scan: torch.Tensor, totals: List[int], cfg: _lib.RefineConfig,
+                generator: Optional[torch.Generator] = None) -> Plan:
+    """Draws the split samples as the reference draws them -- ``torch.randn((samps * n_splits, 3), device=...)`` (:680) --
+    so equal seeds give equal draws (data-parallel replicas seed identically and take identical decisions)."""
     samples = None
     if cfg.densify:
-        samples = torch.randn((cfg.n_split_samples * totals[3], 3), device=dev, generator=generator)
-    return Plan(n, cfg, flags, scan, totals, samples)
+        samples = torch.randn((cfg.n_split_samples * totals[3], 3), device=flags.device, generator=generator)
+    return Plan(int(flags.shape[0]), cfg, flags, scan, totals, samples)
+
+
+def plan_submodel(scales: torch.Tensor, opacities: torch.Tensor, xys_grad_norm: Optional[torch.Tensor],
+                  vis_counts: Optional[torch.Tensor], max_2dsize: Optional[torch.Tensor], cfg: _lib.RefineConfig,
+                  generator: Optional[torch.Generator] = None) -> Plan:
+    """decide -> prefix sums -> the one host read-back -> split samples, for one sub-model."""
+    flags, scan = decide_submodel(scales, opacities, xys_grad_norm, vis_counts, max_2dsize, cfg)
+    return finish_plan(flags, scan, read_totals([scan])[0], cfg, generator)
 
 
 def apply_plan(plan: Plan, src: Sequence[torch.Tensor], dst: Sequence[torch.Tensor],
