@@ -344,6 +344,10 @@ class SceneGraphRasterModel(torch.nn.Module):
             with torch.no_grad():
                 out["background_rgb"] = self._class_rgb(frame, CLS_BACKGROUND, sky)
                 out["object_rgb"] = self._class_rgb(frame, CLS_OBJECT, None)
+                if not any(s.cls == CLS_OBJECT for s in frame.segments):
+                    # without actors the reference's objects-only render returns {'rgb': zeros[H,W,1], 'depth': zeros[H,W,1]}
+                    # (scene graph :264-267), which get_outputs publishes as object_rgb AND object_depth (:371-372)
+                    out["object_depth"] = torch.zeros(H, W, 1, device=self.device)
         return out
 
     def _class_rgb(self, frame: Frame, cls: int, sky):

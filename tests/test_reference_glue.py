@@ -248,3 +248,24 @@ def test_more_scenes_live_against_the_reference_glue(seed, training, with_sky, s
     assert np.abs((1 - fw.obj_T) - out["object_acc"].numpy()[..., 0])[fw.fragile_obj == 0].max() <= 1e-5
     assert np.abs((1 - fw.bg_T) - out["background_acc"].numpy()[..., 0])[fw.fragile_bg == 0].max() <= 1e-5
     np.testing.assert_array_equal(fw.radii, m.radii.numpy())
+
+
+@pytest.mark.skipif(not rl.available(), reason="the reference source is only mounted in the build container")
+def test_scene_without_actors_live_against_the_reference_glue():
+    """No boxes at the timestamp: object_acc is zero, background_acc == accumulation, and in eval the objects-only render
+    degenerates to zeros[H,W,1] published as object_rgb and object_depth (scene graph :264-267, :371-372) -- the keys and
+    shapes SceneGraphRasterModel.get_outputs reproduces."""
+    import reference_glue as rg
+    import street_gaussians_ns_b200.synthetic as syn
+    fr = syn.make_frame(n_background=1500, n_actors=0, width=64, height=48, seed=41)
+    m, cam = rg.build_reference_model(fr, training=False)
+    with torch.no_grad():
+        out = m.get_outputs(cam)
+    assert sorted(out) == ["accumulation", "background_acc", "background_rgb", "depth", "object_acc", "object_depth", "object_rgb", "rgb"]
+    assert tuple(out["object_rgb"].shape) == tuple(out["object_depth"].shape) == (48, 64, 1)
+    assert float(out["object_rgb"].abs().max()) == 0.0 and float(out["object_acc"].abs().max()) == 0.0
+    assert torch.equal(out["background_acc"], out["accumulation"])
+    fw = oracle_c.Oracle(fr).forward()
+    rgb, _, _ = oracle_c.post_ops(torch.from_numpy(fw.img), torch.from_numpy(1 - fw.final_T), None, False)
+    assert np.abs(rgb.numpy() - out["rgb"].numpy())[fw.fragile == 0].max() <= 1e-5
+    assert np.abs(rgb.numpy() - out["background_rgb"].numpy())[fw.fragile == 0].max() <= 1e-5
