@@ -192,6 +192,19 @@ int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, 
                  const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* order, const int32_t* cum,
                  int32_t* sorted_ids /*[M]*/, int32_t* tile_bins /*[tiles,2]*/, void* scratch, size_t scratch_bytes,
                  void* stream);
+/* EXPERIMENTAL alternative to steps 1 + 2 (csrc/binning_local.cu; same lists, same order, same payload): tile histogram +
+ * unordered scatter + a shared-memory sort inside every tile instead of the two device-wide radix sorts.
+ *   sgn_bin_local_count: tile_count[tiles], tile_start[tiles] (exclusive scan), info_dev = {M, longest list} (int64[2]);
+ *   the caller reads info_dev, and when the longest list exceeds sgn_bin_local_cap() uses steps 1 + 2 for this frame;
+ *   sgn_bin_local_sort: sorted_ids[M], tile_bins[tiles,2].  Scratch: sgn_bin_local_scratch_bytes(M, tiles) (M = 0 for count). */
+int sgn_bin_local_cap(void);
+size_t sgn_bin_local_scratch_bytes(int64_t M, int tiles);
+int sgn_bin_local_count(int N, const sgn_camera* cam, const float* records, const int32_t* radii, const uint16_t* tile_bbox,
+                        const uint32_t* touch_mask, int32_t* tile_count, int32_t* tile_start, int64_t* info_dev, void* scratch,
+                        size_t scratch_bytes, void* stream);
+int sgn_bin_local_sort(int N, int64_t M, int longest_list, const sgn_camera* cam, const float* records, const int32_t* radii,
+                       const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* tile_count, const int32_t* tile_start,
+                       int32_t* sorted_ids, int32_t* tile_bins, void* scratch, size_t scratch_bytes, void* stream);
 /* sorted_ids payload: bits 0-30 = Gaussian row (concatenated index space), bit 31 = object class.
  * step 3 (only for the class renders): per-tile class sub-lists, a stable partition of every tile's
  * list into background entries (class 0) and object entries (class 1) -- what the reference's

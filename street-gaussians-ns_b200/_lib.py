@@ -128,6 +128,7 @@ EXPORTS = [
     "sgn_blend_fwd", "sgn_blend_bwd", "sgn_sizeof_adam_tensor", "sgn_adam_chunk_elems", "sgn_adam_step",
     "sgn_loss_scratch_bytes", "sgn_loss_fwd", "sgn_loss_bwd", "sgn_sizeof_densify_segment", "sgn_densify_stats",
     "sgn_sizeof_refine_config", "sgn_sizeof_refine_tensors", "sgn_refine_decide", "sgn_refine_apply",
+    "sgn_bin_local_cap", "sgn_bin_local_scratch_bytes", "sgn_bin_local_count", "sgn_bin_local_sort",
 ]
 
 
@@ -165,6 +166,13 @@ def load():
     L.sgn_bin_sort_scratch_bytes.argtypes = [i64]
     L.sgn_bin_sort_scratch_bytes.restype = sz
     L.sgn_bin_sort.argtypes = [i32, i64, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_local_cap.restype = C.c_int
+    L.sgn_bin_local_scratch_bytes.argtypes = [i64, i32]
+    L.sgn_bin_local_scratch_bytes.restype = sz
+    L.sgn_bin_local_count.argtypes = [i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_local_count.restype = C.c_int
+    L.sgn_bin_local_sort.argtypes = [i32, i64, i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_local_sort.restype = C.c_int
     L.sgn_bin_class_scratch_bytes.argtypes = [i32]
     L.sgn_bin_class_scratch_bytes.restype = sz
     L.sgn_bin_class_lists.argtypes = [C.POINTER(CameraStruct), i64, vp, vp, vp, vp, vp, sz, vp]

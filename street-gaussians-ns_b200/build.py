@@ -19,6 +19,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-
 SOURCES = {
     "project.cu": ["--fmad=false"],
     "binning.cu": [],
+    "binning_local.cu": [],
     "blend.cu": ["--use_fast_math"],
     "loss.cu": [],
     "densify.cu": ["--fmad=false"],

@@ -208,12 +208,48 @@ def project_fwd(table: SegmentTable, cs: _lib.CameraStruct, device) -> Projected
     return Projected(records, ints[0][:N], ints[1][:N], bbox, ints[2][:N], ints[3][:N])
 
 
+BIN_LOCAL = os.environ.get("SGN_BIN_LOCAL", "0") == "1"  # experimental: per-tile shared-memory sort (csrc/binning_local.cu)
+
+
+def _bin_local(cs: _lib.CameraStruct, records, radii, proj: Projected):
+    """The experimental binning variant: tile histogram + scatter + a sort inside every tile.  Same outputs as the
+    device-wide path; returns None when a tile's list is too long for the shared-memory sort (the caller falls back)."""
+    L = _lib.load()
+    device = records.device
+    N = records.shape[0]
+    bw = cs.block_width
+    tiles = ((cs.width + bw - 1) // bw) * ((cs.height + bw - 1) // bw)
+    counts = torch.empty(2, tiles, device=device, dtype=torch.int32)  # per tile: entries, start
+    info = torch.empty(2, device=device, dtype=torch.int64)           # M, longest list
+    sb = L.sgn_bin_local_scratch_bytes(0, tiles)
+    scratch = torch.empty(sb, device=device, dtype=torch.uint8)
+    with _timed("bin_scan"):
+        _lib.check(L.sgn_bin_local_count(N, C.byref(cs), _ptr(records), _ptr(radii), _ptr(proj.bbox), _ptr(proj.touch_mask),
+                                         _ptr(counts[0]), _ptr(counts[1]), _ptr(info), _ptr(scratch), sb, _stream()), "sgn_bin_local_count")
+    M, longest = (int(x) for x in info.tolist())
+    if longest > L.sgn_bin_local_cap():
+        return None
+    tile_bins = torch.empty(tiles, 2, device=device, dtype=torch.int32)
+    sorted_ids = torch.empty(max(M, 1), device=device, dtype=torch.int32)
+    sb2 = L.sgn_bin_local_scratch_bytes(M, tiles)
+    scratch2 = torch.empty(sb2, device=device, dtype=torch.uint8)
+    with _timed("bin_sort"):
+        _lib.check(L.sgn_bin_local_sort(N, M, longest, C.byref(cs), _ptr(records), _ptr(radii), _ptr(proj.bbox), _ptr(proj.touch_mask),
+                                        _ptr(counts[0]), _ptr(counts[1]), _ptr(sorted_ids), _ptr(tile_bins), _ptr(scratch2), sb2,
+                                        _stream()), "sgn_bin_local_sort")
+    return M, sorted_ids, tile_bins
+
+
 def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit=None, bbox=None, proj: Optional[Projected] = None):
     """Returns (M, sorted_ids[M], tile_bins[tiles,2]).  One host sync to read M (as gsplat does).
     Pass ``proj`` (from project_fwd) or plain records/radii/bbox (the touched-tile count is then computed here)."""
     L = _lib.load()
     device = records.device
     N = records.shape[0]
+    if BIN_LOCAL and proj is not None:
+        res = _bin_local(cs, records, radii, proj)
+        if res is not None:
+            return res
     if proj is not None:
         bbox, touched, mask = proj.bbox, proj.tiles_touched, proj.touch_mask
     else:
