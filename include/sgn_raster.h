@@ -204,7 +204,9 @@ int sgn_bin_local_count(int N, const sgn_camera* cam, const float* records, cons
                         size_t scratch_bytes, void* stream);
 int sgn_bin_local_sort(int N, int64_t M, int longest_list, const sgn_camera* cam, const float* records, const int32_t* radii,
                        const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* tile_count, const int32_t* tile_start,
-                       int32_t* sorted_ids, int32_t* tile_bins, void* scratch, size_t scratch_bytes, void* stream);
+                       int32_t* sorted_ids, int32_t* tile_bins, int32_t* cls_ids /*[2,M] or NULL*/,
+                       int32_t* cls_bins /*[2,tiles,2] or NULL: the class sub-lists of step 3, built in the same pass*/,
+                       void* scratch, size_t scratch_bytes, void* stream);
 /* sorted_ids payload: bits 0-30 = Gaussian row (concatenated index space), bit 31 = object class.
  * step 3 (only for the class renders): per-tile class sub-lists, a stable partition of every tile's
  * list into background entries (class 0) and object entries (class 1) -- what the reference's

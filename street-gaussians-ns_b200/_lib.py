@@ -171,7 +171,7 @@ def load():
     L.sgn_bin_local_scratch_bytes.restype = sz
     L.sgn_bin_local_count.argtypes = [i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.sgn_bin_local_count.restype = C.c_int
-    L.sgn_bin_local_sort.argtypes = [i32, i64, i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_local_sort.argtypes = [i32, i64, i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.sgn_bin_local_sort.restype = C.c_int
     L.sgn_bin_class_scratch_bytes.argtypes = [i32]
     L.sgn_bin_class_scratch_bytes.restype = sz

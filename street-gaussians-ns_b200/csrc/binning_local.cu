@@ -16,7 +16,8 @@
 //   local_hist_kernel     per Gaussian (mask replay / warp-cooperative for big AABBs): atomicAdd on its tiles' counters
 //   CUB ExclusiveSum      9600 tile counts -> tile starts;  tile_info_kernel: total M and the longest list
 //   local_scatter_kernel  same traversal: key = depth_bits << 32 | row << 1 | class at start[tile] + atomicAdd(cursor[tile])
-//   local_sort_kernel     CTA per tile: bitonic sort of the 64-bit keys in shared memory, writes payloads + bin edges
+//   local_sort_kernel     CTA per tile: bitonic sort of the 64-bit keys in shared memory, writes payloads + bin edges and,
+//                         while the list is still in shared memory, its background / object class sub-lists
 //
 // Lists longer than sgn_bin_local_cap() do not fit the shared-memory sort: the caller reads the longest list together
 // with M (the one read-back the path has anyway) and uses the device-wide path for such a frame.
@@ -136,13 +137,17 @@ local_scatter_kernel(int N, int tiles_x, int width, int height, int bw, const fl
 // CTA per tile; tiles whose padded length is outside (LO, HI] leave immediately (two launches cover the two size classes)
 template <int HI, int LO, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-local_sort_kernel(int tiles, const int32_t* __restrict__ tile_count, const int32_t* __restrict__ tile_start,
-                  const unsigned long long* __restrict__ keys, int32_t* __restrict__ sorted_ids, int2* __restrict__ tile_bins) {
+local_sort_kernel(int tiles, long long M, const int32_t* __restrict__ tile_count, const int32_t* __restrict__ tile_start,
+                  const unsigned long long* __restrict__ keys, int32_t* __restrict__ sorted_ids, int2* __restrict__ tile_bins,
+                  int32_t* __restrict__ cls_ids /*[2,M] or null*/, int2* __restrict__ cls_bins /*[2,tiles] or null*/) {
     extern __shared__ unsigned long long s_keys[];
     const int tile = blockIdx.x;
     const int n = tile_count[tile];
     if (n <= LO || n > HI) {
-        if (LO == 0 && n == 0 && threadIdx.x == 0) tile_bins[tile] = make_int2(0, 0);  // as the device-wide path leaves empty tiles
+        if (LO == 0 && n == 0 && threadIdx.x == 0) {
+            tile_bins[tile] = make_int2(0, 0);  // as the device-wide path leaves empty tiles
+            if (cls_bins) { cls_bins[tile] = make_int2(0, 0); cls_bins[tiles + tile] = make_int2(0, 0); }
+        }
         return;
     }
     const int start = tile_start[tile];
@@ -167,6 +172,33 @@ local_sort_kernel(int tiles, const int32_t* __restrict__ tile_count, const int32
         sorted_ids[(size_t)start + i] = (int32_t)((low >> 1) | ((low & 1u) << 31));
     }
     if (threadIdx.x == 0) tile_bins[tile] = make_int2(start, start + n);
+    if (cls_ids == nullptr) return;
+    // Per-tile class sub-lists (what sgn_bin_class_lists builds with a count, a device-wide scan and a compaction): the stable
+    // partition of the sorted list into background (class 0) and object (class 1) entries.  Each class array has room for M
+    // entries, so a tile's sub-lists simply live at the tile's own offset in their array -- no global offsets needed.
+    typedef cub::BlockScan<int, THREADS> BS;
+    __shared__ typename BS::TempStorage scan_tmp;
+    int run0 = 0, run1 = 0;
+    for (int k0 = 0; k0 < n; k0 += THREADS) {
+        const int k = k0 + threadIdx.x;
+        const bool in = k < n;
+        const unsigned low = in ? (unsigned)s_keys[k] : 0u;
+        const int flag = (in && (low & 1u)) ? 1 : 0;
+        int pos, total;
+        BS(scan_tmp).ExclusiveSum(flag, pos, total);
+        if (in) {
+            const int32_t payload = (int32_t)((low >> 1) | ((low & 1u) << 31));
+            if (flag) cls_ids[(size_t)M + start + run1 + pos] = payload;
+            else cls_ids[(size_t)start + run0 + ((int)threadIdx.x - pos)] = payload;
+        }
+        run1 += total;
+        run0 += min(THREADS, n - k0) - total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cls_bins[tile] = make_int2(start, start + run0);
+        cls_bins[tiles + tile] = make_int2(start, start + run1);
+    }
 }
 
 struct LocalLayout {
@@ -226,8 +258,8 @@ extern "C" int sgn_bin_local_count(int N, const sgn_camera* cam, const float* re
 
 extern "C" int sgn_bin_local_sort(int N, int64_t M, int longest_list, const sgn_camera* cam, const float* records, const int32_t* radii,
                                   const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* tile_count,
-                                  const int32_t* tile_start, int32_t* sorted_ids, int32_t* tile_bins, void* scratch,
-                                  size_t scratch_bytes, void* stream_) {
+                                  const int32_t* tile_start, int32_t* sorted_ids, int32_t* tile_bins, int32_t* cls_ids,
+                                  int32_t* cls_bins, void* scratch, size_t scratch_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SGN_REQUIRE(cam && records && radii && tile_bbox && touch_mask && tile_count && tile_start && tile_bins && scratch,
                 "sgn_bin_local_sort: null pointer");
@@ -242,8 +274,10 @@ extern "C" int sgn_bin_local_sort(int N, int64_t M, int longest_list, const sgn_
         sgn_set_error("sgn_bin_local_sort: scratch too small (%zu < %zu)", scratch_bytes, L.total);
         return SGN_ERR_WORKSPACE;
     }
+    SGN_REQUIRE((cls_ids == nullptr) == (cls_bins == nullptr), "sgn_bin_local_sort: cls_ids and cls_bins go together");
     if (M == 0 || N == 0) {
         SGN_CHECK_CUDA(cudaMemsetAsync(tile_bins, 0, sizeof(int32_t) * 2 * (size_t)tiles, stream));
+        if (cls_bins) SGN_CHECK_CUDA(cudaMemsetAsync(cls_bins, 0, sizeof(int32_t) * 4 * (size_t)tiles, stream));
         return SGN_OK;
     }
     SGN_REQUIRE(sorted_ids, "sgn_bin_local_sort: sorted_ids is null");
@@ -256,14 +290,16 @@ extern "C" int sgn_bin_local_sort(int N, int64_t M, int longest_list, const sgn_
                                                              reinterpret_cast<const ushort4*>(tile_bbox), touch_mask, tile_start, cursor,
                                                              (long long)M, keys);
     SGN_CHECK_LAUNCH("local_scatter_kernel");
-    local_sort_kernel<LOCAL_SMALL, 0, 256><<<tiles, 256, LOCAL_SMALL * 8, stream>>>(tiles, tile_count, tile_start, keys, sorted_ids,
-                                                                                    reinterpret_cast<int2*>(tile_bins));
+    local_sort_kernel<LOCAL_SMALL, 0, 256><<<tiles, 256, LOCAL_SMALL * 8, stream>>>(tiles, (long long)M, tile_count, tile_start, keys,
+                                                                                    sorted_ids, reinterpret_cast<int2*>(tile_bins), cls_ids,
+                                                                                    reinterpret_cast<int2*>(cls_bins));
     SGN_CHECK_LAUNCH("local_sort_kernel<small>");
     // > 48 KB of dynamic shared memory needs the opt-in (per device; the call is a few hundred nanoseconds)
     SGN_CHECK_CUDA(cudaFuncSetAttribute(local_sort_kernel<LOCAL_CAP, LOCAL_SMALL, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         LOCAL_CAP * 8));
-    local_sort_kernel<LOCAL_CAP, LOCAL_SMALL, 1024><<<tiles, 1024, LOCAL_CAP * 8, stream>>>(tiles, tile_count, tile_start, keys, sorted_ids,
-                                                                                          reinterpret_cast<int2*>(tile_bins));
+    local_sort_kernel<LOCAL_CAP, LOCAL_SMALL, 1024><<<tiles, 1024, LOCAL_CAP * 8, stream>>>(tiles, (long long)M, tile_count, tile_start,
+                                                                                          keys, sorted_ids, reinterpret_cast<int2*>(tile_bins),
+                                                                                          cls_ids, reinterpret_cast<int2*>(cls_bins));
     SGN_CHECK_LAUNCH("local_sort_kernel<large>");
     return SGN_OK;
 }

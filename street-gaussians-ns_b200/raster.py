@@ -231,13 +231,20 @@ def _bin_local(cs: _lib.CameraStruct, records, radii, proj: Projected):
         return None
     tile_bins = torch.empty(tiles, 2, device=device, dtype=torch.int32)
     sorted_ids = torch.empty(max(M, 1), device=device, dtype=torch.int32)
+    cls_ids = torch.empty(2, max(M, 1), device=device, dtype=torch.int32)   # the class sub-lists come out of the same pass
+    cls_bins = torch.empty(2, tiles, 2, device=device, dtype=torch.int32)
     sb2 = L.sgn_bin_local_scratch_bytes(M, tiles)
     scratch2 = torch.empty(sb2, device=device, dtype=torch.uint8)
     with _timed("bin_sort"):
         _lib.check(L.sgn_bin_local_sort(N, M, longest, C.byref(cs), _ptr(records), _ptr(radii), _ptr(proj.bbox), _ptr(proj.touch_mask),
-                                        _ptr(counts[0]), _ptr(counts[1]), _ptr(sorted_ids), _ptr(tile_bins), _ptr(scratch2), sb2,
-                                        _stream()), "sgn_bin_local_sort")
+                                        _ptr(counts[0]), _ptr(counts[1]), _ptr(sorted_ids), _ptr(tile_bins), _ptr(cls_ids), _ptr(cls_bins),
+                                        _ptr(scratch2), sb2, _stream()), "sgn_bin_local_sort")
+    global _LOCAL_CLASSES
+    _LOCAL_CLASSES = (sorted_ids, cls_ids, cls_bins)
     return M, sorted_ids, tile_bins
+
+
+_LOCAL_CLASSES = None  # (sorted_ids, cls_ids, cls_bins) of the last _bin_local call: class_lists() hands them out instead of recomputing
 
 
 def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit=None, bbox=None, proj: Optional[Projected] = None):
@@ -284,6 +291,11 @@ ID_MASK = 0x7FFFFFFF  # sorted payload: bits 0-30 Gaussian row, bit 31 object cl
 def class_lists(cs: _lib.CameraStruct, M: int, sorted_ids, tile_bins):
     """Per-tile class sub-lists (stable partition of the sorted list into background / object entries).
     Returns (cls_ids[2,M], cls_bins[2,tiles,2])."""
+    global _LOCAL_CLASSES
+    if _LOCAL_CLASSES is not None and _LOCAL_CLASSES[0] is sorted_ids:  # built together with the lists (experimental local binning)
+        _, cls_ids, cls_bins = _LOCAL_CLASSES
+        _LOCAL_CLASSES = None
+        return cls_ids, cls_bins
     L = _lib.load()
     device = sorted_ids.device
     tiles = tile_bins.shape[0]

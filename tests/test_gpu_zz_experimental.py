@@ -26,9 +26,31 @@ def _both(fr, monkeypatch):
     table = raster.SegmentTable(frc, [seg.params.tensors() for seg in frc.segments], dev)
     proj = raster.project_fwd(table, cs, dev)
     M, ids, bins = raster.bin_and_sort(cs, proj.records, proj.radii, proj=proj)
+    legacy_cls = raster.class_lists(cs, M, ids, bins)
     res = raster._bin_local(cs, proj.records, proj.radii, proj)
+    local_cls = None
+    if res is not None:
+        local_cls = raster.class_lists(cs, res[0], res[1], res[2])  # handed out by the local path (built in its sort pass)
+        assert raster._LOCAL_CLASSES is None
     torch.cuda.synchronize()
+    _check_class_lists(M, legacy_cls, local_cls)
     return M, ids, bins, res
+
+
+def _check_class_lists(M, legacy, local):
+    """Same per-tile sub-list of every class (the offsets inside the class arrays may differ between the two paths)."""
+    if local is None:
+        return
+    (ids_a, bins_a), (ids_b, bins_b) = legacy, local
+    ids_a, bins_a, ids_b, bins_b = (t.cpu().numpy() for t in (ids_a, bins_a, ids_b, bins_b))
+    assert np.array_equal(bins_a[..., 1] - bins_a[..., 0], bins_b[..., 1] - bins_b[..., 0])
+    tiles = bins_a.shape[1]
+    step = max(1, tiles // 400)  # a strided sample of tiles keeps the python loop short at full size
+    for c in range(2):
+        for t in range(0, tiles, step):
+            a = ids_a[c, bins_a[c, t, 0]:bins_a[c, t, 1]]
+            b = ids_b[c, bins_b[c, t, 0]:bins_b[c, t, 1]]
+            assert np.array_equal(a, b), (c, t)
 
 
 @pytest.mark.parametrize("scene_name", list(SCENES))
