@@ -12,6 +12,7 @@ SGN_TEST_EXPERIMENTAL=1 T 240 python -m pytest tests/test_gpu_zz_experimental.py
 T 240 python bench.py --steps 50 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err
 T 120 python tools/stage_timing.py --cfg 3 --iters 20 > gpurun_out/stage_timing.log 2>&1
 SGN_BIN_LOCAL=1 T 120 python tools/stage_timing.py --cfg 3 --iters 20 > gpurun_out/stage_timing_bin_local.log 2>&1
+SGN_BIN_LOCAL=1 T 240 python bench.py --steps 50 --warmup 10 --no-cpu-baseline > gpurun_out/bench_bin_local.json 2> gpurun_out/bench_bin_local.err
 T 180 python tools/train_cfg4.py --steps 30 --warmup 5 --refine-every 10 --start-step 600 > gpurun_out/train_cfg4.json 2> gpurun_out/train_cfg4.err
 T 180 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_step.csv \
     python tools/ncu_step.py > /dev/null 2>&1
