@@ -379,6 +379,10 @@ def run_ours(args):
         A = sum(s.params.num_points for s in frc.segments if s.cls == CLS_OBJECT)
         M = holder.M
         n_vis = int((holder.radii > 0).sum().item())
+        try:  # longest per-tile list (SURVEY.md 8d asks the harness to print it next to N, N_vis, M)
+            max_per_tile = int((holder.tile_bins[:, 1] - holder.tile_bins[:, 0]).max().item())
+        except Exception:
+            max_per_tile = None
         P = H * W
         S = 3 if settings.class_streams else 1
         alg = algorithmic_bytes(N, A, M, P, n_vis, S)
@@ -449,7 +453,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_config(args.cfg), "N_gaussians": N, "N_actor_gaussians": A,
-                       "M_intersections": M, "N_visible": n_vis, "parallelism": f"camera-sharded dp{world}",
+                       "M_intersections": M, "N_visible": n_vis, "max_per_tile": max_per_tile, "parallelism": f"camera-sharded dp{world}",
                        "l2": "inputs larger than L2 (330 MB of parameters + 0.4 GB of intersection lists per step vs 126 MB)",
                        "collective": "all-reduce(SUM) of the flat gradient arena inside the step" if world > 1 else "none"},
             "clocks": clocks,
