@@ -88,6 +88,20 @@ float sgn_expf_spec(float x) {
     return ldexpf(p, (int)n);
 }
 
+/* Sensitivity switch (tools/exp_sensitivity.py; never used by the parity tests): which exp() the exact section uses.
+ * 0 = sgn_expf_spec (the contract), 1 = libm expf (glibc, < 1 ulp), 2 / 3 = the spec value moved one ulp up / down.
+ * The reference calls torch.exp (sgn_splatfacto.py:857), whose CUDA kernel is within 2 ulp of the true value: modes 1-3
+ * bracket how many integer decisions (radius, tile AABB) could differ from the reference for that reason alone. */
+static int g_exp_mode = 0;
+void sgn_oracle_set_exp_mode(int mode) { g_exp_mode = mode; }
+static inline float oracle_exp(float x) {
+    if (g_exp_mode == 1) return expf(x);
+    const float v = sgn_expf_spec(x);
+    if (g_exp_mode == 2) return nextafterf(v, INFINITY);
+    if (g_exp_mode == 3) return nextafterf(v, 0.f);
+    return v;
+}
+
 static inline int f2i_sat(float x) {
     if (x != x) return 0;
     if (x >= 1.0e9f) return 1000000000;
@@ -157,7 +171,7 @@ static int project_one(const oracle_segment* sg, int i, const oracle_camera* cam
         for (int k = 0; k < 4; ++k) st->qn[k] = st->qr[k] / st->qnorm;
     }
     /* exp(scales) (sgn_splatfacto.py:857) */
-    for (int k = 0; k < 3; ++k) st->s[k] = sgn_expf_spec(ls[k]);
+    for (int k = 0; k < 3; ++k) st->s[k] = oracle_exp(ls[k]);
     {
         const float w = st->qn[0], x = st->qn[1], y = st->qn[2], z = st->qn[3];
         float* R = st->Rg;

@@ -53,7 +53,6 @@ class SceneGraphConfig:
     ssim_lambda: float = 0.2
     sky_acc_loss_mult: float = 1.0
     object_acc_entropy_loss_mult: float = 0.001
-    stop_split_at: int = 25000
     alpha_clamp_fwd: float = 0.999
     alpha_clamp_bwd: float = 0.99
     render_background_acc: bool = True
@@ -66,6 +65,16 @@ class SceneGraphConfig:
     # data parallel: gradients are delivered in an arena that has the layout of ALL sub-models (the
     # optimizer's), so that replicas which see different actors can sum their arenas with one all-reduce
     full_gradient_arena: bool = False
+
+    # ``stop_split_at`` of the BACKGROUND sub-model: what the reference's entropy gate reads
+    # (``config.background_model.stop_split_at``, scene graph :386).  One source: ``refine.stop_split_at``.
+    @property
+    def stop_split_at(self) -> int:
+        return self.refine.stop_split_at
+
+    @stop_split_at.setter
+    def stop_split_at(self, v: int) -> None:
+        self.refine.stop_split_at = int(v)
 
 
 class GaussianSubModel(torch.nn.Module):
@@ -358,6 +367,9 @@ class SceneGraphRasterModel(torch.nn.Module):
         sub, _ = raster.render_frame(Frame(frame.camera, segs), self._settings(class_streams=False), sky=sky)
         return sub["rgb"]
 
+    def _refine_settings_of(self, sub) -> RefineSettings:
+        return self.config.refine if sub is self.all_models._modules["background"] else self.config.object_refine
+
     def _publish_side_effects(self, frame: Frame, holder) -> None:
         # plain tensors, not parameters/buffers: write the instance dicts directly (nn.Module.__setattr__ costs
         # ~5 us per attribute, x6 attributes x33 sub-models per frame)
@@ -390,12 +402,14 @@ class SceneGraphRasterModel(torch.nn.Module):
         running ||xys.grad|| sums, visibility counts and the max screen-space radius ratio, per sub-model."""
         assert step == self.step
         h = self._holder
-        if h is None or h.v_records is None or self.step >= self.config.stop_split_at:
+        if h is None or h.v_records is None:
             return
         import ctypes as C
         from . import _lib
         L = _lib.load()
-        slices = self.__dict__.get("_slices") or []
+        # every sub-model's callback reads ITS OWN config.stop_split_at (sgn_splatfacto.py:516-518)
+        slices = [(sub, sl) for sub, sl in (self.__dict__.get("_slices") or [])
+                  if self.step < self._refine_settings_of(sub).stop_split_at]
         if not slices:
             return
         tab = (_lib.DensifySegment * len(slices))()
@@ -415,7 +429,8 @@ class SceneGraphRasterModel(torch.nn.Module):
                                        raster._ptr(h.radii), H, W, raster._stream()), "sgn_densify_stats")
 
     # ------------------------------------------------------------------------------------------
-    def refinement_after(self, optimizers, step: int, generator: Optional[torch.Generator] = None, sync_stats: bool = True) -> None:
+    def refinement_after(self, optimizers, step: int, generator: Optional[torch.Generator] = None, sync_stats: bool = True,
+                         due_only: bool = False) -> None:
         """The ``refinement_after`` callbacks of all sub-models (sgn_splatfacto.py:550-646; the scene graph registers one
         per sub-model, :127-137): split / duplicate / cull / opacity reset, with the optimizer state carried along
         (dup_in_optim / remove_from_optim, :459-511).  ``optimizers`` is a ``FusedAdam`` built over
@@ -424,7 +439,11 @@ class SceneGraphRasterModel(torch.nn.Module):
 
         Two phases so that nothing is copied twice and the host waits once: decide every sub-model (all launches first,
         then ONE read-back of all the counts), then lay out the new tensors / moment arenas and let ``sgn_refine_apply``
-        write each sub-model's rows into them."""
+        write each sub-model's rows into them.
+
+        ``due_only``: nerfstudio runs each sub-model's callback every ITS OWN ``refine_every`` steps
+        (``update_every_num_iters=self.config.refine_every``, sgn_splatfacto.py:773-781); with ``due_only`` a sub-model
+        whose ``refine_every`` does not divide ``step`` is left alone (callers that run on a global cadence pass False)."""
         assert step == self.step
         names = list(self.all_models._modules)
         subs = [self.all_models[n] for n in names]
@@ -436,6 +455,10 @@ class SceneGraphRasterModel(torch.nn.Module):
         for name, sub in zip(names, subs):
             st = self.config.refine if name == "background" else self.config.object_refine
             densify, cull_only, reset = refine.phase(st, step, self.config.num_train_data)
+            if due_only and (st.refine_every <= 0 or step % st.refine_every != 0):
+                decided.append(None)
+                resets.append(None)
+                continue
             sub.__dict__["refine_record_dict"] = {}
             if step <= st.warmup_length or sub.xys_grad_norm is None:  # :552-555
                 decided.append(None)
@@ -535,7 +558,7 @@ class SceneGraphRasterModel(torch.nn.Module):
         uint8 one the data loader holds (converted as the reference does: ``.float() / 255``)."""
         c = self.config
         want_sky = "semantic" in batch and c.sky_acc_loss_mult > 0
-        want_ent = c.object_acc_entropy_loss_mult > 0.0 and self.step > c.stop_split_at
+        want_ent = c.object_acc_entropy_loss_mult > 0.0 and self.step > c.refine.stop_split_at  # background_model.stop_split_at (:386)
         fused = c.fused_loss and outputs["rgb"].is_cuda
         losses = {}
 
@@ -564,6 +587,10 @@ class SceneGraphRasterModel(torch.nn.Module):
             gt_img, rgb = float_pair()
             simloss = 1 - ssim(gt_img.permute(2, 0, 1)[None, ...], rgb.permute(2, 0, 1)[None, ...])
             losses["simloss"] = c.ssim_lambda * simloss
+        else:
+            # the reference always emits the key (sgn_splatfacto.py:1085-1087); with ssim_lambda == 0 its value is 0 * simloss:
+            # an exact zero that contributes no gradient, so the SSIM convolutions are not run for it
+            losses["simloss"] = torch.zeros((), device=outputs["rgb"].device)
         if want_sky:
             if fused:
                 losses["sky_accumulation"] = sky

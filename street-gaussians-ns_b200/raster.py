@@ -483,6 +483,8 @@ class _SceneGraphRasterize(torch.autograd.Function):
         ctx.frame, ctx.settings, ctx.holder = frame, settings, holder
         ctx.cs, ctx.bo, ctx.table, ctx.params = cs, bo, table, params
         ctx.saved = dict(raw=out["raw"], final_T=out["final_T"], final_idx=out["final_idx"], tile_depth=out["tile_depth"])
+        if "sched" in out:  # the heavy-first work lists' scratch: the backward rebuilds its schedule in it
+            ctx.saved["sched"] = out["sched"]
         ctx.records, ctx.radii, ctx.sorted_ids, ctx.tile_bins, ctx.sky = records, radii, sorted_ids, tile_bins, sky
         ctx.obj_ids, ctx.obj_bins = obj_ids, obj_bins
         ctx.sky_needs_grad = sky is not None and sky.requires_grad

@@ -135,3 +135,37 @@ def cotangents(height: int, width: int, seed: int = 7):
     w = torch.rand(height, width, 3, generator=g)
     v = torch.rand(height, width, generator=g)
     return w, v
+
+
+class WaymoScene:
+    """BASELINE.json configs 4 / 5: Waymo-shape synthetic -- 5 cameras x ``num_frames`` frames, 1.68 M background + 32 x
+    10 k actor Gaussians (2 M).  Actors are boxes parked on the road grid of SURVEY.md 8d; an actor has a box in a frame
+    only while the ego vehicle is within ``actor_range`` metres of it, so the sub-models in view change per frame
+    (as the reference's per-timestamp annotations do, data/utils/dynamic_annotation.py:252-286)."""
+
+    def __init__(self, scale: float = 1.0, num_frames: int = 85, actor_range: float = 45.0, n_actors: int = 32):
+        self.num_frames, self.actor_range = num_frames, actor_range
+        self.n_bg = int(1_680_000 * scale)
+        self.n_act = max(1, int(10_000 * scale))
+        self.width = max(64, int(1920 * scale) // 16 * 16)
+        self.height = max(48, int(1280 * scale) // 16 * 16)
+        self.background = make_background(self.n_bg, seed=0, box=((-40.0, 40.0), (-6.0, 14.0), (-135.0, 45.0)))
+        self.actors = {str(a): make_actor(self.n_act, seed=1 + a) for a in range(n_actors)}
+        self.boxes = [actor_pose(a) for a in range(n_actors)]
+        rig = waymo_rig(num_frames)  # index = frame * 5 + camera
+        self.cameras = [make_camera(self.width, self.height, c2w=rig[i], time=float(i // 5)) for i in range(len(rig))]
+
+    def boxes_at(self, frame: int):
+        """[(actor index, rot, center)] of the actors that have a box in ``frame``."""
+        ego_z = -0.5 * frame
+        return [(a, rot, center) for a, (rot, center) in enumerate(self.boxes) if abs(center[2] - ego_z) <= self.actor_range]
+
+    def frame(self, camera_index: int, fourier_dim: int = 5) -> Frame:
+        """The rasterizer-level Frame (CPU tensors) of camera ``camera_index`` (= frame * 5 + rig camera)."""
+        cam = self.cameras[camera_index]
+        f = int(cam.time)
+        segs = [Segment(params=self.background, cls=CLS_BACKGROUND, name="background")]
+        basis = idft_basis(fourier_time(f, list(range(self.num_frames)), 1.0), fourier_dim)
+        for a, rot, center in self.boxes_at(f):
+            segs.append(Segment(params=self.actors[str(a)], cls=CLS_OBJECT, rot=rot, center=center, idft=basis, name=f"object_{a}"))
+        return Frame(camera=cam, segments=segs)

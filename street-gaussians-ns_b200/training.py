@@ -29,12 +29,16 @@ from .scene import Camera
 
 class TrainStep:
     def __init__(self, model: SceneGraphRasterModel, optimizer: FusedAdam, refine_every: Optional[int] = None,
-                 group: Optional[dist.ProcessGroup] = None, pipeline_chunks: int = 0):
+                 group: Optional[dist.ProcessGroup] = None, pipeline_chunks: int = 0, refine_seed: int = 0,
+                 check_replicas: bool = True):
         """``pipeline_chunks`` > 0 (data parallel only): all-reduce and Adam are pipelined over that many ranges of the
         arena (dp.allreduce_and_step) instead of running one after the other."""
         self.model, self.optimizer, self.group = model, optimizer, group
         self.pipeline_chunks = pipeline_chunks
-        self.refine_every = refine_every if refine_every is not None else model.config.refine.refine_every
+        self.refine_seed, self.check_replicas, self._gen = refine_seed, check_replicas, None
+        # None: every sub-model on its own ``refine_every`` (the reference registers one callback per sub-model with
+        # ``update_every_num_iters = config.refine_every``); a number: one cadence for all of them
+        self.refine_every = refine_every
         assert optimizer.num_segments == len(model.all_models), "build FusedAdam over model.optimizer_params()"
 
     def world_size(self) -> int:
@@ -72,8 +76,11 @@ class TrainStep:
             total.backward()
             arena = m._holder.grad_arena
         else:
-            # nothing in view on this replica (the reference's early-out, sgn_splatfacto.py:878-886): no gradient here
+            # nothing in view on this replica (the reference's early-out, sgn_splatfacto.py:878-886): no gradient here.
+            # A single replica skips backward / optimizer / after_train only: the refinement callbacks still run
+            # (nerfstudio fires them on the step count, whatever was rendered)
             if world == 1:
+                self._maybe_refine(step)
                 return losses
             arena = m.zero_gradient_arena()
         if world > 1:
@@ -89,6 +96,31 @@ class TrainStep:
             opt.step(arena, present=None if everything else present, full_layout=full)
         if rendered:
             m.after_train(step)                           # AFTER_TRAIN_ITERATION callbacks, in the reference's order
-        if self.refine_every > 0 and step % self.refine_every == 0:
-            m.refinement_after(opt, step)
+        self._maybe_refine(step)
         return losses
+
+    def _refine_generator(self, step: int) -> torch.Generator:
+        """Split samples must be identical on every replica whatever else consumed the global CUDA generator (a sky
+        map, augmentation, a different number of randn calls per rank): a dedicated generator reseeded from
+        (base seed, step) before each refinement."""
+        if self._gen is None:
+            self._gen = torch.Generator(device=self.model.device)
+        self._gen.manual_seed((self.refine_seed * 1_000_003 + step) & 0x7FFFFFFFFFFFFFFF)
+        return self._gen
+
+    def _maybe_refine(self, step: int) -> None:
+        m = self.model
+        if self.refine_every is not None:
+            due = self.refine_every > 0 and step % self.refine_every == 0
+        else:
+            due = any(st.refine_every > 0 and step % st.refine_every == 0 for st in (m.config.refine, m.config.object_refine))
+        if not due:
+            return
+        m.refinement_after(self.optimizer, step, generator=self._refine_generator(step), due_only=self.refine_every is None)
+        if self.world_size() > 1 and self.check_replicas:
+            # replicas must have taken identical decisions: same row count in every sub-model
+            rows = torch.tensor([sub.num_points for sub in m.all_models.values()], device=m.device, dtype=torch.int64)
+            lo, hi = rows.clone(), rows.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+            assert torch.equal(lo, hi), "replicas diverged in a refinement (row counts differ)"
