@@ -18,6 +18,7 @@ nerfstudio is not a dependency here: ``camera`` is any object with the fields of
 """
 from __future__ import annotations
 
+import itertools
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -232,6 +233,9 @@ class _FullArenaSink(_GradSink):
         return self.arena
 
 
+_MODEL_SERIAL = itertools.count()
+
+
 class SceneGraphRasterModel(torch.nn.Module):
     def __init__(self, background: GaussianSet, actors: Dict[str, GaussianSet], config: Optional[SceneGraphConfig] = None,
                  poses_at: Optional[Callable[[float], List[ActorPose]]] = None,
@@ -250,6 +254,7 @@ class SceneGraphRasterModel(torch.nn.Module):
         self.last_size = None
         self._holder = None
         self._frame_cache: dict = {}
+        self.__dict__["_serial"] = next(_MODEL_SERIAL)  # names this model in raster's static segment-table cache (ids are recycled)
         self._grad_sink = _FullArenaSink() if self.config.full_gradient_arena else _GradSink()
         self._anchor = None
 
@@ -266,47 +271,118 @@ class SceneGraphRasterModel(torch.nn.Module):
             own = {k[len(prefix):]: state_dict.pop(k) for k in list(state_dict) if k.startswith(prefix)}
             if own:
                 sub.load_state_dict(own, **kwargs)
-        self._frame_cache.clear()
+        self.invalidate_frames()
         return torch.nn.Module.load_state_dict(self, state_dict, strict=False)
 
     @property
     def device(self):
         return self.all_models["background"].gauss_params["means"].device
 
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): parameter storage moves, staged pointers are stale
+        out = super()._apply(fn, *args, **kwargs)
+        if "_frame_cache" in self.__dict__:
+            self.invalidate_frames()
+        return out
+
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _pose_digest(poses) -> tuple:
+        """Content key of a timestamp's boxes: an integration may move boxes at a fixed timestamp (the reference's
+        ``bbox_optimizer.apply_to_bbox`` rewrites them every training step) or hand out fresh objects whose ``id`` CPython
+        recycles -- identity says nothing, the bytes do."""
+        return tuple((p.track_id, p.frame, len(p.frame_list), p.frame_list[0], p.frame_list[-1],
+                      np.asarray(p.rot, np.float64).tobytes(), np.asarray(p.center, np.float64).tobytes()) for p in poses)
+
     def _frame(self, camera: Camera) -> Frame:
+        """The Frame of ``camera``.  The segment rows of a timestamp (poses, IDFT bases, parameter pointers, row offsets) are
+        static data while the parameter tensors stay the same objects and the boxes keep their values: they are kept per
+        timestamp -- device-resident when ``prepare_frames`` built them up front -- and validated by content."""
         poses = self.poses_at(camera.time)
-        # box poses are static data per timestamp: reuse the Frame (and its staged segment table) while the
-        # parameter tensors are the same objects (densification replaces them, which invalidates the entry)
-        pid = tuple(map(id, (p for m in self.all_models._modules.values() for p in m.gauss_params._parameters.values())))
-        key = (camera.time, id(camera), pid, tuple(map(id, poses)))
-        hit = self._frame_cache.get(key)
-        if hit is not None:
-            self.visible_model_names = hit[1]
-            return hit[0]
+        digest = self._pose_digest(poses)
+        hit = self._frame_cache.get(camera.time)
+        if hit is not None and hit["digest"] == digest and hit["ptr0"] == self.all_models._modules["background"].gauss_params._parameters["means"].data_ptr():
+            self.visible_model_names = hit["names"]
+            frame = Frame(camera, hit["segments"])
+            frame._prebuilt, frame._table_slot = hit["table"], hit
+            frame._static_key = ("model", self.__dict__["_serial"], self.__dict__.get("_param_epoch", 0), tuple(hit["names"]), str(self.device))
+            return frame
         frame = self._build_frame(camera, poses)
-        if len(self._frame_cache) > 512:
-            self._frame_cache.clear()
-        self._frame_cache[key] = (frame, list(self.visible_model_names))
+        frame._table_slot = self._remember_frame(camera.time, digest, frame, None)
         return frame
 
+    def invalidate_frames(self) -> None:
+        """Drop the per-timestamp segment rows (call after replacing parameter tensors by hand; ``refinement_after`` and
+        ``load_state_dict`` do it themselves)."""
+        self._frame_cache.clear()
+        self.__dict__.pop("_frame_table_blob", None)
+        self.__dict__["_param_epoch"] = self.__dict__.get("_param_epoch", 0) + 1
+        self.__dict__["_sets"] = {}
+
+    def _remember_frame(self, time, digest, frame: Frame, table):
+        if len(self._frame_cache) > 4096:
+            self._frame_cache.clear()
+        slot = self._frame_cache[time] = dict(
+            digest=digest, segments=frame.segments, names=list(self.visible_model_names), table=table,
+            ptr0=self.all_models._modules["background"].gauss_params._parameters["means"].data_ptr())
+        return slot
+
+    def prepare_frames(self, times: Sequence[float]) -> int:
+        """the segment table of EVERY (timestamp, actor) -- object->world rotation / translation /
+        quaternion (``object2world_gs``, scene graph :404-417), IDFT basis (:420-433), Fourier time (:239-245), parameter
+        pointers and row offsets -- built once from the annotation table (``poses_at``; for the reference's
+        ``InterpolatedAnnotation`` that includes slerp-interpolated boxes with ``frame = -1``,
+        dynamic_annotation.py:157-171,252-286) and uploaded with ONE copy.  ``get_outputs`` then indexes it by timestamp: no
+        per-frame host build, no per-frame H2D.  Rebuilt by the caller after a refinement replaced parameter tensors
+        (the cache is dropped there).  Returns the bytes resident on the device."""
+        dev = self.device
+        built = []
+        for t in times:
+            poses = self.poses_at(t)
+            frame = self._build_frame(None, poses)
+            params = [list(seg.params.tensors()) for seg in frame.segments]
+            tab = raster.SegmentTable(frame, params, dev, upload=False)
+            built.append((t, self._pose_digest(poses), frame, tab))
+        if not built:
+            return 0
+        blob = np.concatenate([tab.host.view(np.uint8).reshape(-1) for _, _, _, tab in built])
+        resident = torch.from_numpy(blob).to(dev)
+        off = 0
+        for t, digest, frame, tab in built:
+            nbytes = tab.host.nbytes
+            tab.dev = resident[off:off + nbytes]
+            off += nbytes
+            self.visible_model_names = [seg.name for seg in frame.segments]
+            self._remember_frame(t, digest, frame, tab)
+        self.__dict__["_frame_table_blob"] = resident
+        return int(resident.numel())
+
+    def _set_of(self, name: str) -> GaussianSet:
+        sets = self.__dict__.setdefault("_sets", {})
+        g = sets.get(name)
+        if g is None:
+            g = sets[name] = self.all_models._modules[name].as_set()
+        return g
+
     def _build_frame(self, camera: Camera, poses) -> Frame:
-        segs = [Segment(self.all_models["background"].as_set(), CLS_BACKGROUND, name="background")]
-        self.visible_model_names = ["background"]
+        segs = [Segment(self._set_of("background"), CLS_BACKGROUND, name="background")]
+        names = ["background"]
         for pose in poses:
             name = self.get_object_model_name(pose.track_id)
-            assert name not in self.visible_model_names
-            sub = self.all_models[name]
-            if sub.num_points == 0:  # "prevent empty object" (scene graph :337-338)
+            assert name not in names
+            ps = self._set_of(name)
+            if ps.means.shape[0] == 0:  # "prevent empty object" (scene graph :337-338)
                 continue
-            ps = sub.as_set()
             basis = None
-            if ps.fourier_dim > 1:
+            F = ps.features_dc.shape[1]
+            if F > 1:
                 t = fourier_time(pose.frame, pose.frame_list, self.config.fourier_features_scale)
-                basis = idft_basis(t, ps.fourier_dim)
+                basis = idft_basis(t, F)
             segs.append(Segment(ps, CLS_OBJECT, rot=pose.rot, center=pose.center, idft=basis, name=name))
-            self.visible_model_names.append(name)
-        return Frame(camera, segs)
+            names.append(name)
+        self.visible_model_names = names
+        frame = Frame(camera, segs)
+        frame._static_key = ("model", self.__dict__["_serial"], self.__dict__.get("_param_epoch", 0), tuple(names), str(self.device))
+        return frame
 
     def _settings(self, class_streams: bool) -> raster.RenderSettings:
         c = self.config
@@ -499,7 +575,7 @@ class SceneGraphRasterModel(torch.nn.Module):
                     for k, t in zip(PARAM_NAMES, new[i]):
                         subs[i].gauss_params[k] = torch.nn.Parameter(t)
             adapter.commit([[sub.gauss_params[k] for k in PARAM_NAMES] for sub in subs], [p is not None for p in plans])
-            self._frame_cache.clear()
+            self.invalidate_frames()
         for i, st in enumerate(resets):
             if st is not None:  # opacity reset on the survivors (:629-642)
                 subs[i].gauss_params["opacities"].data.clamp_(max=refine.opacity_reset_logit(st))

@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import scene as scene_mod
 from .scene import PARAM_NAMES, Camera, Frame
 
 
@@ -124,12 +125,23 @@ class SegmentTable:
     The per-model part (pointers, row offsets, shapes; validated once) is cached on the parameter
     storage addresses; per frame only the poses and the IDFT bases are rewritten."""
 
-    def __init__(self, frame: Frame, params: List[List[torch.Tensor]], device):
+    def __init__(self, frame: Frame, params: List[List[torch.Tensor]], device, upload: bool = True):
+        pre = getattr(frame, "_prebuilt", None)
+        if pre is not None and pre.dev is not None and pre.dev.device == device:
+            # a row block of the device-resident (frame, actor) table (model.prepare_frames): nothing to build, nothing to copy
+            self.host, self.N, self.num_chunks, self.nseg, self.static, self.dev = pre.host, pre.N, pre.num_chunks, pre.nseg, pre.static, pre.dev
+            return
         n = len(frame.segments)
-        ptrs = tuple(t.data_ptr() for ps in params for t in ps)
-        key = (ptrs, tuple(ps[0].shape[0] for ps in params), tuple(ps[3].shape[1] for ps in params),
-               tuple(ps[4].shape[1] for ps in params), str(device))
-        st = _STATIC_CACHE.get(key)
+        # the per-model part is cached on the parameter storage addresses -- or on a key the model vouches for
+        # (model._frame: (model id, parameter epoch, visible sub-models): spares ~200 data_ptr() calls per frame)
+        key = getattr(frame, "_static_key", None)
+        st = _STATIC_CACHE.get(key) if key is not None else None
+        if st is None:
+            ptrs = tuple(t.data_ptr() for ps in params for t in ps)
+            if key is None:
+                key = (ptrs, tuple(ps[0].shape[0] for ps in params), tuple(ps[3].shape[1] for ps in params),
+                       tuple(ps[4].shape[1] for ps in params), str(device))
+                st = _STATIC_CACHE.get(key)
         if st is None:
             for i, ps in enumerate(params):
                 for t, nm in zip(ps, PARAM_NAMES):
@@ -152,12 +164,27 @@ class SegmentTable:
         dyn = getattr(frame, "_dyn_table", None)
         if dyn is None or dyn[0] is not st:
             host = st["host"].copy()
-            host["cls"] = [s.cls for s in frame.segments]
-            host["has_pose"] = [int(s.has_pose) for s in frame.segments]
-            for i, seg in enumerate(frame.segments):
-                R, t, q = seg.pose_f32()
-                host["R"][i], host["t"][i], host["q"][i] = R, t, q
-                host["idft"][i] = seg.idft_f32()
+            segs = frame.segments
+            host["cls"] = [s.cls for s in segs]
+            posed = [i for i, s in enumerate(segs) if s.has_pose]
+            host["has_pose"] = 0
+            host["R"] = np.eye(3, dtype=np.float32).reshape(-1)
+            host["q"] = (1.0, 0.0, 0.0, 0.0)
+            if posed:
+                # object2world_gs (scene graph :404-417): float64 box pose -> float32; the quaternion of every box of the
+                # frame from ONE batched eigen-decomposition (nerfstudio quaternion_from_matrix, restated in scene.py)
+                R64 = np.stack([np.asarray(segs[i].rot, np.float64) for i in posed])
+                host["has_pose"][posed] = 1
+                host["R"][posed] = R64.reshape(-1, 9).astype(np.float32)
+                host["t"][posed] = np.stack([np.asarray(segs[i].center, np.float64) for i in posed]).astype(np.float32)
+                host["q"][posed] = scene_mod.quaternions_from_matrices(R64).astype(np.float32)
+            padded = {}  # the actors of a frame share a handful of basis arrays (scene.idft_basis caches per (time, dim))
+            for i, seg in enumerate(segs):
+                k = (id(seg.idft), seg.params.features_dc.shape[1])
+                b = padded.get(k)
+                if b is None:
+                    b = padded[k] = seg.idft_f32()
+                host["idft"][i] = b
             try:
                 frame._dyn_table = (st, host)  # poses of a Frame object do not change: reuse on re-render
             except Exception:
@@ -169,7 +196,10 @@ class SegmentTable:
         self.num_chunks = st["num_chunks"]
         self.nseg = n
         self.static = st
-        self.dev = torch.from_numpy(host.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
+        self.dev = torch.from_numpy(host.view(np.uint8).reshape(-1)).to(device, non_blocking=True) if upload else None
+        slot = getattr(frame, "_table_slot", None)
+        if slot is not None and upload:  # the model keeps a timestamp's rows (validated by content, model._frame)
+            slot["table"] = self
 
 
 def _grads_table(arena: torch.Tensor, static: dict, device) -> torch.Tensor:

@@ -144,6 +144,29 @@ def quaternion_from_matrix(matrix: np.ndarray) -> np.ndarray:
     return q
 
 
+def quaternions_from_matrices(mats: np.ndarray) -> np.ndarray:
+    """Batched :func:`quaternion_from_matrix` over ``mats[n,3,3]``: one ``np.linalg.eigh`` call for all boxes of a frame
+    (the same LAPACK routine per matrix, so the same bits as the one-by-one form; tests/test_scene_host.py checks it)."""
+    M = np.asarray(mats, dtype=np.float64).reshape(-1, 3, 3)
+    n = M.shape[0]
+    K = np.zeros((n, 4, 4))
+    K[:, 0, 0] = M[:, 0, 0] - M[:, 1, 1] - M[:, 2, 2]
+    K[:, 1, 0] = M[:, 0, 1] + M[:, 1, 0]
+    K[:, 1, 1] = M[:, 1, 1] - M[:, 0, 0] - M[:, 2, 2]
+    K[:, 2, 0] = M[:, 0, 2] + M[:, 2, 0]
+    K[:, 2, 1] = M[:, 1, 2] + M[:, 2, 1]
+    K[:, 2, 2] = M[:, 2, 2] - M[:, 0, 0] - M[:, 1, 1]
+    K[:, 3, 0] = M[:, 2, 1] - M[:, 1, 2]
+    K[:, 3, 1] = M[:, 0, 2] - M[:, 2, 0]
+    K[:, 3, 2] = M[:, 1, 0] - M[:, 0, 1]
+    K[:, 3, 3] = M[:, 0, 0] + M[:, 1, 1] + M[:, 2, 2]
+    K /= 3.0
+    w, V = np.linalg.eigh(K)
+    q = V[np.arange(n), :, np.argmax(w, axis=1)][:, [3, 0, 1, 2]]
+    q[q[:, 0] < 0.0] *= -1.0
+    return q
+
+
 @dataclass
 class Segment:
     """One visible sub-model for one frame: parameters + (for actors) the object->world pose."""

@@ -176,3 +176,41 @@ def test_after_train_statistics_match_reference_expressions(setup):
         assert torch.equal(model.all_models["background"].vis_counts, before)
     finally:
         model.step = 30000
+
+
+def test_device_resident_frame_table_and_pose_content_key():
+    """prepare_frames() builds every timestamp's segment rows once (one upload); get_outputs then indexes
+    the resident table.  Same images as the per-frame host build; a box moved IN PLACE at a fixed timestamp (what the
+    reference's bbox_optimizer.apply_to_bbox does every step) is noticed by content and re-staged."""
+    dev = torch.device("cuda", 0)
+    sc = syn.WaymoScene(scale=0.04, num_frames=12, actor_range=20.0)
+    cfg = SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0)
+    boxes = {f: [ActorPose(str(a), rot.copy(), center.copy(), f, list(range(sc.num_frames))) for a, rot, center in sc.boxes_at(f)]
+             for f in range(sc.num_frames)}
+
+    def build():
+        m = SceneGraphRasterModel(sc.background.to(dev), {k: v.to(dev) for k, v in sc.actors.items()}, cfg,
+                                  poses_at=lambda t: boxes[int(t)]).to(dev)
+        m.train()
+        m.step = 5000
+        return m
+
+    plain, resident = build(), build()
+    nbytes = resident.prepare_frames([float(f) for f in range(sc.num_frames)])
+    assert nbytes == sum((1 + len(boxes[f])) * 168 for f in range(sc.num_frames))
+    for ci in (0, 7, 23, 58):
+        cam = sc.cameras[ci]
+        a, b = plain.get_outputs(cam), resident.get_outputs(cam)
+        assert resident._holder is not None and plain.visible_model_names == resident.visible_model_names
+        for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc"):
+            assert torch.equal(a[k], b[k]), (ci, k)
+    # the resident rows were used as they are (no rebuild): the Frame handed to the rasterizer carries the prebuilt block
+    fr = resident._frame(sc.cameras[7])
+    assert fr._prebuilt is not None and fr._prebuilt.dev.data_ptr() >= resident.__dict__["_frame_table_blob"].data_ptr()
+    # move one box in place: identity unchanged, content changed -> the image must change and match a fresh model's
+    cam = sc.cameras[7]
+    before = resident.get_outputs(cam)["rgb"].clone()
+    boxes[int(cam.time)][0].center[0] += 0.75
+    after = resident.get_outputs(cam)["rgb"]
+    assert not torch.equal(before, after)
+    assert torch.equal(after, build().get_outputs(cam)["rgb"])
