@@ -8,8 +8,8 @@ Reported per scene (gpurun_out/fullsize_parity_<scene>.json, copied to profiles/
   * max |rgb - oracle| on the non-fragile pixels (bar 1e-4, the north-star's) and on the fragile ones (reported; bounded by
     one marginal Gaussian's contribution);
   * gradients: relative L2 per tensor with cotangents masked to the non-fragile pixels (bar 1e-3, the north-star's) AND with
-    UNMASKED cotangents (every pixel contributes, bar 2e-3: a flipped marginal decision adds or drops one alpha ~ 1/255
-    contribution).
+    UNMASKED cotangents (every pixel contributes; same bar -- measured on the B200: <= 7e-5 on all three scenes,
+    profiles/r02a_fullsize_parity_*.json).
 """
 import json
 import os
@@ -27,7 +27,7 @@ pytestmark = pytest.mark.gpu
 
 RGB_TOL = 1e-4
 GRAD_TOL = 1e-3
-GRAD_TOL_UNMASKED = 2e-3
+GRAD_TOL_UNMASKED = 1e-3
 FRAGILE_MAX = 0.005
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -158,7 +158,9 @@ def test_fullsize_forward_images(full):
     assert rep["object_acc_max_err_nonfragile"] <= RGB_TOL and rep["background_acc_max_err_nonfragile"] <= RGB_TOL
     # a fragile pixel differs by at most one marginal Gaussian: alpha ~ 1/255 of a colour <= ~2 (clamped SH), or the tail
     # behind a termination at T ~ 1e-4
-    assert rep["rgb_max_err_all"] <= 0.02, rep["rgb_max_err_all"]
+    # (measured: 1.2e-3 on 2-5 pixels of 2.46 M; profiles/r02a_fullsize_parity_*.json)
+    assert rep["rgb_max_err_all"] <= 5e-3, rep["rgb_max_err_all"]
+    assert rep["rgb_fragile_pixels_over_tol"] <= 50
     assert np.isfinite(rgb).all()
 
 

@@ -125,7 +125,8 @@ def test_fused_loss_epilogue_matches_torch(setup, u8):
             if with_mask:
                 batch["mask"] = mask
             losses = model.get_loss_dict({"rgb": rgb, "accumulation": acc, "object_acc": obj}, batch)
-            assert set(losses) == {"Ll1", "sky_accumulation", "object_acc_entropy_loss"}
+            assert set(losses) == {"Ll1", "simloss", "sky_accumulation", "object_acc_entropy_loss"}
+            assert float(losses["simloss"]) == 0.0  # ssim_lambda == 0: the key the reference always emits, as an exact zero
             (2.0 * losses["Ll1"] + 0.5 * losses["sky_accumulation"] + 3.0 * losses["object_acc_entropy_loss"]).backward()
             res[(fused, with_mask)] = ({k: float(v) for k, v in losses.items()}, rgb.grad, acc.grad, obj.grad)
     model.config.fused_loss = True

@@ -137,7 +137,8 @@ def test_blend_forward_parity(scene):
     alpha = (1 - fw.final_T)
     rgb_ref, a_ref, depth_ref = oracle_c.post_ops(torch.from_numpy(fw.img), torch.from_numpy(alpha), None, True)
     ok = fw.fragile == 0
-    assert ok.mean() > 0.97
+    print(f"[{name}] fragile fraction {1 - ok.mean():.5f}")
+    assert ok.mean() >= 0.99  # small images with long lists (dense_small_image) are the worst case; full size: <= 0.4 %
     rgb = out["rgb"].cpu().numpy()
     assert np.abs(rgb - rgb_ref.numpy())[ok].max() <= RGB_TOL
     assert np.abs(out["accumulation"].cpu().numpy()[..., 0] - alpha)[ok].max() <= RGB_TOL
@@ -147,18 +148,22 @@ def test_blend_forward_parity(scene):
     assert np.abs(out["object_acc"].cpu().numpy()[..., 0] - (1 - fw.obj_T))[fw.fragile_obj == 0].max() <= RGB_TOL
     assert np.abs(out["background_acc"].cpu().numpy()[..., 0] - (1 - fw.bg_T))[fw.fragile_bg == 0].max() <= RGB_TOL
     # fragile pixels are still sane: one marginal Gaussian (alpha ~ 1/255) more or less
-    assert np.abs(rgb - rgb_ref.numpy()).max() <= 0.2
+    print(f"[{name}] max |rgb - oracle| over ALL pixels {np.abs(rgb - rgb_ref.numpy()).max():.2e}")
+    assert np.abs(rgb - rgb_ref.numpy()).max() <= 0.02
     assert np.isfinite(rgb).all()
 
 
-def test_backward_parity(scene):
+@pytest.mark.parametrize("masked", [True, False])
+def test_backward_parity(scene, masked):
+    """``masked``: cotangents zeroed on the fragile pixels (the gradient the two sides agree to compute); unmasked: every
+    pixel contributes, including those whose marginal skip / termination decision the approximate exp may flip."""
     name, fr, orc, fw = scene
     frc = to_cuda(fr, requires_grad=True)
     out, holder = _render(frc)
     H, W = fr.camera.height, fr.camera.width
     g = torch.Generator().manual_seed(7)
     ok = ((fw.fragile == 0) & (fw.fragile_obj == 0) & (fw.fragile_bg == 0)).astype(np.float32)
-    okt = torch.from_numpy(ok)
+    okt = torch.from_numpy(ok) if masked else torch.ones(H, W)
     w_rgb = torch.rand(H, W, 3, generator=g) * okt[..., None]
     w_a = torch.rand(H, W, generator=g) * okt
     w_d = 0.05 * torch.rand(H, W, generator=g) * okt

@@ -182,7 +182,8 @@ def test_cuda_model_reproduces_the_reference_glue(oracle_run):
             if np.linalg.norm(ref) == 0:
                 assert np.abs(got).max() == 0.0, (name, k)
             else:
-                assert rel_l2(got, ref) <= 1e-2, (name, k, rel_l2(got, ref))  # unmasked fragile pixels + approx ex2 / rcp; a glue error is O(1)
+                # UNMASKED cotangents (fragile pixels included) + approx ex2 / rcp; a glue error would be O(1)
+                assert rel_l2(got, ref) <= 5e-3, (name, k, rel_l2(got, ref))
 
 
 @pytest.mark.gpu

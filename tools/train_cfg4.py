@@ -23,17 +23,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--scale", type=float, default=1.0, help="shrinks Gaussian counts and the image (smoke runs)")
-    ap.add_argument("--refine-every", type=int, default=100)
-    ap.add_argument("--start-step", type=int, default=600, help="past warmup_length so that refinement is live")
-    ap.add_argument("--actor-range", type=float, default=45.0)
-    ap.add_argument("--pipeline-chunks", type=int, default=0, help="> 0: all-reduce and Adam pipelined over that many arena ranges")
-    args = ap.parse_args()
-
+def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int = 100, start_step: int = 600,
+        actor_range: float = 45.0, pipeline_chunks: int = 0, overlap: bool = False, resident_table: bool = True) -> dict:
+    """One measurement.  torch.distributed must already be initialised when WORLD_SIZE > 1.  Returns the result dict on
+    rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
 
@@ -44,53 +37,41 @@ def main():
     from street_gaussians_ns_b200.refine import RefineSettings
     from street_gaussians_ns_b200.training import TrainStep
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "needs a CUDA device (no CPU path)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(0)  # the split samples of a refinement come from the global CUDA generator: equal on every replica
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(0)
 
-    n_bg = int(1_680_000 * args.scale)
-    n_act = max(1, int(10_000 * args.scale))
-    W, H = max(64, int(1920 * args.scale) // 16 * 16), max(48, int(1280 * args.scale) // 16 * 16)
-    num_frames = 85
-    bg = syn.make_background(n_bg, seed=0, box=((-40.0, 40.0), (-6.0, 14.0), (-135.0, 45.0))).to(dev)
-    actors = {str(a): syn.make_actor(n_act, seed=1 + a).to(dev) for a in range(32)}
-    boxes = [syn.actor_pose(a) for a in range(32)]
-    rig = syn.waymo_rig(num_frames)  # index = frame * 5 + camera
-    cams = [syn.make_camera(W, H, c2w=rig[i], time=float(i // 5)) for i in range(len(rig))]
+    sc = syn.WaymoScene(scale=scale, actor_range=actor_range)
+    W, H, num_frames, cams = sc.width, sc.height, sc.num_frames, sc.cameras
+    frame_list = list(range(num_frames))
 
-    pose_cache = {}
-
-    def poses_at(t):
+    def poses_at(t):  # fresh objects per call, as a data manager hands them out
         f = int(t)
-        hit = pose_cache.get(f)
-        if hit is None:
-            ego_z = -0.5 * f
-            hit = pose_cache[f] = [ActorPose(str(a), rot, center, f, list(range(num_frames)))
-                                   for a, (rot, center) in enumerate(boxes) if abs(center[2] - ego_z) <= args.actor_range]
-        return hit
+        return [ActorPose(str(a), rot, center, f, frame_list) for a, rot, center in sc.boxes_at(f)]
 
-    rs = RefineSettings(refine_every=args.refine_every)
+    rs = RefineSettings(refine_every=refine_every)
     cfg = SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0, full_gradient_arena=world > 1, refine=rs,
-                           object_refine=RefineSettings(refine_every=args.refine_every, cull_alpha_thresh=0.005),
+                           object_refine=RefineSettings(refine_every=refine_every, cull_alpha_thresh=0.005),
                            num_train_data=len(cams), refine_record=True)
-    model = SceneGraphRasterModel(bg, actors, cfg, poses_at=poses_at).to(dev)
+    model = SceneGraphRasterModel(sc.background.to(dev), {k: v.to(dev) for k, v in sc.actors.items()}, cfg, poses_at=poses_at).to(dev)
     model.train()
     opt = FusedAdam(model.optimizer_params())
-    step_fn = TrainStep(model, opt, refine_every=args.refine_every, pipeline_chunks=args.pipeline_chunks)
+    step_fn = TrainStep(model, opt, refine_every=refine_every, pipeline_chunks=pipeline_chunks, overlap=overlap)
     g = torch.Generator().manual_seed(5)
     gt = (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).to(dev)  # get_loss_dict consumes uint8 directly
     counts0 = [sub.num_points for sub in model.all_models.values()]
+    times = [float(f) for f in range(num_frames)]
+    if resident_table:
+        model.prepare_frames(times)
 
     def one(i):
-        step = args.start_step + i
+        step = start_step + i
         mine = [cams[dp.camera_for_rank(step, r, world, len(cams))] for r in range(world)]
-        return step_fn(step, mine[rank], {"image": gt}, all_cameras=mine if world > 1 else None)
+        out = step_fn(step, mine[rank], {"image": gt}, all_cameras=mine if world > 1 else None)
+        if resident_table and refine_every > 0 and step % refine_every == 0:
+            model.prepare_frames(times)  # a refinement replaced parameter tensors: the resident table is rebuilt (one upload)
+        return out
 
     def sync():
         if world > 1:
@@ -98,35 +79,68 @@ def main():
         torch.cuda.synchronize()
 
     first = None
-    for i in range(args.warmup):
+    for i in range(warmup):
         losses = one(i)
         first = first if first is not None else float(sum(v.detach() for v in losses.values()))
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    for i in range(args.steps):
-        losses = one(args.warmup + i)
+    for i in range(steps):
+        losses = one(warmup + i)
     e1.record()
     sync()
-    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    dev_ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    dev_ms = torch.tensor([e0.elapsed_time(e1) / steps, wall_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
     last = float(sum(v.detach() for v in losses.values()))
-    if rank == 0:
-        counts1 = [sub.num_points for sub in model.all_models.values()]
-        print(json.dumps({
-            "metric": "training steps/s (render 1 camera + L1 + Adam + densification statistics, refinement every "
-                      f"{args.refine_every} steps)", "value": world / (float(dev_ms.item()) * 1e-3), "unit": "steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(dev_ms.item()),
-            "wall_ms_per_step": wall_ms, "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg4/5: 5 cameras x 85 frames, 1.68M background + 32 x 10k actor Gaussians, "
-                                   f"{W}x{H}, scale {args.scale}", "parallelism": f"camera-sharded dp{world}",
-                       "collective": "all-reduce(SUM)/N of the gradient arena (layout of all sub-models)" if world > 1 else "none"},
-            "gaussians_before": int(sum(counts0)), "gaussians_after": int(sum(counts1)),
-            "submodels_changed": int(sum(a != b for a, b in zip(counts0, counts1))),
-            "loss_first": first, "loss_last": last}))
+    if rank != 0:
+        return None
+    counts1 = [sub.num_points for sub in model.all_models.values()]
+    ms = float(dev_ms[0].item())
+    return {
+        "metric": "training steps/s (render 1 camera per rank + L1 + backward + gradient all-reduce + fused Adam + densification "
+                  f"statistics, refinement every {refine_every} steps)", "value": world / (ms * 1e-3), "unit": "steps/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "wall_ms_per_step": float(dev_ms[1].item()),
+        "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg{4 if world == 1 else 5}: 5 cameras x 85 frames, {sc.n_bg} background + 32 x {sc.n_act} actor Gaussians, "
+                               f"{W}x{H}; rank r renders camera (step*g + r) mod 425; actors have a box within {actor_range} m of the ego vehicle",
+                   "parallelism": f"camera-sharded dp{world}", "start_step": start_step, "refine_every": refine_every,
+                   "segment_table": "device-resident, rebuilt after each refinement" if resident_table else "host build per frame",
+                   "collective": ("all-reduce(AVG) of the gradient arena (layout of all sub-models), "
+                                  + ("overlapped with project_bwd / Adam over arena ranges" if overlap else
+                                     (f"pipelined with Adam over {pipeline_chunks} ranges" if pipeline_chunks else "serial"))) if world > 1 else "none"},
+        "gaussians_before": int(sum(counts0)), "gaussians_after": int(sum(counts1)),
+        "submodels_changed": int(sum(a != b for a, b in zip(counts0, counts1))),
+        "loss_first": first, "loss_last": last}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--scale", type=float, default=1.0, help="shrinks Gaussian counts and the image (smoke runs)")
+    ap.add_argument("--refine-every", type=int, default=100)
+    ap.add_argument("--start-step", type=int, default=600, help="past warmup_length so that refinement is live")
+    ap.add_argument("--actor-range", type=float, default=45.0)
+    ap.add_argument("--pipeline-chunks", type=int, default=0, help="> 0: all-reduce and Adam pipelined over that many arena ranges")
+    ap.add_argument("--overlap", action="store_true", help="all-reduce launched per arena range from project_bwd's ranges (dp.OverlappedStep)")
+    ap.add_argument("--host-table", action="store_true", help="build the segment table on the host per frame instead of prepare_frames")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "needs a CUDA device (no CPU path)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = run(args.steps, args.warmup, args.scale, args.refine_every, args.start_step, args.actor_range, args.pipeline_chunks,
+              args.overlap, not args.host_table)
+    if res is not None:
+        print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 
