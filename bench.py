@@ -25,6 +25,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "rendered frames/sec (fwd+bwd) at 1920x1280, 1M+32x10k Gaussians"
+NCU_STEP_PROFILE = "r01j_ncu_step_v10.json"  # the committed full ncu capture of one step the roofline's pipe / instruction figures quote
 UNIT = "frames/s"
 
 
@@ -277,7 +278,8 @@ def run_ours(args):
     e1.record()
     barrier_sync()
     ms = e0.elapsed_time(e1)
-    per_step = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))  # diagnostic: spread of the K steps
+    per_step_raw = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+    per_step = sorted(per_step_raw)  # diagnostic: spread of the K steps
     launches = L.sgn_launch_count() - launches0
     stage_ms = raster.TIMER.mean_ms()
     raster.TIMER = None
@@ -288,23 +290,45 @@ def run_ours(args):
     value = world / (ms_per_step * 1e-3)
 
     # ---- timed region 2: end to end through the model API with host inputs ------------------------
-    # per step: camera + segment table built on the host, the ground-truth image copied H2D from pinned
-    # memory, get_outputs(), L1 loss, backward, and the loss read back D2H.
+    # Every step is a NEW timestamp: a fresh Camera object, fresh box objects whose poses are a function of the timestamp
+    # (actors creep 1 cm per frame and yaw by 0.2 mrad: a new rotation matrix -> a new quaternion per box), as the
+    # reference's data manager hands a new Cameras / a new annotation frame to every step (sgn_datamanager.py:281-293).
+    # So every step pays: pose conversion of 32 boxes, IDFT basis, segment-table build + its H2D copy, camera struct;
+    # then the pinned uint8 ground-truth image H2D, get_outputs(), get_loss_dict (L1 + object-accumulation entropy),
+    # backward, after_train (the densification-statistics callback; a no-op in this phase of training exactly as in the
+    # reference: step >= stop_split_at), and the loss D2H.
     bg = frc.segments[0].params
     actors = {s.name.replace("object_", ""): s.params for s in frc.segments[1:]}
-    poses = [ActorPose(s.name.replace("object_", ""), s.rot, s.center, 21, list(range(85))) for s in frc.segments[1:]]
-    model = SceneGraphRasterModel(bg, actors, SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0),
-                                  poses_at=lambda t: poses).to(dev)
-    model.train()
-    model.step = 30000
+    base_boxes = [(s.name.replace("object_", ""), np.asarray(s.rot, np.float64), np.asarray(s.center, np.float64)) for s in frc.segments[1:]]
+    frame_list = list(range(85))
+
+    def boxes_at(t):
+        k = int(t)
+        a = 2e-4 * (k % 1000)
+        ca, sa = np.cos(a), np.sin(a)
+        Ry = np.array([[ca, 0.0, sa], [0.0, 1.0, 0.0], [-sa, 0.0, ca]])
+        shift = np.array([0.0, 0.0, -0.01 * (k % 50)])
+        return [ActorPose(name, Ry @ rot, center + shift, k % 85, frame_list) for name, rot, center in base_boxes]
+
+    def make_model():
+        m = SceneGraphRasterModel(bg, actors, SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0), poses_at=boxes_at).to(dev)
+        m.train()
+        m.step = 30000
+        return m
+
+    model = make_model()
     g = torch.Generator().manual_seed(5)
     gt_host = (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).pin_memory()
     mparams = [p for p in model.parameters()]
+    c2w = np.asarray(fr.camera.c2w)
+
+    def camera_at(k):  # what a data manager does per step: a new camera object with this step's timestamp
+        return syn.make_camera(W, H, c2w=c2w, time=float(k))
 
     # The loss of every step is read back D2H inside the timed region, asynchronously into a pinned ring (as a
     # training loop that logs lazily does): the host does not wait for step i before preparing step i+1.
     n_e2e_warm = max(args.warmup, 3)
-    loss_ring = torch.zeros(n_e2e_warm + args.steps, dtype=torch.float32).pin_memory()
+    loss_ring = torch.zeros(2 * (n_e2e_warm + args.steps), dtype=torch.float32).pin_memory()
 
     # the data-loader side: this step's uint8 image goes H2D on a copy stream while the render runs (double
     # buffered; the loss waits for it); get_loss_dict consumes the uint8 image directly (gt = u8 / 255)
@@ -315,38 +339,52 @@ def run_ours(args):
     for ev in gt_free:
         ev.record()
 
-    def e2e_step(i):
+    def e2e_step(mdl, i, timestamp):
         b = i & 1
         main = torch.cuda.current_stream()
         copy_stream.wait_event(gt_free[b])  # the step that last read this buffer has finished with it
         with torch.cuda.stream(copy_stream):
             gt_dev[b].copy_(gt_host, non_blocking=True)
             gt_ready[b].record(copy_stream)
-        out = model.get_outputs(fr.camera)
+        out = mdl.get_outputs(camera_at(timestamp))
         main.wait_event(gt_ready[b])
-        losses = model.get_loss_dict(out, {"image": gt_dev[b]})
+        losses = mdl.get_loss_dict(out, {"image": gt_dev[b]})
         loss = sum(losses.values())
         loss.backward()
         gt_free[b].record(main)
-        dp.allreduce_gradients(model._holder.grad_arena)
+        dp.allreduce_gradients(mdl._holder.grad_arena)
+        mdl.after_train(mdl.step)
         loss_ring[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         for p in mparams:
             p.grad = None
 
-    for i in range(n_e2e_warm):
-        e2e_step(i)
-    barrier_sync()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(n_e2e_warm + i)
-    barrier_sync()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    if not bool(torch.isfinite(loss_ring).all()) or float(loss_ring[n_e2e_warm:].abs().min()) == 0.0:
-        raise RuntimeError("end-to-end losses were not all read back: %r" % loss_ring.tolist())
-    t2 = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world / (float(t2.item()) / args.steps * 1e-3)
+    def time_e2e(mdl, first_timestamp, slot0):
+        for i in range(n_e2e_warm):
+            e2e_step(mdl, slot0 + i, first_timestamp + i)
+        barrier_sync()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(mdl, slot0 + n_e2e_warm + i, first_timestamp + n_e2e_warm + i)
+        barrier_sync()
+        ms_ = (time.perf_counter() - t0) * 1e3
+        ring = loss_ring[slot0:slot0 + n_e2e_warm + args.steps]
+        if not bool(torch.isfinite(ring).all()) or float(ring[n_e2e_warm:].abs().min()) == 0.0:
+            raise RuntimeError("end-to-end losses were not all read back: %r" % ring.tolist())
+        t2 = torch.tensor([ms_], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        return world / (float(t2.item()) / args.steps * 1e-3)
+
+    # headline e2e: every step a first-visit timestamp (1000 * rank keeps the ranks' timestamps apart)
+    e2e_value = time_e2e(model, 1000 * (rank + 1), 0)
+    table_bytes = 0
+    e2e_resident = None
+    try:  # secondary: the annotation table staged once (model.prepare_frames): the per-step host build and H2D disappear
+        stamps = [float(5000 + 1000 * rank + i) for i in range(n_e2e_warm + args.steps)]
+        table_bytes = model.prepare_frames(stamps)
+        e2e_resident = time_e2e(model, int(stamps[0]), n_e2e_warm + args.steps)
+    except Exception as e:  # a secondary number must never cost the bench line
+        e2e_resident = f"{type(e).__name__}: {e}"[:200]
     clocks = sampler.stop() if sampler else None
 
     # ---- secondary: the training step of SURVEY 8f rank 1 (render fwd+bwd + all-reduce + fused Adam) -------------
@@ -368,6 +406,22 @@ def run_ours(args):
     train_ms = (time.perf_counter() - t0) / args.steps * 1e3
     adam_ms = sum(a.elapsed_time(b) for a, b in adam_ev) / len(adam_ev)
 
+    # ---- BASELINE configs 4 / 5: the Waymo-shape training loop (tools/train_cfg4.py), all ranks take part -----------------
+    cfg45 = None
+    if not args.no_cfg45:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("train_cfg4", os.path.join(ROOT, "tools", "train_cfg4.py"))
+            tc = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(tc)
+            cfg45 = tc.run(steps=max(args.steps, 20), warmup=max(args.warmup, 5), refine_every=10, start_step=600,
+                           overlap=world > 1)
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                cfg45["cpu_baseline"] = cfg4_cpu_baseline()
+        except Exception as e:
+            if world > 1:
+                raise  # ranks must not leave a collective half-way: fail loudly
+            cfg45 = {"error": f"{type(e).__name__}: {e}"[:400]}
     refinement = None
     if rank == 0 and world == 1:  # a single-GPU measurement; ranks of a multi-GPU run leave together
         try:
@@ -401,31 +455,52 @@ def run_ours(args):
                 per_kernel[k] = {"ms": round(t, 4), "alg_bytes": int(b), "GBps": round(b / t / 1e6, 1),
                                  "frac": round(b / t / 1e6 / peak, 4)}
         dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"]) if per_kernel else None
+        # dram bytes per launch need an ncu capture: bench.py cannot measure them live.  `traffic` stays null here; the
+        # last committed capture is attached as `traffic_committed_capture`, labelled with its file
         traffic = None
+        traffic_committed = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+            traffic_committed = {"bytes": json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom),
+                                 "source": "profiles/ncu_traffic.json (an earlier ncu --set full capture of the same command; not from this run)"}
         except Exception:
             pass
         roofline = None
         if dom:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                        "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                        "frac": per_kernel[dom]["frac"], "traffic": traffic, "traffic_committed_capture": traffic_committed,
+                        "peak_source": peak_src,
                         "note": "alpha-blend kernels are FP32/MUFU issue-bound, not HBM-bound (SURVEY.md 8d); "
                                 "all per-kernel fractions are in roofline_all",
                         "pair_evals_per_s": None}
             try:  # what actually bounds it: pipe utilisation of the stage's main kernel from the committed ncu capture
-                prof = json.load(open(os.path.join(ROOT, "profiles", "r01j_ncu_step_v10.json")))
+                prof = json.load(open(os.path.join(ROOT, "profiles", NCU_STEP_PROFILE)))
                 want = {"blend_bwd": "blend_bwd_kernel", "blend_fwd": "blend_fwd_kernel"}.get(dom, dom + "_kernel")
                 for k in prof["kernels"]:
                     if want in k["kernel"]:
                         pct = lambda key: float(k[key].split()[0])  # noqa: E731
                         roofline["ncu"] = {
-                            "source": "profiles/r01j_ncu_step_v10.json (one step under ncu --set full; not a timing)",
+                            "source": f"profiles/{NCU_STEP_PROFILE} (one step under ncu --set full; not a timing)",
                             "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                             "fma_pipe_pct": pct("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                             "alu_pipe_pct": pct("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
                             "dram_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}
                         break
+            except Exception:
+                pass
+            try:
+                # what bounds the alpha-blend stages is instruction issue: warp instructions of the stage's kernels (counted by
+                # ncu in the committed capture of the same workload) / the stage's LIVE duration, against 4 warp instructions
+                # per SM per cycle x 148 SMs x the SM clock sampled during this run
+                prof = json.load(open(os.path.join(ROOT, "profiles", NCU_STEP_PROFILE)))
+                names = {"blend_bwd": ("blend_bwd_kernel", "acc_bwd_kernel"), "blend_fwd": ("blend_fwd_kernel", "acc_fwd_kernel")}.get(dom, (dom + "_kernel",))
+                inst = sum(float(k["smsp__inst_executed.sum"].split()[0]) for k in prof["kernels"] if any(n in k["kernel"] for n in names))
+                clk = (clocks or {}).get("sm_mhz") or 1965.0
+                peak_ips = 4.0 * 148 * clk * 1e6
+                ach = inst / (per_kernel[dom]["ms"] * 1e-3)
+                roofline["issue"] = {"bound": "warp-instruction issue", "warp_inst_per_launch": inst, "achieved": round(ach / 1e9, 1),
+                                     "peak": round(peak_ips / 1e9, 1), "unit": "G warp-inst/s", "frac": round(ach / peak_ips, 4),
+                                     "inst_source": f"profiles/{NCU_STEP_PROFILE} (smsp__inst_executed.sum of {'+'.join(names)}; "
+                                                    "stale if the kernels changed since)", "duration": "live (CUDA events, this run)"}
             except Exception:
                 pass
             try:  # (pixel, Gaussian) pairs the traversals actually evaluate: 256 x entries traversed per tile and pass
@@ -450,6 +525,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_max": per_step[-1],
+            "ms_per_step_argmax": int(per_step_raw.index(per_step[-1])),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_config(args.cfg), "N_gaussians": N, "N_actor_gaussians": A,
@@ -460,10 +536,18 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(gt_host.numel() + len(frc.segments) * 168 + 96),
                     "d2h_bytes_per_step": 4 + 8,
-                    "what": "SceneGraphRasterModel.get_outputs(camera) + get_loss_dict (L1 + object-accumulation entropy, "
-                            "ssim_lambda 0) + backward through the model API; host camera/poses, pinned uint8 ground-truth "
-                            "image H2D on a copy stream, loss D2H (async, pinned) each step; "
-                            "Gaussian parameters are model state and stay resident (as in the reference)"},
+                    "what": "per step: NEW timestamp (fresh Camera object, 32 fresh box objects with new rotations -> 32 pose "
+                            "conversions, IDFT basis, segment-table build + H2D: no cache hit), SceneGraphRasterModel.get_outputs + "
+                            "get_loss_dict (L1 + object-accumulation entropy) + backward + after_train through the model API; pinned "
+                            "uint8 ground-truth image H2D on a copy stream, loss D2H (async, pinned) each step; Gaussian parameters "
+                            "are model state and stay resident (as in the reference)",
+                    "ssim": "off (ssim_lambda = 0; the reference default 0.2 runs pytorch_msssim, which is outside the rasterizer path)",
+                    "sky": "off (the sky cube map stays on nvdiffrast by the north-star; absent from this image)",
+                    "after_train": "called every step; step 30000 >= stop_split_at, so it returns early as the reference's does "
+                                   "(the live statistics kernel is timed inside training_step_cfg4/5)",
+                    "resident_table": {"value": e2e_resident, "unit": UNIT, "table_bytes_on_device": int(table_bytes),
+                                       "what": "same steps with the (timestamp, actor) segment table staged once by "
+                                               "model.prepare_frames (SURVEY 8f rank 4): no per-step table build / H2D"}},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_all": per_kernel,
@@ -471,6 +555,7 @@ def run_ours(args):
                               "ms_per_step": round(train_ms, 4), "steps_per_s": round(world / (train_ms * 1e-3), 2),
                               "adam_ms": round(adam_ms, 4)},
             "refinement": refinement,
+            ("training_step_cfg4" if world == 1 else "training_step_cfg5"): cfg45,
             "whole_step": {"alg_bytes": int(total_alg), "GBps": round(total_alg / ms_per_step / 1e6, 1),
                            "frac": round(total_alg / ms_per_step / 1e6 / peak, 4)},
         }
@@ -487,6 +572,43 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cfg4_cpu_baseline():
+    """The reference-side cost of ONE cfg4 training step on the host cores: the C port renders camera 106 of the Waymo-shape
+    scene forward + backward (oracle/sgn_oracle.c, all granted threads), then torch.optim.Adam (the reference's optimizer,
+    sgn_config.py:71-108) steps the 2 M Gaussians' parameters on the CPU.  Bounded sample: 1 warm-up + 2 timed steps."""
+    import numpy as np
+    import torch
+    import street_gaussians_ns_b200.synthetic as syn
+    from oracle import oracle_c  # CPU baseline only
+    oracle_c.lib().sgn_oracle_set_threads(host_threads())
+    sc = syn.WaymoScene()
+    fr = sc.frame(106)
+    orc = oracle_c.Oracle(fr)
+    H, W = fr.camera.height, fr.camera.width
+    w, v = syn.cotangents(H, W)
+    v_img = np.concatenate([w.numpy() / (3.0 * H * W), np.zeros((H, W, 1), np.float32)], axis=2)  # an L1-like cotangent scale
+    v_alpha = np.zeros((H, W), np.float32)
+    old_threads = torch.get_num_threads()
+    torch.set_num_threads(host_threads())
+    params = [t.clone().requires_grad_(True) for seg in fr.segments for t in seg.params.tensors()]
+    opt = torch.optim.Adam(params, lr=1e-3, eps=1e-15)
+    times = []
+    for it in range(3):
+        t0 = time.perf_counter()
+        fw = orc.forward(class_renders=True)
+        grads, _ = orc.backward(fw, v_img, v_alpha, None, None)
+        flat = [torch.from_numpy(g[k]) for g in grads for k in ("means", "scales", "quats", "features_dc", "features_rest", "opacities")]
+        for p_, g_ in zip(params, flat):
+            p_.grad = g_.reshape(p_.shape)
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    torch.set_num_threads(old_threads)
+    dt = sum(times[1:]) / 2
+    return {"value": 1.0 / dt, "unit": "steps/s", "cores": host_threads(), "kind": "port",
+            "sample": "2 training steps after 1 warm-up: C-port render of one cfg4 camera (fwd+bwd) + torch.optim.Adam over the 2 M "
+                      "Gaussians' parameters on the host cores", "ms_per_step": dt * 1e3}
 
 
 def measure_refinement(frc, adam, H, W, dev, reps: int = 5, cpu_baseline: bool = True):
@@ -567,6 +689,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cfg", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg45", action="store_true", help="skip the BASELINE config 4 / 5 training-loop measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

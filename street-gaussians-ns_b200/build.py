@@ -15,9 +15,10 @@ LIB = os.path.join(HERE, "libsgn_raster.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
-# per-file extra flags: the per-Gaussian projection keeps IEEE, unfused arithmetic (sgn_exact.cuh)
+# per-file extra flags.  project.cu: the exact section is built from never-contracted intrinsics (sgn_exact.cuh: xf), the
+# colour / gradient code around it may use FMAs
 SOURCES = {
-    "project.cu": ["--fmad=false"],
+    "project.cu": [],
     "binning.cu": [],
     "binning_local.cu": [],
     "blend.cu": ["--use_fast_math"],

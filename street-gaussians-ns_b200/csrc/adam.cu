@@ -69,6 +69,7 @@ extern "C" int sgn_adam_chunk_elems(void) { return ADAM_CHUNK; }
 
 extern "C" int sgn_adam_step(const sgn_adam_tensor* table_dev, int ntensors, int num_chunks, const float* grad_arena,
                              float* exp_avg, float* exp_avg_sq, void* stream) {
+    SGN_RANGE("sgn_adam_step");
     SGN_REQUIRE(table_dev && grad_arena && exp_avg && exp_avg_sq, "sgn_adam_step: null pointer");
     SGN_REQUIRE(ntensors >= 1 && ntensors <= 8192, "sgn_adam_step: ntensors=%d out of range [1,8192]", ntensors);
     SGN_REQUIRE(sgn_aligned16(grad_arena) && sgn_aligned16(exp_avg) && sgn_aligned16(exp_avg_sq), "arenas must be 16-byte aligned");

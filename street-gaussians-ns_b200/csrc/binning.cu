@@ -34,6 +34,7 @@ count_tiles_kernel(int N, int width, int height, int bw, const float4* __restric
 
 extern "C" int sgn_bin_count(int N, const sgn_camera* cam, const float* records, const int32_t* radii,
                              const uint16_t* tile_bbox, int32_t* tiles_touched, uint32_t* touch_mask, void* stream) {
+    SGN_RANGE("sgn_bin_count");
     SGN_REQUIRE(cam && records && radii && tile_bbox && tiles_touched && touch_mask, "sgn_bin_count: null pointer");
     if (N == 0) return SGN_OK;
     count_tiles_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
@@ -98,6 +99,7 @@ extern "C" size_t sgn_bin_scan_scratch_bytes(int N) { return scan_layout(N).tota
 extern "C" int sgn_bin_scan(int N, const float* records, const int32_t* radii, const int32_t* tiles_touched,
                             int32_t* order /* out: rank[g], the position of row g in depth order */, int32_t* cum,
                             int64_t* total_dev, void* scratch, size_t scratch_bytes, void* stream_) {
+    SGN_RANGE("sgn_bin_scan");
     cudaStream_t stream = (cudaStream_t)stream_;
     SGN_REQUIRE(records && radii && tiles_touched && order && cum && total_dev && scratch, "sgn_bin_scan: null pointer");
     const ScanLayout L = scan_layout(N);
@@ -239,6 +241,7 @@ extern "C" size_t sgn_bin_sort_scratch_bytes(int64_t M) { return sort_layout(M).
 extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, const int32_t* radii,
                             const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* order, const int32_t* cum,
                             int32_t* sorted_ids, int32_t* tile_bins, void* scratch, size_t scratch_bytes, void* stream_) {
+    SGN_RANGE("sgn_bin_sort");
     cudaStream_t stream = (cudaStream_t)stream_;
     SGN_REQUIRE(cam && records && radii && tile_bbox && touch_mask && order && cum && tile_bins && scratch,
                 "sgn_bin_sort: null pointer");
@@ -338,6 +341,7 @@ extern "C" size_t sgn_bin_class_scratch_bytes(int tiles) {
 
 extern "C" int sgn_bin_class_lists(const sgn_camera* cam, int64_t M, const int32_t* sorted_ids, const int32_t* tile_bins,
                                    int32_t* cls_ids, int32_t* cls_bins, void* scratch, size_t scratch_bytes, void* stream_) {
+    SGN_RANGE("sgn_bin_class_lists");
     cudaStream_t stream = (cudaStream_t)stream_;
     SGN_REQUIRE(cam && tile_bins && cls_ids && cls_bins && scratch, "sgn_bin_class_lists: null pointer");
     const int bw = cam->block_width;

@@ -229,6 +229,7 @@ static int local_tiles(const sgn_camera* cam, int& tiles_x) {
 extern "C" int sgn_bin_local_count(int N, const sgn_camera* cam, const float* records, const int32_t* radii, const uint16_t* tile_bbox,
                                    const uint32_t* touch_mask, int32_t* tile_count, int32_t* tile_start, int64_t* info_dev,
                                    void* scratch, size_t scratch_bytes, void* stream_) {
+    SGN_RANGE("sgn_bin_local_count");
     cudaStream_t stream = (cudaStream_t)stream_;
     SGN_REQUIRE(cam && records && radii && tile_bbox && touch_mask && tile_count && tile_start && info_dev && scratch,
                 "sgn_bin_local_count: null pointer");
@@ -260,6 +261,7 @@ extern "C" int sgn_bin_local_sort(int N, int64_t M, int longest_list, const sgn_
                                   const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* tile_count,
                                   const int32_t* tile_start, int32_t* sorted_ids, int32_t* tile_bins, int32_t* cls_ids,
                                   int32_t* cls_bins, void* scratch, size_t scratch_bytes, void* stream_) {
+    SGN_RANGE("sgn_bin_local_sort");
     cudaStream_t stream = (cudaStream_t)stream_;
     SGN_REQUIRE(cam && records && radii && tile_bbox && touch_mask && tile_count && tile_start && tile_bins && scratch,
                 "sgn_bin_local_sort: null pointer");

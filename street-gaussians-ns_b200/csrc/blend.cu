@@ -657,6 +657,7 @@ static void launch_blend_fwd(const BlendFwdParams& p, int tuning, cudaStream_t s
 extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
                              const int32_t* sorted_ids, const int32_t* tile_bins, int64_t M, const int32_t* cls_ids,
                              const int32_t* cls_bins, const float* sky, const sgn_blend_fwd_out* out, void* stream) {
+    SGN_RANGE("sgn_blend_fwd");
     if (int rc = check_cam(cam)) return rc;
     SGN_REQUIRE(opts && records && tile_bins && out, "sgn_blend_fwd: null pointer");
     SGN_REQUIRE(out->rgb && out->accumulation && out->depth && out->raw && out->final_T && out->final_idx,
@@ -1094,6 +1095,7 @@ __global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p, con
 extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
                              const int32_t* sorted_ids, const int32_t* tile_bins, int64_t M, const int32_t* cls_ids,
                              const int32_t* cls_bins, const sgn_blend_bwd_in* in, float* v_records, void* stream_) {
+    SGN_RANGE("sgn_blend_bwd");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (int rc = check_cam(cam)) return rc;
     SGN_REQUIRE(opts && records && tile_bins && in && v_records, "sgn_blend_bwd: null pointer");

@@ -46,6 +46,7 @@ extern "C" size_t sgn_sizeof_densify_segment(void) { return sizeof(sgn_densify_s
 
 extern "C" int sgn_densify_stats(const sgn_densify_segment* table_dev, int nseg, int N, const float* v_records, const int32_t* radii,
                                  int height, int width, void* stream_) {
+    SGN_RANGE("sgn_densify_stats");
     cudaStream_t stream = (cudaStream_t)stream_;
     SGN_REQUIRE(nseg >= 0 && N >= 0 && height > 0 && width > 0, "sgn_densify_stats: bad sizes");
     if (nseg == 0 || N == 0) return SGN_OK;

@@ -158,6 +158,7 @@ static int fill(LossParams& p, int H, int W, const sgn_loss_in* in) {
 extern "C" size_t sgn_loss_scratch_bytes(void) { return sizeof(float) * 3 * LOSS_BLOCKS; }
 
 extern "C" int sgn_loss_fwd(int H, int W, const sgn_loss_in* in, float* losses, void* scratch, size_t scratch_bytes, void* stream_) {
+    SGN_RANGE("sgn_loss_fwd");
     cudaStream_t stream = (cudaStream_t)stream_;
     LossParams p;
     if (int rc = fill(p, H, W, in)) return rc;
@@ -175,6 +176,7 @@ extern "C" int sgn_loss_fwd(int H, int W, const sgn_loss_in* in, float* losses, 
 
 extern "C" int sgn_loss_bwd(int H, int W, const sgn_loss_in* in, const float* grad_losses, float* v_rgb, float* v_accumulation,
                             float* v_object_acc, void* stream_) {
+    SGN_RANGE("sgn_loss_bwd");
     cudaStream_t stream = (cudaStream_t)stream_;
     LossParams p;
     if (int rc = fill(p, H, W, in)) return rc;

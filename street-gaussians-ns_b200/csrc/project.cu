@@ -28,6 +28,7 @@ extern "C" size_t sgn_sizeof_segment_grads(void) { return sizeof(sgn_segment_gra
 extern "C" size_t sgn_sizeof_camera(void) { return sizeof(sgn_camera); }
 
 extern "C" int sgn_upload(const void* host, size_t bytes, void* dev, void* stream) {
+    SGN_RANGE("sgn_upload");
     SGN_REQUIRE(host && dev, "sgn_upload: null pointer");
     SGN_CHECK_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return SGN_OK;
@@ -80,60 +81,131 @@ __device__ __forceinline__ void coop_store(float* __restrict__ dst, const float*
     }
 }
 
-// Forward: one thread per row, direct loads (independent per-thread loads keep more requests in flight
-// than a stage-sync-compute split; measured).  Rows the camera does not see skip the colour work:
-// nothing downstream ever reads the colour of an invisible Gaussian.
+// Forward, two phases per 128-row chunk (profiles/r01j: the one-phase form was issue-bound at 17 of 32 active lanes per
+// instruction -- visible and invisible rows mixed in every warp -- with 45 row-strided scalar loads per thread):
+//   A  every thread projects its row (exact section); invisible rows write their record and leave;
+//   -  the chunk's visible rows are compacted (stable), and ONLY their colour parameters (features_rest: 180 B per row,
+//      features_dc) are gathered into shared memory with coalesced loads: consecutive threads read consecutive words;
+//   B  thread c takes visible row c: view direction, SH, Fourier DC, sigmoid, record, exact tile count -- full warps.
 __global__ void __launch_bounds__(CH)
 project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, const sgn_camera cam,
                    float4* __restrict__ records, int32_t* __restrict__ radii, int32_t* __restrict__ num_tiles_hit,
                    ushort4* __restrict__ tile_bbox, int32_t* __restrict__ tiles_touched, uint32_t* __restrict__ touch_mask) {
     extern __shared__ int s_chunk0[];
+    __shared__ __align__(16) float s_rest[CH * MAX_REST];
+    __shared__ __align__(16) float s_dc[CH * MAX_DC];
+    __shared__ __align__(16) float s_means[CH * 3];
+    __shared__ __align__(16) float s_scales[CH * 3];
+    __shared__ float s_geo[CH][9];  // per visible row (compact index): xy, conic, depth, world mean
+    __shared__ int s_row[CH];       // compact index -> row of the chunk
+    __shared__ int s_warp_base[CH / 32 + 1];
     for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_chunk0[i] = segs[i].chunk0;
     __syncthreads();
     const int si = find_segment_by_chunk(s_chunk0, nseg, blockIdx.x);
     const sgn_segment& sg = segs[si];
-    const int i = (blockIdx.x - sg.chunk0) * CH + threadIdx.x;
-    const bool active = i < sg.count;  // idle lanes of a tail chunk still take part in the warp-collective tile count
-    const size_t g = (size_t)sg.row0 + i;
+    const int r0 = (blockIdx.x - sg.chunk0) * CH;
+    const int rows = min(CH, sg.count - r0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = (cam.sh_degree + 1) * (cam.sh_degree + 1);
+    const int nrest = (K - 1) * 3, ndc = sg.F * 3;
+    coop_load(s_means, sg.means + 3 * (size_t)r0, rows * 3);
+    coop_load(s_scales, sg.scales + 3 * (size_t)r0, rows * 3);
+    __syncthreads();
+
+    // ---- phase A: projection of every row
+    const bool active = tid < rows;
+    const size_t g = (size_t)sg.row0 + r0 + tid;
+    const int cls_bit = sg.cls == 1 ? SGN_AUX_OBJECT : 0;
     bool vis = false;
+    SgnProj st;
+    if (active) {
+        const float m[3] = {s_means[3 * tid], s_means[3 * tid + 1], s_means[3 * tid + 2]};
+        const float ls[3] = {s_scales[3 * tid], s_scales[3 * tid + 1], s_scales[3 * tid + 2]};
+        const float4 qq = __ldg(reinterpret_cast<const float4*>(sg.quats) + r0 + tid);
+        const float q[4] = {qq.x, qq.y, qq.z, qq.w};
+        vis = sgn_project_exact(sg, cam, m, ls, q, st);
+        radii[g] = st.radius;
+        num_tiles_hit[g] = vis ? (st.tmax[0] - st.tmin[0]) * (st.tmax[1] - st.tmin[1]) : 0;
+        tile_bbox[g] = make_ushort4((unsigned short)st.tmin[0], (unsigned short)st.tmin[1],
+                                    (unsigned short)st.tmax[0], (unsigned short)st.tmax[1]);
+        float4* rec = records + 3 * g;
+        rec[0] = make_float4(st.xy[0], st.xy[1], st.conic[0], st.conic[1]);
+        if (!vis) {  // nothing downstream reads the colour of a Gaussian the camera does not see
+            rec[1] = make_float4(st.conic[2], 0.f, 0.f, 0.f);
+            rec[2] = make_float4(0.f, 0.f, __int_as_float(cls_bit), 0.f);
+            tiles_touched[g] = 0;
+            touch_mask[g] = 0u;
+        }
+    }
+    // stable compaction of the visible rows
+    const unsigned bal = __ballot_sync(0xffffffffu, vis);
+    if (lane == 0) s_warp_base[warp + 1] = __popc(bal);
+    __syncthreads();
+    if (tid == 0) {
+        s_warp_base[0] = 0;
+#pragma unroll
+        for (int w = 0; w < CH / 32; ++w) s_warp_base[w + 1] += s_warp_base[w];
+    }
+    __syncthreads();
+    const int nvis = s_warp_base[CH / 32];
+    if (vis) {
+        const int c = s_warp_base[warp] + __popc(bal & ((1u << lane) - 1u));
+        s_row[c] = tid;
+        float* ge = s_geo[c];
+        ge[0] = st.xy[0]; ge[1] = st.xy[1]; ge[2] = st.conic[0]; ge[3] = st.conic[1]; ge[4] = st.conic[2];
+        ge[5] = st.pv[2]; ge[6] = st.mw[0]; ge[7] = st.mw[1]; ge[8] = st.mw[2];
+    }
+    __syncthreads();
+    if (nvis == 0) return;
+
+    // ---- gather the colour parameters of the visible rows (word e of the compacted block: row e / width, column e % width)
+    {
+        const unsigned inv_rest = nrest > 0 ? (0xffffffffu / (unsigned)nrest) + 1u : 0u;  // e / nrest == umulhi(e, inv) for e < 2^16
+        const float* __restrict__ rest = sg.features_rest + (size_t)r0 * nrest;
+        for (int e = tid; e < nvis * nrest; e += CH) {
+            const int r = (int)__umulhi((unsigned)e, inv_rest);
+            s_rest[e] = __ldg(rest + s_row[r] * nrest + (e - r * nrest));
+        }
+        const unsigned inv_dc = (0xffffffffu / (unsigned)ndc) + 1u;
+        const float* __restrict__ dc = sg.features_dc + (size_t)r0 * ndc;
+        for (int e = tid; e < nvis * ndc; e += CH) {
+            const int r = (int)__umulhi((unsigned)e, inv_dc);
+            s_dc[e] = __ldg(dc + s_row[r] * ndc + (e - r * ndc));
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: colour, opacity, record and tile count of visible row c = tid
+    const bool mine = tid < nvis;
     ushort4 bb = make_ushort4(0, 0, 0, 0);
     TouchCtx tc = {};
-    if (active) {
-
-    float m[3], ls[3], q[4];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { m[k] = __ldg(sg.means + 3 * (size_t)i + k); ls[k] = __ldg(sg.scales + 3 * (size_t)i + k); }
-    {
-        const float4 qq = __ldg(reinterpret_cast<const float4*>(sg.quats) + i);
-        q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
-    }
-    SgnProj st;
-    vis = sgn_project_exact(sg, cam, m, ls, q, st);
-
-    float rgb[3] = {0.f, 0.f, 0.f};
-    float opac = 0.f;
-    int aux = 0;
-    if (vis) {
+    size_t gb = 0;
+    if (mine) {
+        const int row = s_row[tid];
+        gb = (size_t)sg.row0 + r0 + row;
+        const float* ge = s_geo[tid];
         // colour: Fourier DC (scene graph :239-247), SH (sgn_splatfacto.py:933-940)
         float c0[3] = {0.f, 0.f, 0.f};
+        const float* dcr = s_dc + tid * ndc;
         for (int f = 0; f < sg.F; ++f) {
             const float w = sg.idft[f];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) c0[ch] += __ldg(sg.features_dc + ((size_t)i * sg.F + f) * 3 + ch) * w;
+            for (int ch = 0; ch < 3; ++ch) c0[ch] += dcr[f * 3 + ch] * w;
         }
+        float rgb[3];
+        int aux = SGN_AUX_VISIBLE | cls_bit;
         if (cam.sh_degree > 0) {
-            float d[3] = {st.mw[0] - cam.cam_pos[0], st.mw[1] - cam.cam_pos[1], st.mw[2] - cam.cam_pos[2]};
+            float d[3] = {ge[6] - cam.cam_pos[0], ge[7] - cam.cam_pos[1], ge[8] - cam.cam_pos[2]};
             const float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
             d[0] /= n; d[1] /= n; d[2] /= n;
             float Y[16];
             sgn_sh_basis(cam.sh_degree_to_use, d[0], d[1], d[2], Y);
             const int Kuse = min((cam.sh_degree_to_use + 1) * (cam.sh_degree_to_use + 1), K);
             float acc[3] = {Y[0] * c0[0], Y[0] * c0[1], Y[0] * c0[2]};
-            const float* rest = sg.features_rest + (size_t)i * (K - 1) * 3;
+            const float* rr = s_rest + tid * nrest;
             for (int k = 1; k < Kuse; ++k) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) acc[ch] += Y[k] * __ldg(rest + (k - 1) * 3 + ch);
+                for (int ch = 0; ch < 3; ++ch) acc[ch] += Y[k] * rr[(k - 1) * 3 + ch];
             }
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
@@ -145,34 +217,28 @@ project_fwd_kernel(const sgn_segment* __restrict__ segs, int nseg, const sgn_cam
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) { rgb[ch] = 1.f / (1.f + expf(-c0[ch])); aux |= (1 << ch); }
         }
-        opac = 1.f / (1.f + expf(-__ldg(sg.opacities + i)));
-        aux |= SGN_AUX_VISIBLE;
+        const float opac = 1.f / (1.f + expf(-__ldg(sg.opacities + r0 + row)));
+        float4* rec = records + 3 * gb;
+        rec[1] = make_float4(ge[4], opac, rgb[0], rgb[1]);
+        rec[2] = make_float4(rgb[2], ge[5], __int_as_float(aux), 0.f);
+        bb = tile_bbox[gb];  // written by this block in phase A (visible to the block after the barriers above)
+        tc = make_touch_ctx(make_float4(ge[0], ge[1], ge[2], ge[3]), make_float4(ge[4], opac, 0.f, 0.f));
     }
-    if (sg.cls == 1) aux |= SGN_AUX_OBJECT;
-
-    float4* rec = records + 3 * g;
-    rec[0] = make_float4(st.xy[0], st.xy[1], st.conic[0], st.conic[1]);
-    rec[1] = make_float4(st.conic[2], opac, rgb[0], rgb[1]);
-    rec[2] = make_float4(rgb[2], vis ? st.pv[2] : 0.f, __int_as_float(aux), 0.f);
-    radii[g] = st.radius;
-    num_tiles_hit[g] = vis ? (st.tmax[0] - st.tmin[0]) * (st.tmax[1] - st.tmin[1]) : 0;
-    bb = make_ushort4((unsigned short)st.tmin[0], (unsigned short)st.tmin[1],
-                      (unsigned short)st.tmax[0], (unsigned short)st.tmax[1]);
-    tile_bbox[g] = bb;
-    if (vis) tc = make_touch_ctx(make_float4(st.xy[0], st.xy[1], st.conic[0], st.conic[1]), make_float4(st.conic[2], opac, 0.f, 0.f));
-    }  // active
-    // tiles the Gaussian can really reach (exact ellipse-vs-tile test, sgn_touch.cuh); binning lists only those
+    // tiles the Gaussian can really reach (exact ellipse-vs-tile test, sgn_touch.cuh); binning lists only those.
+    // Warp-collective: whole warps without a visible row skip it together.
+    if ((warp << 5) >= nvis) return;
     uint32_t mask;
-    const int nt = count_touched_tiles(vis, tc, bb, cam.width, cam.height, cam.block_width, mask);
-    if (active) {
-        tiles_touched[g] = nt;
-        touch_mask[g] = mask;
+    const int nt = count_touched_tiles(mine, tc, bb, cam.width, cam.height, cam.block_width, mask);
+    if (mine) {
+        tiles_touched[gb] = nt;
+        touch_mask[gb] = mask;
     }
 }
 
 extern "C" int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, int num_chunks, const sgn_camera* cam,
                                float* records, int32_t* radii, int32_t* num_tiles_hit, uint16_t* tile_bbox,
                                int32_t* tiles_touched, uint32_t* touch_mask, void* stream) {
+    SGN_RANGE("sgn_project_fwd");
     SGN_REQUIRE(segs_dev && cam && records && radii && num_tiles_hit && tile_bbox && tiles_touched && touch_mask,
                 "sgn_project_fwd: null pointer");
     SGN_REQUIRE(nseg >= 1 && nseg <= SGN_MAX_SEGMENTS, "sgn_project_fwd: nseg=%d out of range [1,%d]", nseg, SGN_MAX_SEGMENTS);
@@ -412,6 +478,7 @@ project_bwd_kernel(const sgn_segment* __restrict__ segs, const sgn_segment_grads
 extern "C" int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N, int num_chunks,
                                const sgn_camera* cam, const float* records, const int32_t* radii,
                                const float* v_records, void* stream) {
+    SGN_RANGE("sgn_project_bwd");
     SGN_REQUIRE(segs_dev && grads_dev && cam && records && radii && v_records, "sgn_project_bwd: null pointer");
     SGN_REQUIRE(nseg >= 1 && nseg <= SGN_MAX_SEGMENTS, "sgn_project_bwd: nseg=%d out of range", nseg);
     SGN_REQUIRE(sgn_aligned16(records) && sgn_aligned16(v_records), "records / v_records must be 16-byte aligned");
@@ -462,6 +529,7 @@ l1_project_fwd_kernel(int N, const float* __restrict__ means, const float* __res
 extern "C" int sgn_l1_project_fwd(int N, const float* means, const float* scales, float glob_scale, const float* quats,
                                   const sgn_camera* cam, float* xys, float* depths, int32_t* radii, float* conics,
                                   float* compensation, int32_t* num_tiles_hit, float* cov3d, void* stream) {
+    SGN_RANGE("sgn_l1_project_fwd");
     SGN_REQUIRE(means && scales && quats && cam && xys && depths && radii && conics && compensation && num_tiles_hit && cov3d,
                 "sgn_l1_project_fwd: null pointer");
     SGN_REQUIRE(cam->block_width >= 2 && cam->block_width <= 16, "block_width must be between 2 and 16 (got %d)", cam->block_width);
@@ -506,6 +574,7 @@ l1_project_bwd_kernel(int N, const float* __restrict__ means, const float* __res
 extern "C" int sgn_l1_project_bwd(int N, const float* means, const float* scales, float glob_scale, const float* quats,
                                   const sgn_camera* cam, const int32_t* radii, const float* v_xys, const float* v_depths,
                                   const float* v_conics, float* v_means, float* v_scales, float* v_quats, void* stream) {
+    SGN_RANGE("sgn_l1_project_bwd");
     SGN_REQUIRE(means && scales && quats && cam && radii && v_means && v_scales && v_quats, "sgn_l1_project_bwd: null pointer");
     if (N == 0) return SGN_OK;
     l1_project_bwd_kernel<<<(N + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, 0, (cudaStream_t)stream>>>(
@@ -540,6 +609,7 @@ l1_sh_kernel(int N, int K, int degree, const float* __restrict__ viewdirs, const
 
 extern "C" int sgn_l1_sh(int N, int K, int degree, const float* viewdirs, const float* coeffs, const float* v_colors,
                          float* colors, float* v_coeffs, void* stream) {
+    SGN_RANGE("sgn_l1_sh");
     SGN_REQUIRE(viewdirs && (colors || v_coeffs), "sgn_l1_sh: null pointer");
     SGN_REQUIRE(degree >= 0 && degree <= 3 && K >= 1 && K <= 16, "sgn_l1_sh: degree must be in [0,3], K in [1,16]");
     SGN_REQUIRE(!colors || coeffs, "sgn_l1_sh: forward needs coeffs");

@@ -75,6 +75,7 @@ static int refine_check_config(const sgn_refine_config* cfg, const char* who) {
 extern "C" int sgn_refine_decide(int n, const sgn_refine_config* cfg, const float* scales, const float* opacities,
                                  const float* xys_grad_norm, const float* vis_counts, const float* max_2Dsize, uint8_t* flags,
                                  int32_t* marks, void* stream) {
+    SGN_RANGE("sgn_refine_decide");
     SGN_REQUIRE(n >= 0, "sgn_refine_decide: n=%d", n);
     if (int rc = refine_check_config(cfg, "sgn_refine_decide")) return rc;
     if (n == 0) return SGN_OK;
@@ -89,6 +90,7 @@ extern "C" int sgn_refine_decide(int n, const sgn_refine_config* cfg, const floa
 
 extern "C" int sgn_refine_apply(int n, const sgn_refine_config* cfg, const sgn_refine_tensors* tensors, const uint8_t* flags,
                                 const int32_t* scan, const int32_t* totals, const float* samples, void* stream) {
+    SGN_RANGE("sgn_refine_apply");
     SGN_REQUIRE(n >= 0, "sgn_refine_apply: n=%d", n);
     if (int rc = refine_check_config(cfg, "sgn_refine_apply")) return rc;
     SGN_REQUIRE(tensors && totals, "sgn_refine_apply: null tensors / totals");

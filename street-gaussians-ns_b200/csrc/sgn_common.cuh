@@ -18,6 +18,14 @@ void sgn_set_error(const char* fmt, ...);
         }                                                                                        \
     } while (0)
 
+// NVTX range per C-ABI call (nsys / ncu --nvtx timelines name the stages); a no-op function-pointer call when no tool is attached
+#include <nvtx3/nvToolsExt.h>
+struct SgnRange {
+    explicit SgnRange(const char* name) { nvtxRangePushA(name); }
+    ~SgnRange() { nvtxRangePop(); }
+};
+#define SGN_RANGE(name) SgnRange sgn_nvtx_range_(name)
+
 #define SGN_REQUIRE(cond, ...)                 \
     do {                                       \
         if (!(cond)) {                         \

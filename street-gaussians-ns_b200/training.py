@@ -30,11 +30,11 @@ from .scene import Camera
 class TrainStep:
     def __init__(self, model: SceneGraphRasterModel, optimizer: FusedAdam, refine_every: Optional[int] = None,
                  group: Optional[dist.ProcessGroup] = None, pipeline_chunks: int = 0, refine_seed: int = 0,
-                 check_replicas: bool = True):
+                 check_replicas: bool = True, overlap: bool = False):
         """``pipeline_chunks`` > 0 (data parallel only): all-reduce and Adam are pipelined over that many ranges of the
         arena (dp.allreduce_and_step) instead of running one after the other."""
         self.model, self.optimizer, self.group = model, optimizer, group
-        self.pipeline_chunks = pipeline_chunks
+        self.pipeline_chunks = pipeline_chunks if pipeline_chunks > 0 or not overlap else 4
         self.refine_seed, self.check_replicas, self._gen = refine_seed, check_replicas, None
         # None: every sub-model on its own ``refine_every`` (the reference registers one callback per sub-model with
         # ``update_every_num_iters = config.refine_every``); a number: one cadence for all of them
