@@ -240,10 +240,35 @@ def run_ours(args):
 
     cot = {"rgb": w, "accumulation": v, "object_acc": vo}
 
+    # camera-sharded DP: ONE exchange per step, the SUM of the flat gradient arena over the ranks.  By default it
+    # is this library's own kernel over symmetric memory (csrc/collective.cu: in-switch reduction through the multicast
+    # address, or peer loads / stores), issued range by range behind the project backward that produces the arena;
+    # SGN_DP_EXCHANGE=nccl selects dist.all_reduce after the backward instead.
+    exchange, plan, collective = None, None, {"kind": "none"}
+    if world > 1:
+        counts, offs, widths, total = dp.frame_arena_layout(frc)
+        collective = {"kind": "nccl all_reduce(SUM) of the arena after the backward", "bytes": 4 * total}
+        if os.environ.get("SGN_DP_EXCHANGE", "sym") != "nccl":
+            try:
+                exchange = dp.SymmetricExchange(total, dev, use_multicast=os.environ.get("SGN_DP_MULTICAST", "1") != "0")
+                nr = int(os.environ.get("SGN_DP_RANGES", "4"))
+                plan = dp.plan_ranges(counts, offs, widths, nr)
+                collective = {"kind": "sgn_allreduce_sym (this library's kernel over symmetric memory), range by range behind project_bwd",
+                              "mode": exchange.mode, "ranges": len(plan), "bytes": 4 * total}
+            except Exception as e:
+                exchange = None
+                collective["symmetric_memory_unavailable"] = f"{type(e).__name__}: {e}"[:300]
+
     def step():
         # the hot path straight through the C-ABI stages (same kernels as render_frame + backward())
-        out, holder = raster.forward_backward(frc, settings, cot)
-        dp.allreduce_gradients(holder.grad_arena)  # camera-sharded DP: one SUM over the flat arena
+        if exchange is None:
+            out, holder = raster.forward_backward(frc, settings, cot)
+            dp.allreduce_gradients(holder.grad_arena)
+        else:
+            out, holder = raster.forward_backward(frc, settings, cot, grad_out=exchange.arena[:total],
+                                                  chunk_ranges=[(a, b) for a, b, _ in plan],
+                                                  after_range=lambda k: exchange.after_range(k, plan[k][2]))
+            exchange.wait_all()
         return holder
 
     def barrier_sync():
@@ -288,6 +313,31 @@ def run_ours(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_ms.item()) / args.steps
     value = world / (ms_per_step * 1e-3)
+
+    if world > 1:  # the exchange alone (all ranks): this library's kernel and NCCL on the same bytes, CUDA events, max over ranks
+        def alone(fn, reps=10):
+            for _ in range(3):
+                fn()
+            barrier_sync()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            barrier_sync()
+            t = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        nbytes = collective["bytes"]
+        scratch = torch.zeros(nbytes // 4, device=dev)
+        t_nccl = alone(lambda: dist.all_reduce(scratch))
+        collective["alone"] = {"nccl_ms": round(t_nccl, 4), "nccl_bus_GBps": round(2 * (world - 1) / world * nbytes / t_nccl / 1e6, 1)}
+        if exchange is not None:
+            exchange.arena.zero_()
+            t_sym = alone(lambda: exchange.all_reduce())
+            collective["alone"].update({"sgn_allreduce_sym_ms": round(t_sym, 4),
+                                        "sgn_bus_GBps": round(2 * (world - 1) / world * nbytes / t_sym / 1e6, 1)})
+        del scratch
 
     # ---- timed region 2: end to end through the model API with host inputs ------------------------
     # Every step is a NEW timestamp: a fresh Camera object, fresh box objects whose poses are a function of the timestamp
@@ -531,7 +581,7 @@ def run_ours(args):
             "config": {"workload": workload_config(args.cfg), "N_gaussians": N, "N_actor_gaussians": A,
                        "M_intersections": M, "N_visible": n_vis, "max_per_tile": max_per_tile, "parallelism": f"camera-sharded dp{world}",
                        "l2": "inputs larger than L2 (330 MB of parameters + 0.4 GB of intersection lists per step vs 126 MB)",
-                       "collective": "all-reduce(SUM) of the flat gradient arena inside the step" if world > 1 else "none"},
+                       "collective": collective},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(gt_host.numel() + len(frc.segments) * 168 + 96),

@@ -155,6 +155,12 @@ int sgn_project_fwd(const sgn_segment* segs_dev, int nseg, int N, int num_chunks
 int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N, int num_chunks,
                     const sgn_camera* cam, const float* records, const int32_t* radii,
                     const float* v_records, void* stream);
+/* The same backward over the chunks [chunk_begin, chunk_end) only (rows of the concatenated row space in 128-row chunks):
+ * the data-parallel step produces the gradient arena range by range so that the exchange of a finished range
+ * (sgn_allreduce_sym) overlaps the production of the next one. */
+int sgn_project_bwd_range(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N, int num_chunks,
+                          const sgn_camera* cam, const float* records, const int32_t* radii, const float* v_records,
+                          int chunk_begin, int chunk_end, void* stream);
 
 /* ---- Level-1: gsplat 0.1.x function API on plain tensors (sgn_splatfacto.py:11-14) -------------------
  * gsplat.project_gaussians(means3d, scales, glob_scale, quats, viewmat, fx, fy, cx, cy, H, W, block_width,
@@ -324,6 +330,19 @@ size_t sgn_sizeof_adam_tensor(void);
 int sgn_adam_chunk_elems(void);
 int sgn_adam_step(const sgn_adam_tensor* table_dev, int ntensors, int num_chunks, const float* grad_arena,
                   float* exp_avg, float* exp_avg_sq, void* stream);
+
+/* ---- gradient exchange of the camera-sharded data-parallel step ---------------------------------
+ * The reference has no distributed code; SURVEY 8e defines the exchange: SUM (or mean) of the flat per-Gaussian gradient
+ * arena over the replicas.  sgn_allreduce_sym is that exchange as ONE kernel of this library over peer-mapped
+ * ("symmetric") memory -- what a training loop would otherwise hand to ncclAllReduce: rank r reduces the r-th part of
+ * every listed slice (multimem.ld_reduce through `multicast`, i.e. inside the NVSwitch; or, with multicast == NULL, loads
+ * from every peer pointer in rank order), multiplies by `scale` and pushes the result to all replicas (multimem.st / one
+ * store per peer), in place.  `local` is this rank's arena, `peer_ptrs_dev` a DEVICE array of `world` arena base pointers
+ * (this rank's own included).  Slice offsets / lengths are in floats, multiples of 4.  The caller orders the call between
+ * two cross-GPU barriers on the same stream (all replicas written; all parts pushed).  Bit-identical results on all ranks. */
+#define SGN_AR_MAX_SLICES 48
+int sgn_allreduce_sym(void* local, void* multicast, const uint64_t* peer_ptrs_dev, int rank, int world, int nslices,
+                      const int64_t* slice_offsets, const int64_t* slice_lengths, float scale, int max_ctas, void* stream);
 
 /* ---- refinement: split / duplicate / cull ---------------------------------------------
  * What `SplatfactoModel.refinement_after` does to ONE sub-model every `refine_every` steps

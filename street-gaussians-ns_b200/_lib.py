@@ -129,7 +129,9 @@ EXPORTS = [
     "sgn_loss_scratch_bytes", "sgn_loss_fwd", "sgn_loss_bwd", "sgn_sizeof_densify_segment", "sgn_densify_stats",
     "sgn_sizeof_refine_config", "sgn_sizeof_refine_tensors", "sgn_refine_decide", "sgn_refine_apply",
     "sgn_bin_local_cap", "sgn_bin_local_scratch_bytes", "sgn_bin_local_count", "sgn_bin_local_sort",
+    "sgn_project_bwd_range", "sgn_allreduce_sym",
 ]
+AR_MAX_SLICES = 48  # SGN_AR_MAX_SLICES
 
 
 def load():
@@ -152,6 +154,10 @@ def load():
     L.sgn_upload.argtypes = [vp, sz, vp, vp]
     L.sgn_project_fwd.argtypes = [vp, i32, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp]
     L.sgn_project_bwd.argtypes = [vp, vp, i32, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp]
+    L.sgn_project_bwd_range.argtypes = [vp, vp, i32, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, i32, i32, vp]
+    L.sgn_project_bwd_range.restype = C.c_int
+    L.sgn_allreduce_sym.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_float, i32, vp]
+    L.sgn_allreduce_sym.restype = C.c_int
     fl = C.c_float
     L.sgn_l1_project_fwd.argtypes = [i32, vp, vp, fl, vp, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp]
     L.sgn_l1_project_bwd.argtypes = [i32, vp, vp, fl, vp, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp]

@@ -25,7 +25,8 @@ SOURCES = {
     "loss.cu": [],
     "densify.cu": ["--fmad=false"],
     "adam.cu": ["--fmad=false"],  # keep torch.optim.Adam's rounding sequence (no contraction)
-    "refine.cu": ["--fmad=false"],  # the refinement rules mirror torch's separately rounded elementwise kernels
+    "refine.cu": ["--fmad=false"],
+    "collective.cu": [],  # the refinement rules mirror torch's separately rounded elementwise kernels
 }
 
 

@@ -616,23 +616,34 @@ static cudaStream_t aux_stream() {
     }
     return streams[dev];
 }
+// fork / join events are created once per device (event creation + destruction cost ~4 us per blend call on a 2 ms step)
+struct ForkJoinEvents {
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static ForkJoinEvents* fork_join_events() {
+    static thread_local ForkJoinEvents events[64];  // per host thread: a viewer thread rendering next to the trainer has its own pair
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    ForkJoinEvents& e = events[dev];
+    if (!e.fork && cudaEventCreateWithFlags(&e.fork, cudaEventDisableTiming) != cudaSuccess) { e.fork = nullptr; return nullptr; }
+    if (!e.join && cudaEventCreateWithFlags(&e.join, cudaEventDisableTiming) != cudaSuccess) { e.join = nullptr; return nullptr; }
+    return &e;
+}
+// (re-recording an event that an earlier wait still references is fine: cudaStreamWaitEvent captures the event's state at
+// the time of the call)
 struct ForkJoin {
     cudaStream_t main, aux;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    ForkJoinEvents* ev = nullptr;
     bool ok = false;
     ForkJoin(cudaStream_t m) : main(m), aux(aux_stream()) {
         if (!aux) return;
-        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return;
-        if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) return;
-        ok = cudaEventRecord(fork, main) == cudaSuccess && cudaStreamWaitEvent(aux, fork, 0) == cudaSuccess;
+        ev = fork_join_events();
+        if (!ev) return;
+        ok = cudaEventRecord(ev->fork, main) == cudaSuccess && cudaStreamWaitEvent(aux, ev->fork, 0) == cudaSuccess;
     }
     cudaStream_t side() const { return ok ? aux : main; }
     void finish() {
-        if (ok) { cudaEventRecord(join, aux); cudaStreamWaitEvent(main, join, 0); }
-    }
-    ~ForkJoin() {
-        if (fork) cudaEventDestroy(fork);
-        if (join) cudaEventDestroy(join);
+        if (ok) { cudaEventRecord(ev->join, aux); cudaStreamWaitEvent(main, ev->join, 0); }
     }
 };
 

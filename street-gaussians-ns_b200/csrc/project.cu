@@ -352,7 +352,7 @@ __device__ __forceinline__ void sgn_project_vjp(const sgn_camera& cam, const Sgn
 __global__ void __launch_bounds__(CH)
 project_bwd_kernel(const sgn_segment* __restrict__ segs, const sgn_segment_grads* __restrict__ grads, int nseg,
                    const sgn_camera cam, const float4* __restrict__ records, const int32_t* __restrict__ radii,
-                   const float4* __restrict__ v_records) {
+                   const float4* __restrict__ v_records, const int chunk_begin) {
     extern __shared__ int s_chunk0[];
     __shared__ __align__(16) float s_rest[CH * MAX_REST];   // out: features_rest gradient rows
     __shared__ __align__(16) float s_dc[CH * MAX_DC];       // out: features_dc gradient rows
@@ -360,10 +360,11 @@ project_bwd_kernel(const sgn_segment* __restrict__ segs, const sgn_segment_grads
     __shared__ __align__(16) float s_scales[CH * 3];        // in: scales, then out: scales gradient
     for (int i = threadIdx.x; i < nseg; i += blockDim.x) s_chunk0[i] = segs[i].chunk0;
     __syncthreads();
-    const int si = find_segment_by_chunk(s_chunk0, nseg, blockIdx.x);
+    const int chunk = chunk_begin + (int)blockIdx.x;
+    const int si = find_segment_by_chunk(s_chunk0, nseg, chunk);
     const sgn_segment& sg = segs[si];
     const sgn_segment_grads& gr = grads[si];
-    const int r0 = (blockIdx.x - sg.chunk0) * CH;
+    const int r0 = (chunk - sg.chunk0) * CH;
     const int rows = min(CH, sg.count - r0);
     const int K = (cam.sh_degree + 1) * (cam.sh_degree + 1);
     const int nrest = (K - 1) * 3, ndc = sg.F * 3;
@@ -475,19 +476,27 @@ project_bwd_kernel(const sgn_segment* __restrict__ segs, const sgn_segment_grads
     if (nrest > 0) coop_store(gr.features_rest + (size_t)r0 * nrest, s_rest, rows * nrest);
 }
 
-extern "C" int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N, int num_chunks,
-                               const sgn_camera* cam, const float* records, const int32_t* radii,
-                               const float* v_records, void* stream) {
+extern "C" int sgn_project_bwd_range(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N, int num_chunks,
+                                     const sgn_camera* cam, const float* records, const int32_t* radii,
+                                     const float* v_records, int chunk_begin, int chunk_end, void* stream) {
     SGN_RANGE("sgn_project_bwd");
     SGN_REQUIRE(segs_dev && grads_dev && cam && records && radii && v_records, "sgn_project_bwd: null pointer");
     SGN_REQUIRE(nseg >= 1 && nseg <= SGN_MAX_SEGMENTS, "sgn_project_bwd: nseg=%d out of range", nseg);
     SGN_REQUIRE(sgn_aligned16(records) && sgn_aligned16(v_records), "records / v_records must be 16-byte aligned");
-    if (N == 0 || num_chunks == 0) return SGN_OK;
-    project_bwd_kernel<<<num_chunks, CH, nseg * sizeof(int), (cudaStream_t)stream>>>(
+    SGN_REQUIRE(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= num_chunks, "sgn_project_bwd: chunk range [%d, %d) outside [0, %d)",
+                chunk_begin, chunk_end, num_chunks);
+    if (N == 0 || chunk_end == chunk_begin) return SGN_OK;
+    project_bwd_kernel<<<chunk_end - chunk_begin, CH, nseg * sizeof(int), (cudaStream_t)stream>>>(
         segs_dev, grads_dev, nseg, *cam, reinterpret_cast<const float4*>(records), radii,
-        reinterpret_cast<const float4*>(v_records));
+        reinterpret_cast<const float4*>(v_records), chunk_begin);
     SGN_CHECK_LAUNCH("project_bwd_kernel");
     return SGN_OK;
+}
+
+extern "C" int sgn_project_bwd(const sgn_segment* segs_dev, const sgn_segment_grads* grads_dev, int nseg, int N, int num_chunks,
+                               const sgn_camera* cam, const float* records, const int32_t* radii,
+                               const float* v_records, void* stream) {
+    return sgn_project_bwd_range(segs_dev, grads_dev, nseg, N, num_chunks, cam, records, radii, v_records, 0, num_chunks > 0 ? num_chunks : 0, stream);
 }
 
 // ================================================================================================

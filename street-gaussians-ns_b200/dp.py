@@ -68,3 +68,142 @@ def allreduce_and_step(arena: torch.Tensor, optimizer, present, chunks: int = 4,
         if not avg:
             arena[lo:hi].div_(world)
         optimizer.launch(optimizer.rows_in_range(tab, lo, hi), arena)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# The exchange as this library's own kernel over symmetric memory (csrc/collective.cu)
+# --------------------------------------------------------------------------------------------------------------------
+def plan_ranges(seg_counts, seg_arena_offsets, seg_widths, num_ranges: int, chunk_rows: int = 128):
+    """Cuts the project backward of a frame into ``num_ranges`` chunk ranges and names the arena slices each one writes.
+
+    ``seg_counts[s]``: rows of segment s (frame order); ``seg_arena_offsets[s][k]`` / ``seg_widths[s][k]``: where tensor k of
+    segment s starts in the arena (floats) and its floats per row.  The first (largest) segment -- the background -- is cut
+    into row ranges at chunk boundaries; every other segment stays whole, and runs of whole segments whose arena regions are
+    adjacent collapse into one slice.  Returns [(chunk_begin, chunk_end, [(offset, length), ...]), ...]; lengths are
+    rounded up to 4 floats (the arena pads every tensor to 16 bytes).  Plain integer arithmetic (CPU-tested)."""
+    def pad4(x):
+        return (x + 3) // 4 * 4
+    chunks = [(n + chunk_rows - 1) // chunk_rows for n in seg_counts]
+    chunk0 = [sum(chunks[:i]) for i in range(len(chunks))]
+    out = []
+    head = max(1, num_ranges - 1) if len(seg_counts) > 1 else max(1, num_ranges)
+    per = (chunks[0] + head - 1) // head if chunks[0] else 0
+    c = 0
+    while c < chunks[0]:
+        c1 = min(chunks[0], c + per)
+        r0, r1 = c * chunk_rows, min(seg_counts[0], c1 * chunk_rows)
+        sl = [(int(seg_arena_offsets[0][k] + r0 * seg_widths[0][k]), int(pad4((r1 - r0) * seg_widths[0][k]))) for k in range(6)]
+        out.append((chunk0[0] + c, chunk0[0] + c1, [x for x in sl if x[1] > 0]))
+        c = c1
+    if len(seg_counts) > 1:
+        runs = []
+        for s in range(1, len(seg_counts)):
+            for k in range(6):
+                o, ln = int(seg_arena_offsets[s][k]), int(pad4(seg_counts[s] * seg_widths[s][k]))
+                if ln == 0:
+                    continue
+                if runs and runs[-1][0] + runs[-1][1] == o:
+                    runs[-1][1] += ln
+                else:
+                    runs.append([o, ln])
+        out.append((chunk0[1], chunk0[-1] + chunks[-1], [tuple(r) for r in runs]))
+    return out
+
+
+def frame_arena_layout(frame):
+    """(row counts, per-tensor arena offsets, floats per row, total floats) of the gradient arena project_bwd writes for a
+    frame: segment-major, six tensors per segment, every tensor padded to 16 bytes (raster.arena_layout)."""
+    counts, widths, offs, cur = [], [], [], 0
+    for seg in frame.segments:
+        p = seg.params
+        n = int(p.means.shape[0])
+        w = [3, 3, 4, 3 * int(p.features_dc.shape[1]), 3 * int(p.features_rest.shape[1]), 1]
+        row = []
+        for k in range(6):
+            row.append(cur)
+            cur += (n * w[k] + 3) // 4 * 4
+        counts.append(n)
+        widths.append(w)
+        offs.append(row)
+    return counts, offs, widths, cur
+
+
+class SymmetricExchange:
+    """The gradient arena in symmetric memory + the exchange kernels over it.
+
+    ``arena`` is the tensor the project backward writes (and Adam reads); ``all_reduce(slices)`` sums (or averages) the listed
+    slices over the ranks IN PLACE with ``sgn_allreduce_sym`` between two device-side barriers, on ``stream`` (default: the
+    current one).  With ``comm_stream`` the exchange of range k runs next to the production of range k+1:
+    ``begin()`` ... ``after_range(k, slices)`` ... ``wait_range(k)``.
+    Needs CUDA peer access between the ranks' GPUs (NVLink); the multicast path additionally needs an NVSwitch fabric --
+    without it the kernel pulls from / pushes to the peers' arenas directly."""
+
+    def __init__(self, numel: int, device, group: Optional[dist.ProcessGroup] = None, use_multicast: bool = True):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.numel = int((numel + 3) // 4 * 4)
+        self.arena = symm.empty(self.numel, dtype=torch.float32, device=device)
+        self.arena.zero_()
+        self.hdl = symm.rendezvous(self.arena, self.group)
+        mc = 0
+        if use_multicast:
+            try:
+                mc = int(self.hdl.multicast_ptr or 0)
+            except Exception:
+                mc = 0
+        self.multicast_ptr = mc
+        self.peers_dev = int(self.hdl.buffer_ptrs_dev)
+        self.comm_stream = torch.cuda.Stream(device=device)
+        self._done = {}
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    @property
+    def mode(self) -> str:
+        return "multimem (in-switch reduction)" if self.multicast_ptr else "peer loads/stores"
+
+    def _launch(self, slices, scale: float, max_ctas: int = 0):
+        C = self._C
+        n = len(slices)
+        if n == 0:
+            return
+        assert n <= self._lib.AR_MAX_SLICES, n
+        off = (C.c_int64 * n)(*[int(o) for o, _ in slices])
+        ln = (C.c_int64 * n)(*[int(l) for _, l in slices])
+        L = self._lib.load()
+        self._lib.check(L.sgn_allreduce_sym(C.c_void_p(self.arena.data_ptr()), C.c_void_p(self.multicast_ptr or None),
+                                            C.c_void_p(self.peers_dev), self.rank, self.world, n, off, ln, C.c_float(scale), max_ctas,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "sgn_allreduce_sym")
+
+    def all_reduce(self, slices=None, average: bool = False, max_ctas: int = 0):
+        """In place, on the current stream.  ``slices``: [(offset, length)] in floats (multiples of 4); None = the whole arena."""
+        if slices is None:
+            slices = [(0, self.numel)]
+        self.hdl.barrier(channel=0)   # every replica has written these slices
+        self._launch(slices, 1.0 / self.world if average else 1.0, max_ctas)
+        self.hdl.barrier(channel=1)   # every part has been pushed to every replica
+
+    # ---- range by range, on the communication stream ------------------------------------------------------------
+    def after_range(self, k: int, slices, average: bool = False, max_ctas: int = 0):
+        """Call right after the launch that PRODUCES range k was enqueued on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            self.all_reduce(slices, average, max_ctas)
+            done = torch.cuda.Event()
+            done.record()
+        self._done[k] = done
+
+    def wait_range(self, k: int):
+        """The current stream waits until range k has been exchanged."""
+        torch.cuda.current_stream().wait_event(self._done.pop(k))
+
+    def wait_all(self):
+        for k in sorted(self._done):
+            torch.cuda.current_stream().wait_event(self._done[k])
+        self._done.clear()

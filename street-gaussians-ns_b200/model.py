@@ -204,12 +204,21 @@ class _FullArenaSink(_GradSink):
     def grad_offsets(self, static: dict):
         return self.offsets[self._tensor_ids()]
 
+    def total_elems(self) -> int:
+        return int(self.sizes.sum())
+
+    def set_arena(self, arena: torch.Tensor) -> None:
+        """Install the arena the gradients are delivered in (data parallel: a view of a symmetric allocation, so that the
+        exchange kernel of csrc/collective.cu can address every replica's copy)."""
+        assert arena.dtype == torch.float32 and arena.is_contiguous() and arena.numel() == self.total_elems()
+        self.arena = arena
+        chunks = arena.split_with_sizes([int(x) for x in self.sizes])
+        self.all_views = [c[:int(np.prod(shp))].view(shp) for c, shp in zip(chunks, self.all_shapes)]
+
     def target(self, static: dict, device):
         total = int(self.sizes.sum())
         if self.arena is None or self.arena.numel() != total or self.arena.device != device:
-            self.arena = torch.zeros(total, device=device, dtype=torch.float32)
-            chunks = self.arena.split_with_sizes([int(x) for x in self.sizes])
-            self.all_views = [c[:int(np.prod(shp))].view(shp) for c, shp in zip(chunks, self.all_shapes)]
+            self.set_arena(torch.zeros(total, device=device, dtype=torch.float32))
         self.views = [self.all_views[t] for t in self._tensor_ids()]
         for p in self.params:
             if p.grad is not None:

@@ -431,7 +431,7 @@ def arena_views(arena: torch.Tensor, static: dict) -> List[torch.Tensor]:
 
 
 def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, records, radii, v_records, make_views: bool = True,
-                out: Optional[torch.Tensor] = None, out_offsets: Optional[np.ndarray] = None):
+                out: Optional[torch.Tensor] = None, out_offsets: Optional[np.ndarray] = None, chunk_ranges=None, after_range=None):
     """Dense parameter gradients, one flat arena (a single allocation, 16-byte aligned slices; ``out`` reuses one).
     ``out_offsets`` (floats, one per parameter tensor of the frame, multiples of 4) places the slices inside a larger
     ``out`` -- the data-parallel arena that has the layout of ALL sub-models (model._FullArenaSink)."""
@@ -451,8 +451,18 @@ def project_bwd(table: SegmentTable, params: List[List[torch.Tensor]], cs, recor
         gt = _grads_table(arena, st, device)
     flat = arena_views(arena, st) if make_views else None
     with _timed("project_bwd"):
-        _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, table.num_chunks, C.byref(cs), _ptr(records),
-                                     _ptr(radii), _ptr(v_records), _stream()), "sgn_project_bwd")
+        if chunk_ranges is None:
+            _lib.check(L.sgn_project_bwd(_ptr(table.dev), _ptr(gt), table.nseg, table.N, table.num_chunks, C.byref(cs), _ptr(records),
+                                         _ptr(radii), _ptr(v_records), _stream()), "sgn_project_bwd")
+        else:
+            # range by range (data parallel): ``after_range(k)`` is called once range k's launch is enqueued -- the exchange of
+            # that range's slices starts there and overlaps the production of the next range (dp.SymmetricExchange)
+            for k, (c0, c1) in enumerate(chunk_ranges):
+                _lib.check(L.sgn_project_bwd_range(_ptr(table.dev), _ptr(gt), table.nseg, table.N, table.num_chunks, C.byref(cs),
+                                                   _ptr(records), _ptr(radii), _ptr(v_records), int(c0), int(c1), _stream()),
+                           "sgn_project_bwd_range")
+                if after_range is not None:
+                    after_range(k)
     return flat, arena
 
 
@@ -550,7 +560,8 @@ class _SceneGraphRasterize(torch.autograd.Function):
 
 
 def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[str, Optional[torch.Tensor]],
-                     sky: Optional[torch.Tensor] = None, want_param_grads: bool = False):
+                     sky: Optional[torch.Tensor] = None, want_param_grads: bool = False, grad_out: Optional[torch.Tensor] = None,
+                     chunk_ranges=None, after_range=None):
     """One frame, forward AND backward, straight through the C-ABI stages (no autograd graph).
 
     ``cotangents`` maps output names (rgb, accumulation, depth, object_acc, background_acc) to their
@@ -558,7 +569,9 @@ def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[st
     ``holder.grad_arena`` is the flat dense gradient arena (what the data-parallel all-reduce and a
     fused optimizer consume), ``holder.v_records[:, 0:2]`` the pixel-space mean gradients the
     densification statistics read.  With ``want_param_grads`` the per-parameter views are returned in
-    ``holder.param_grads``.  Same kernels and same arithmetic as ``render_frame`` + ``backward()``."""
+    ``holder.param_grads``.  Same kernels and same arithmetic as ``render_frame`` + ``backward()``.
+    ``grad_out``: a persistent arena to write into (data parallel: a symmetric allocation); ``chunk_ranges`` / ``after_range``:
+    see ``project_bwd``."""
     params = [seg.params.tensors() for seg in frame.segments]
     device = params[0][0].device
     cs = camera_struct(frame.camera, settings)
@@ -575,7 +588,8 @@ def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[st
     out = blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky, cls_ids, cls_bins)
     v = {k: cotangents.get(k) for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc")}
     v_records, v_sky = blend_bwd(cs, bo, records, sorted_ids, tile_bins, out, sky, v, sky is not None, cls_ids, cls_bins)
-    flat, arena = project_bwd(table, params, cs, records, radii, v_records, make_views=want_param_grads)
+    flat, arena = project_bwd(table, params, cs, records, radii, v_records, make_views=want_param_grads, out=grad_out,
+                              chunk_ranges=chunk_ranges, after_range=after_range)
     holder = _Holder()
     holder.records, holder.radii, holder.num_tiles_hit, holder.M = records, radii, tiles_hit, M
     holder.xys, holder.conics, holder.depths = records[:, 0:2], records[:, 2:5], records[:, 9]

@@ -30,12 +30,15 @@ from .scene import Camera
 class TrainStep:
     def __init__(self, model: SceneGraphRasterModel, optimizer: FusedAdam, refine_every: Optional[int] = None,
                  group: Optional[dist.ProcessGroup] = None, pipeline_chunks: int = 0, refine_seed: int = 0,
-                 check_replicas: bool = True, overlap: bool = False):
+                 check_replicas: bool = True, overlap: bool = False, exchange: str = "auto"):
         """``pipeline_chunks`` > 0 (data parallel only): all-reduce and Adam are pipelined over that many ranges of the
         arena (dp.allreduce_and_step) instead of running one after the other."""
         self.model, self.optimizer, self.group = model, optimizer, group
         self.pipeline_chunks = pipeline_chunks if pipeline_chunks > 0 or not overlap else 4
         self.refine_seed, self.check_replicas, self._gen = refine_seed, check_replicas, None
+        # how the gradient arena is exchanged: "sym" = this library's kernel over symmetric memory (csrc/collective.cu),
+        # "nccl" = dist.all_reduce, "auto" = sym on NCCL process groups when the symmetric allocation succeeds
+        self.exchange_mode, self._exchange = exchange, None
         # None: every sub-model on its own ``refine_every`` (the reference registers one callback per sub-model with
         # ``update_every_num_iters = config.refine_every``); a number: one cadence for all of them
         self.refine_every = refine_every
@@ -65,6 +68,8 @@ class TrainStep:
         if world > 1:
             assert full, "data parallel needs SceneGraphConfig(full_gradient_arena=True): replicas see different actors"
             assert all_cameras is not None and len(all_cameras) == world
+        if world > 1:
+            self._ensure_exchange()
         m.step = step                                     # step_cb (sgn_splatfacto.py:754-755)
         for p in m.parameters():                          # Optimizers.zero_grad_all()
             p.grad = None
@@ -88,7 +93,9 @@ class TrainStep:
         else:
             present = m.present_submodels()
         everything = len(present) == opt.num_segments and (full or present == list(range(opt.num_segments)))
-        if world > 1 and self.pipeline_chunks > 0:
+        if world > 1 and self._exchange is not None:
+            self._exchange_and_step(arena, None if everything else present)
+        elif world > 1 and self.pipeline_chunks > 0:
             dp.allreduce_and_step(arena, opt, None if everything else present, self.pipeline_chunks, self.group)
         else:
             if world > 1:
@@ -98,6 +105,44 @@ class TrainStep:
             m.after_train(step)                           # AFTER_TRAIN_ITERATION callbacks, in the reference's order
         self._maybe_refine(step)
         return losses
+
+    def _ensure_exchange(self) -> None:
+        """(Re)allocates the symmetric gradient arena when the model's layout changed (first step, after a refinement).
+        Collective: every replica reaches it at the same step with the same sizes."""
+        if self.exchange_mode == "nccl" or dist.get_backend(self.group) != "nccl":
+            return
+        m = self.model
+        sink = m._grad_sink
+        sink.bind_model(m.optimizer_params(), [])
+        total = sink.total_elems()
+        ex = self._exchange
+        if ex is not None and ex.numel == (total + 3) // 4 * 4 and sink.arena is not None and sink.arena.data_ptr() == ex.arena.data_ptr():
+            return
+        try:
+            self._exchange = None
+            ex = dp.SymmetricExchange(total, m.device, self.group)
+            sink.set_arena(ex.arena[:total])
+            self._exchange = ex
+        except Exception as e:  # no peer access / no symmetric-memory support on this box: the NCCL path is the fallback
+            if self.exchange_mode == "sym":
+                raise
+            self._exchange = None
+            self.exchange_mode = "nccl"
+            self.exchange_error = f"{type(e).__name__}: {e}"[:300]
+
+    def _exchange_and_step(self, arena: torch.Tensor, present) -> None:
+        """Mean of the arena over the replicas with sgn_allreduce_sym, range by range on the communication stream, and the
+        fused Adam of range k as soon as range k has been exchanged (while range k+1 is on the wire)."""
+        ex, opt = self._exchange, self.optimizer
+        assert arena.data_ptr() == ex.arena.data_ptr(), "the gradient arena is not the symmetric allocation"
+        opt.step_count += 1
+        tab = opt.step_table(present, full_layout=True)
+        bounds = dp.chunk_bounds(opt.arena_elems, max(1, self.pipeline_chunks))
+        for k, (lo, hi) in enumerate(bounds):
+            ex.after_range(k, [(lo, hi - lo)], average=True)
+        for k, (lo, hi) in enumerate(bounds):
+            ex.wait_range(k)
+            opt.launch(opt.rows_in_range(tab, lo, hi), arena)
 
     def _refine_generator(self, step: int) -> torch.Generator:
         """Split samples must be identical on every replica whatever else consumed the global CUDA generator (a sky

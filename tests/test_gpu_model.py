@@ -209,9 +209,10 @@ def test_device_resident_frame_table_and_pose_content_key():
     fr = resident._frame(sc.cameras[7])
     assert fr._prebuilt is not None and fr._prebuilt.dev.data_ptr() >= resident.__dict__["_frame_table_blob"].data_ptr()
     # move one box in place: identity unchanged, content changed -> the image must change and match a fresh model's
-    cam = sc.cameras[7]
+    cam = sc.cameras[5]  # frame 1, the forward-looking rig camera: the nearest boxes are in view
     before = resident.get_outputs(cam)["rgb"].clone()
-    boxes[int(cam.time)][0].center[0] += 0.75
+    for pose in boxes[int(cam.time)]:
+        pose.center[0] += 0.75
     after = resident.get_outputs(cam)["rgb"]
     assert not torch.equal(before, after)
     assert torch.equal(after, build().get_outputs(cam)["rgb"])
