@@ -106,6 +106,10 @@ class ClockSampler:
             except Exception:
                 pass
 
+    def reset(self):
+        """Forget what was sampled so far (warm-up): the report covers the timed regions only."""
+        self.samples, self.reasons = [], set()
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": []}
         if self._h is None:
@@ -276,21 +280,31 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier_sync()
-    # Host hygiene for sub-3 ms steps: a full cyclic-GC pass over the heap torch builds at import takes several
-    # milliseconds.  Everything allocated so far is moved to the permanent generation (the collector stays enabled).
+    # Everything that happens ONCE happens before the warm-up, not between the warm-up and the timed region: NVML
+    # initialisation and its first queries, the stage timers' first events, the cyclic-GC freeze.  (On fresh boxes a one-off
+    # HOST stall of 20-220 ms hit the second timed step in 4 of 8 runs while those sat right before the timed region -- the
+    # per-stage events show no kernel absorbed it -- profiles/r02b_bench_outliers.txt.)  The sampler thread polls through
+    # warm-up and timed regions alike; its samples are reset where the timed region starts.
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     import gc
     gc.collect()
-    gc.freeze()
+    gc.freeze()  # a full cyclic-GC pass over the heap torch builds at import takes several milliseconds (4 steps' worth)
+    # warm-up with EXACTLY the timed loop's body (stage timers on, an event per step): the first execution of a host code path
+    # on a fresh box pages its code in (tens of ms for one step), which must not land inside the timed region either
+    raster.TIMER = raster.StageTimer()
+    for _ in range(args.warmup):
+        step()
+        torch.cuda.Event(enable_timing=True).record()
+    barrier_sync()
+    raster.TIMER.mean_ms()
 
     # ---- timed region 1: device-resident inputs, CUDA events, max over ranks --------------------
-    sampler = ClockSampler(local) if rank == 0 else None
     raster.TIMER = raster.StageTimer()
     launches0 = L.sgn_launch_count()
     if sampler:
-        sampler.start()
+        sampler.reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier_sync()
     e0.record()

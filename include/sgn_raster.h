@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SGN_ABI_VERSION 1
+#define SGN_ABI_VERSION 2
 #define SGN_MAX_FOURIER 8
 #define SGN_RECORD_FLOATS 12 /* per-Gaussian projected record, see below */
 
@@ -122,6 +122,9 @@ typedef struct sgn_blend_opts {
 #define SGN_TUNE_BWD_PACKED 8
 /* the accumulation-only (object / background) kernels do NOT skip unreachable row pairs */
 #define SGN_TUNE_ACC_NO_ROW_SKIP 16
+/* experiment: the main forward reads its lists as materialised 48-byte staged entries moved by cp.async.bulk + mbarrier
+ * (sgn_blend_fwd_out.staged must then point to 48 * M bytes of scratch) instead of gathering records per lane */
+#define SGN_TUNE_FWD_TMA 32
 
 const char* sgn_last_error(void);
 int sgn_abi_version(void);
@@ -239,6 +242,7 @@ typedef struct sgn_blend_fwd_out {
     int32_t* tile_depth;   /* [3,tiles] entries traversed per tile (main, object, background pass); sizes the backward */
     int32_t* sched;        /* scratch of sgn_blend_sched_ints(tiles) int32, or NULL: heavy-first work lists (longest tile
                               lists are scheduled first; without it CTAs take the tiles in raster order) */
+    float* staged;         /* scratch of 12 * M floats (16-byte aligned) for SGN_TUNE_FWD_TMA, or NULL */
 } sgn_blend_fwd_out;
 
 size_t sgn_blend_sched_ints(int tiles);
@@ -260,6 +264,12 @@ typedef struct sgn_blend_bwd_in {
     int32_t* sched;                /* scratch of sgn_blend_sched_ints(tiles) int32 (may be the forward's), or NULL */
     const float* sky;              /* [H,W,3] or NULL */
     float* v_sky;                  /* [H,W,3] or NULL: gradient to the sky colour */
+    /* Deterministic mode (NULL = off): the per-Gaussian gradients are accumulated in 64-bit fixed point (one rounding per
+     * addend, integer adds: bit-identical totals whatever the execution order) instead of with float atomics, then written
+     * to v_records.  v_fixed: [num_gaussians,12] int64, ZERO on entry; fixed_scale: one float of device scratch. */
+    int64_t* v_fixed;
+    float* fixed_scale;
+    int64_t num_gaussians;
 } sgn_blend_bwd_in;
 
 /* Backward: gsplat rasterize_backward for all streams in one traversal.  v_records[N,12] must be

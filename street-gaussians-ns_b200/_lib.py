@@ -106,7 +106,7 @@ class BlendFwdOut(C.Structure):
         ("rgb", C.c_void_p), ("accumulation", C.c_void_p), ("depth", C.c_void_p),
         ("object_acc", C.c_void_p), ("background_acc", C.c_void_p),
         ("raw", C.c_void_p), ("final_T", C.c_void_p), ("final_idx", C.c_void_p), ("tile_depth", C.c_void_p),
-        ("sched", C.c_void_p),
+        ("sched", C.c_void_p), ("staged", C.c_void_p),
     ]
 
 
@@ -116,6 +116,7 @@ class BlendBwdIn(C.Structure):
         ("v_object_acc", C.c_void_p), ("v_background_acc", C.c_void_p),
         ("raw", C.c_void_p), ("final_T", C.c_void_p), ("final_idx", C.c_void_p), ("tile_depth", C.c_void_p),
         ("sched", C.c_void_p), ("sky", C.c_void_p), ("v_sky", C.c_void_p),
+        ("v_fixed", C.c_void_p), ("fixed_scale", C.c_void_p), ("num_gaussians", C.c_int64),
     ]
 
 

@@ -51,6 +51,7 @@ struct BlendFwdParams {
     int has_sky, eval_clamp, raw_mode;
     float bg[4];
     const float4* records;
+    const float4* staged;  // experiment (SGN_TUNE_FWD_TMA): the lists materialised as staged entries, 48 B each, in list order
     const int32_t* sorted_ids;
     const int2* tile_bins;
     const int32_t* cls_ids[2];  // class sub-lists: [0] background, [1] object
@@ -177,6 +178,35 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return y;
 }
 
+// ---- bulk-asynchronous staging (experiment, SGN_TUNE_FWD_TMA) --------------------------------------------------------
+// The north-star names "TMA / shared-memory staging of per-tile sorted Gaussian records".  With the lists materialised as
+// 48-byte staged entries in list order (sgn_blend_stage_entries), a batch of 32 entries is ONE contiguous 1.5 KB run, which
+// the copy engine moves with cp.async.bulk (SASS: UBLKCP) and signals on an mbarrier -- no per-lane gathers, no log2 /
+// rescale in the consumer.  Measured against the gather path in profiles/ (the gathers cost < 1 instruction per entry of a
+// ~180-instruction entry, and materialising costs a 48 B write + read per entry): kept as a switchable variant.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // Blackwell packed FP32: one FFMA2/FMUL2/FADD2 issues two IEEE fp32 operations on a register pair.
 // The slot loops below are FP32-issue bound, so the row-slot pairs (2p, 2p+1) of a lane are packed.
 struct f2 {
@@ -288,9 +318,10 @@ __device__ __forceinline__ bool take_work(const int32_t* __restrict__ sched, int
     return true;
 }
 
-template <int PPL, bool CLS, bool SKIP, bool PACK>
+template <int PPL, bool CLS, bool SKIP, bool PACK, bool TMA = false>
 __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int tile, int strip, const int2 range,
-                                                float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32]) {
+                                                float4 (*sA)[32], float4 (*sB)[32], float4 (*sC)[32],
+                                                float4 (*sE)[96] = nullptr, uint64_t* mbar = nullptr) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int lane = threadIdx.x;
     const int j = tx * SGN_TILE + (lane & 15);
@@ -315,7 +346,24 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
     }
 
     Staged nxt;
-    if (range.x + lane < range.y) nxt = gather_entry(p.records, p.sorted_ids[range.x + lane]);
+    unsigned parity = 0;    // TMA: phase parity of the two mbarriers (bit b = buffer b)
+    int pending_buf = -1;   // TMA: buffer with a bulk copy in flight that nobody has waited for yet
+    if constexpr (TMA) {
+        if (lane == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (range.x < range.y) {
+                const uint32_t bytes = (uint32_t)min(32, range.y - range.x) * 48u;
+                mbar_expect_tx(&mbar[0], bytes);
+                bulk_g2s(sE[0], p.staged + 3 * (size_t)range.x, bytes, &mbar[0]);
+            }
+        }
+        __syncwarp();
+    } else {
+        if (range.x + lane < range.y) nxt = gather_entry(p.records, p.sorted_ids[range.x + lane]);
+    }
     int buf = 0;
     bool finished = false;
     const float yc0 = (float)((tile / p.tiles_x) * SGN_TILE + strip * (2 * PPL)) + 1.0f;
@@ -330,10 +378,26 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
     }
     const float clampf = in_register(p.clamp_fwd), nclamp = in_register(-p.clamp_fwd);
     for (int base = range.x; base < range.y && !finished; base += 32) {
+        if constexpr (TMA) {
+            __syncwarp();  // every lane has finished reading the other buffer (previous batch)
+            pending_buf = -1;
+            if (base + 32 < range.y) {
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const uint32_t bytes = (uint32_t)min(32, range.y - base - 32) * 48u;
+                    mbar_expect_tx(&mbar[buf ^ 1], bytes);
+                    bulk_g2s(sE[buf ^ 1], p.staged + 3 * (size_t)(base + 32), bytes, &mbar[buf ^ 1]);
+                }
+                pending_buf = buf ^ 1;
+            }
+            mbar_wait(&mbar[buf], (parity >> buf) & 1u);
+            parity ^= 1u << buf;
+        } else {
         sA[buf][lane] = nxt.A; sB[buf][lane] = nxt.B;
         sC[buf][lane] = make_float4(nxt.C.x, nxt.C.y, nxt.C.z, SKIP ? row_reach(nxt) + 0.5f : 0.f);
         __syncwarp();
         if (base + 32 + lane < range.y) nxt = gather_entry(p.records, p.sorted_ids[base + 32 + lane]);
+        }
         if (SKIP) {
             slot_live = 0;
 #pragma unroll
@@ -353,9 +417,9 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
                 for (int s = 0; s < PPL; ++s) ymin = fminf(ymin, PK ? ((s & 1) ? yoff2[s / 2].y : yoff2[s / 2].x) : yoff[s]);
                 if (__all_sync(FULL, ymin >= 0.5f * DEAD)) { finished = true; break; }
             }
-            const float4 A = sA[buf][t];
-            const float4 B = sB[buf][t];
-            const float4 Cc = sC[buf][t];
+            const float4 A = TMA ? sE[buf][3 * t] : sA[buf][t];
+            const float4 B = TMA ? sE[buf][3 * t + 1] : sB[buf][t];
+            const float4 Cc = TMA ? sE[buf][3 * t + 2] : sC[buf][t];
             const float objflag = (CLS && (__float_as_int(Cc.z) < 0)) ? 1.f : 0.f;
             const float dyc = A.y - yc0;
             const float dx = A.x - px;
@@ -415,6 +479,9 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
             }
         }
         buf ^= 1;
+    }
+    if constexpr (TMA) {  // a copy issued for a batch the traversal never reached must land before the CTA may exit
+        if (pending_buf >= 0) mbar_wait(&mbar[pending_buf], (parity >> pending_buf) & 1u);
     }
     if constexpr (PK) {
 #pragma unroll
@@ -489,6 +556,32 @@ __global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
         case 4: blend_fwd_strip<2, CLS, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
         default: blend_fwd_strip<1, CLS, SKIP, PACK>(p, tile, strip, range, sA, sB, sC); break;
     }
+}
+
+template <bool CLS>
+__global__ void __launch_bounds__(32) blend_fwd_tma_kernel(const BlendFwdParams p) {
+    __shared__ __align__(128) float4 sE[2][96];
+    __shared__ __align__(8) uint64_t mbar[2];
+    int tile, strip;
+    if (!take_work(p.sched, SLOT_MAIN, p.tiles, tile, strip)) return;
+    const int2 range = p.tile_bins[tile];
+    const int W = strips_for(range.y - range.x, p.split_main);
+    if (strip >= W) return;
+    switch (W) {
+        case 1: blend_fwd_strip<8, CLS, false, true, true>(p, tile, strip, range, nullptr, nullptr, nullptr, sE, mbar); break;
+        case 2: blend_fwd_strip<4, CLS, false, true, true>(p, tile, strip, range, nullptr, nullptr, nullptr, sE, mbar); break;
+        case 4: blend_fwd_strip<2, CLS, false, true, true>(p, tile, strip, range, nullptr, nullptr, nullptr, sE, mbar); break;
+        default: blend_fwd_strip<1, CLS, false, true, true>(p, tile, strip, range, nullptr, nullptr, nullptr, sE, mbar); break;
+    }
+}
+
+// materialises the per-tile lists as staged entries (the TMA experiment's input): entry k of the sorted list -> 48 bytes
+__global__ void __launch_bounds__(256)
+stage_entries_kernel(long long M, const float4* __restrict__ records, const int32_t* __restrict__ sorted_ids, float4* __restrict__ staged) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const Staged s = gather_entry(records, sorted_ids[k]);
+    staged[3 * k] = s.A; staged[3 * k + 1] = s.B; staged[3 * k + 2] = s.C;
 }
 
 // accumulation-only pass over one class's per-tile sub-lists (objects-only / background-only render)
@@ -657,6 +750,10 @@ static int check_cam(const sgn_camera* cam) {
 template <bool CLS>
 static void launch_blend_fwd(const BlendFwdParams& p, int tuning, cudaStream_t stream) {
     const dim3 grid(p.tiles * 8), block(32);
+    if ((tuning & SGN_TUNE_FWD_TMA) && p.staged) {
+        blend_fwd_tma_kernel<CLS><<<grid, block, 0, stream>>>(p);
+        return;
+    }
     switch (((tuning & SGN_TUNE_FWD_ROW_SKIP) ? 2 : 0) | ((tuning & SGN_TUNE_FWD_PACKED) ? 1 : 0)) {
         case 0: blend_fwd_kernel<CLS, false, false><<<grid, block, 0, stream>>>(p); break;
         case 1: blend_fwd_kernel<CLS, false, true><<<grid, block, 0, stream>>>(p); break;
@@ -687,10 +784,17 @@ extern "C" int sgn_blend_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.has_sky = opts->has_sky; p.eval_clamp = opts->eval_clamp; p.raw_mode = opts->raw_mode;
     for (int c = 0; c < 4; ++c) p.bg[c] = opts->background[c];
     p.records = reinterpret_cast<const float4*>(records);
+    p.staged = nullptr;
     p.sorted_ids = sorted_ids;
     p.tile_bins = reinterpret_cast<const int2*>(tile_bins);
     const int tiles = p.tiles_x * tiles_y;
     p.tiles = tiles;
+    if ((opts->tuning & SGN_TUNE_FWD_TMA) && out->staged && sorted_ids && M > 0) {
+        SGN_REQUIRE(sgn_aligned16(out->staged), "staged entries must be 16-byte aligned");
+        stage_entries_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(M, p.records, sorted_ids, reinterpret_cast<float4*>(out->staged));
+        SGN_CHECK_LAUNCH("stage_entries_kernel");
+        p.staged = reinterpret_cast<const float4*>(out->staged);
+    }
     p.cls_ids[0] = cls_ids; p.cls_ids[1] = cls_ids ? cls_ids + M : nullptr;
     p.cls_bins[0] = reinterpret_cast<const int2*>(cls_bins);
     p.cls_bins[1] = cls_bins ? reinterpret_cast<const int2*>(cls_bins) + tiles : nullptr;
@@ -755,7 +859,17 @@ struct BlendBwdParams {
     const float* sky;
     float* v_sky;
     float* v_records;
+    long long* v_fixed;        // deterministic mode: [N,12] fixed-point accumulators instead of float atomics (or null)
+    const float* fixed_scale;  // device scalar: fixed-point units per unit of gradient
 };
+
+// Per-Gaussian gradient accumulation.  Default: float RED (summation order varies from run to run).  Deterministic mode
+// (sgn_blend_bwd_in.v_fixed): the addend is rounded ONCE to 64-bit fixed point and added as an integer -- integer addition
+// is associative, so the total is bit-identical whatever order the tiles and strips arrive in.
+__device__ __forceinline__ void accumulate_grad(const BlendBwdParams& p, float fscale, size_t idx, float v) {
+    if (p.v_fixed) atomicAdd(reinterpret_cast<unsigned long long*>(p.v_fixed) + idx, (unsigned long long)__float2ll_rn(v * fscale));
+    else atomicAdd(p.v_records + idx, v);
+}
 
 // DEPTHG: the depth output has a cotangent.
 // (Measured and dropped: software-pipelining the reduction of entry t-1 under the arithmetic of entry t -- it
@@ -839,6 +953,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
     constexpr int NV = DEPTHG ? 10 : 9;
     const int my_comp = multi_reduce_slot<NV>(lane);
     const float clampb = in_register(p.clamp_bwd), nclamp = -clampb;
+    const float fscale = p.v_fixed ? __ldg(p.fixed_scale) : 0.f;
     constexpr bool PK = PACK && PPL >= 2;
     constexpr int NP = PK ? PPL / 2 : 1;
     f2 T2[NP], d2[NP], vr2[NP], vg2[NP], vb2[NP], vd2[NP];
@@ -951,9 +1066,9 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
             // one component of the record-layout gradient per lane pair
             float comps[NV] = {l0, l1, l2, l3, l4, l5, cr, cg, cb};
             if (DEPTHG) comps[NV - 1] = cd;
-            float* const dst = p.v_records + (size_t)(__float_as_int(Cc.z) & ID_MASK) * SGN_RECORD_FLOATS + (my_comp >= 0 ? my_comp : 0);
+            const size_t dst = (size_t)(__float_as_int(Cc.z) & ID_MASK) * SGN_RECORD_FLOATS + (my_comp >= 0 ? my_comp : 0);
             const float mine = warp_multi_reduce<NV>(comps, lane);
-            if (my_comp >= 0) atomicAdd(dst, mine);
+            if (my_comp >= 0) accumulate_grad(p, fscale, dst, mine);
         }
         buf ^= 1;
     }
@@ -1012,6 +1127,7 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
     if (hi0 <= range.x) return;
     const int my_comp = multi_reduce_slot<6>(lane);
     const float clampb = in_register(p.clamp_bwd), nclamp = -clampb;
+    const float fscale = p.v_fixed ? __ldg(p.fixed_scale) : 0.f;
     Staged nxt;
     if (hi0 - 1 - lane >= range.x) nxt = gather_entry(p.records, ids[hi0 - 1 - lane]);
     int buf = 0;
@@ -1079,7 +1195,7 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
             float l5 = -S0 / o;
             float comps[6] = {l0, l1, l2, l3, l4, l5};
             const float mine = warp_multi_reduce<6>(comps, lane);
-            if (my_comp >= 0) atomicAdd(p.v_records + (size_t)(__float_as_int(B.z) & ID_MASK) * SGN_RECORD_FLOATS + my_comp, mine);
+            if (my_comp >= 0) accumulate_grad(p, fscale, (size_t)(__float_as_int(B.z) & ID_MASK) * SGN_RECORD_FLOATS + my_comp, mine);
         }
         buf ^= 1;
     }
@@ -1101,6 +1217,29 @@ __global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p, con
         case 4: acc_bwd_strip<2, SKIP>(p, cls, tile, strip, range, sA, sB, sR); break;
         default: acc_bwd_strip<1, SKIP>(p, cls, tile, strip, range, sA, sB, sR); break;
     }
+}
+
+// ---- deterministic mode helpers: scale = 2^32 / max |cotangent| (gradients are linear in the cotangents: the fixed-point
+// grid adapts to their magnitude; 2^31 of headroom above it), then fixed point -> float
+__global__ void __launch_bounds__(256)
+cot_max_kernel(const float* __restrict__ a, long long n, unsigned* __restrict__ out_bits) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = fabsf(a[i]);
+        m = (v == v && v < 3.0e38f) ? fmaxf(m, v) : m;
+    }
+    m = fmaxf(m, __shfl_xor_sync(FULL, m, 16)); m = fmaxf(m, __shfl_xor_sync(FULL, m, 8)); m = fmaxf(m, __shfl_xor_sync(FULL, m, 4));
+    m = fmaxf(m, __shfl_xor_sync(FULL, m, 2)); m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order like their bits
+}
+__global__ void fixed_scale_kernel(float* scale) {
+    const float m = scale[0];  // the bits cot_max_kernel left are the float itself
+    scale[0] = m > 0.f ? exp2f(32.f - ceilf(log2f(m))) : 4294967296.f;  // a power of two: scaling is exact
+}
+__global__ void __launch_bounds__(256)
+fixed_to_float_kernel(const long long* __restrict__ fx, const float* __restrict__ scale, float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)((double)fx[i] / (double)scale[0]);
 }
 
 extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records,
@@ -1139,6 +1278,21 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     p.final_T = in->final_T; p.final_idx = in->final_idx;
     p.sky = in->sky; p.v_sky = in->v_sky;
     p.v_records = v_records;
+    p.v_fixed = reinterpret_cast<long long*>(in->v_fixed);
+    p.fixed_scale = in->fixed_scale;
+    const long long P_ = (long long)cam->width * cam->height;
+    if (in->v_fixed) {
+        SGN_REQUIRE(in->fixed_scale && in->num_gaussians > 0, "deterministic mode needs fixed_scale (1 float) and num_gaussians");
+        SGN_CHECK_CUDA(cudaMemsetAsync(in->fixed_scale, 0, sizeof(float), stream));
+        const float* cots[5] = {in->v_rgb, in->v_accumulation, in->v_depth, in->v_object_acc, in->v_background_acc};
+        for (int c = 0; c < 5; ++c) {
+            if (!cots[c]) continue;
+            cot_max_kernel<<<296, 256, 0, stream>>>(cots[c], c == 0 ? 3 * P_ : P_, reinterpret_cast<unsigned*>(in->fixed_scale));
+            SGN_CHECK_LAUNCH("cot_max_kernel");
+        }
+        fixed_scale_kernel<<<1, 1, 0, stream>>>(in->fixed_scale);
+        SGN_CHECK_LAUNCH("fixed_scale_kernel");
+    }
     SGN_REQUIRE(in->tile_depth, "sgn_blend_bwd: tile_depth (saved by the forward) is null");
     p.tile_depth = in->tile_depth;
     p.sched = in->sched;
@@ -1173,6 +1327,12 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
         }
         SGN_CHECK_LAUNCH("blend_bwd_kernel");
         fj.finish();
+    }
+    if (in->v_fixed) {
+        const long long n = (long long)in->num_gaussians * SGN_RECORD_FLOATS;
+        fixed_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const long long*>(in->v_fixed), in->fixed_scale,
+                                                                                v_records, n);
+        SGN_CHECK_LAUNCH("fixed_to_float_kernel");
     }
     return SGN_OK;
 }

@@ -78,8 +78,54 @@ class SceneGraphConfig:
         self.refine.stop_split_at = int(v)
 
 
+_MISSING = object()
+
+
+class _FrameSlice:
+    """A per-frame side-effect attribute of a sub-model (``xys``, ``depths``, ``radii``, ``conics``, ``num_tiles_hit``;
+    sgn_splatfacto.py:513-541 reads them): this sub-model's rows of the frame's arrays, sliced on first access.  Publishing
+    them eagerly costs 5 slices x 33 sub-models of host time per frame, and nothing on the hot path reads them (the
+    densification statistics work on the frame's arrays directly)."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __get__(self, obj, cls=None):
+        if obj is None:
+            return self
+        d = obj.__dict__
+        cache = d.get("_fs_cache")
+        if cache is not None:
+            v = cache.get(self.name, _MISSING)
+            if v is not _MISSING:
+                return v
+        src = d.get("_fs_src")
+        if src is None:
+            return None
+        holder, sl = src
+        t = getattr(holder, self.name)[sl]
+        if self.name == "xys" and holder.v_records is not None:  # after backward: the reference reads ``self.xys.grad``
+            t.grad = holder.v_records[:, 0:2][sl]
+        if cache is None:
+            cache = d["_fs_cache"] = {}
+        cache[self.name] = t
+        return t
+
+    def __set__(self, obj, value):
+        cache = obj.__dict__.get("_fs_cache")
+        if cache is None:
+            cache = obj.__dict__["_fs_cache"] = {}
+        cache[self.name] = value
+
+
 class GaussianSubModel(torch.nn.Module):
     """One entry of ``all_models``: the ``gauss_params`` ParameterDict (sgn_splatfacto.py:291-300)."""
+
+    xys = _FrameSlice("xys")
+    depths = _FrameSlice("depths")
+    radii = _FrameSlice("radii")
+    conics = _FrameSlice("conics")
+    num_tiles_hit = _FrameSlice("num_tiles_hit")
 
     def __init__(self, params: GaussianSet):
         super().__init__()
@@ -465,17 +511,16 @@ class SceneGraphRasterModel(torch.nn.Module):
         visible = set(self.visible_model_names)
         for name, sub in mods.items():
             if name not in visible:
-                sub.__dict__["xys"] = None
+                sd = sub.__dict__
+                sd["_fs_src"], sd["_fs_cache"] = None, None
         row = 0
         slices = []
-        xs, ds, rs, cs_, ts = holder.xys, holder.depths, holder.radii, holder.conics, holder.num_tiles_hit
         for seg in frame.segments:
             sub = mods[seg.name]
             n = seg.params.means.shape[0]
             sl = slice(row, row + n)
             sd = sub.__dict__
-            sd["xys"], sd["depths"], sd["radii"] = xs[sl], ds[sl], rs[sl]
-            sd["conics"], sd["num_tiles_hit"], sd["last_size"] = cs_[sl], ts[sl], self.last_size
+            sd["_fs_src"], sd["_fs_cache"], sd["last_size"] = (holder, sl), None, self.last_size  # sliced on first access
             slices.append((sub, sl))
             row += n
         d["_slices"] = slices
@@ -630,11 +675,17 @@ class SceneGraphRasterModel(torch.nn.Module):
     @staticmethod
     def _split_xys_grad(slices):
         """After ``loss.backward()``: ``sub.xys.grad`` for every visible sub-model, as the reference's
-        ``set_split_tensor_variable(..., retain_grad=True)`` provides (scene graph :153-179)."""
+        ``set_split_tensor_variable(..., retain_grad=True)`` provides (scene graph :153-179).  ``sub.xys`` is sliced on access
+        (with its gradient, once the backward has run); only a ``sub.xys`` that was read BEFORE the backward needs it set here."""
         def hook(h):
-            v_xy = h.v_records[:, 0:2]
+            v_xy = None
             for sub, sl in slices:
-                sub.__dict__["xys"].grad = v_xy[sl]
+                cache = sub.__dict__.get("_fs_cache")
+                if cache:
+                    t = cache.get("xys")
+                    if t is not None:
+                        v_xy = h.v_records[:, 0:2] if v_xy is None else v_xy
+                        t.grad = v_xy[sl]
         return hook
 
     # ------------------------------------------------------------------------------------------

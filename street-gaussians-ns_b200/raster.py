@@ -34,6 +34,9 @@ class RenderSettings:
     alpha_clamp_bwd: float = 0.99   # gsplat rasterize_backward
     class_streams: bool = True      # object_acc / background_acc (scene graph :364-366)
     training: bool = True           # eval adds rgb.clamp(0,1) (sgn_splatfacto.py:974-975)
+    # bit-reproducible gradients: the backward accumulates per-Gaussian gradients in 64-bit fixed point instead of with
+    # float atomics (whose summation order varies from run to run).  None -> the SGN_DETERMINISTIC environment variable
+    deterministic: Optional[bool] = None
 
 
 class StageTimer:
@@ -351,7 +354,7 @@ def blend_opts(s: RenderSettings, has_sky: bool) -> _lib.BlendOpts:
     bo.split_fwd_acc = int(os.environ.get("SGN_SPLIT_FWD_ACC", "0"))
     bo.split_bwd_main = int(os.environ.get("SGN_SPLIT_BWD_MAIN", "0"))
     bo.split_bwd_acc = int(os.environ.get("SGN_SPLIT_BWD_ACC", "0"))
-    # SGN_TUNE_* bits (include/sgn_raster.h): 1 fwd row skip, 2 bwd row skip, 4 fwd packed f32x2, 8 bwd packed f32x2
+    # SGN_TUNE_* bits (include/sgn_raster.h): 1 fwd row skip, 2 bwd row skip, 4 fwd packed f32x2, 8 bwd packed f32x2, 32 fwd TMA staging
     bo.tuning = int(os.environ.get("SGN_TUNING", str(DEFAULT_TUNING)))
     return bo
 
@@ -375,6 +378,10 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
     fo.background_acc = out["background_acc"].data_ptr() if bo.class_streams else None
     fo.raw, fo.final_T, fo.final_idx = out["raw"].data_ptr(), out["final_T"].data_ptr(), out["final_idx"].data_ptr()
     fo.tile_depth = out["tile_depth"].data_ptr()
+    fo.staged = None
+    if bo.tuning & 32:  # SGN_TUNE_FWD_TMA (experiment): scratch for the materialised staged entries, 48 B per list entry
+        out["staged"] = torch.empty(max(sorted_ids.shape[0], 1) * _lib.RECORD_FLOATS, device=device, dtype=torch.float32)
+        fo.staged = out["staged"].data_ptr()
     if HEAVY_FIRST:  # scratch for the heavy-first work lists (scheduling only), reused by the backward
         out["sched"] = torch.empty(L.sgn_blend_sched_ints(tile_bins.shape[0]), device=device, dtype=torch.int32)
         fo.sched = out["sched"].data_ptr()
@@ -385,13 +392,25 @@ def blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky: Optional[torch.Tensor
     return out
 
 
+DETERMINISTIC = os.environ.get("SGN_DETERMINISTIC", "0") == "1"
+
+
 def blend_bwd(cs, bo, records, sorted_ids, tile_bins, saved: Dict[str, torch.Tensor], sky, v: Dict[str, Optional[torch.Tensor]],
-              want_v_sky: bool, obj_ids=None, obj_bins=None):
+              want_v_sky: bool, obj_ids=None, obj_bins=None, deterministic: Optional[bool] = None):
     """Returns (v_records[N,12], v_sky or None)."""
     L = _lib.load()
     device = records.device
-    v_records = torch.zeros_like(records)
     bi = _lib.BlendBwdIn()
+    det = DETERMINISTIC if deterministic is None else deterministic
+    if det:  # fixed-point accumulators (zeroed) + one float of scratch; v_records is then written, not accumulated into
+        v_records = torch.empty_like(records)
+        v_fixed = torch.zeros(records.shape[0], _lib.RECORD_FLOATS, device=device, dtype=torch.int64)
+        fixed_scale = torch.empty(1, device=device, dtype=torch.float32)
+        bi.v_fixed, bi.fixed_scale, bi.num_gaussians = v_fixed.data_ptr(), fixed_scale.data_ptr(), records.shape[0]
+    else:
+        v_records = torch.zeros_like(records)
+        bi.v_fixed = bi.fixed_scale = None
+        bi.num_gaussians = records.shape[0]
 
     def c(t):
         return None if t is None else t.contiguous()
@@ -538,7 +557,7 @@ class _SceneGraphRasterize(torch.autograd.Function):
         names = ["rgb", "accumulation", "depth", "object_acc", "background_acc"][: len(v)]
         vd = {k: t for k, t in zip(names, v)}
         v_records, v_sky = blend_bwd(ctx.cs, ctx.bo, ctx.records, ctx.sorted_ids, ctx.tile_bins, ctx.saved, ctx.sky, vd,
-                                     ctx.sky_needs_grad, ctx.obj_ids, ctx.obj_bins)
+                                     ctx.sky_needs_grad, ctx.obj_ids, ctx.obj_bins, deterministic=ctx.settings.deterministic)
         h = ctx.holder
         sink = h.grad_sink
         if sink is not None:
@@ -587,7 +606,8 @@ def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[st
         cls_ids, cls_bins = class_lists(cs, M, sorted_ids, tile_bins)
     out = blend_fwd(cs, bo, records, sorted_ids, tile_bins, sky, cls_ids, cls_bins)
     v = {k: cotangents.get(k) for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc")}
-    v_records, v_sky = blend_bwd(cs, bo, records, sorted_ids, tile_bins, out, sky, v, sky is not None, cls_ids, cls_bins)
+    v_records, v_sky = blend_bwd(cs, bo, records, sorted_ids, tile_bins, out, sky, v, sky is not None, cls_ids, cls_bins,
+                                 deterministic=settings.deterministic)
     flat, arena = project_bwd(table, params, cs, records, radii, v_records, make_views=want_param_grads, out=grad_out,
                               chunk_ranges=chunk_ranges, after_range=after_range)
     holder = _Holder()

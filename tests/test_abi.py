@@ -35,7 +35,7 @@ def test_header_symbols_exported(lib):
 
 def test_abi_version_and_layouts(lib):
     L, mod = lib
-    assert L.sgn_abi_version() == 1
+    assert L.sgn_abi_version() == 2
     assert L.sgn_sizeof_segment() == ctypes.sizeof(mod.Segment) == 168
     assert L.sgn_sizeof_camera() == ctypes.sizeof(mod.CameraStruct)
     assert L.sgn_sizeof_segment_grads() == ctypes.sizeof(mod.SegmentGrads) == 48

@@ -318,7 +318,7 @@ def test_execution_variants_agree(scene_name, monkeypatch):
     cots = {"rgb": w.cuda(), "accumulation": v.cuda(), "depth": 0.05 * v.cuda(), "object_acc": 0.1 * v.cuda(),
             "background_acc": 0.1 * v.cuda()}
     res = {}
-    for tuning in (0, 1, 4 | 8, 1 | 4 | 8 | 16):
+    for tuning in (0, 1, 4 | 8, 1 | 4 | 8 | 16, 4 | 8 | 32):  # 32: lists materialised as staged entries, moved by cp.async.bulk
         monkeypatch.setenv("SGN_TUNING", str(tuning))
         frc = to_cuda(fr, requires_grad=True)
         out, h = raster.forward_backward(frc, raster.RenderSettings(), cots, want_param_grads=True)
@@ -333,3 +333,27 @@ def test_execution_variants_agree(scene_name, monkeypatch):
             # a different rounding can flip a threshold decision on a handful of pixels: bound their count
             assert (diff > 2e-6).sum().item() <= max(4, diff.numel() // 20000), (tuning, k, diff.max().item())
         assert rel_l2(g.cpu().numpy(), base_g.cpu().numpy()) < 1e-5, tuning
+
+
+def test_deterministic_mode_is_bit_repeatable_and_close():
+    """RenderSettings(deterministic=True) / SGN_DETERMINISTIC=1: per-Gaussian gradients accumulated in 64-bit fixed point (one
+    rounding per addend, integer adds) instead of with float atomics -> the whole gradient arena is bit-identical from run
+    to run, and agrees with the float-atomic path to its own run-to-run noise."""
+    fr = syn.make_frame(**SCENES["dense_small_image"])
+    H, W = fr.camera.height, fr.camera.width
+    w, v = syn.cotangents(H, W)
+    cots = {"rgb": w.cuda(), "accumulation": v.cuda(), "depth": 0.05 * v.cuda(), "object_acc": 0.1 * v.cuda(),
+            "background_acc": 0.1 * v.cuda()}
+    frc = to_cuda(fr)
+    runs = []
+    for _ in range(3):
+        out, h = raster.forward_backward(frc, raster.RenderSettings(deterministic=True), cots, want_param_grads=True)
+        runs.append((h.v_records.clone(), h.grad_arena.clone()))
+    for vr, ga in runs[1:]:
+        assert torch.equal(vr, runs[0][0]) and torch.equal(ga, runs[0][1])
+    out, h = raster.forward_backward(frc, raster.RenderSettings(deterministic=False), cots, want_param_grads=True)
+    assert rel_l2(runs[0][1].cpu().numpy(), h.grad_arena.cpu().numpy()) < 1e-5
+    # tiny cotangents (a mean-type loss over 2.4 M pixels): the fixed-point grid follows the cotangents' magnitude
+    small = {k: t * 1e-7 for k, t in cots.items()}
+    o2, h2 = raster.forward_backward(frc, raster.RenderSettings(deterministic=True), small, want_param_grads=True)
+    assert rel_l2(h2.grad_arena.cpu().numpy() * 1e7, runs[0][1].cpu().numpy()) < 1e-5
