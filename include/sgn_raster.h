@@ -279,6 +279,19 @@ int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float
                   const int32_t* cls_ids /*[2,M] or NULL*/, const int32_t* cls_bins /*[2,tiles,2] or NULL*/,
                   const sgn_blend_bwd_in* in, float* v_records, void* stream);
 
+/* Generic per-Gaussian channels (the north-star's per-Gaussian semantic logits; the reference's dormant consumer:
+ * scripts/render.py:188,231-236): extra[N,C] is composited with the weights of the main render -- out[p,c] = sum_k
+ * extra[k,c] alpha_k T_k over the entries the main pass blended (final_T / final_idx slot 0 of sgn_blend_fwd) -- 8 channels per
+ * traversal.  What the reference would obtain from one more gsplat rasterize_gaussians(colors = logits) call.  The backward
+ * ACCUMULATES into v_extra[N,C] (zero it first) and into v_records[N,12] (geometry part: call it between sgn_blend_bwd and
+ * sgn_project_bwd). */
+int sgn_blend_extra_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records, const int32_t* sorted_ids,
+                        const int32_t* tile_bins, const float* final_T, const int32_t* final_idx, const float* extra, int C,
+                        float* out /*[H,W,C]*/, void* stream);
+int sgn_blend_extra_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records, const int32_t* sorted_ids,
+                        const int32_t* tile_bins, const float* final_T, const int32_t* final_idx, const float* extra, int C,
+                        const float* v_out /*[H,W,C]*/, float* v_extra /*[N,C]*/, float* v_records /*[N,12]*/, void* stream);
+
 /* ---- loss epilogue ------------------------------------------------------------------
  * The image-space loss terms of the reference that re-read the rasterizer's outputs right after the render, and
  * their cotangents: L1 = w_l1 * mean|gt - rgb| (sgn_splatfacto.py:1079-1084; with mask: both sides times mask,

@@ -1336,3 +1336,222 @@ extern "C" int sgn_blend_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, 
     }
     return SGN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Generic per-Gaussian channels (the north-star's "per-Gaussian 4D-SH semantic logits"; dormant consumer in the reference:
+// street_gaussians_ns/scripts/render.py:188,231-236, group `semantic` in sgn_config.py:30): C extra values per Gaussian are
+// composited with the SAME weights as the colours -- out[p, c] = sum_k e[k, c] * alpha_k * T_k over the entries the main pass
+// blended (it saved, per pixel, the index of the last one) -- EXTRA_CG channels per traversal, forward and backward.
+// The weights are recomputed with the main pass's arithmetic (same sigma, same ex2, same FMA for T), bounded by final_idx,
+// so every pixel sees exactly the entries and weights of the main render.
+// ------------------------------------------------------------------------------------------------
+#define EXTRA_CG 8
+
+struct ExtraParams {
+    int width, height, tiles_x, tiles, C;
+    float clamp_fwd, clamp_bwd;
+    const float4* records;
+    const int32_t* sorted_ids;
+    const int2* tile_bins;
+    const float* final_T;      // slot 0 (main)
+    const int32_t* final_idx;  // slot 0 (main)
+    const float* extra;        // [N, C]
+    float* out;                // forward: [H, W, C]
+    const float* v_out;        // backward: [H, W, C]
+    float* v_extra;            // backward: [N, C] (accumulated)
+    float* v_records;          // backward: [N, 12] (geometry part accumulated)
+};
+
+// one warp per tile, lane = (column, row parity), 8 pixels per lane (rows two apart); blockIdx.y = channel group
+template <bool BWD>
+__global__ void __launch_bounds__(32) extra_kernel(const ExtraParams p) {
+    constexpr int PPL = 8;
+    __shared__ float4 sA[32], sB[32];
+    __shared__ float sX[32][EXTRA_CG + 1];
+    __shared__ int sId[32];
+    const int tile = blockIdx.x, c0 = blockIdx.y * EXTRA_CG;
+    const int nch = min(EXTRA_CG, p.C - c0);
+    const int2 range = p.tile_bins[tile];
+    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    const int lane = threadIdx.x;
+    const int j = tx * SGN_TILE + (lane & 15);
+    const int i0 = ty * SGN_TILE + (lane >> 4);
+    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f;
+    float T[PPL], acc[PPL][EXTRA_CG], bv[PPL];
+    int idx[PPL];
+    int kmax = -1;
+#pragma unroll
+    for (int s = 0; s < PPL; ++s) {
+        const int i = i0 + 2 * s;
+        const bool inside = j < p.width && i < p.height;
+        const size_t pid = (size_t)i * p.width + j;
+        idx[s] = inside ? p.final_idx[pid] : -1;
+        T[s] = BWD ? (inside ? p.final_T[pid] : 1.f) : 1.f;
+        bv[s] = 0.f;
+        kmax = max(kmax, idx[s]);
+#pragma unroll
+        for (int c = 0; c < EXTRA_CG; ++c) acc[s][c] = (BWD && inside && c < nch) ? p.v_out[pid * p.C + c0 + c] : 0.f;  // backward: the cotangents
+    }
+    const int hi0 = min(range.y, warp_max(kmax) + 1);
+    if (!BWD) {
+        if (hi0 <= range.x) {
+#pragma unroll
+            for (int s = 0; s < PPL; ++s) {
+                const int i = i0 + 2 * s;
+                if (j < p.width && i < p.height)
+                    for (int c = 0; c < nch; ++c) p.out[((size_t)i * p.width + j) * p.C + c0 + c] = 0.f;
+            }
+            return;
+        }
+    } else if (hi0 <= range.x) {
+        return;
+    }
+    const float clampf = in_register(p.clamp_fwd), clampb = in_register(p.clamp_bwd);
+    constexpr int NV = 6 + EXTRA_CG;
+    const int my_comp = multi_reduce_slot<NV>(lane);
+    const int nbatch = (hi0 - range.x + 31) / 32;
+    for (int b = 0; b < nbatch; ++b) {
+        // forward walks front to back, backward back to front; entry t of the batch is list position k(t)
+        const int first = BWD ? hi0 - 1 - 32 * b : range.x + 32 * b;
+        const int n = BWD ? min(32, first - range.x + 1) : min(32, hi0 - first);
+        __syncwarp();
+        if (lane < n) {
+            const int k = BWD ? first - lane : first + lane;
+            const int id = p.sorted_ids[k];
+            const Staged e = gather_entry(p.records, id);
+            sA[lane] = e.A;
+            sB[lane] = make_float4(e.B.x, e.B.y, e.C.w /* opacity */, 0.f);
+            sId[lane] = id & ID_MASK;
+            const float* ex = p.extra + (size_t)(id & ID_MASK) * p.C + c0;
+            for (int c = 0; c < EXTRA_CG; ++c) sX[lane][c] = c < nch ? ex[c] : 0.f;
+        }
+        __syncwarp();
+        for (int t = 0; t < n; ++t) {
+            const int k = BWD ? first - t : first + t;
+            const float4 A = sA[t], B = sB[t];
+            const float dx = A.x - px;
+            const float bdx = A.w * dx, ax2 = A.z * dx * dx;
+            const float dy0 = A.y - py0;
+            const unsigned lim1 = (unsigned)(max(__float_as_int(LOG2_255 + B.y), -1) + 1);
+            float e[EXTRA_CG];
+#pragma unroll
+            for (int c = 0; c < EXTRA_CG; ++c) e[c] = sX[t][c];
+            if (!BWD) {
+#pragma unroll
+                for (int s = 0; s < PPL; ++s) {
+                    const float dy = dy0 - (float)(2 * s);
+                    const float sg = __fmaf_rn(dy, __fmaf_rn(B.x, dy, bdx), ax2);
+                    const bool valid = (__float_as_uint(sg) < lim1) && (k <= idx[s]);
+                    const float am = valid ? fminf(clampf, fast_ex2(B.y - sg)) : 0.f;
+                    const float w = am * T[s];
+                    T[s] = __fmaf_rn(-am, T[s], T[s]);
+#pragma unroll
+                    for (int c = 0; c < EXTRA_CG; ++c) acc[s][c] = __fmaf_rn(e[c], w, acc[s][c]);
+                }
+            } else {
+                float S0 = 0.f, Sy = 0.f, Syy = 0.f, ve[EXTRA_CG];
+#pragma unroll
+                for (int c = 0; c < EXTRA_CG; ++c) ve[c] = 0.f;
+                float activity = 0.f;
+#pragma unroll
+                for (int s = 0; s < PPL; ++s) {
+                    const float dy = dy0 - (float)(2 * s);
+                    const float sg = __fmaf_rn(dy, __fmaf_rn(B.x, dy, bdx), ax2);
+                    const bool valid = (__float_as_uint(sg) < lim1) && (k <= idx[s]);
+                    const float raw = fast_ex2(B.y - sg);
+                    const float alpha = fminf(clampb, raw);
+                    const float ra = fast_rcp(1.f - alpha);
+                    const float Tk = valid ? T[s] * ra : T[s];
+                    T[s] = Tk;
+                    const float fac = valid ? alpha * Tk : 0.f;
+                    activity += fac;
+                    float dotc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < EXTRA_CG; ++c) {
+                        ve[c] = __fmaf_rn(fac, acc[s][c], ve[c]);
+                        dotc = __fmaf_rn(e[c], acc[s][c], dotc);
+                    }
+                    // v_alpha = sum_c (e_c T_k - buffer_c / (1 - alpha)) v_c, buffer = what lies behind entry k
+                    const float v_alpha = __fmaf_rn(Tk, dotc, -ra * bv[s]);
+                    bv[s] = __fmaf_rn(fac, dotc, bv[s]);
+                    const float vs = valid ? -raw * v_alpha : 0.f;
+                    S0 += vs;
+                    const float vsy = vs * dy;
+                    Sy += vsy;
+                    Syy = __fmaf_rn(vsy, dy, Syy);
+                }
+                if (!__any_sync(FULL, activity != 0.f)) continue;
+                const float ca = A.z * (2.f * LN2), cbb = A.w * LN2, cc = B.x * (2.f * LN2);
+                float comps[NV];
+                comps[0] = ca * dx * S0 + cbb * Sy;
+                comps[1] = cbb * dx * S0 + cc * Sy;
+                comps[2] = 0.5f * dx * dx * S0;
+                comps[3] = dx * Sy;
+                comps[4] = 0.5f * Syy;
+                comps[5] = -S0 / B.z;
+#pragma unroll
+                for (int c = 0; c < EXTRA_CG; ++c) comps[6 + c] = ve[c];
+                const float mine = warp_multi_reduce<NV>(comps, lane);
+                if (my_comp >= 0) {
+                    const size_t g = (size_t)sId[t];
+                    if (my_comp < 6) atomicAdd(p.v_records + g * SGN_RECORD_FLOATS + my_comp, mine);
+                    else if (my_comp - 6 < nch) atomicAdd(p.v_extra + g * p.C + c0 + (my_comp - 6), mine);
+                }
+            }
+        }
+    }
+    if (!BWD) {
+#pragma unroll
+        for (int s = 0; s < PPL; ++s) {
+            const int i = i0 + 2 * s;
+            if (j < p.width && i < p.height)
+                for (int c = 0; c < nch; ++c) p.out[((size_t)i * p.width + j) * p.C + c0 + c] = acc[s][c];
+        }
+    }
+}
+
+static int extra_params(ExtraParams& p, const sgn_camera* cam, const sgn_blend_opts* opts, const float* records, const int32_t* sorted_ids,
+                        const int32_t* tile_bins, const float* final_T, const int32_t* final_idx, const float* extra, int C) {
+    if (int rc = check_cam(cam)) return rc;
+    SGN_REQUIRE(opts && records && sorted_ids && tile_bins && final_T && final_idx && extra, "sgn_blend_extra: null pointer");
+    SGN_REQUIRE(C >= 1 && C <= 4096, "sgn_blend_extra: C=%d out of range", C);
+    SGN_REQUIRE(sgn_aligned16(records), "records must be 16-byte aligned");
+    p.width = cam->width; p.height = cam->height;
+    p.tiles_x = (cam->width + SGN_TILE - 1) / SGN_TILE;
+    p.tiles = p.tiles_x * ((cam->height + SGN_TILE - 1) / SGN_TILE);
+    p.C = C;
+    p.clamp_fwd = opts->alpha_clamp_fwd; p.clamp_bwd = opts->alpha_clamp_bwd;
+    p.records = reinterpret_cast<const float4*>(records);
+    p.sorted_ids = sorted_ids;
+    p.tile_bins = reinterpret_cast<const int2*>(tile_bins);
+    p.final_T = final_T; p.final_idx = final_idx;
+    p.extra = extra;
+    p.out = nullptr; p.v_out = nullptr; p.v_extra = nullptr; p.v_records = nullptr;
+    return SGN_OK;
+}
+
+extern "C" int sgn_blend_extra_fwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records, const int32_t* sorted_ids,
+                                   const int32_t* tile_bins, const float* final_T, const int32_t* final_idx, const float* extra, int C,
+                                   float* out, void* stream) {
+    SGN_RANGE("sgn_blend_extra_fwd");
+    ExtraParams p;
+    if (int rc = extra_params(p, cam, opts, records, sorted_ids, tile_bins, final_T, final_idx, extra, C)) return rc;
+    SGN_REQUIRE(out, "sgn_blend_extra_fwd: null output");
+    p.out = out;
+    extra_kernel<false><<<dim3(p.tiles, (C + EXTRA_CG - 1) / EXTRA_CG), 32, 0, (cudaStream_t)stream>>>(p);
+    SGN_CHECK_LAUNCH("extra_kernel<fwd>");
+    return SGN_OK;
+}
+
+extern "C" int sgn_blend_extra_bwd(const sgn_camera* cam, const sgn_blend_opts* opts, const float* records, const int32_t* sorted_ids,
+                                   const int32_t* tile_bins, const float* final_T, const int32_t* final_idx, const float* extra, int C,
+                                   const float* v_out, float* v_extra, float* v_records, void* stream) {
+    SGN_RANGE("sgn_blend_extra_bwd");
+    ExtraParams p;
+    if (int rc = extra_params(p, cam, opts, records, sorted_ids, tile_bins, final_T, final_idx, extra, C)) return rc;
+    SGN_REQUIRE(v_out && v_extra && v_records, "sgn_blend_extra_bwd: null pointer");
+    p.v_out = v_out; p.v_extra = v_extra; p.v_records = v_records;
+    extra_kernel<true><<<dim3(p.tiles, (C + EXTRA_CG - 1) / EXTRA_CG), 32, 0, (cudaStream_t)stream>>>(p);
+    SGN_CHECK_LAUNCH("extra_kernel<bwd>");
+    return SGN_OK;
+}

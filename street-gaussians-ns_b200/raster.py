@@ -508,7 +508,8 @@ class _Holder:
 
 class _SceneGraphRasterize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, frame: Frame, settings: RenderSettings, holder: _Holder, sky: Optional[torch.Tensor], *flat):
+    def forward(ctx, frame: Frame, settings: RenderSettings, holder: _Holder, sky: Optional[torch.Tensor],
+                extra: Optional[torch.Tensor], *flat):
         # unused outputs must reach backward as None, not as zero tensors: the kernels specialise on
         # which cotangents exist (depth / background_acc have none in training)
         ctx.set_materialize_grads(False)
@@ -550,14 +551,27 @@ class _SceneGraphRasterize(torch.autograd.Function):
         outs = [out["rgb"], out["accumulation"], out["depth"]]
         if settings.class_streams:
             outs += [out["object_acc"], out["background_acc"]]
+        ctx.extra = None
+        if extra is not None:  # generic per-Gaussian channels composited with the main render's weights, 8 per traversal
+            assert extra.dim() == 2 and extra.shape[0] == records.shape[0] and extra.dtype == torch.float32 and extra.is_cuda
+            extra = extra.contiguous()
+            ctx.extra = extra.detach()
+            outs.append(blend_extra_fwd(cs, bo, records, sorted_ids, tile_bins, out["final_T"], out["final_idx"], ctx.extra))
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *v):
+        v_extra_img = None
+        if ctx.extra is not None:
+            v, v_extra_img = v[:-1], v[-1]
         names = ["rgb", "accumulation", "depth", "object_acc", "background_acc"][: len(v)]
         vd = {k: t for k, t in zip(names, v)}
         v_records, v_sky = blend_bwd(ctx.cs, ctx.bo, ctx.records, ctx.sorted_ids, ctx.tile_bins, ctx.saved, ctx.sky, vd,
                                      ctx.sky_needs_grad, ctx.obj_ids, ctx.obj_bins, deterministic=ctx.settings.deterministic)
+        v_extra = None
+        if v_extra_img is not None:  # adds the extra channels' share of the geometry gradients to v_records before project_bwd
+            v_extra = blend_extra_bwd(ctx.cs, ctx.bo, ctx.records, ctx.sorted_ids, ctx.tile_bins, ctx.saved["final_T"],
+                                      ctx.saved["final_idx"], ctx.extra, v_extra_img, v_records)
         h = ctx.holder
         sink = h.grad_sink
         if sink is not None:
@@ -575,7 +589,7 @@ class _SceneGraphRasterize(torch.autograd.Function):
         h.xys.grad = v_records[:, 0:2]
         if h.post_backward is not None:
             h.post_backward(h)
-        return (None, None, None, v_sky, *flat)
+        return (None, None, None, v_sky, v_extra, *flat)
 
 
 def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[str, Optional[torch.Tensor]],
@@ -620,9 +634,36 @@ def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[st
     return res, holder
 
 
+def blend_extra_fwd(cs, bo, records, sorted_ids, tile_bins, final_T, final_idx, extra: torch.Tensor) -> torch.Tensor:
+    """extra[N,C] composited with the main render's weights -> [H,W,C] (sgn_blend_extra_fwd)."""
+    L = _lib.load()
+    Cn = extra.shape[1]
+    out = torch.empty(cs.height, cs.width, Cn, device=records.device, dtype=torch.float32)
+    with _timed("blend_extra_fwd"):
+        _lib.check(L.sgn_blend_extra_fwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins), _ptr(final_T),
+                                         _ptr(final_idx), _ptr(extra), Cn, _ptr(out), _stream()), "sgn_blend_extra_fwd")
+    return out
+
+
+def blend_extra_bwd(cs, bo, records, sorted_ids, tile_bins, final_T, final_idx, extra, v_out, v_records) -> torch.Tensor:
+    """Returns v_extra[N,C]; adds the geometry part (xy, conic, opacity) to ``v_records`` in place."""
+    L = _lib.load()
+    v_extra = torch.zeros_like(extra)
+    v_out = v_out.contiguous()
+    with _timed("blend_extra_bwd"):
+        _lib.check(L.sgn_blend_extra_bwd(C.byref(cs), C.byref(bo), _ptr(records), _ptr(sorted_ids), _ptr(tile_bins), _ptr(final_T),
+                                         _ptr(final_idx), _ptr(extra), extra.shape[1], _ptr(v_out), _ptr(v_extra), _ptr(v_records),
+                                         _stream()), "sgn_blend_extra_bwd")
+    return v_extra
+
+
 def render_frame(frame: Frame, settings: Optional[RenderSettings] = None, sky: Optional[torch.Tensor] = None,
-                 grad_sink=None, anchor: Optional[torch.Tensor] = None):
+                 grad_sink=None, anchor: Optional[torch.Tensor] = None, extra: Optional[torch.Tensor] = None):
     """Render one camera.  Returns (outputs dict, holder).  Segment parameters must be CUDA tensors.
+
+    ``extra`` [N, C] (rows in the frame's concatenated order, float32): generic per-Gaussian channels -- e.g. semantic
+    logits -- composited with the weights of the main render into ``out["extra"]`` [H, W, C], 8 channels per traversal,
+    differentiable w.r.t. ``extra`` and the Gaussian parameters.
 
     With ``grad_sink`` (+ ``anchor``, a 1-element leaf that requires grad) the parameter gradients are handed
     to the sink after backward instead of flowing through one autograd leaf per parameter tensor."""
@@ -630,9 +671,14 @@ def render_frame(frame: Frame, settings: Optional[RenderSettings] = None, sky: O
     holder = _Holder()
     holder.grad_sink = grad_sink
     flat = [anchor] if grad_sink is not None else [t for seg in frame.segments for t in seg.params.tensors()]
-    outs = _SceneGraphRasterize.apply(frame, settings, holder, sky, *flat)
+    outs = _SceneGraphRasterize.apply(frame, settings, holder, sky, extra, *flat)
+    extra_img = None
+    if extra is not None:
+        outs, extra_img = outs[:-1], outs[-1]
     names = ["rgb", "accumulation", "depth", "object_acc", "background_acc"][: len(outs)]
     out = {k: t for k, t in zip(names, outs)}
+    if extra_img is not None:
+        out["extra"] = extra_img
     if sky is not None:
         out["sky"] = sky
     return out, holder
