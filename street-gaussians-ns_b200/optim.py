@@ -46,14 +46,20 @@ class FusedAdam:
     """``params``: per sub-model (segment), the six parameter tensors in PARAM_NAMES order (the order of the gradient arena)."""
 
     def __init__(self, params: Sequence[Sequence[torch.Tensor]], lrs: Dict[str, float] = None, betas=(0.9, 0.999),
-                 eps: float = 1e-15, chunk_elems: Optional[int] = None):
+                 eps: float = 1e-15, chunk_elems: Optional[int] = None, extra: Optional[Dict[str, Tuple[torch.Tensor, float]]] = None):
+        """``extra``: further tensors stepped by the same launch, name -> (tensor, lr): the reference's other Adam groups on
+        the step -- the sky cube map ``env_map.base`` [6, res, res, 3] (sgn_splatfacto.py:114-116; group ``sky`` of
+        sgn_config.py:71-108).  Their gradients are not part of the rasterizer's arena (the sky gradient comes out of
+        nvdiffrast's backward): pass them to ``step(..., extra_grads={name: grad})``; a tensor without a gradient in a step is
+        skipped like any parameter whose ``.grad`` is None."""
         self._chunk = chunk_elems if chunk_elems is not None else _lib.load().sgn_adam_chunk_elems()
         self.lrs = dict(REFERENCE_LRS if lrs is None else lrs)
         self.betas, self.eps = betas, eps
+        self._extra = dict(extra or {})
         self.step_count = 0  # calls of step(); the bias correction uses the per-tensor counts below
         self._install(params)
-        self.exp_avg = torch.zeros(self.arena_elems, device=self.device)
-        self.exp_avg_sq = torch.zeros(self.arena_elems, device=self.device)
+        self.exp_avg = torch.zeros(self.moment_elems, device=self.device)
+        self.exp_avg_sq = torch.zeros(self.moment_elems, device=self.device)
         self.steps = np.zeros(len(self._params), np.int64)  # torch.optim.Adam keeps state["step"] per parameter
 
     # ---- layout ---------------------------------------------------------------------------------------------
@@ -61,6 +67,13 @@ class FusedAdam:
         assert all(len(ps) == 6 for ps in params), "six parameter tensors per sub-model, in PARAM_NAMES order"
         flat = [t for ps in params for t in ps]
         self.kinds = [PARAM_NAMES[i % 6] for i in range(len(flat))]
+        self.extra_index = {}
+        for name, (t, lr) in self._extra.items():  # appended behind the sub-models' tensors: moments at the end of the arenas
+            assert t.is_contiguous() and t.dtype == torch.float32 and t.data_ptr() % 16 == 0, name
+            self.extra_index[name] = len(flat)
+            flat.append(t)
+            self.kinds.append("extra:" + name)
+            self.lrs["extra:" + name] = lr
         self.device = flat[0].device
         self.sizes = np.array([padded(t.numel()) for t in flat], np.int64)
         self.offsets = np.concatenate([[0], np.cumsum(self.sizes)[:-1]]).astype(np.int64)
@@ -75,9 +88,11 @@ class FusedAdam:
         tab["one_minus_beta1"], tab["one_minus_beta2"] = 1.0 - b1, 1.0 - b2  # double, then rounded (torch)
         self.table = tab
         self.num_chunks = int(self.chunks.sum())
-        self.arena_elems = int(self.sizes.sum())
         self.num_segments = len(params)
+        self.arena_elems = int(self.sizes[:6 * len(params)].sum())  # the gradient arena of the rasterizer (all sub-models)
+        self.moment_elems = int(self.sizes.sum())                   # + the extra tensors' moments behind it
         self._params = flat  # keep the tensors (and their storage) alive
+        self._extra_ptrs = {t.data_ptr() for t, _ in self._extra.values()}
         self._lr_vec = np.array([self.lrs[k] for k in self.kinds], np.float64)
 
     def set_lr(self, kind: str, lr: float) -> None:
@@ -92,23 +107,39 @@ class FusedAdam:
         return self.exp_avg[o:o + t.numel()].view(t.shape), self.exp_avg_sq[o:o + t.numel()].view(t.shape)
 
     # ---- the step -------------------------------------------------------------------------------------------
-    def step_table(self, present: Optional[Sequence[int]] = None, full_layout: bool = False) -> np.ndarray:
+    def step_table(self, present: Optional[Sequence[int]] = None, full_layout: bool = False, grad_arena: Optional[torch.Tensor] = None,
+                   extra_grads: Optional[Dict[str, torch.Tensor]] = None) -> np.ndarray:
         """Advance the step counts of the tensors that have a gradient and return their sgn_adam_tensor rows.
         ``present``: indices of the sub-models that have a gradient this step (None = all).  The gradient arena
         either holds exactly those, back to back in that order (a frame's arena, the default), or has the optimizer's
         own layout with the absent sub-models' slices unused (``full_layout``: the data-parallel arena, model.py)."""
-        if present is None:
+        extras = []
+        if self.extra_index:  # rows of the extra tensors that have a gradient this step
+            assert not extra_grads or grad_arena is not None, "extra_grads need grad_arena (their offsets are relative to it)"
+            for name, g in (extra_grads or {}).items():
+                if g is None:
+                    continue
+                i = self.extra_index[name]
+                assert g.is_contiguous() and g.dtype == torch.float32 and g.numel() == self._params[i].numel()
+                delta = g.data_ptr() - grad_arena.data_ptr()
+                assert delta % 4 == 0
+                extras.append((i, delta // 4))  # the kernel addresses gradients as grad_arena + offset: any float address works
+        if present is None and not self.extra_index:
             idx = slice(None)
             tab = self.table  # grad_offset == arena_offset, chunk0 as installed
         else:
-            present = list(present)
+            present = list(range(self.num_segments)) if present is None else list(present)
             assert len(set(present)) == len(present) and all(0 <= s < self.num_segments for s in present), present
             idx = (np.asarray(present, np.int64)[:, None] * 6 + np.arange(6)[None, :]).reshape(-1)
+            idx = np.concatenate([idx, np.asarray([i for i, _ in extras], np.int64)]) if extras else idx
             tab = self.table[idx]
             sz, ch = self.sizes[idx], self.chunks[idx]
-            if not full_layout:
-                tab["grad_offset"] = np.concatenate([[0], np.cumsum(sz)[:-1]])
+            if not full_layout and len(present) < self.num_segments:
+                tab["grad_offset"][:6 * len(present)] = np.concatenate([[0], np.cumsum(sz[:6 * len(present)])[:-1]])
+            for r, (_, off) in enumerate(extras):
+                tab["grad_offset"][6 * len(present) + r] = off
             tab["chunk0"] = np.concatenate([[0], np.cumsum(ch)[:-1]])
+
         self.steps[idx] += 1
         st = self.steps[idx].astype(np.float64)
         b1, b2 = self.betas
@@ -116,17 +147,22 @@ class FusedAdam:
         tab["sqrt_bc2"] = np.sqrt(1.0 - b2 ** st)
         return tab
 
-    def step(self, grad_arena: torch.Tensor, present: Optional[Sequence[int]] = None, full_layout: bool = False) -> None:
+    def step(self, grad_arena: torch.Tensor, present: Optional[Sequence[int]] = None, full_layout: bool = False,
+             extra_grads: Optional[Dict[str, torch.Tensor]] = None) -> None:
         self.step_count += 1
-        self.launch(self.step_table(present, full_layout), grad_arena)
+        self._keep = extra_grads  # the launch is asynchronous: keep the gradient tensors alive until the next step
+        self.launch(self.step_table(present, full_layout, grad_arena, extra_grads), grad_arena)
 
     def launch(self, tab: np.ndarray, grad_arena: torch.Tensor) -> None:
         """One ``sgn_adam_step`` over the rows of ``tab`` (from step_table, possibly cut by rows_in_range)."""
         assert grad_arena.is_cuda, "FusedAdam runs on the CUDA library only"
         if len(tab) == 0:
             return
-        need = int((tab["grad_offset"] + tab["numel"]).max())
-        assert grad_arena.numel() >= need, (grad_arena.numel(), need)
+        # rows of the extra tensors (always last) address their gradient relative to the arena, wherever it lives
+        inside = tab[: len(tab) - sum(1 for k in tab["param"] if int(k) in self._extra_ptrs)] if self.extra_index else tab
+        if len(inside):
+            need = int((inside["grad_offset"] + inside["numel"]).max())
+            assert grad_arena.numel() >= need, (grad_arena.numel(), need)
         num_chunks = int(tab["chunk0"][-1] + (int(tab["numel"][-1]) + self._chunk - 1) // self._chunk)
         dev_tab = torch.from_numpy(np.ascontiguousarray(tab).view(np.uint8).reshape(-1)).to(self.device, non_blocking=True)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -162,14 +198,19 @@ class FusedAdam:
         assert len(params) == self.num_segments
         old = (self.exp_avg, self.exp_avg_sq, self.offsets.copy())
         self._install(params)
-        self.exp_avg = torch.zeros(self.arena_elems, device=self.device)
-        self.exp_avg_sq = torch.zeros(self.arena_elems, device=self.device)
+        self.exp_avg = torch.zeros(self.moment_elems, device=self.device)
+        self.exp_avg_sq = torch.zeros(self.moment_elems, device=self.device)
+        for i in self.extra_index.values():  # the extra tensors do not change in a refinement: their moments move along
+            a, b, n = int(old[2][i]), int(self.offsets[i]), int(self.sizes[i])
+            self.exp_avg[b:b + n].copy_(old[0][a:a + n])
+            self.exp_avg_sq[b:b + n].copy_(old[1][a:a + n])
         return old
 
     def rebuild_pointers(self, params: Sequence[Sequence[torch.Tensor]]) -> None:
         """The layout is unchanged but the tensors were re-wrapped (``nn.Parameter(t)`` shares storage): refresh the
         pointer column and the keep-alive list."""
         flat = [t for ps in params for t in ps]
-        assert [t.numel() for t in flat] == [int(x) for x in self.table["numel"]]
-        self.table["param"] = [t.data_ptr() for t in flat]
-        self._params = flat
+        n = len(flat)
+        assert [t.numel() for t in flat] == [int(x) for x in self.table["numel"][:n]]
+        self.table["param"][:n] = [t.data_ptr() for t in flat]
+        self._params = flat + self._params[n:]

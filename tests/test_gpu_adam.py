@@ -58,3 +58,43 @@ def test_training_step_reduces_loss():
         out, holder = raster.forward_backward(frc, s, {"rgb": torch.sign(diff) / diff.numel()})
         opt.step(holder.grad_arena)
     assert losses[-1] < losses[0] * 0.97, losses
+
+
+def test_extra_tensor_sky_cube_steps_in_the_same_launch():
+    """SURVEY 8f rank 1 'and the sky cube': a further tensor (env_map.base, [6,res,res,3]) stepped by the same launch; its
+    gradient lives outside the rasterizer's arena.  Against torch.optim.Adam, including a step without a sky gradient."""
+    import street_gaussians_ns_b200.synthetic as syn
+    from street_gaussians_ns_b200.optim import FusedAdam
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    sets = [syn.make_background(3000, seed=1).to(dev), syn.make_actor(500, seed=2).to(dev)]
+    params = [[t.clone() for t in s.tensors()] for s in sets]
+    sky = torch.rand(6, 16, 16, 3, device=dev, generator=g)
+    ref_params = [[t.clone().requires_grad_(True) for t in ps] for ps in params]
+    ref_sky = sky.clone().requires_grad_(True)
+    lrs = {"means": 1.6e-4, "scales": 0.005, "quats": 0.001, "features_dc": 0.0025, "features_rest": 0.0025 / 20, "opacities": 0.05}
+    names = list(lrs)
+    opts = [torch.optim.Adam([ps[k] for ps in ref_params], lr=lrs[names[k]], eps=1e-15) for k in range(6)]
+    opt_sky = torch.optim.Adam([ref_sky], lr=0.01, eps=1e-15)
+    fused = FusedAdam(params, lrs=lrs, extra={"sky": (sky, 0.01)})
+    assert fused.moment_elems == fused.arena_elems + sky.numel()
+    for it in range(4):
+        arena = torch.randn(fused.arena_elems, device=dev, generator=g)
+        sky_grad = torch.randn(sky.shape, device=dev, generator=g) if it != 2 else None
+        off = 0
+        for ps in ref_params:
+            for t in ps:
+                n = (t.numel() + 3) // 4 * 4
+                t.grad = arena[off:off + t.numel()].view(t.shape).clone()
+                off += n
+        ref_sky.grad = None if sky_grad is None else sky_grad.clone()
+        for o in opts:
+            o.step()
+        if sky_grad is not None:
+            opt_sky.step()
+        fused.step(arena, extra_grads={"sky": sky_grad})
+    torch.cuda.synchronize()
+    for ps, rs in zip(params, ref_params):
+        for a, b in zip(ps, rs):
+            assert torch.allclose(a, b.detach(), rtol=0, atol=1e-7), float((a - b.detach()).abs().max())
+    assert torch.allclose(sky, ref_sky.detach(), rtol=0, atol=1e-7)
