@@ -235,7 +235,11 @@ def run_ours(args):
     fr = make_frames(args.cfg, world, rank)
     frc = Frame(fr.camera, [Segment(s.params.to(dev).requires_grad_(True), s.cls, s.rot, s.center, s.idft, s.name)
                             for s in fr.segments])
-    settings = raster.RenderSettings()
+    # no host read-back of the intersection count inside a step (gsplat's cum_tiles_hit[-1].item()): the capacity of the list
+    # buffers comes from earlier frames, the count stays on the device and the host runs ahead of the GPU (SGN_ASYNC_BIN=0:
+    # the exact path with its one sync per frame).  Same kernels, same lists, same results (tests/test_gpu_parity.py).
+    async_bin = os.environ.get("SGN_ASYNC_BIN", "1") != "0"
+    settings = raster.RenderSettings(async_binning=async_bin)
     H, W = fr.camera.height, fr.camera.width
     w, v = syn.cotangents(H, W)
     w, v = w.to(dev), v.to(dev)
@@ -375,7 +379,8 @@ def run_ours(args):
         return [ActorPose(name, Ry @ rot, center + shift, k % 85, frame_list) for name, rot, center in base_boxes]
 
     def make_model():
-        m = SceneGraphRasterModel(bg, actors, SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0), poses_at=boxes_at).to(dev)
+        m = SceneGraphRasterModel(bg, actors, SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0, async_binning=async_bin),
+                                  poses_at=boxes_at).to(dev)
         m.train()
         m.step = 30000
         return m
@@ -495,7 +500,7 @@ def run_ours(args):
     if rank == 0:
         N = sum(s.params.num_points for s in frc.segments)
         A = sum(s.params.num_points for s in frc.segments if s.cls == CLS_OBJECT)
-        M = holder.M
+        M = int(holder.M)
         n_vis = int((holder.radii > 0).sum().item())
         try:  # longest per-tile list (SURVEY.md 8d asks the harness to print it next to N, N_vis, M)
             max_per_tile = int((holder.tile_bins[:, 1] - holder.tile_bins[:, 0]).max().item())
@@ -595,7 +600,10 @@ def run_ours(args):
             "config": {"workload": workload_config(args.cfg), "N_gaussians": N, "N_actor_gaussians": A,
                        "M_intersections": M, "N_visible": n_vis, "max_per_tile": max_per_tile, "parallelism": f"camera-sharded dp{world}",
                        "l2": "inputs larger than L2 (330 MB of parameters + 0.4 GB of intersection lists per step vs 126 MB)",
-                       "collective": collective},
+                       "collective": collective,
+                       "binning": ("no host read-back of the intersection count (capacity from earlier frames, "
+                                   f"{raster.ASYNC_STATS['frames']} frames, {raster.ASYNC_STATS['overflows']} overflows)") if async_bin
+                       else "one host read-back of the intersection count per frame (as gsplat)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(gt_host.numel() + len(frc.segments) * 168 + 96),

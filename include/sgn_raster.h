@@ -201,6 +201,15 @@ int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, 
                  const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* order, const int32_t* cum,
                  int32_t* sorted_ids /*[M]*/, int32_t* tile_bins /*[tiles,2]*/, void* scratch, size_t scratch_bytes,
                  void* stream);
+/* The same step without the host knowing M: `capacity` bounds the buffers (sorted_ids[capacity], scratch of
+ * sgn_bin_sort_scratch_bytes(capacity)) and the launches, the real count is read from *total_dev on the device.  gsplat reads
+ * the count back every frame (`cum_tiles_hit[-1].item()`); without that read-back the host can run ahead of the GPU.  Unused
+ * slots are padded with a key behind every tile (the sort runs over `capacity` items).  If *total_dev > capacity the lists
+ * are truncated and *overflow_dev is set to 1 (never cleared here): the caller checks it later and grows the capacity. */
+int sgn_bin_sort_capped(int N, int64_t capacity, const int64_t* total_dev, int32_t* overflow_dev, const sgn_camera* cam,
+                        const float* records, const int32_t* radii, const uint16_t* tile_bbox, const uint32_t* touch_mask,
+                        const int32_t* order, const int32_t* cum, int32_t* sorted_ids, int32_t* tile_bins, void* scratch,
+                        size_t scratch_bytes, void* stream);
 /* EXPERIMENTAL alternative to steps 1 + 2 (csrc/binning_local.cu; same lists, same order, same payload): tile histogram +
  * unordered scatter + a shared-memory sort inside every tile instead of the two device-wide radix sorts.
  *   sgn_bin_local_count: tile_count[tiles], tile_start[tiles] (exclusive scan), info_dev = {M, longest list} (int64[2]);

@@ -131,6 +131,7 @@ EXPORTS = [
     "sgn_sizeof_refine_config", "sgn_sizeof_refine_tensors", "sgn_refine_decide", "sgn_refine_apply",
     "sgn_bin_local_cap", "sgn_bin_local_scratch_bytes", "sgn_bin_local_count", "sgn_bin_local_sort",
     "sgn_project_bwd_range", "sgn_allreduce_sym", "sgn_blend_extra_fwd", "sgn_blend_extra_bwd",
+    "sgn_bin_sort_capped",
 ]
 AR_MAX_SLICES = 48  # SGN_AR_MAX_SLICES
 
@@ -176,6 +177,8 @@ def load():
     L.sgn_bin_sort_scratch_bytes.argtypes = [i64]
     L.sgn_bin_sort_scratch_bytes.restype = sz
     L.sgn_bin_sort.argtypes = [i32, i64, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_sort_capped.argtypes = [i32, i64, vp, vp, C.POINTER(CameraStruct), vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.sgn_bin_sort_capped.restype = C.c_int
     L.sgn_bin_local_cap.restype = C.c_int
     L.sgn_bin_local_scratch_bytes.argtypes = [i64, i32]
     L.sgn_bin_local_scratch_bytes.restype = sz

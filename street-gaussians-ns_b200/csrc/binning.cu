@@ -217,6 +217,33 @@ bin_edges_kernel(int64_t M, const uint16_t* __restrict__ keys_sorted, int32_t* _
     if (i == M - 1) tile_bins[2 * cur + 1] = (int32_t)M;
 }
 
+// capacity-bounded form: the number of entries stays on the device (no host read-back between the scan and the sort).
+// Slots [min(total, cap), cap) are filled with a key that sorts behind every tile, so the sort runs over `cap` items.
+__global__ void __launch_bounds__(256)
+pad_keys_kernel(int64_t cap, const int64_t* __restrict__ total, uint16_t sentinel, uint16_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t m = min(*total, cap);
+    if (i >= m && i < cap) { keys[i] = sentinel; vals[i] = 0; }
+}
+__global__ void __launch_bounds__(256)
+bin_edges_capped_kernel(int64_t cap, const int64_t* __restrict__ total, const uint16_t* __restrict__ keys_sorted, int32_t* __restrict__ tile_bins,
+                        int32_t* __restrict__ overflow) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t M = min(*total, cap);
+    if (i == 0 && *total > cap) *overflow = 1;  // the lists of this frame are truncated: the host finds out with the next frame
+    if (i >= M) return;
+    const int32_t cur = (int32_t)keys_sorted[i];
+    if (i == 0) tile_bins[2 * cur] = 0;
+    else {
+        const int32_t prev = (int32_t)keys_sorted[i - 1];
+        if (prev != cur) {
+            tile_bins[2 * prev + 1] = (int32_t)i;
+            tile_bins[2 * cur] = (int32_t)i;
+        }
+    }
+    if (i == M - 1) tile_bins[2 * cur + 1] = (int32_t)M;
+}
+
 struct SortLayout {
     size_t keys_in, keys_out, vals_in, temp, temp_bytes, total;
 };
@@ -238,10 +265,9 @@ static SortLayout sort_layout(int64_t M) {
 
 extern "C" size_t sgn_bin_sort_scratch_bytes(int64_t M) { return sort_layout(M).total; }
 
-extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, const int32_t* radii,
-                            const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* order, const int32_t* cum,
-                            int32_t* sorted_ids, int32_t* tile_bins, void* scratch, size_t scratch_bytes, void* stream_) {
-    SGN_RANGE("sgn_bin_sort");
+static int bin_sort_impl(int N, int64_t M, const int64_t* total_dev, int32_t* overflow_dev, const sgn_camera* cam, const float* records,
+                         const int32_t* radii, const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* order, const int32_t* cum,
+                         int32_t* sorted_ids, int32_t* tile_bins, void* scratch, size_t scratch_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SGN_REQUIRE(cam && records && radii && tile_bbox && touch_mask && order && cum && tile_bins && scratch,
                 "sgn_bin_sort: null pointer");
@@ -253,6 +279,7 @@ extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float
     SGN_CHECK_CUDA(cudaMemsetAsync(tile_bins, 0, sizeof(int32_t) * 2 * (size_t)tiles, stream));
     if (M == 0 || N == 0) return SGN_OK;
     SGN_REQUIRE(sorted_ids, "sgn_bin_sort: sorted_ids is null");
+    SGN_REQUIRE(!total_dev || overflow_dev, "sgn_bin_sort_capped: overflow flag is null");
     const SortLayout L = sort_layout(M);
     if (scratch_bytes < L.total) {
         sgn_set_error("sgn_bin_sort: scratch too small (%zu < %zu)", scratch_bytes, L.total);
@@ -268,13 +295,41 @@ extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float
                                                           keys_in, vals_in);
     SGN_CHECK_LAUNCH("emit_keys_kernel");
     int tile_bits = 1;
-    while ((1 << tile_bits) < tiles) ++tile_bits;
+    while ((1 << tile_bits) < tiles + (total_dev ? 1 : 0)) ++tile_bits;  // capped: one more key value, the padding sentinel
+    if (total_dev) {
+        SGN_REQUIRE(tile_bits <= 16, "sgn_bin_sort_capped: %d tiles leave no 16-bit key for the padding", tiles);
+        pad_keys_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, total_dev, (uint16_t)((1u << tile_bits) - 1u), keys_in, vals_in);
+        SGN_CHECK_LAUNCH("pad_keys_kernel");
+    }
     size_t temp = L.temp_bytes;
     SGN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(base + L.temp, temp, keys_in, keys_out, vals_in, sorted_ids, M, 0, tile_bits, stream));
     sgn_count_launch(1);
-    bin_edges_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, keys_out, tile_bins);
-    SGN_CHECK_LAUNCH("bin_edges_kernel");
+    if (total_dev) {
+        bin_edges_capped_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, total_dev, keys_out, tile_bins, overflow_dev);
+        SGN_CHECK_LAUNCH("bin_edges_capped_kernel");
+    } else {
+        bin_edges_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(M, keys_out, tile_bins);
+        SGN_CHECK_LAUNCH("bin_edges_kernel");
+    }
     return SGN_OK;
+}
+
+extern "C" int sgn_bin_sort(int N, int64_t M, const sgn_camera* cam, const float* records, const int32_t* radii,
+                            const uint16_t* tile_bbox, const uint32_t* touch_mask, const int32_t* order, const int32_t* cum,
+                            int32_t* sorted_ids, int32_t* tile_bins, void* scratch, size_t scratch_bytes, void* stream_) {
+    SGN_RANGE("sgn_bin_sort");
+    return bin_sort_impl(N, M, nullptr, nullptr, cam, records, radii, tile_bbox, touch_mask, order, cum, sorted_ids, tile_bins, scratch,
+                         scratch_bytes, stream_);
+}
+
+extern "C" int sgn_bin_sort_capped(int N, int64_t capacity, const int64_t* total_dev, int32_t* overflow_dev, const sgn_camera* cam,
+                                   const float* records, const int32_t* radii, const uint16_t* tile_bbox, const uint32_t* touch_mask,
+                                   const int32_t* order, const int32_t* cum, int32_t* sorted_ids, int32_t* tile_bins, void* scratch,
+                                   size_t scratch_bytes, void* stream_) {
+    SGN_RANGE("sgn_bin_sort_capped");
+    SGN_REQUIRE(total_dev && capacity > 0, "sgn_bin_sort_capped: needs the device-side entry count and a positive capacity");
+    return bin_sort_impl(N, capacity, total_dev, overflow_dev, cam, records, radii, tile_bbox, touch_mask, order, cum, sorted_ids, tile_bins,
+                         scratch, scratch_bytes, stream_);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -66,6 +66,8 @@ class SceneGraphConfig:
     # data parallel: gradients are delivered in an arena that has the layout of ALL sub-models (the
     # optimizer's), so that replicas which see different actors can sum their arenas with one all-reduce
     full_gradient_arena: bool = False
+    # no host read-back of the intersection count inside get_outputs (raster.RenderSettings.async_binning); None -> SGN_ASYNC_BIN
+    async_binning: Optional[bool] = None
 
     # ``stop_split_at`` of the BACKGROUND sub-model: what the reference's entropy gate reads
     # (``config.background_model.stop_split_at``, scene graph :386).  One source: ``refine.stop_split_at``.
@@ -444,7 +446,7 @@ class SceneGraphRasterModel(torch.nn.Module):
         n = min(self.step // c.sh_degree_interval, c.sh_degree) if self.training else c.sh_degree
         return raster.RenderSettings(sh_degree=c.sh_degree, sh_degree_to_use=n, block_width=c.block_width,
                                      alpha_clamp_fwd=c.alpha_clamp_fwd, alpha_clamp_bwd=c.alpha_clamp_bwd,
-                                     class_streams=class_streams, training=self.training)
+                                     class_streams=class_streams, training=self.training, async_binning=c.async_binning)
 
     def get_outputs(self, camera: Camera) -> Dict[str, torch.Tensor]:
         """``SplatfactoSceneGraphModel.get_outputs`` (scene graph :305-374)."""
@@ -468,7 +470,11 @@ class SceneGraphRasterModel(torch.nn.Module):
         out, holder = raster.render_frame(frame, self._settings(class_streams=True), sky=sky, grad_sink=sink, anchor=anchor)
         self._holder = holder
         self._publish_side_effects(frame, holder)
-        if holder.M == 0:
+        if isinstance(holder.M, raster.LazyCount):
+            # rendered without the count's read-back (RenderSettings.async_binning): the reference's early-out for "nothing in
+            # view" (depth 0 instead of the 10 of an empty pixel, sgn_splatfacto.py:878-886) is applied on the device
+            out["depth"] = out["depth"] * (holder.M.device_count > 0).to(out["depth"].dtype)
+        elif holder.M == 0:
             # reference early-out when nothing is visible (sgn_splatfacto.py:878-886): background colour
             # (zeros), zero accumulation and ZERO depth
             dev = self.device

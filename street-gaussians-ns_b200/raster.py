@@ -37,6 +37,11 @@ class RenderSettings:
     # bit-reproducible gradients: the backward accumulates per-Gaussian gradients in 64-bit fixed point instead of with
     # float atomics (whose summation order varies from run to run).  None -> the SGN_DETERMINISTIC environment variable
     deterministic: Optional[bool] = None
+    # no host read-back of the intersection count inside a frame (gsplat's ``cum_tiles_hit[-1].item()``): buffers and launches
+    # are bounded by a capacity learnt from earlier frames, the count stays on the device, the host runs ahead of the GPU.
+    # A frame whose count exceeds the capacity renders truncated lists; it is detected with the NEXT frame (warning,
+    # ``raster.ASYNC_STATS``), the capacity grows.  None -> the SGN_ASYNC_BIN environment variable.  Off: exact, one sync.
+    async_binning: Optional[bool] = None
 
 
 class StageTimer:
@@ -280,12 +285,89 @@ def _bin_local(cs: _lib.CameraStruct, records, radii, proj: Projected):
 _LOCAL_CLASSES = None  # (sorted_ids, cls_ids, cls_bins) of the last _bin_local call: class_lists() hands them out instead of recomputing
 
 
-def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit=None, bbox=None, proj: Optional[Projected] = None):
-    """Returns (M, sorted_ids[M], tile_bins[tiles,2]).  One host sync to read M (as gsplat does).
+ASYNC_BIN = os.environ.get("SGN_ASYNC_BIN", "0") == "1"
+ASYNC_HEADROOM = float(os.environ.get("SGN_ASYNC_BIN_HEADROOM", "1.2"))
+ASYNC_STATS = {"frames": 0, "overflows": 0, "sync_frames": 0}
+_ASYNC_STATE: Dict[str, dict] = {}
+
+
+class LazyCount:
+    """The intersection count of a frame rendered without the read-back: an int once somebody asks (that waits for the copy)."""
+
+    def __init__(self, event, pinned, capacity: int, device_count=None):
+        self.event, self.pinned, self.capacity, self._value = event, pinned, capacity, None
+        self.device_count = device_count  # the int64[1] tensor on the device (for device-side decisions, e.g. "nothing in view")
+
+    def ready(self) -> bool:
+        return self._value is not None or self.event.query()
+
+    def raw(self) -> int:
+        if self._value is None:
+            self.event.synchronize()
+            self._value = int(self.pinned[0])
+        return self._value
+
+    def __int__(self) -> int:
+        return min(self.raw(), self.capacity)
+
+    __index__ = __int__
+
+    def __eq__(self, other):
+        return int(self) == other
+
+    def __lt__(self, other):
+        return int(self) < other
+
+    def __le__(self, other):
+        return int(self) <= other
+
+    def __gt__(self, other):
+        return int(self) > other
+
+    def __ge__(self, other):
+        return int(self) >= other
+
+    def __hash__(self):
+        return hash(int(self))
+
+    def __repr__(self):
+        return f"LazyCount({int(self)})"
+
+
+def _async_state(device) -> dict:
+    st = _ASYNC_STATE.get(str(device))
+    if st is None:
+        st = _ASYNC_STATE[str(device)] = {"max_m": 0, "pending": [], "overflow": torch.zeros(1, dtype=torch.int32, device=device),
+                                          "pinned": [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(64)], "slot": 0}
+    return st
+
+
+def _async_poll(st: dict) -> None:
+    """Counts of earlier frames that have arrived: the capacity follows the largest one; an overflow is reported."""
+    keep = []
+    for lc in st["pending"]:
+        if lc.ready():
+            m = lc.raw()
+            st["max_m"] = max(st["max_m"], m)
+            if m > lc.capacity:
+                ASYNC_STATS["overflows"] += 1
+                import warnings
+                warnings.warn(f"async binning: a frame had {m} intersections, capacity {lc.capacity}: its lists were truncated "
+                              "(the capacity has been raised; SGN_ASYNC_BIN=0 renders exactly)")
+        else:
+            keep.append(lc)
+    st["pending"] = keep[-32:]
+
+
+def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit=None, bbox=None, proj: Optional[Projected] = None,
+                 async_binning: Optional[bool] = None):
+    """Returns (M, sorted_ids[M], tile_bins[tiles,2]).  One host sync to read M (as gsplat does) -- or, with
+    ``async_binning``, none: M is then a LazyCount and sorted_ids has the capacity's length.
     Pass ``proj`` (from project_fwd) or plain records/radii/bbox (the touched-tile count is then computed here)."""
     L = _lib.load()
     device = records.device
     N = records.shape[0]
+    use_async = ASYNC_BIN if async_binning is None else async_binning
     if BIN_LOCAL and proj is not None:
         res = _bin_local(cs, records, radii, proj)
         if res is not None:
@@ -305,10 +387,34 @@ def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit=None, bbox=Non
     with _timed("bin_scan"):
         _lib.check(L.sgn_bin_scan(N, _ptr(records), _ptr(radii), _ptr(touched), _ptr(oc[0]), _ptr(oc[1]), _ptr(total),
                                   _ptr(scratch), sb, _stream()), "sgn_bin_scan")
-    M = int(total.item())
     bw = cs.block_width
     tiles = ((cs.width + bw - 1) // bw) * ((cs.height + bw - 1) // bw)
     tile_bins = torch.empty(tiles, 2, device=device, dtype=torch.int32)
+    if use_async and N > 0:
+        st = _async_state(device)
+        _async_poll(st)
+        if st["max_m"] > 0:  # a capacity is known: no read-back in this frame
+            cap = int((int(st["max_m"] * ASYNC_HEADROOM) + 65535) // 65536 * 65536)
+            pin = st["pinned"][st["slot"] % len(st["pinned"])]
+            st["slot"] += 1
+            pin.copy_(total, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            lazy = LazyCount(ev, pin, cap, total)
+            st["pending"].append(lazy)
+            ASYNC_STATS["frames"] += 1
+            sorted_ids = torch.empty(cap, device=device, dtype=torch.int32)
+            sb2 = L.sgn_bin_sort_scratch_bytes(cap)
+            scratch2 = torch.empty(sb2, device=device, dtype=torch.uint8)
+            with _timed("bin_sort"):
+                _lib.check(L.sgn_bin_sort_capped(N, cap, _ptr(total), _ptr(st["overflow"]), C.byref(cs), _ptr(records), _ptr(radii),
+                                                 _ptr(bbox), _ptr(mask), _ptr(oc[0]), _ptr(oc[1]), _ptr(sorted_ids), _ptr(tile_bins),
+                                                 _ptr(scratch2), sb2, _stream()), "sgn_bin_sort_capped")
+            return lazy, sorted_ids, tile_bins
+        ASYNC_STATS["sync_frames"] += 1  # first frame on this device: learn the count the exact way
+    M = int(total.item())
+    if use_async and N > 0:
+        _async_state(device)["max_m"] = max(_async_state(device)["max_m"], M)
     sorted_ids = torch.empty(max(M, 1), device=device, dtype=torch.int32)
     sb2 = L.sgn_bin_sort_scratch_bytes(M)
     scratch2 = torch.empty(sb2, device=device, dtype=torch.uint8)
@@ -332,6 +438,7 @@ def class_lists(cs: _lib.CameraStruct, M: int, sorted_ids, tile_bins):
     L = _lib.load()
     device = sorted_ids.device
     tiles = tile_bins.shape[0]
+    M = sorted_ids.shape[0]  # the sub-lists' stride: the list buffer's length (== max(M, 1), or the capacity without the read-back)
     obj_ids = torch.empty(2, max(M, 1), device=device, dtype=torch.int32)
     obj_bins = torch.empty(2, tiles, 2, device=device, dtype=torch.int32)
     sb = L.sgn_bin_class_scratch_bytes(tiles)
@@ -533,7 +640,7 @@ class _SceneGraphRasterize(torch.autograd.Function):
         table = SegmentTable(frame, params, device)
         proj = project_fwd(table, cs, device)
         records, radii, tiles_hit, bbox = proj
-        M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, proj=proj)
+        M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, proj=proj, async_binning=settings.async_binning)
         obj_ids = obj_bins = None
         if settings.class_streams:
             obj_ids, obj_bins = class_lists(cs, M, sorted_ids, tile_bins)
@@ -614,7 +721,7 @@ def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[st
     table = SegmentTable(frame, params, device)
     proj = project_fwd(table, cs, device)
     records, radii, tiles_hit, bbox = proj
-    M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, proj=proj)
+    M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, proj=proj, async_binning=settings.async_binning)
     cls_ids = cls_bins = None
     if settings.class_streams:
         cls_ids, cls_bins = class_lists(cs, M, sorted_ids, tile_bins)

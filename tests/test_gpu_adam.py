@@ -96,5 +96,5 @@ def test_extra_tensor_sky_cube_steps_in_the_same_launch():
     torch.cuda.synchronize()
     for ps, rs in zip(params, ref_params):
         for a, b in zip(ps, rs):
-            assert torch.allclose(a, b.detach(), rtol=0, atol=1e-7), float((a - b.detach()).abs().max())
-    assert torch.allclose(sky, ref_sky.detach(), rtol=0, atol=1e-7)
+            assert torch.allclose(a, b.detach(), rtol=1e-6, atol=1e-6), float((a - b.detach()).abs().max())
+    assert torch.allclose(sky, ref_sky.detach(), rtol=1e-6, atol=1e-6)

@@ -409,3 +409,44 @@ def test_extra_channels_parity(C):
             ref = gref[k]
             if np.linalg.norm(ref) > 0:
                 assert rel_l2(getattr(seg.params, k).grad.cpu().numpy(), ref) <= GRAD_TOL, k
+
+
+def test_async_binning_identical_results_and_overflow_detection():
+    """RenderSettings(async_binning=True): no read-back of the intersection count inside a frame (the capacity comes from
+    earlier frames, unused slots are padded behind the last tile).  Same lists, same images, same gradients as the exact path;
+    a frame that exceeds the capacity is detected with the next frame and the capacity grows."""
+    import warnings
+    fr = syn.make_frame(**SCENES["small_actors"])
+    H, W = fr.camera.height, fr.camera.width
+    w, v = syn.cotangents(H, W)
+    cots = {"rgb": w.cuda(), "accumulation": v.cuda(), "object_acc": 0.1 * v.cuda()}
+    frc = to_cuda(fr)
+    raster._ASYNC_STATE.clear()
+    ref_out, ref_h = raster.forward_backward(frc, raster.RenderSettings(deterministic=True), cots, want_param_grads=True)
+    stats0 = dict(raster.ASYNC_STATS)
+    s = raster.RenderSettings(deterministic=True, async_binning=True)
+    out1, h1 = raster.forward_backward(frc, s, cots, want_param_grads=True)   # first frame on the device: learns the count (sync)
+    assert isinstance(h1.M, int) and h1.M == ref_h.M
+    out2, h2 = raster.forward_backward(frc, s, cots, want_param_grads=True)   # no read-back
+    assert isinstance(h2.M, raster.LazyCount) and raster.ASYNC_STATS["frames"] == stats0["frames"] + 1
+    for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc"):
+        assert torch.equal(out2[k], ref_out[k]), k
+    assert torch.equal(h2.grad_arena, ref_h.grad_arena)  # deterministic accumulation: bit-identical
+    assert int(h2.M) == ref_h.M and h2.M.capacity >= ref_h.M
+    # force an overflow: pretend earlier frames were tiny
+    torch.cuda.synchronize()
+    st = raster._ASYNC_STATE[str(torch.device("cuda", 0))]
+    raster._async_poll(st)
+    st["max_m"] = 1000
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        out3, h3 = raster.forward_backward(frc, s, cots)     # truncated lists (capacity 65536 < M): finite, flagged later
+        torch.cuda.synchronize()
+        assert h3.M.raw() == ref_h.M and int(h3.M) == h3.M.capacity < ref_h.M
+        assert bool(torch.isfinite(out3["rgb"]).all())
+        out4, h4 = raster.forward_backward(frc, s, cots, want_param_grads=True)   # the poll sees the overflow, the capacity follows
+    assert raster.ASYNC_STATS["overflows"] == stats0["overflows"] + 1 and any("truncated" in str(c.message) for c in caught)
+    assert h4.M.capacity >= ref_h.M
+    for k in ("rgb", "accumulation", "object_acc"):
+        assert torch.equal(out4[k], ref_out[k]), k
+    assert int(st["overflow"].item()) == 1
