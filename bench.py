@@ -258,11 +258,15 @@ def run_ours(args):
         collective = {"kind": "nccl all_reduce(SUM) of the arena after the backward", "bytes": 4 * total}
         if os.environ.get("SGN_DP_EXCHANGE", "sym") != "nccl":
             try:
-                exchange = dp.SymmetricExchange(total, dev, use_multicast=os.environ.get("SGN_DP_MULTICAST", "1") != "0")
+                skip_unseen = os.environ.get("SGN_DP_SKIP_UNSEEN", "1") != "0"
+                exchange = dp.SymmetricExchange(total, dev, use_multicast={"0": False, "1": True}.get(os.environ.get("SGN_DP_MULTICAST", ""), "auto"),
+                                                flag_rows=counts[0] if skip_unseen else 0)
                 nr = int(os.environ.get("SGN_DP_RANGES", "4"))
                 plan = dp.plan_ranges(counts, offs, widths, nr)
                 collective = {"kind": "sgn_allreduce_sym (this library's kernel over symmetric memory), range by range behind project_bwd",
-                              "mode": exchange.mode, "ranges": len(plan), "bytes": 4 * total}
+                              "mode": exchange.mode, "autotune": exchange.tuned, "ranges": len(plan), "bytes": 4 * total,
+                              "skip_unseen_rows": ("background rows no replica saw are not exchanged (their gradient is exactly zero "
+                                                   "on every replica)") if skip_unseen else "off"}
             except Exception as e:
                 exchange = None
                 collective["symmetric_memory_unavailable"] = f"{type(e).__name__}: {e}"[:300]
@@ -275,7 +279,8 @@ def run_ours(args):
         else:
             out, holder = raster.forward_backward(frc, settings, cot, grad_out=exchange.arena[:total],
                                                   chunk_ranges=[(a, b) for a, b, _ in plan],
-                                                  after_range=lambda k: exchange.after_range(k, plan[k][2]))
+                                                  after_range=lambda k: exchange.after_range(k, plan[k][2], skip_unseen=skip_unseen),
+                                                  after_project=(exchange.publish_visible if skip_unseen else None))
             exchange.wait_all()
         return holder
 

@@ -373,8 +373,17 @@ int sgn_adam_step(const sgn_adam_tensor* table_dev, int ntensors, int num_chunks
  * (this rank's own included).  Slice offsets / lengths are in floats, multiples of 4.  The caller orders the call between
  * two cross-GPU barriers on the same stream (all replicas written; all parts pushed).  Bit-identical results on all ranks. */
 #define SGN_AR_MAX_SLICES 48
+/* Row skipping (optional, NULL = exchange everything): a slice with slice_widths[s] > 0 holds slice_rows[s] rows of that many
+ * floats, row j of the slice is entry slice_row0[s] + j of `visible_union` (uint8, 1 = some replica saw the Gaussian).  Rows
+ * nobody saw carry an all-zero gradient on every replica (sgn_project_bwd writes zeros there): their sum is already in place,
+ * so they are neither pulled nor pushed.  sgn_visible_flags writes this rank's flags (radii > 0) -- into symmetric memory --
+ * and sgn_visible_union ORs the peers' flags (peer base + flags_byte_offset) into a local array. */
 int sgn_allreduce_sym(void* local, void* multicast, const uint64_t* peer_ptrs_dev, int rank, int world, int nslices,
-                      const int64_t* slice_offsets, const int64_t* slice_lengths, float scale, int max_ctas, void* stream);
+                      const int64_t* slice_offsets, const int64_t* slice_lengths, const int32_t* slice_widths,
+                      const int64_t* slice_row0, const int64_t* slice_rows, const uint8_t* visible_union, float scale, int max_ctas,
+                      void* stream);
+int sgn_visible_flags(const int32_t* radii, int64_t n, uint8_t* flags, void* stream);
+int sgn_visible_union(const uint64_t* peer_ptrs_dev, int64_t flags_byte_offset, int world, int64_t n, uint8_t* out, void* stream);
 
 /* ---- refinement: split / duplicate / cull ---------------------------------------------
  * What `SplatfactoModel.refinement_after` does to ONE sub-model every `refine_every` steps

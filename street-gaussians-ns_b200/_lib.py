@@ -131,7 +131,7 @@ EXPORTS = [
     "sgn_sizeof_refine_config", "sgn_sizeof_refine_tensors", "sgn_refine_decide", "sgn_refine_apply",
     "sgn_bin_local_cap", "sgn_bin_local_scratch_bytes", "sgn_bin_local_count", "sgn_bin_local_sort",
     "sgn_project_bwd_range", "sgn_allreduce_sym", "sgn_blend_extra_fwd", "sgn_blend_extra_bwd",
-    "sgn_bin_sort_capped",
+    "sgn_bin_sort_capped", "sgn_visible_flags", "sgn_visible_union",
 ]
 AR_MAX_SLICES = 48  # SGN_AR_MAX_SLICES
 
@@ -158,8 +158,11 @@ def load():
     L.sgn_project_bwd.argtypes = [vp, vp, i32, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, vp]
     L.sgn_project_bwd_range.argtypes = [vp, vp, i32, i32, i32, C.POINTER(CameraStruct), vp, vp, vp, i32, i32, vp]
     L.sgn_project_bwd_range.restype = C.c_int
-    L.sgn_allreduce_sym.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_float, i32, vp]
-    L.sgn_allreduce_sym.restype = C.c_int
+    L.sgn_allreduce_sym.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_float, i32, vp]
+    L.sgn_visible_flags.argtypes = [vp, i64, vp, vp]
+    L.sgn_visible_union.argtypes = [vp, i64, i32, i64, vp, vp]
+    L.sgn_allreduce_sym.restype = L.sgn_visible_flags.restype = L.sgn_visible_union.restype = C.c_int
     L.sgn_blend_extra_fwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.sgn_blend_extra_bwd.argtypes = [C.POINTER(CameraStruct), C.POINTER(BlendOpts), vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     L.sgn_blend_extra_fwd.restype = L.sgn_blend_extra_bwd.restype = C.c_int

@@ -79,8 +79,9 @@ def plan_ranges(seg_counts, seg_arena_offsets, seg_widths, num_ranges: int, chun
     ``seg_counts[s]``: rows of segment s (frame order); ``seg_arena_offsets[s][k]`` / ``seg_widths[s][k]``: where tensor k of
     segment s starts in the arena (floats) and its floats per row.  The first (largest) segment -- the background -- is cut
     into row ranges at chunk boundaries; every other segment stays whole, and runs of whole segments whose arena regions are
-    adjacent collapse into one slice.  Returns [(chunk_begin, chunk_end, [(offset, length), ...]), ...]; lengths are
-    rounded up to 4 floats (the arena pads every tensor to 16 bytes).  Plain integer arithmetic (CPU-tested)."""
+    adjacent collapse into one slice.  Returns [(chunk_begin, chunk_end, [slice, ...]), ...] with slice = (offset, length) or,
+    for the first segment, (offset, length, floats per row, first row, rows); lengths are rounded up to 4 floats (the arena pads
+    every tensor to 16 bytes).  Plain integer arithmetic (CPU-tested)."""
     def pad4(x):
         return (x + 3) // 4 * 4
     chunks = [(n + chunk_rows - 1) // chunk_rows for n in seg_counts]
@@ -92,7 +93,9 @@ def plan_ranges(seg_counts, seg_arena_offsets, seg_widths, num_ranges: int, chun
     while c < chunks[0]:
         c1 = min(chunks[0], c + per)
         r0, r1 = c * chunk_rows, min(seg_counts[0], c1 * chunk_rows)
-        sl = [(int(seg_arena_offsets[0][k] + r0 * seg_widths[0][k]), int(pad4((r1 - r0) * seg_widths[0][k]))) for k in range(6)]
+        # (offset, length, floats per row, first row, rows): the row description lets the exchange skip rows no replica saw
+        sl = [(int(seg_arena_offsets[0][k] + r0 * seg_widths[0][k]), int(pad4((r1 - r0) * seg_widths[0][k])), int(seg_widths[0][k]), int(r0),
+               int(r1 - r0)) for k in range(6)]
         out.append((chunk0[0] + c, chunk0[0] + c1, [x for x in sl if x[1] > 0]))
         c = c1
     if len(seg_counts) > 1:
@@ -136,9 +139,12 @@ class SymmetricExchange:
     current one).  With ``comm_stream`` the exchange of range k runs next to the production of range k+1:
     ``begin()`` ... ``after_range(k, slices)`` ... ``wait_range(k)``.
     Needs CUDA peer access between the ranks' GPUs (NVLink); the multicast path additionally needs an NVSwitch fabric --
-    without it the kernel pulls from / pushes to the peers' arenas directly."""
+    without it the kernel pulls from / pushes to the peers' arenas directly.  ``use_multicast``: True / False / "auto"
+    (time both paths once on this arena and keep the faster)."""
 
-    def __init__(self, numel: int, device, group: Optional[dist.ProcessGroup] = None, use_multicast: bool = True):
+    def __init__(self, numel: int, device, group: Optional[dist.ProcessGroup] = None, use_multicast="auto", flag_rows: int = 0):
+        """``flag_rows`` > 0: room for that many per-row visibility flags behind the arena (same symmetric allocation), so that
+        the exchange can skip the rows no replica saw (``publish_visible`` / ``all_reduce(..., skip_unseen=True)``)."""
         import ctypes as C
         import torch.distributed._symmetric_memory as symm
         from . import _lib
@@ -146,9 +152,15 @@ class SymmetricExchange:
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.numel = int((numel + 3) // 4 * 4)
-        self.arena = symm.empty(self.numel, dtype=torch.float32, device=device)
-        self.arena.zero_()
-        self.hdl = symm.rendezvous(self.arena, self.group)
+        self.flag_rows = int(flag_rows)
+        flag_floats = (self.flag_rows + 15) // 16 * 4
+        self._storage = symm.empty(self.numel + flag_floats, dtype=torch.float32, device=device)
+        self._storage.zero_()
+        self.arena = self._storage[:self.numel]
+        self.flags = self._storage[self.numel:].view(torch.uint8)[:self.flag_rows] if self.flag_rows else None
+        self.union = torch.zeros(max(self.flag_rows, 1), dtype=torch.uint8, device=device)
+        self._union_fresh = False
+        self.hdl = symm.rendezvous(self._storage, self.group)
         mc = 0
         if use_multicast:
             try:
@@ -159,42 +171,91 @@ class SymmetricExchange:
         self.peers_dev = int(self.hdl.buffer_ptrs_dev)
         self.comm_stream = torch.cuda.Stream(device=device)
         self._done = {}
+        self.tuned = None
         torch.cuda.synchronize(device)
         dist.barrier(self.group)
+        if mc and use_multicast == "auto":
+            self._autotune(device)
+
+    def _autotune(self, device) -> None:
+        """Which path is faster on THIS box and world size is measured, not assumed: at two GPUs the peer loads / stores beat
+        the in-switch reduction (0.53 vs 0.85 ms for 330 MB on a B200 pair, profiles/), with more replicas the multicast path
+        moves 1/(2 - 2/g) of the bytes.  Three exchanges of the (zeroed) arena per mode, max over ranks, every rank takes the
+        same decision."""
+        mc = self.multicast_ptr
+        times = []
+        for mode_mc in (mc, 0):
+            self.multicast_ptr = mode_mc
+            self.all_reduce()
+            torch.cuda.synchronize(device)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                self.all_reduce()
+            b.record()
+            torch.cuda.synchronize(device)
+            t = torch.tensor([a.elapsed_time(b) / 3], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            times.append(float(t.item()))
+        self.multicast_ptr = mc if times[0] <= times[1] else 0
+        self.tuned = {"multimem_ms": round(times[0], 4), "peer_ms": round(times[1], 4)}
+        self.arena.zero_()
 
     @property
     def mode(self) -> str:
         return "multimem (in-switch reduction)" if self.multicast_ptr else "peer loads/stores"
 
-    def _launch(self, slices, scale: float, max_ctas: int = 0):
+    def publish_visible(self, radii: torch.Tensor) -> None:
+        """This rank's per-row visibility (radii > 0, the frame's first ``flag_rows`` rows -- the background, whose rows mean the
+        same Gaussian on every replica) into the symmetric flags; call on the stream that produced ``radii``, before the
+        backward.  The next exchange with ``skip_unseen`` ORs the replicas' flags once and skips the rows nobody saw."""
+        assert self.flags is not None and radii.dtype == torch.int32 and radii.shape[0] >= self.flag_rows
+        C = self._C
+        self._lib.check(self._lib.load().sgn_visible_flags(C.c_void_p(radii.data_ptr()), self.flag_rows, C.c_void_p(self.flags.data_ptr()),
+                                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)), "sgn_visible_flags")
+        self._union_fresh = False
+
+    def _launch(self, slices, scale: float, max_ctas: int = 0, skip_unseen: bool = False):
         C = self._C
         n = len(slices)
         if n == 0:
             return
         assert n <= self._lib.AR_MAX_SLICES, n
-        off = (C.c_int64 * n)(*[int(o) for o, _ in slices])
-        ln = (C.c_int64 * n)(*[int(l) for _, l in slices])
+        off = (C.c_int64 * n)(*[int(sl[0]) for sl in slices])
+        ln = (C.c_int64 * n)(*[int(sl[1]) for sl in slices])
         L = self._lib.load()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        widths = row0 = rows = union = None
+        if skip_unseen and self.flags is not None and any(len(sl) == 5 for sl in slices):
+            if not self._union_fresh:  # once per step, after the first barrier: every replica's flags are in place
+                self._lib.check(L.sgn_visible_union(C.c_void_p(self.peers_dev), 4 * self.numel, self.world, self.flag_rows,
+                                                    C.c_void_p(self.union.data_ptr()), stream), "sgn_visible_union")
+                self._union_fresh = True
+            widths = (C.c_int32 * n)(*[int(sl[2]) if len(sl) == 5 else 0 for sl in slices])
+            row0 = (C.c_int64 * n)(*[int(sl[3]) if len(sl) == 5 else 0 for sl in slices])
+            rows = (C.c_int64 * n)(*[int(sl[4]) if len(sl) == 5 else 0 for sl in slices])
+            union = C.c_void_p(self.union.data_ptr())
         self._lib.check(L.sgn_allreduce_sym(C.c_void_p(self.arena.data_ptr()), C.c_void_p(self.multicast_ptr or None),
-                                            C.c_void_p(self.peers_dev), self.rank, self.world, n, off, ln, C.c_float(scale), max_ctas,
-                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "sgn_allreduce_sym")
+                                            C.c_void_p(self.peers_dev), self.rank, self.world, n, off, ln, widths, row0, rows, union,
+                                            C.c_float(scale), max_ctas, stream), "sgn_allreduce_sym")
 
-    def all_reduce(self, slices=None, average: bool = False, max_ctas: int = 0):
-        """In place, on the current stream.  ``slices``: [(offset, length)] in floats (multiples of 4); None = the whole arena."""
+    def all_reduce(self, slices=None, average: bool = False, max_ctas: int = 0, skip_unseen: bool = False):
+        """In place, on the current stream.  ``slices``: [(offset, length)] in floats (multiples of 4), or with a row
+        description (offset, length, floats per row, first row, rows) for ``skip_unseen``; None = the whole arena."""
         if slices is None:
             slices = [(0, self.numel)]
-        self.hdl.barrier(channel=0)   # every replica has written these slices
-        self._launch(slices, 1.0 / self.world if average else 1.0, max_ctas)
+        self.hdl.barrier(channel=0)   # every replica has written these slices (and published its visibility flags)
+        self._launch(slices, 1.0 / self.world if average else 1.0, max_ctas, skip_unseen)
         self.hdl.barrier(channel=1)   # every part has been pushed to every replica
 
     # ---- range by range, on the communication stream ------------------------------------------------------------
-    def after_range(self, k: int, slices, average: bool = False, max_ctas: int = 0):
+    def after_range(self, k: int, slices, average: bool = False, max_ctas: int = 0, skip_unseen: bool = False):
         """Call right after the launch that PRODUCES range k was enqueued on the current stream."""
         ev = torch.cuda.Event()
         ev.record()
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
-            self.all_reduce(slices, average, max_ctas)
+            self.all_reduce(slices, average, max_ctas, skip_unseen)
             done = torch.cuda.Event()
             done.record()
         self._done[k] = done

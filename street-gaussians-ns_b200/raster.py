@@ -701,7 +701,7 @@ class _SceneGraphRasterize(torch.autograd.Function):
 
 def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[str, Optional[torch.Tensor]],
                      sky: Optional[torch.Tensor] = None, want_param_grads: bool = False, grad_out: Optional[torch.Tensor] = None,
-                     chunk_ranges=None, after_range=None):
+                     chunk_ranges=None, after_range=None, after_project=None):
     """One frame, forward AND backward, straight through the C-ABI stages (no autograd graph).
 
     ``cotangents`` maps output names (rgb, accumulation, depth, object_acc, background_acc) to their
@@ -721,6 +721,8 @@ def forward_backward(frame: Frame, settings: RenderSettings, cotangents: Dict[st
     table = SegmentTable(frame, params, device)
     proj = project_fwd(table, cs, device)
     records, radii, tiles_hit, bbox = proj
+    if after_project is not None:  # data parallel: the rows this replica sees are published early (dp.SymmetricExchange)
+        after_project(radii)
     M, sorted_ids, tile_bins = bin_and_sort(cs, records, radii, proj=proj, async_binning=settings.async_binning)
     cls_ids = cls_bins = None
     if settings.class_streams:

@@ -27,9 +27,13 @@ def test_ranges_cover_every_chunk_and_every_arena_float_once():
         cover = np.zeros(total, np.int32)
         for _, _, slices in plan:
             assert len(slices) <= 48
-            for o, ln in slices:
+            for sl in slices:
+                o, ln = sl[0], sl[1]
                 assert o % 4 == 0 and ln % 4 == 0 and o + ln <= total
                 cover[o:o + ln] += 1
+                if len(sl) == 5:  # row description of a background slice: rows * width floats fit, first row is chunk-aligned
+                    w, r0, rows = sl[2:]
+                    assert r0 % 128 == 0 and rows * w <= ln < rows * w + 4
         # every float that holds a gradient is exchanged exactly once; padding floats at most once per neighbouring range
         for s, (n, w) in enumerate(zip(counts, widths)):
             for k in range(6):
@@ -38,7 +42,7 @@ def test_ranges_cover_every_chunk_and_every_arena_float_once():
         # the rows of a background range are exactly the rows its chunks cover
         for c0, c1, slices in plan[:-1]:
             r0, r1 = c0 * 128, min(counts[0], c1 * 128)
-            assert slices[0] == (offs[0][0] + 3 * r0, (3 * (r1 - r0) + 3) // 4 * 4)
+            assert slices[0] == (offs[0][0] + 3 * r0, (3 * (r1 - r0) + 3) // 4 * 4, 3, r0, r1 - r0)
 
 
 def test_single_segment_frame():

@@ -77,6 +77,39 @@ def main():
         for ctas in (32, 64, 148):
             res[f"{tag}_ms_{ctas}ctas"] = round(timeit(lambda: ex.all_reduce(max_ctas=ctas)), 4)
         del ex
+    # rows nobody saw are skipped: a background of 1 M rows in the arena layout of project_bwd (6 tensors), ~50 % of the rows visible per
+    # rank with a large overlap; unseen rows are all-zero on every rank (as project_bwd leaves them)
+    rows = 1_000_000
+    widths = [3, 3, 4, 3, 45, 1]
+    offs, cur = [], 0
+    for w in widths:
+        offs.append(cur)
+        cur += (rows * w + 3) // 4 * 4
+    exs = dp.SymmetricExchange(cur, dev, flag_rows=rows)
+    g = torch.Generator(device=dev).manual_seed(7)
+    common = torch.rand(rows, device=dev, generator=g) < 0.45            # same on every rank (same seed)
+    g2 = torch.Generator(device=dev).manual_seed(1000 + rank)
+    own = common | (torch.rand(rows, device=dev, generator=g2) < 0.05)
+    src = torch.zeros(cur, device=dev)
+    for w, o in zip(widths, offs):
+        src[o:o + rows * w].view(rows, w).copy_(torch.randn(rows, w, device=dev, generator=g2) * own[:, None])
+    ref = src.clone()
+    dist.all_reduce(ref)
+    slices = [(o, (rows * w + 3) // 4 * 4, w, 0, rows) for w, o in zip(widths, offs)]
+    exs.arena.copy_(src)
+    exs.publish_visible(own.to(torch.int32))
+    exs.all_reduce(slices, skip_unseen=True)
+    torch.cuda.synchronize()
+    assert float((exs.arena - ref).abs().max()) <= 1e-6 * float(ref.abs().max()), "row skipping changed the sum"
+    def prep():
+        exs.publish_visible(own.to(torch.int32))
+    res["skip_unseen"] = {"rows": rows, "visible_on_some_rank": float(common.float().mean()) + 0.05,
+                          "dense_ms": round(timeit(lambda: exs.all_reduce(slices)), 4),
+                          "skipping_ms": round(timeit(lambda: (prep(), exs.all_reduce(slices, skip_unseen=True))), 4), "mode": exs.mode}
+    del exs
+    auto = dp.SymmetricExchange(n, dev)
+    res["auto"] = {"mode": auto.mode, **(auto.tuned or {})}
+    del auto
     tmp = torch.zeros(n, device=dev)
     res["nccl_ms"] = round(timeit(lambda: dist.all_reduce(tmp)), 4)
     if rank == 0:
