@@ -287,6 +287,7 @@ _LOCAL_CLASSES = None  # (sorted_ids, cls_ids, cls_bins) of the last _bin_local 
 
 ASYNC_BIN = os.environ.get("SGN_ASYNC_BIN", "0") == "1"
 ASYNC_HEADROOM = float(os.environ.get("SGN_ASYNC_BIN_HEADROOM", "1.2"))
+ASYNC_GRANULE = 65536  # capacities are multiples of this many entries
 ASYNC_STATS = {"frames": 0, "overflows": 0, "sync_frames": 0}
 _ASYNC_STATE: Dict[str, dict] = {}
 
@@ -394,7 +395,7 @@ def bin_and_sort(cs: _lib.CameraStruct, records, radii, tiles_hit=None, bbox=Non
         st = _async_state(device)
         _async_poll(st)
         if st["max_m"] > 0:  # a capacity is known: no read-back in this frame
-            cap = int((int(st["max_m"] * ASYNC_HEADROOM) + 65535) // 65536 * 65536)
+            cap = int((int(st["max_m"] * ASYNC_HEADROOM) + ASYNC_GRANULE - 1) // ASYNC_GRANULE * ASYNC_GRANULE)
             pin = st["pinned"][st["slot"] % len(st["pinned"])]
             st["slot"] += 1
             pin.copy_(total, non_blocking=True)

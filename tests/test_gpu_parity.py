@@ -438,13 +438,15 @@ def test_async_binning_identical_results_and_overflow_detection():
     st = raster._ASYNC_STATE[str(torch.device("cuda", 0))]
     raster._async_poll(st)
     st["max_m"] = 1000
+    monkey_granule, raster.ASYNC_GRANULE = raster.ASYNC_GRANULE, 1024
     with warnings.catch_warnings(record=True) as caught:
         warnings.simplefilter("always")
-        out3, h3 = raster.forward_backward(frc, s, cots)     # truncated lists (capacity 65536 < M): finite, flagged later
+        out3, h3 = raster.forward_backward(frc, s, cots)     # truncated lists (capacity 2048 < M): finite, flagged later
         torch.cuda.synchronize()
         assert h3.M.raw() == ref_h.M and int(h3.M) == h3.M.capacity < ref_h.M
         assert bool(torch.isfinite(out3["rgb"]).all())
         out4, h4 = raster.forward_backward(frc, s, cots, want_param_grads=True)   # the poll sees the overflow, the capacity follows
+    raster.ASYNC_GRANULE = monkey_granule
     assert raster.ASYNC_STATS["overflows"] == stats0["overflows"] + 1 and any("truncated" in str(c.message) for c in caught)
     assert h4.M.capacity >= ref_h.M
     for k in ("rgb", "accumulation", "object_acc"):
