@@ -189,6 +189,18 @@ class FusedAdam:
         out["chunk0"] = np.concatenate([[0], np.cumsum(ch)[:-1]]) if len(out) else []
         return out
 
+    def rows_in_slices(self, tab: np.ndarray, slices) -> np.ndarray:
+        """The part of a step's table inside a LIST of arena slices [(offset, length, ...)] (full layout): what one exchanged
+        range of the data-parallel step covers -- the six tensors' rows [r0, r1) of the background, or everything behind it."""
+        parts = [self.rows_in_range(tab, int(sl[0]), int(sl[0]) + int(sl[1])) for sl in slices]
+        parts = [p for p in parts if len(p)]
+        if not parts:
+            return tab[:0]
+        out = np.concatenate(parts)
+        ch = (out["numel"] + self._chunk - 1) // self._chunk
+        out["chunk0"] = np.concatenate([[0], np.cumsum(ch)[:-1]])
+        return out
+
     # ---- refinement (sgn_splatfacto.py:459-511) ---------------------------------------------------------------
     def rebuild(self, params: Sequence[Sequence[torch.Tensor]]) -> Tuple[torch.Tensor, torch.Tensor, np.ndarray]:
         """Move the optimizer onto new parameter tensors (same sub-models, new row counts).  Allocates new, ZEROED

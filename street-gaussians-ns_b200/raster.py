@@ -685,8 +685,12 @@ class _SceneGraphRasterize(torch.autograd.Function):
         if sink is not None:
             target = sink.target(ctx.table.static, v_records.device)
             offsets = sink.grad_offsets(ctx.table.static) if target is not None else None  # None: the frame's own layout
+            chunk_ranges = after_range = None
+            plan = getattr(sink, "exchange_plan", None)  # data parallel: the arena is produced and exchanged range by range
+            if plan is not None and target is not None:
+                chunk_ranges, after_range = plan(ctx.table)
             _, arena = project_bwd(ctx.table, ctx.params, ctx.cs, ctx.records, ctx.radii, v_records, make_views=False,
-                                   out=target, out_offsets=offsets)
+                                   out=target, out_offsets=offsets, chunk_ranges=chunk_ranges, after_range=after_range)
             sink.publish(arena, ctx.table.static)
             flat = (None,)
         else:

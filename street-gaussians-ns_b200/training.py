@@ -74,6 +74,13 @@ class TrainStep:
         for p in m.parameters():                          # Optimizers.zero_grad_all()
             p.grad = None
         out = m.get_outputs(camera)
+        if world > 1 and self._exchange is not None:  # which background rows this replica sees (rows nobody sees are not exchanged)
+            h = m._holder
+            if h is not None and h.radii is not None and h.radii.shape[0] >= self._exchange.flag_rows and m.visible_model_names[:1] == ["background"]:
+                self._exchange.publish_visible(h.radii)
+            else:
+                self._exchange.flags.zero_()
+                self._exchange._union_fresh = False
         losses = m.get_loss_dict(out, batch)
         total = sum(losses.values())
         rendered = isinstance(total, torch.Tensor) and total.requires_grad
@@ -94,7 +101,7 @@ class TrainStep:
             present = m.present_submodels()
         everything = len(present) == opt.num_segments and (full or present == list(range(opt.num_segments)))
         if world > 1 and self._exchange is not None:
-            self._exchange_and_step(arena, None if everything else present)
+            self._exchange_and_step(arena, None if everything else present, rendered)
         elif world > 1 and self.pipeline_chunks > 0:
             dp.allreduce_and_step(arena, opt, None if everything else present, self.pipeline_chunks, self.group)
         else:
@@ -115,14 +122,37 @@ class TrainStep:
         sink = m._grad_sink
         sink.bind_model(m.optimizer_params(), [])
         total = sink.total_elems()
+        n_bg = m.all_models["background"].num_points
         ex = self._exchange
-        if ex is not None and ex.numel == (total + 3) // 4 * 4 and sink.arena is not None and sink.arena.data_ptr() == ex.arena.data_ptr():
+        if (ex is not None and ex.numel == (total + 3) // 4 * 4 and ex.flag_rows == n_bg and sink.arena is not None
+                and sink.arena.data_ptr() == ex.arena.data_ptr()):
             return
         try:
             self._exchange = None
-            ex = dp.SymmetricExchange(total, m.device, self.group)
+            sink.exchange_plan = None
+            # the faster path (multimem / peer) is timed once; later arenas (after refinements) reuse the decision
+            ex = dp.SymmetricExchange(total, m.device, self.group, flag_rows=n_bg, use_multicast=getattr(self, "_use_multicast", "auto"))
+            self._use_multicast = bool(ex.multicast_ptr)
             sink.set_arena(ex.arena[:total])
             self._exchange = ex
+            # the background's six tensors are the first six slices of the full layout: K - 1 row ranges + "everything else"
+            K = max(2, self.pipeline_chunks or 4)
+            widths = [3, 3, 4, 3 * int(m.all_models["background"].gauss_params["features_dc"].shape[1]),
+                      3 * int(m.all_models["background"].gauss_params["features_rest"].shape[1]), 1]
+            offs = [int(sink.offsets[k]) for k in range(6)]
+            bg_end = int(sink.offsets[5] + sink.sizes[5])
+            chunks = (n_bg + 127) // 128
+            per = (chunks + (K - 1) - 1) // (K - 1)
+            self._ranges = []
+            c = 0
+            while c < chunks:
+                c1 = min(chunks, c + per)
+                r0, r1 = c * 128, min(n_bg, c1 * 128)
+                self._ranges.append((c, c1, [(offs[k] + r0 * widths[k], ((r1 - r0) * widths[k] + 3) // 4 * 4, widths[k], r0, r1 - r0)
+                                             for k in range(6)]))
+                c = c1
+            self._tail = (bg_end, total - bg_end)
+            sink.exchange_plan = self._plan
         except Exception as e:  # no peer access / no symmetric-memory support on this box: the NCCL path is the fallback
             if self.exchange_mode == "sym":
                 raise
@@ -130,19 +160,39 @@ class TrainStep:
             self.exchange_mode = "nccl"
             self.exchange_error = f"{type(e).__name__}: {e}"[:300]
 
-    def _exchange_and_step(self, arena: torch.Tensor, present) -> None:
-        """Mean of the arena over the replicas with sgn_allreduce_sym, range by range on the communication stream, and the
-        fused Adam of range k as soon as range k has been exchanged (while range k+1 is on the wire)."""
+    def _plan(self, table):
+        """Called by the render's backward (raster._SceneGraphRasterize.backward) with the frame's segment table: the chunk
+        ranges project_bwd runs in and the callback that starts range k's exchange as soon as its launch is enqueued."""
+        ex = self._exchange
+        bg_chunks = self._ranges[-1][1]
+        ranges = [(a, b) for a, b, _ in self._ranges]
+        slices = [sl for _, _, sl in self._ranges]
+        if table.num_chunks > bg_chunks or self._tail[1] > 0:  # the actors' rows of this frame, and every sub-model behind the background
+            ranges.append((bg_chunks, table.num_chunks))
+            slices.append([self._tail] if self._tail[1] > 0 else [])
+        self._planned = slices
+
+        def after_range(k):
+            ex.after_range(k, slices[k], average=True, skip_unseen=True)
+        return ranges, after_range
+
+    def _exchange_and_step(self, arena: torch.Tensor, present, rendered: bool) -> None:
+        """Mean of the arena over the replicas with sgn_allreduce_sym -- range by range behind project_bwd when this replica
+        rendered (the exchanges were started by the backward), all ranges here when it did not -- and the fused Adam of range
+        k as soon as range k has been exchanged (while range k+1 is on the wire)."""
         ex, opt = self._exchange, self.optimizer
         assert arena.data_ptr() == ex.arena.data_ptr(), "the gradient arena is not the symmetric allocation"
         opt.step_count += 1
         tab = opt.step_table(present, full_layout=True)
-        bounds = dp.chunk_bounds(opt.arena_elems, max(1, self.pipeline_chunks))
-        for k, (lo, hi) in enumerate(bounds):
-            ex.after_range(k, [(lo, hi - lo)], average=True)
-        for k, (lo, hi) in enumerate(bounds):
+        if rendered:
+            slices = self._planned
+        else:  # nothing in view here: an all-zero arena, exchanged in the same ranges as on the replicas that rendered
+            slices = [sl for _, _, sl in self._ranges] + ([[self._tail]] if self._tail[1] > 0 else [])
+            for k, sl in enumerate(slices):
+                ex.after_range(k, sl, average=True, skip_unseen=True)
+        for k, sl in enumerate(slices):
             ex.wait_range(k)
-            opt.launch(opt.rows_in_range(tab, lo, hi), arena)
+            opt.launch(opt.rows_in_slices(tab, sl), arena)
 
     def _refine_generator(self, step: int) -> torch.Generator:
         """Split samples must be identical on every replica whatever else consumed the global CUDA generator (a sky
