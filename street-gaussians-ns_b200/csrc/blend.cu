@@ -25,6 +25,18 @@
 // Sorted payloads carry the Gaussian row in bits 0-30 and the object-class flag in bit 31.
 #include "sgn_common.cuh"
 
+// Resident CTAs per SM the compiler must leave room for (register budget = 65536 / (32 * N) per thread); one warp per CTA, at
+// most 32 CTAs per SM.  -maxrregcount is ignored for kernels with launch bounds, so the occupancy experiments go through these.
+#ifndef BLEND_FWD_MIN_BLOCKS
+#define BLEND_FWD_MIN_BLOCKS 1
+#endif
+#ifndef BLEND_BWD_MIN_BLOCKS
+#define BLEND_BWD_MIN_BLOCKS 1
+#endif
+#ifndef BLEND_ACC_MIN_BLOCKS
+#define BLEND_ACC_MIN_BLOCKS 1
+#endif
+
 #define ALPHA_MIN (1.f / 255.f)
 #define T_STOP 1e-4f
 #define ID_MASK 0x7fffffff
@@ -541,7 +553,7 @@ __device__ __forceinline__ void blend_fwd_strip(const BlendFwdParams& p, int til
 }
 
 template <bool CLS, bool SKIP, bool PACK>
-__global__ void __launch_bounds__(32) blend_fwd_kernel(const BlendFwdParams p) {
+__global__ void __launch_bounds__(32, BLEND_FWD_MIN_BLOCKS) blend_fwd_kernel(const BlendFwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
     __shared__ float4 sC[2][32];
@@ -678,7 +690,7 @@ __device__ __forceinline__ void acc_fwd_strip(const BlendFwdParams& p, int cls, 
 }
 
 template <bool SKIP>
-__global__ void __launch_bounds__(32) acc_fwd_kernel(const BlendFwdParams p, const int cls) {
+__global__ void __launch_bounds__(32, BLEND_ACC_MIN_BLOCKS) acc_fwd_kernel(const BlendFwdParams p, const int cls) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
     int tile, strip;
@@ -1077,7 +1089,7 @@ __device__ __forceinline__ void blend_bwd_strip(const BlendBwdParams& p, int til
 // the prologue (v_sky, cotangent chain) must run for every pixel, so strips are always launched for the
 // whole tile: W strips of 16/W rows
 template <bool DEPTHG, bool PACK>
-__global__ void __launch_bounds__(32) blend_bwd_kernel(const BlendBwdParams p) {
+__global__ void __launch_bounds__(32, BLEND_BWD_MIN_BLOCKS) blend_bwd_kernel(const BlendBwdParams p) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
     __shared__ float4 sC[2][32];
@@ -1202,7 +1214,7 @@ __device__ __forceinline__ void acc_bwd_strip(const BlendBwdParams& p, int cls, 
 }
 
 template <bool SKIP>
-__global__ void __launch_bounds__(32) acc_bwd_kernel(const BlendBwdParams p, const int cls) {
+__global__ void __launch_bounds__(32, BLEND_ACC_MIN_BLOCKS) acc_bwd_kernel(const BlendBwdParams p, const int cls) {
     __shared__ float4 sA[2][32];
     __shared__ float4 sB[2][32];
     __shared__ float sR[2][32];
