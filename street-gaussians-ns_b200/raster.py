@@ -343,6 +343,13 @@ def _async_state(device) -> dict:
     return st
 
 
+def async_learn(device, count: int) -> None:
+    """Tell the capacity logic about an intersection count observed elsewhere (e.g. a look at the widest cameras in exact mode
+    before a training run switches the read-back off)."""
+    st = _async_state(device)
+    st["max_m"] = max(st["max_m"], int(count))
+
+
 def _async_poll(st: dict) -> None:
     """Counts of earlier frames that have arrived: the capacity follows the largest one; an overflow is reported."""
     keep = []

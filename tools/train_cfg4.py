@@ -24,7 +24,8 @@ sys.path.insert(0, ROOT)
 
 
 def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int = 100, start_step: int = 600,
-        actor_range: float = 45.0, pipeline_chunks: int = 0, overlap: bool = False, resident_table: bool = True) -> dict:
+        actor_range: float = 45.0, pipeline_chunks: int = 0, overlap: bool = False, resident_table: bool = True,
+        async_binning: bool = True) -> dict:
     """One measurement.  torch.distributed must already be initialised when WORLD_SIZE > 1.  Returns the result dict on
     rank 0 (None elsewhere)."""
     import torch
@@ -51,7 +52,7 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
         return [ActorPose(str(a), rot, center, f, frame_list) for a, rot, center in sc.boxes_at(f)]
 
     rs = RefineSettings(refine_every=refine_every)
-    cfg = SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0, full_gradient_arena=world > 1, refine=rs,
+    cfg = SceneGraphConfig(use_sky_sphere=False, ssim_lambda=0.0, full_gradient_arena=world > 1, refine=rs, async_binning=async_binning,
                            object_refine=RefineSettings(refine_every=refine_every, cull_alpha_thresh=0.005),
                            num_train_data=len(cams), refine_record=True)
     model = SceneGraphRasterModel(sc.background.to(dev), {k: v.to(dev) for k, v in sc.actors.items()}, cfg, poses_at=poses_at).to(dev)
@@ -64,6 +65,18 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
     times = [float(f) for f in range(num_frames)]
     if resident_table:
         model.prepare_frames(times)
+    if async_binning:
+        # without the per-frame read-back of the intersection count the list buffers have a capacity learnt from earlier frames:
+        # look at every rig camera at three points of the drive once (no gradients) so that the capacity covers the widest view
+        from street_gaussians_ns_b200 import raster
+        model.config.async_binning = False
+        with torch.no_grad():
+            for f in (0, num_frames // 2, num_frames - 1):
+                for c in range(5):
+                    model.get_outputs(cams[f * 5 + c])
+                    raster.async_learn(dev, int(model._holder.M))
+        model.config.async_binning = True
+        torch.cuda.synchronize()
 
     def one(i):
         step = start_step + i
@@ -106,6 +119,7 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
         "config": {"workload": f"cfg{4 if world == 1 else 5}: 5 cameras x 85 frames, {sc.n_bg} background + 32 x {sc.n_act} actor Gaussians, "
                                f"{W}x{H}; rank r renders camera (step*g + r) mod 425; actors have a box within {actor_range} m of the ego vehicle",
                    "parallelism": f"camera-sharded dp{world}", "start_step": start_step, "refine_every": refine_every,
+                   "binning": "no host read-back of the intersection count" if async_binning else "one read-back per frame",
                    "segment_table": "device-resident (staged up front; re-staged per timestamp on first use after a refinement)" if resident_table else "host build per frame",
                    "collective": ("all-reduce(AVG) of the gradient arena (layout of all sub-models), "
                                   + ("overlapped with project_bwd / Adam over arena ranges" if overlap else
