@@ -53,9 +53,12 @@ def make_frames(cfg: int, n_ranks: int, rank: int):
 # clocks sampling (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock and throttle reasons DURING the timed region through NVML in a background thread
-    (spawning `nvidia-smi -lms` next to a sub-second timed region perturbs the driver and the measurement;
-    the queries are the same: clocks.sm, clocks.max.sm, clocks_event_reasons.*)."""
+    """Samples SM clock and throttle reasons DURING the timed regions through NVML (spawning `nvidia-smi -lms` next to a
+    sub-second timed region perturbs the driver and the measurement; the queries are the same: clocks.sm, clocks.max.sm,
+    clocks_event_reasons.*).  The queries are issued by the MAIN thread between steps (``poll()``, every few steps, while the GPU
+    works through the queued launches): issued from a background thread they contend with the launching thread for a driver
+    lock -- an interleaved A/B on one box gave 2 of 6 runs with an 8-9 ms stall on the second timed step with the thread and
+    0 of 6 without (profiles/r02b_bench_outliers.txt).  SGN_BENCH_CLOCK_THREAD=1 restores the thread."""
 
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
@@ -85,8 +88,18 @@ class ClockSampler:
             self._sample()  # the first NVML clock query initialises driver state (tens of ms): keep it out of the timed region
         except Exception:
             pass
-        self._thread = threading.Thread(target=self._run, daemon=True)
-        self._thread.start()
+        if os.environ.get("SGN_BENCH_CLOCK_THREAD", "0") == "1":
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def poll(self, step: int, every: int = 4):
+        """Main-thread sample between two steps of a timed loop (every ``every``-th step)."""
+        if self._h is None or self._thread is not None or step % every:
+            return
+        try:
+            self._sample()
+        except Exception:
+            pass
 
     def _sample(self):
         nv = self._nv
@@ -115,11 +128,13 @@ class ClockSampler:
         if self._h is None:
             return out
         self._stop.set()
-        self._thread.join(timeout=2)
+        if self._thread is not None:
+            self._thread.join(timeout=2)
         sm = sorted(self.samples)
         if sm:
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.smax, "reasons": sorted(self.reasons), "samples": len(sm),
-                   "how": f"NVML in-process, every {int(self.interval * 1e3)} ms during both timed regions"}
+            how = (f"NVML in-process, background thread every {int(self.interval * 1e3)} ms" if self._thread is not None
+                   else "NVML in-process, from the main thread between steps (every 4th step)") + " during both timed regions"
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.smax, "reasons": sorted(self.reasons), "samples": len(sm), "how": how}
         return out
 
 
@@ -303,9 +318,11 @@ def run_ours(args):
     # warm-up with EXACTLY the timed loop's body (stage timers on, an event per step): the first execution of a host code path
     # on a fresh box pages its code in (tens of ms for one step), which must not land inside the timed region either
     raster.TIMER = raster.StageTimer()
-    for _ in range(args.warmup):
+    for i_step in range(args.warmup):
         step()
         torch.cuda.Event(enable_timing=True).record()
+        if sampler:
+            sampler.poll(i_step + 1)
     barrier_sync()
     raster.TIMER.mean_ms()
 
@@ -318,11 +335,13 @@ def run_ours(args):
     barrier_sync()
     e0.record()
     marks = []
-    for _ in range(args.steps):
+    for i_step in range(args.steps):
         holder = step()
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
         marks.append(ev)
+        if sampler:
+            sampler.poll(i_step + 1)
     e1.record()
     barrier_sync()
     ms = e0.elapsed_time(e1)
@@ -439,6 +458,8 @@ def run_ours(args):
         t0 = time.perf_counter()
         for i in range(args.steps):
             e2e_step(mdl, slot0 + n_e2e_warm + i, first_timestamp + n_e2e_warm + i)
+            if sampler:
+                sampler.poll(i + 1)
         barrier_sync()
         ms_ = (time.perf_counter() - t0) * 1e3
         ring = loss_ring[slot0:slot0 + n_e2e_warm + args.steps]
