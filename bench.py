@@ -29,6 +29,15 @@ NCU_STEP_PROFILE = "r01j_ncu_step_v10.json"  # the committed full ncu capture of
 UNIT = "frames/s"
 
 
+L2_NOTE = "inputs larger than L2 (330 MB of parameters + 0.4 GB of intersection lists per step vs 126 MB)"
+
+
+def config_block(cfg: int, n_gaussians: int, n_actor_gaussians: int, gpus: int):
+    """The `config` object: identical in both arms (--impl ours / reference), so that the two lines name the same workload."""
+    return {"workload": workload_config(cfg), "N_gaussians": int(n_gaussians), "N_actor_gaussians": int(n_actor_gaussians),
+            "parallelism": f"camera-sharded dp{gpus}", "l2": L2_NOTE}
+
+
 def workload_config(cfg: int):
     return {
         1: "cfg1: 50k background Gaussians, 640x480",
@@ -177,7 +186,7 @@ def cpu_frame_fn(cfg: int):
         orc.backward(fw, v_img, v_alpha, v_obj, None)
         return fw.M
 
-    return fn, dict(cores=oracle_c.num_threads(), N=orc.N)
+    return fn, dict(cores=oracle_c.num_threads(), N=orc.N, A=sum(s.params.num_points for s in fr.segments if s.cls == 1))
 
 
 def run_reference(args):
@@ -196,7 +205,9 @@ def run_reference(args):
         "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": workload_config(args.cfg), "M_intersections": int(M), "N_gaussians": info["N"]},
+        "config": config_block(args.cfg, info["N"], info["A"], args.gpus),
+        "workload_stats": {"M_intersections_gsplat_aabb": int(M), "note": "the CPU port lists every tile of the 3-sigma AABB, as gsplat does; "
+                           "the CUDA path drops the (tile, Gaussian) pairs no pixel can accept (exact culling), hence its smaller M"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": "port",
                          "sample": f"{args.steps} full frames (forward+backward) of the same workload, OpenMP C port of "
                                    "the gsplat-0.1.x path (oracle/sgn_oracle.c); the reference itself needs gsplat's "
@@ -623,13 +634,12 @@ def run_ours(args):
             "ms_per_step_argmax": int(per_step_raw.index(per_step[-1])),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_config(args.cfg), "N_gaussians": N, "N_actor_gaussians": A,
-                       "M_intersections": M, "N_visible": n_vis, "max_per_tile": max_per_tile, "parallelism": f"camera-sharded dp{world}",
-                       "l2": "inputs larger than L2 (330 MB of parameters + 0.4 GB of intersection lists per step vs 126 MB)",
-                       "collective": collective,
-                       "binning": ("no host read-back of the intersection count (capacity from earlier frames, "
-                                   f"{raster.ASYNC_STATS['frames']} frames, {raster.ASYNC_STATS['overflows']} overflows)") if async_bin
-                       else "one host read-back of the intersection count per frame (as gsplat)"},
+            "config": config_block(args.cfg, N, A, world),
+            "workload_stats": {"M_intersections": M, "N_visible": n_vis, "max_per_tile": max_per_tile},
+            "collective": collective,
+            "binning": ("no host read-back of the intersection count (capacity from earlier frames, "
+                        f"{raster.ASYNC_STATS['frames']} frames, {raster.ASYNC_STATS['overflows']} overflows)") if async_bin
+            else "one host read-back of the intersection count per frame (as gsplat)",
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(gt_host.numel() + len(frc.segments) * 168 + 96),

@@ -13,7 +13,7 @@ import json
 try:
     d=json.loads(open("gpurun_out/bench_$f.json").read().strip().splitlines()[-1])
     print("$f", {k:d.get(k) for k in ("value","ms_per_step","ms_per_step_median","ms_per_step_max")}, "e2e", round(d["e2e"]["value"],1))
-    print("    ", json.dumps(d["config"]["collective"])[:900])
+    print("    ", json.dumps(d.get("collective", d["config"].get("collective")))[:900])
     if d.get("training_step_cfg5"): print("    cfg5", json.dumps(d.get("training_step_cfg5"))[:400])
 except Exception as e: print("$f", e); print(open("gpurun_out/bench_$f.err").read()[-3000:])
 PY
