@@ -287,6 +287,17 @@ def run_ours(args):
                 skip_unseen = os.environ.get("SGN_DP_SKIP_UNSEEN", "1") != "0"
                 exchange = dp.SymmetricExchange(total, dev, use_multicast={"0": False, "1": True}.get(os.environ.get("SGN_DP_MULTICAST", ""), "auto"),
                                                 flag_rows=counts[0] if skip_unseen else 0)
+                # self-check on this box and world size before anything is timed: the exchange must reproduce NCCL's sum
+                probe = torch.arange(total, device=dev, dtype=torch.float32).remainder_(977.0).mul_(0.001 * (rank + 1))
+                exchange.arena[:total].copy_(probe)
+                exchange.all_reduce()
+                dist.all_reduce(probe)
+                bad = torch.tensor([float((exchange.arena[:total] - probe).abs().max() > 1e-4 * float(probe.abs().max()))], device=dev)
+                dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+                del probe
+                if float(bad.item()) > 0:
+                    raise RuntimeError("sgn_allreduce_sym self-check failed against dist.all_reduce")
+                exchange.arena.zero_()
                 nr = int(os.environ.get("SGN_DP_RANGES", "4"))
                 plan = dp.plan_ranges(counts, offs, widths, nr)
                 collective = {"kind": "sgn_allreduce_sym (this library's kernel over symmetric memory), range by range behind project_bwd",
