@@ -432,6 +432,12 @@ def run_ours(args):
         return m
 
     model = make_model()
+    if exchange is not None:  # the model path delivers its gradients in the symmetric arena too, exchanged range by range
+        def attach(m):
+            m._grad_sink.allocator = lambda n, d: exchange.arena[:n]
+            m._grad_sink.exchange_plan = lambda table: ([(a, b2) for a, b2, _ in plan],
+                                                        lambda k: exchange.after_range(k, plan[k][2], skip_unseen=skip_unseen))
+        attach(model)
     g = torch.Generator().manual_seed(5)
     gt_host = (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).pin_memory()
     mparams = [p for p in model.parameters()]
@@ -462,12 +468,17 @@ def run_ours(args):
             gt_dev[b].copy_(gt_host, non_blocking=True)
             gt_ready[b].record(copy_stream)
         out = mdl.get_outputs(camera_at(timestamp))
+        if exchange is not None and skip_unseen:
+            exchange.publish_visible(mdl._holder.radii)
         main.wait_event(gt_ready[b])
         losses = mdl.get_loss_dict(out, {"image": gt_dev[b]})
         loss = sum(losses.values())
         loss.backward()
         gt_free[b].record(main)
-        dp.allreduce_gradients(mdl._holder.grad_arena)
+        if exchange is not None:
+            exchange.wait_all()  # the ranges' exchanges were started by the backward (project_bwd range by range)
+        else:
+            dp.allreduce_gradients(mdl._holder.grad_arena)
         mdl.after_train(mdl.step)
         loss_ring[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         for p in mparams:

@@ -190,11 +190,15 @@ class _GradSink:
         if key != self.key:
             self.key, self.params, self.arena, self.views = key, list(params), None, []
 
+    allocator = None  # optional callable(total, device) -> float32 tensor: where the persistent arena lives (data parallel: a
+    #                   symmetric allocation the exchange kernel can address on every replica)
+
     def target(self, static: dict, device):
         sizes, _, _ = raster.arena_layout(static)
         total = sum(sizes)
         if self.arena is None or self.arena.numel() != total or self.arena.device != device:
-            self.arena = torch.empty(total, device=device, dtype=torch.float32)
+            self.arena = self.allocator(total, device) if self.allocator is not None else torch.empty(total, device=device, dtype=torch.float32)
+            assert self.arena.numel() == total and self.arena.dtype == torch.float32
             self.views = raster.arena_views(self.arena, static)
         for p in self.params:
             if p.grad is not None:
