@@ -216,3 +216,35 @@ def test_device_resident_frame_table_and_pose_content_key():
     after = resident.get_outputs(cam)["rgb"]
     assert not torch.equal(before, after)
     assert torch.equal(after, build().get_outputs(cam)["rgb"])
+
+
+def test_model_without_the_count_read_back_matches_the_exact_path(setup):
+    """SceneGraphConfig.async_binning: get_outputs without the per-frame host read-back of the intersection count -- same images,
+    same gradients; an empty view gets the reference's early-out depth (0, not the 10 of an empty pixel) on the device."""
+    fr, model, gt = setup
+    for p in model.parameters():
+        p.grad = None
+    ref = model.get_outputs(fr.camera)
+    _loss(model, ref, gt).backward()
+    g_ref = _model_grads(model).clone()
+    raster._ASYNC_STATE.clear()
+    model.config.async_binning = True
+    try:
+        for it in range(3):  # the first frame learns the count, the next ones run without the read-back
+            for p in model.parameters():
+                p.grad = None
+            out = model.get_outputs(fr.camera)
+            _loss(model, out, gt).backward()
+        assert isinstance(model._holder.M, raster.LazyCount)
+        for k in ("rgb", "accumulation", "depth", "object_acc", "background_acc"):
+            assert torch.equal(out[k].detach(), ref[k].detach()), k
+        assert rel_l2(_model_grads(model).cpu().numpy(), g_ref.cpu().numpy()) < 1e-5
+        # nothing in view: look away from the scene
+        import street_gaussians_ns_b200.synthetic as syn2
+        away = syn2.make_camera(fr.camera.width, fr.camera.height, c2w=np.array([[-1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, -1.0, 500.0]]),
+                                time=fr.camera.time)
+        empty = model.get_outputs(away)
+        assert isinstance(model._holder.M, raster.LazyCount) and int(model._holder.M) == 0
+        assert float(empty["depth"].abs().max()) == 0.0 and float(empty["accumulation"].abs().max()) == 0.0
+    finally:
+        model.config.async_binning = None
