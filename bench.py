@@ -25,7 +25,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "rendered frames/sec (fwd+bwd) at 1920x1280, 1M+32x10k Gaussians"
-NCU_STEP_PROFILE = "r01j_ncu_step_v10.json"  # the committed full ncu capture of one step the roofline's pipe / instruction figures quote
+NCU_STEP_PROFILE = "r02i_ncu_step.json"  # the committed full ncu capture of one step the roofline's pipe / instruction figures quote
 UNIT = "frames/s"
 
 

@@ -3,7 +3,7 @@ tools/ncu_step.py) out of a tools/ncu_summary.py summary.   python tools/ncu_tra
 import json
 import sys
 
-STAGE = [("project_fwd", ("project_fwd_kernel",)), ("project_bwd", ("project_bwd_kernel",)),
+STAGE = [("project_fwd", ("project_fwd_",)), ("project_bwd", ("project_bwd_kernel",)),
          ("blend_fwd", ("blend_fwd_kernel", "acc_fwd_kernel")), ("blend_bwd", ("blend_bwd_kernel", "acc_bwd_kernel")),
          ("adam", ("adam_kernel",)),
          ("bin_sort", ("depth_keys", "DeviceRadixSort", "DeviceScan", "inverse_perm", "write_total", "emit_keys", "bin_edges",
