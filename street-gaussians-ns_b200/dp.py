@@ -171,6 +171,7 @@ class SymmetricExchange:
         self.peers_dev = int(self.hdl.buffer_ptrs_dev)
         self.comm_stream = torch.cuda.Stream(device=device)
         self._done = {}
+        self._open = None
         self.tuned = None
         torch.cuda.synchronize(device)
         dist.barrier(self.group)
@@ -249,22 +250,42 @@ class SymmetricExchange:
         self.hdl.barrier(channel=1)   # every part has been pushed to every replica
 
     # ---- range by range, on the communication stream ------------------------------------------------------------
+    # Barriers: range k's exchange starts behind a barrier ("every replica has written range k").  On each rank that barrier
+    # also follows range k-1's kernel in stream order, so passing it means every replica has finished PUSHING range k-1: the
+    # trailing barrier is only needed once, after the last range (K + 1 barriers per step instead of 2 K).
     def after_range(self, k: int, slices, average: bool = False, max_ctas: int = 0, skip_unseen: bool = False):
         """Call right after the launch that PRODUCES range k was enqueued on the current stream."""
         ev = torch.cuda.Event()
         ev.record()
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
-            self.all_reduce(slices, average, max_ctas, skip_unseen)
+            self.hdl.barrier(channel=0)
+            if self._open is not None:  # the previous range has arrived everywhere
+                done = torch.cuda.Event()
+                done.record()
+                self._done[self._open] = done
+            self._launch(slices, 1.0 / self.world if average else 1.0, max_ctas, skip_unseen)
+            self._open = k
+
+    def _close(self):
+        if self._open is None:
+            return
+        with torch.cuda.stream(self.comm_stream):
+            self.hdl.barrier(channel=1)
             done = torch.cuda.Event()
             done.record()
-        self._done[k] = done
+            self._done[self._open] = done
+        self._open = None
 
     def wait_range(self, k: int):
-        """The current stream waits until range k has been exchanged."""
+        """The current stream waits until range k has been exchanged (closes the sequence when k is the last range issued)."""
+        if k not in self._done:
+            assert k == self._open, (k, self._open)
+            self._close()
         torch.cuda.current_stream().wait_event(self._done.pop(k))
 
     def wait_all(self):
+        self._close()
         for k in sorted(self._done):
             torch.cuda.current_stream().wait_event(self._done[k])
         self._done.clear()

@@ -59,6 +59,13 @@ def main():
         ex.wait_all()
         torch.cuda.synchronize()
         assert float((ex.arena - ref).abs().max() / ref.abs().max()) < 1e-6, (tag, "ranges")
+        ex.arena.copy_(src)  # the same with the consumer waiting range by range (what Adam does)
+        for k, (lo, hi) in enumerate(bounds):
+            ex.after_range(k, [(lo, hi - lo)])
+        for k in range(len(bounds)):
+            ex.wait_range(k)
+        torch.cuda.synchronize()
+        assert float((ex.arena - ref).abs().max() / ref.abs().max()) < 1e-6, (tag, "ranges, waited one by one")
         # timing
         def timeit(fn, reps=10):
             for _ in range(3):
