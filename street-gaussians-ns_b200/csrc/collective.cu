@@ -65,14 +65,18 @@ visible_flags_kernel(const int32_t* __restrict__ radii, int64_t n, uint8_t* __re
 }
 
 __device__ __forceinline__ bool rows_unseen(const ArSlices& sl, int s, const uint8_t* __restrict__ vis, int64_t i) {
-    // float4 i of the slice covers floats [4i, 4i+3]: rows (4i)/w .. (4i+3)/w (one row for w >= 4 aligned, up to four for w = 1)
-    const int w = sl.width[s];
-    const int64_t f0 = 4 * i, rows = sl.nrows[s];
-    const int64_t ra = f0 / w;
+    // float4 i of the slice covers floats [4i, 4i+3]: rows (4i)/w .. (4i+3)/w (one or two rows for w >= 4, up to four for w = 1).
+    // 32-bit arithmetic: a slice holds fewer than 2^31 floats (64-bit divisions made this test cost as much as it saved).
+    const unsigned w = (unsigned)sl.width[s];
+    const unsigned f0 = (unsigned)(4 * i), rows = (unsigned)sl.nrows[s];
+    const unsigned ra = f0 / w;
     if (ra >= rows) return true;  // padding behind the last row: zeros on every replica
-    const int64_t rb = min((f0 + 3) / w, rows - 1);
-    uint8_t seen = 0;
-    for (int64_t r = ra; r <= rb; ++r) seen |= vis[sl.row0[s] + r];
+    const unsigned rem = f0 - ra * w;
+    const unsigned more = w >= 4 ? (rem + 3 >= w ? 1u : 0u) : (rem + 3) / w;
+    const unsigned rb = min(ra + more, rows - 1);
+    const uint8_t* v = vis + sl.row0[s];
+    uint8_t seen = v[ra];
+    for (unsigned r = ra + 1; r <= rb; ++r) seen |= v[r];
     return !seen;
 }
 
