@@ -206,15 +206,17 @@ class SymmetricExchange:
     def mode(self) -> str:
         return "multimem (in-switch reduction)" if self.multicast_ptr else "peer loads/stores"
 
-    def publish_visible(self, radii: torch.Tensor) -> None:
+    def publish_visible(self, radii: torch.Tensor, rows: Optional[int] = None) -> None:
         """This rank's per-row visibility (radii > 0, the frame's first ``flag_rows`` rows -- the background, whose rows mean the
         same Gaussian on every replica) into the symmetric flags; call on the stream that produced ``radii``, before the
         backward.  The next exchange with ``skip_unseen`` ORs the replicas' flags once and skips the rows nobody saw."""
-        assert self.flags is not None and radii.dtype == torch.int32 and radii.shape[0] >= self.flag_rows
+        rows = self.flag_rows if rows is None else int(rows)  # the allocation may have room for more rows than the model has now
+        assert self.flags is not None and radii.dtype == torch.int32 and 0 <= rows <= min(self.flag_rows, radii.shape[0])
         C = self._C
-        self._lib.check(self._lib.load().sgn_visible_flags(C.c_void_p(radii.data_ptr()), self.flag_rows, C.c_void_p(self.flags.data_ptr()),
+        self._lib.check(self._lib.load().sgn_visible_flags(C.c_void_p(radii.data_ptr()), rows, C.c_void_p(self.flags.data_ptr()),
                                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "sgn_visible_flags")
         self._union_fresh = False
+        self._union_rows = rows
 
     def _launch(self, slices, scale: float, max_ctas: int = 0, skip_unseen: bool = False):
         C = self._C
@@ -229,7 +231,7 @@ class SymmetricExchange:
         widths = row0 = rows = union = None
         if skip_unseen and self.flags is not None and any(len(sl) == 5 for sl in slices):
             if not self._union_fresh:  # once per step, after the first barrier: every replica's flags are in place
-                self._lib.check(L.sgn_visible_union(C.c_void_p(self.peers_dev), 4 * self.numel, self.world, self.flag_rows,
+                self._lib.check(L.sgn_visible_union(C.c_void_p(self.peers_dev), 4 * self.numel, self.world, getattr(self, "_union_rows", self.flag_rows),
                                                     C.c_void_p(self.union.data_ptr()), stream), "sgn_visible_union")
                 self._union_fresh = True
             widths = (C.c_int32 * n)(*[int(sl[2]) if len(sl) == 5 else 0 for sl in slices])

@@ -650,12 +650,12 @@ class SceneGraphRasterModel(torch.nn.Module):
         SUM / SUM / MAX per sub-model; a replica that has not seen a sub-model since the last refinement contributes
         zeros, and a sub-model nobody saw stays without statistics (the collectives are the same on every replica)."""
         import torch.distributed as dist
-        from . import dp
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
         dev = self.device
         has = torch.tensor([float(sub.xys_grad_norm is not None) for sub in subs], device=dev)
         dist.all_reduce(has, op=dist.ReduceOp.MAX)
+        live = []
         for sub, h in zip(subs, has.tolist()):
             if not h:
                 continue
@@ -663,7 +663,23 @@ class SceneGraphRasterModel(torch.nn.Module):
                 d = sub.__dict__
                 d["xys_grad_norm"], d["vis_counts"], d["max_2Dsize"] = (torch.zeros(sub.num_points, device=dev) for _ in range(3))
                 d["last_size"] = sub.last_size or self.last_size
-            dp.allreduce_densification_stats(sub.xys_grad_norm, sub.vis_counts, sub.max_2Dsize)
+            live.append(sub)
+        if not live:
+            return
+        # TWO collectives for all sub-models (33 x 3 small ones cost ~3 ms per refinement at eight GPUs): the SUM statistics and the
+        # MAX statistic are packed into flat buffers, reduced, and copied back
+        sums = torch.cat([t for sub in live for t in (sub.xys_grad_norm, sub.vis_counts)])
+        maxs = torch.cat([sub.max_2Dsize for sub in live])
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
+        o = m_ = 0
+        for sub in live:
+            n = sub.num_points
+            sub.xys_grad_norm.copy_(sums[o:o + n])
+            sub.vis_counts.copy_(sums[o + n:o + 2 * n])
+            sub.max_2Dsize.copy_(maxs[m_:m_ + n])
+            o += 2 * n
+            m_ += n
 
     def zero_gradient_arena(self) -> torch.Tensor:
         """Data parallel: this replica rendered nothing (early-out) but the others did -- its contribution to the

@@ -76,11 +76,13 @@ class TrainStep:
         out = m.get_outputs(camera)
         if world > 1 and self._exchange is not None:  # which background rows this replica sees (rows nobody sees are not exchanged)
             h = m._holder
-            if h is not None and h.radii is not None and h.radii.shape[0] >= self._exchange.flag_rows and m.visible_model_names[:1] == ["background"]:
-                self._exchange.publish_visible(h.radii)
+            n_bg = self._layout[1]
+            if h is not None and h.radii is not None and h.radii.shape[0] >= n_bg and m.visible_model_names[:1] == ["background"]:
+                self._exchange.publish_visible(h.radii, rows=n_bg)
             else:
                 self._exchange.flags.zero_()
                 self._exchange._union_fresh = False
+                self._exchange._union_rows = n_bg
         losses = m.get_loss_dict(out, batch)
         total = sum(losses.values())
         rendered = isinstance(total, torch.Tensor) and total.requires_grad
@@ -124,17 +126,22 @@ class TrainStep:
         total = sink.total_elems()
         n_bg = m.all_models["background"].num_points
         ex = self._exchange
-        if (ex is not None and ex.numel == (total + 3) // 4 * 4 and ex.flag_rows == n_bg and sink.arena is not None
-                and sink.arena.data_ptr() == ex.arena.data_ptr()):
+        layout = (total, n_bg, tuple(int(x) for x in sink.sizes[:6]))
+        if ex is not None and getattr(self, "_layout", None) == layout and sink.arena is not None and sink.arena.data_ptr() == ex.arena.data_ptr():
             return
         try:
-            self._exchange = None
             sink.exchange_plan = None
-            # the faster path (multimem / peer) is timed once; later arenas (after refinements) reuse the decision
-            ex = dp.SymmetricExchange(total, m.device, self.group, flag_rows=n_bg, use_multicast=getattr(self, "_use_multicast", "auto"))
-            self._use_multicast = bool(ex.multicast_ptr)
+            if ex is None or total > ex.numel or n_bg > ex.flag_rows:
+                # a symmetric allocation is a collective (allocation + handle exchange + barrier): allocate with headroom so
+                # that refinements -- which grow the model by a few per cent at a time -- re-use it; the faster path
+                # (multimem / peer) is timed once, later allocations reuse the decision
+                self._exchange = None
+                ex = dp.SymmetricExchange(int(total * 1.25), m.device, self.group, flag_rows=int(n_bg * 1.25) + 128,
+                                          use_multicast=getattr(self, "_use_multicast", "auto"))
+                self._use_multicast = bool(ex.multicast_ptr)
+            ex.arena[:total].zero_()
             sink.set_arena(ex.arena[:total])
-            self._exchange = ex
+            self._exchange, self._layout = ex, layout
             # the background's six tensors are the first six slices of the full layout: K - 1 row ranges + "everything else"
             K = max(2, self.pipeline_chunks or 4)
             widths = [3, 3, 4, 3 * int(m.all_models["background"].gauss_params["features_dc"].shape[1]),
