@@ -148,16 +148,7 @@ class TrainStep:
                       3 * int(m.all_models["background"].gauss_params["features_rest"].shape[1]), 1]
             offs = [int(sink.offsets[k]) for k in range(6)]
             bg_end = int(sink.offsets[5] + sink.sizes[5])
-            chunks = (n_bg + 127) // 128
-            per = (chunks + (K - 1) - 1) // (K - 1)
-            self._ranges = []
-            c = 0
-            while c < chunks:
-                c1 = min(chunks, c + per)
-                r0, r1 = c * 128, min(n_bg, c1 * 128)
-                self._ranges.append((c, c1, [(offs[k] + r0 * widths[k], ((r1 - r0) * widths[k] + 3) // 4 * 4, widths[k], r0, r1 - r0)
-                                             for k in range(6)]))
-                c = c1
+            self._ranges = dp.plan_ranges([n_bg], [offs], [widths], K - 1)  # row ranges of the background, with row descriptions
             self._tail = (bg_end, total - bg_end)
             sink.exchange_plan = self._plan
         except Exception as e:  # no peer access / no symmetric-memory support on this box: the NCCL path is the fallback
