@@ -107,6 +107,16 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
     if world > 1:
         dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
     last = float(sum(v.detach() for v in losses.values()))
+    replicas_identical = None
+    if world > 1:
+        try:  # every replica must hold bit-identical parameters after the run: same exchange result, same Adam, same refinements
+            chk = torch.stack([p.detach().double().sum() for p in model.all_models["background"].gauss_params.values()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            replicas_identical = bool(torch.equal(lo, hi))
+        except Exception:
+            replicas_identical = None
     if rank != 0:
         return None
     counts1 = [sub.num_points for sub in model.all_models.values()]
@@ -126,7 +136,7 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
                                      (f"pipelined with Adam over {pipeline_chunks} ranges" if pipeline_chunks else "serial"))) if world > 1 else "none"},
         "gaussians_before": int(sum(counts0)), "gaussians_after": int(sum(counts1)),
         "submodels_changed": int(sum(a != b for a, b in zip(counts0, counts1))),
-        "loss_first": first, "loss_last": last}
+        "loss_first": first, "loss_last": last, "replicas_identical": replicas_identical}
 
 
 def main():
