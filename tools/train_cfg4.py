@@ -123,7 +123,7 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
     ms = float(dev_ms[0].item())
     return {
         "metric": "training steps/s (render 1 camera per rank + L1 + backward + gradient all-reduce + fused Adam + densification "
-                  f"statistics, refinement every {refine_every} steps)", "value": world / (ms * 1e-3), "unit": "steps/s",
+                  f"statistics, refinement every {refine_every} steps; timed steps {start_step + warmup}..{start_step + warmup + steps - 1})", "value": world / (ms * 1e-3), "unit": "steps/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "wall_ms_per_step": float(dev_ms[1].item()),
         "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"cfg{4 if world == 1 else 5}: 5 cameras x 85 frames, {sc.n_bg} background + 32 x {sc.n_act} actor Gaussians, "
