@@ -65,6 +65,16 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
     times = [float(f) for f in range(num_frames)]
     if resident_table:
         model.prepare_frames(times)
+    if world > 1:
+        # NCCL sets up its channels lazily, at the first collective of a size class: the statistics exchange of the first
+        # refinement would otherwise pay that one-time cost (tens of ms) inside the timed steps
+        warm = torch.zeros(1 << 22, device=dev)
+        dist.all_reduce(warm, op=dist.ReduceOp.SUM)
+        dist.all_reduce(warm, op=dist.ReduceOp.MAX)
+        small = torch.zeros(64, device=dev, dtype=torch.int64)
+        dist.all_reduce(small, op=dist.ReduceOp.MIN)
+        dist.all_reduce(small, op=dist.ReduceOp.MAX)
+        del warm, small
     if async_binning:
         # without the per-frame read-back of the intersection count the list buffers have a capacity learnt from earlier frames:
         # look at every rig camera at three points of the drive once (no gradients) so that the capacity covers the widest view
