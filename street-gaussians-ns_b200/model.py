@@ -618,13 +618,13 @@ class SceneGraphRasterModel(torch.nn.Module):
             d = sub.__dict__
             d["xys_grad_norm"] = d["vis_counts"] = d["max_2Dsize"] = None  # :644-646
         totals = iter(refine.read_totals([e[1] for e in decided if e is not None]))
-        plans = []
+        plans, records = [], []
         for sub, entry in zip(subs, decided):  # split samples are drawn in sub-model order, as the reference's callbacks run
             plan = None
             if entry is not None:
                 plan = refine.finish_plan(entry[0], entry[1], next(totals), entry[2], generator)
                 if self.config.refine_record:
-                    sub.__dict__["refine_record_dict"] = plan.record()
+                    records.append((sub, plan, plan.record_counts()))
                 if not plan.changed:
                     plan = None
             plans.append(plan)
@@ -644,6 +644,9 @@ class SceneGraphRasterModel(torch.nn.Module):
             if st is not None:  # opacity reset on the survivors (:629-642)
                 subs[i].gauss_params["opacities"].data.clamp_(max=refine.opacity_reset_logit(st))
                 adapter.zero_moments(i, 5)
+        if records:  # the logged counters of all sub-models: one read-back, after everything else has been enqueued
+            for (sub, plan, _), counts in zip(records, torch.stack([r[2] for r in records]).tolist()):
+                sub.__dict__["refine_record_dict"] = plan.record_from(counts)
 
     def _sync_densification_stats(self, subs) -> None:
         """Replicas rendered different cameras: identical split / cull decisions need identical statistics.

@@ -110,19 +110,27 @@ class Plan:
         """False when every row survives and nothing is added: the tensors can stay as they are."""
         return not (self.totals[0] == self.n and self.totals[1] == 0 and self.totals[2] == 0)
 
-    def record(self) -> Dict[str, int]:
-        """The counters the reference logs in ``refine_record_dict`` (:572-588, :655, :668); one read-back."""
-        f = self.flags
-        split, dup, alpha = (f & _lib.RF_SPLIT) != 0, (f & _lib.RF_DUP) != 0, (f & _lib.RF_ALPHA) != 0
-        copies = 1 + self.cfg.n_split_samples * split.to(torch.int64) + dup.to(torch.int64)  # rows cull_gaussians sees per source row
-        vals = torch.stack([((f & _lib.RF_HIGH_GRAD) != 0).sum(), split.sum(), dup.sum(), (alpha * copies).sum(),
-                            ((f & _lib.RF_TOOBIG) != 0).sum()]).tolist()
-        out = {"refine_culls_alpha_count": vals[3]}
+    def record_counts(self) -> torch.Tensor:
+        """Seven flag-pattern counts as a device tensor (three launches, nothing read back): rows with HIGH_GRAD, SPLIT, DUP,
+        TOOBIG, ALPHA, ALPHA and SPLIT, ALPHA and DUP set."""
+        masks = torch.tensor([_lib.RF_HIGH_GRAD, _lib.RF_SPLIT, _lib.RF_DUP, _lib.RF_TOOBIG, _lib.RF_ALPHA,
+                              _lib.RF_ALPHA | _lib.RF_SPLIT, _lib.RF_ALPHA | _lib.RF_DUP], dtype=torch.uint8).to(self.flags.device, non_blocking=True)
+        return ((self.flags.view(-1, 1) & masks) == masks).sum(0)
+
+    def record_from(self, counts: Sequence[int]) -> Dict[str, int]:
+        """The counters the reference logs in ``refine_record_dict`` (:572-588, :655, :668) from ``record_counts()`` read
+        back by the caller (one read-back for all sub-models of a refinement)."""
+        high, split, dup, toobig, alpha, alpha_split, alpha_dup = (int(x) for x in counts)
+        # cull_gaussians sees 1 + n_split_samples * split + dup rows per source row; the alpha mark of a source row counts for all of them
+        out = {"refine_culls_alpha_count": alpha + self.cfg.n_split_samples * alpha_split + alpha_dup}
         if self.cfg.densify:
-            out.update(high_grads_count=vals[0], refine_splits_count=vals[1], refine_dups_count=vals[2])
+            out.update(high_grads_count=high, refine_splits_count=split, refine_dups_count=dup)
         if self.cfg.cull_big:
-            out["refine_culls_toobigs_count"] = vals[4]  # old rows only (the flag byte does not keep it for new rows)
+            out["refine_culls_toobigs_count"] = toobig  # old rows only (the flag byte does not keep it for new rows)
         return out
+
+    def record(self) -> Dict[str, int]:
+        return self.record_from(self.record_counts().tolist())
 
 
 def decide_submodel(scales: torch.Tensor, opacities: torch.Tensor, xys_grad_norm: Optional[torch.Tensor],

@@ -106,12 +106,29 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
         first = first if first is not None else float(sum(v.detach() for v in losses.values()))
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]  # per-step device time: where a refinement's cost lands
+    host_ms = []
+    profile_refine = os.environ.get("SGN_PROFILE_REFINE") == "1" and rank == 0
     t0 = time.perf_counter()
     e0.record()
     for i in range(steps):
-        losses = one(warmup + i)
+        h0 = time.perf_counter()
+        if profile_refine and refine_every > 0 and (start_step + warmup + i) % refine_every == 0:
+            import cProfile
+            import pstats
+            prof = cProfile.Profile()
+            prof.enable()
+            losses = one(warmup + i)
+            torch.cuda.synchronize()
+            prof.disable()
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
+        else:
+            losses = one(warmup + i)
+        marks[i].record()
+        host_ms.append((time.perf_counter() - h0) * 1e3)
     e1.record()
     sync()
+    step_ms = [round((e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 3) for i in range(steps)]
     wall_ms = (time.perf_counter() - t0) * 1e3 / steps
     dev_ms = torch.tensor([e0.elapsed_time(e1) / steps, wall_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -146,7 +163,8 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
                                      (f"pipelined with Adam over {pipeline_chunks} ranges" if pipeline_chunks else "serial"))) if world > 1 else "none"},
         "gaussians_before": int(sum(counts0)), "gaussians_after": int(sum(counts1)),
         "submodels_changed": int(sum(a != b for a, b in zip(counts0, counts1))),
-        "loss_first": first, "loss_last": last, "replicas_identical": replicas_identical}
+        "loss_first": first, "loss_last": last, "replicas_identical": replicas_identical,
+        "step_ms_rank0": step_ms, "host_ms_rank0": [round(x, 3) for x in host_ms]}
 
 
 def main():
