@@ -550,11 +550,11 @@ def run_ours(args):
             spec = importlib.util.spec_from_file_location("train_cfg4", os.path.join(ROOT, "tools", "train_cfg4.py"))
             tc = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(tc)
-            # the reference's schedule (refine_every 100); the window is placed so that ONE real refinement (step 600: densify --
-            # split / duplicate / cull with the Adam state carried along, then re-staging of the resident tables) falls into the
-            # timed steps -- i.e. refinements are over-represented (1 in K instead of 1 in 100), never under-represented
             w45 = max(args.warmup, 5)
-            cfg45 = tc.run(steps=max(args.steps, 20), warmup=w45, refine_every=100, start_step=600 - w45 - 3, overlap=world > 1)
+            # one full refinement period of the reference's schedule (refine_every = 100): whatever the alignment, exactly ONE real
+            # refinement (step 600: densify -- statistics exchange, split / duplicate / cull with the Adam state carried along,
+            # then re-staging of the resident tables) is inside the timed steps, as in 100 steps of a training run
+            cfg45 = tc.run(steps=100, warmup=w45, refine_every=100, start_step=600 - w45 - 3, overlap=world > 1)
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
                 cfg45["cpu_baseline"] = cfg4_cpu_baseline()
         except Exception as e:

@@ -42,11 +42,26 @@ def padded(numel: int) -> int:
     return (numel + 3) // 4 * 4
 
 
+def arena_capacity(elems: int) -> int:
+    """Moment arenas are allocated on a geometric grid of sizes (eight per octave, >= 2 % above the request): a refinement
+    changes the model by a few per cent, so the arenas of the new layout almost always have the SAME capacity as the ones
+    they replace and come out of the caching allocator's pool instead of cudaMalloc -- which, with peer access enabled
+    (data parallel), maps every new allocation into all peers (measured: 42 ms per 0.5 GB on two B200s,
+    profiles/r02p_refine_profile_2gpu.txt)."""
+    want = max(int(elems * 1.02), 1024)
+    octave = 1 << (want.bit_length() - 1)
+    for k in range(8, 17):
+        if octave * k // 8 >= want:
+            return octave * k // 8
+    return octave * 2
+
+
 class FusedAdam:
     """``params``: per sub-model (segment), the six parameter tensors in PARAM_NAMES order (the order of the gradient arena)."""
 
     def __init__(self, params: Sequence[Sequence[torch.Tensor]], lrs: Dict[str, float] = None, betas=(0.9, 0.999),
-                 eps: float = 1e-15, chunk_elems: Optional[int] = None, extra: Optional[Dict[str, Tuple[torch.Tensor, float]]] = None):
+                 eps: float = 1e-15, chunk_elems: Optional[int] = None, extra: Optional[Dict[str, Tuple[torch.Tensor, float]]] = None,
+                 reserve_spare: bool = False):
         """``extra``: further tensors stepped by the same launch, name -> (tensor, lr): the reference's other Adam groups on
         the step -- the sky cube map ``env_map.base`` [6, res, res, 3] (sgn_splatfacto.py:114-116; group ``sky`` of
         sgn_config.py:71-108).  Their gradients are not part of the rasterizer's arena (the sky gradient comes out of
@@ -58,9 +73,17 @@ class FusedAdam:
         self._extra = dict(extra or {})
         self.step_count = 0  # calls of step(); the bias correction uses the per-tensor counts below
         self._install(params)
-        self.exp_avg = torch.zeros(self.moment_elems, device=self.device)
-        self.exp_avg_sq = torch.zeros(self.moment_elems, device=self.device)
+        self.exp_avg, self.exp_avg_sq = self._new_moments(), self._new_moments()
+        if reserve_spare:
+            # a refinement needs the old and the new arenas at the same time: put a second pair into the caching allocator's
+            # pool now, so that the first refinement does not call cudaMalloc in the middle of training either
+            spare = [torch.empty(arena_capacity(self.moment_elems), device=self.device) for _ in range(2)]
+            del spare
         self.steps = np.zeros(len(self._params), np.int64)  # torch.optim.Adam keeps state["step"] per parameter
+
+    def _new_moments(self) -> torch.Tensor:
+        """A zeroed moment arena of the current layout: the first ``moment_elems`` floats of an allocation of grid capacity."""
+        return torch.zeros(arena_capacity(self.moment_elems), device=self.device)[:self.moment_elems]
 
     # ---- layout ---------------------------------------------------------------------------------------------
     def _install(self, params: Sequence[Sequence[torch.Tensor]]) -> None:
@@ -210,8 +233,7 @@ class FusedAdam:
         assert len(params) == self.num_segments
         old = (self.exp_avg, self.exp_avg_sq, self.offsets.copy())
         self._install(params)
-        self.exp_avg = torch.zeros(self.moment_elems, device=self.device)
-        self.exp_avg_sq = torch.zeros(self.moment_elems, device=self.device)
+        self.exp_avg, self.exp_avg_sq = self._new_moments(), self._new_moments()
         for i in self.extra_index.values():  # the extra tensors do not change in a refinement: their moments move along
             a, b, n = int(old[2][i]), int(self.offsets[i]), int(self.sizes[i])
             self.exp_avg[b:b + n].copy_(old[0][a:a + n])

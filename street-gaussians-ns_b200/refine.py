@@ -94,6 +94,9 @@ def _stream(t: torch.Tensor):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream) if t.is_cuda else None
 
 
+_RECORD_MASKS: Dict[torch.device, torch.Tensor] = {}
+
+
 class Plan:
     """Decision for one sub-model: flag byte per row, prefix sums, the four totals and the split samples."""
 
@@ -113,8 +116,11 @@ class Plan:
     def record_counts(self) -> torch.Tensor:
         """Seven flag-pattern counts as a device tensor (three launches, nothing read back): rows with HIGH_GRAD, SPLIT, DUP,
         TOOBIG, ALPHA, ALPHA and SPLIT, ALPHA and DUP set."""
-        masks = torch.tensor([_lib.RF_HIGH_GRAD, _lib.RF_SPLIT, _lib.RF_DUP, _lib.RF_TOOBIG, _lib.RF_ALPHA,
-                              _lib.RF_ALPHA | _lib.RF_SPLIT, _lib.RF_ALPHA | _lib.RF_DUP], dtype=torch.uint8).to(self.flags.device, non_blocking=True)
+        masks = _RECORD_MASKS.get(self.flags.device)
+        if masks is None:  # uploaded once per device: a pageable host-to-device copy per sub-model would wait for the stream each time
+            masks = _RECORD_MASKS[self.flags.device] = torch.tensor(
+                [_lib.RF_HIGH_GRAD, _lib.RF_SPLIT, _lib.RF_DUP, _lib.RF_TOOBIG, _lib.RF_ALPHA, _lib.RF_ALPHA | _lib.RF_SPLIT,
+                 _lib.RF_ALPHA | _lib.RF_DUP], dtype=torch.uint8).to(self.flags.device)
         return ((self.flags.view(-1, 1) & masks) == masks).sum(0)
 
     def record_from(self, counts: Sequence[int]) -> Dict[str, int]:
