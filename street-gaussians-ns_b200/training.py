@@ -217,3 +217,51 @@ class TrainStep:
             dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
             assert torch.equal(lo, hi), "replicas diverged in a refinement (row counts differ)"
+
+
+def warm_up_refinement(model: SceneGraphRasterModel, rows: Sequence[int] = (65536, 10000, 10000), step: Optional[int] = None) -> Dict[str, object]:
+    """Runs ONE refinement of a throwaway model (same configuration and tensor widths as ``model``, random rows and
+    statistics that straddle every threshold, its own generator) and drops it.  Nothing of ``model`` is touched and no
+    collective is issued.
+
+    Why: CUDA loads a kernel's module at its first launch.  The first refinement of a process is the first launch of ~20
+    kernels nothing else on the training step uses (the decide / apply kernels, scans, reductions, the normal sampler,
+    bitwise and comparison kernels, ...), which cost tens of milliseconds of host time in the middle of training
+    (profiles/r02p_refine_profile_*: 60 ms for a refinement whose kernels run a few ms).  Calling this once after the
+    model is built moves that one-time cost out of the loop, like the warm-up steps of a benchmark."""
+    from dataclasses import replace
+
+    from .scene import PARAM_NAMES, GaussianSet
+    dev = model.device
+    subs = list(model.all_models.values())
+    widths = [subs[0]] + [s for s in subs[1:]][:len(rows) - 1]
+    g = torch.Generator(device=dev).manual_seed(12345)
+
+    def rand(*shape):
+        return torch.randn(shape, device=dev, generator=g)
+
+    sets = []
+    for n, like in zip(rows, widths):
+        F, R = int(like.gauss_params["features_dc"].shape[1]), int(like.gauss_params["features_rest"].shape[1])
+        sets.append(GaussianSet(rand(n, 3) * 5, rand(n, 3) * 1.5 - 4.0, rand(n, 4), rand(n, F, 3), rand(n, R, 3), rand(n, 1) * 2.5 - 1.0))
+    st = model.config.refine
+    step = step if step is not None else st.warmup_length + st.refine_every * max(1, -(-(model.config.num_train_data + st.refine_every + 1) // st.refine_every))
+    cfg = replace(model.config, full_gradient_arena=False, refine_record=True)
+    tmp = SceneGraphRasterModel(sets[0], {str(i): s for i, s in enumerate(sets[1:])}, cfg).to(dev)
+    tmp.train()
+    tmp.step = step
+    for sub in tmp.all_models.values():
+        n, d = sub.num_points, sub.__dict__
+        vis = torch.randint(1, 9, (n,), device=dev, generator=g).float()
+        d["vis_counts"] = vis
+        d["xys_grad_norm"] = torch.rand(n, device=dev, generator=g) * vis * 2.5e-6
+        d["max_2Dsize"] = torch.rand(n, device=dev, generator=g) * 0.2
+        d["last_size"] = (240, 320)
+    opt = FusedAdam(tmp.optimizer_params())
+    tmp.refinement_after(opt, step, generator=g, sync_stats=False)
+    rowsum = torch.tensor([s.num_points for s in tmp.all_models.values()], device=dev, dtype=torch.int64)
+    torch.equal(rowsum, rowsum.clone())  # the replica check of TrainStep._maybe_refine
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    return {"step": step, "rows_before": [int(n) for n in rows[:len(sets)]], "rows_after": rowsum.tolist(),
+            "records": [dict(s.refine_record_dict) for s in tmp.all_models.values()]}

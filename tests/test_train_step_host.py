@@ -51,3 +51,20 @@ def test_per_submodel_cadence_when_no_global_one_is_given(monkeypatch):
     for s in (100, 125, 150, 300):
         step_fn(s, camera=None, batch={})
     assert calls == [(100, True), (150, True), (300, True)]
+
+
+def test_warm_up_refinement_exercises_every_branch_and_leaves_the_model_alone(monkeypatch):
+    from tests.host_harness import load_refine_harness
+    from street_gaussians_ns_b200 import refine, training
+    harness = load_refine_harness()
+    monkeypatch.setattr(refine, "_backend", lambda: harness)
+    monkeypatch.setattr(refine, "_require_cuda", lambda t, what: None)
+    model, _ = build_model()
+    model.config.num_train_data = 425
+    before = [p.detach().clone() for p in model.parameters()]
+    info = training.warm_up_refinement(model, rows=(4000, 1000, 1000))
+    assert all(torch.equal(a, b) for a, b in zip(before, model.parameters()))
+    assert refine.phase(model.config.refine, info["step"], 425)[0]               # a densifying step was picked
+    assert all(a != b for a, b in zip(info["rows_before"], info["rows_after"]))  # every sub-model was re-laid out
+    for rec in info["records"]:  # splits, duplicates and culls all happened: the kernels' branches and the sampler ran
+        assert rec["refine_splits_count"] > 0 and rec["refine_dups_count"] > 0 and rec["refine_culls_alpha_count"] > 0

@@ -75,6 +75,14 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
         dist.all_reduce(small, op=dist.ReduceOp.MIN)
         dist.all_reduce(small, op=dist.ReduceOp.MAX)
         del warm, small
+    # CUDA loads a kernel's module at its first launch: the first refinement of a process would pay for ~20 kernels nothing else
+    # on the step uses (tens of ms of host time).  One refinement of a throwaway model loads them; best effort, process-local
+    try:
+        from street_gaussians_ns_b200.training import warm_up_refinement
+        info = warm_up_refinement(model)
+        refine_warm = {"ok": True, "rows_before": info["rows_before"], "rows_after": info["rows_after"]}
+    except Exception as e:  # the measurement is still valid without it (the first refinement then includes the module loads)
+        refine_warm = {"ok": False, "error": f"{type(e).__name__}: {e}"[:200]}
     if async_binning:
         # without the per-frame read-back of the intersection count the list buffers have a capacity learnt from earlier frames:
         # look at every rig camera at three points of the drive once (no gradients) so that the capacity covers the widest view
@@ -156,6 +164,7 @@ def run(steps: int = 50, warmup: int = 5, scale: float = 1.0, refine_every: int 
         "config": {"workload": f"cfg{4 if world == 1 else 5}: 5 cameras x 85 frames, {sc.n_bg} background + 32 x {sc.n_act} actor Gaussians, "
                                f"{W}x{H}; rank r renders camera (step*g + r) mod 425; actors have a box within {actor_range} m of the ego vehicle",
                    "parallelism": f"camera-sharded dp{world}", "start_step": start_step, "refine_every": refine_every,
+                   "refinement_kernels_loaded_before_timing": refine_warm,
                    "binning": "no host read-back of the intersection count" if async_binning else "one read-back per frame",
                    "segment_table": "device-resident (staged up front; re-staged per timestamp on first use after a refinement)" if resident_table else "host build per frame",
                    "collective": ("all-reduce(AVG) of the gradient arena (layout of all sub-models), "
