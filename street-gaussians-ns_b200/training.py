@@ -231,7 +231,7 @@ def warm_up_refinement(model: SceneGraphRasterModel, rows: Sequence[int] = (6553
     model is built moves that one-time cost out of the loop, like the warm-up steps of a benchmark."""
     from dataclasses import replace
 
-    from .scene import PARAM_NAMES, GaussianSet
+    from .scene import GaussianSet
     dev = model.device
     subs = list(model.all_models.values())
     widths = [subs[0]] + [s for s in subs[1:]][:len(rows) - 1]
